@@ -1,0 +1,145 @@
+"""ctypes binding of libhiccup_b200.so (include/hiccup_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is usable, the numeric entry
+points raise `HicError` / `RuntimeError` rather than computing on the host.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhiccup_b200.so")
+
+c_void_p, c_int, c_int32, c_uint32, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
+                                                ctypes.c_uint32, ctypes.c_size_t)
+TIE_STATS = 4
+TIE_RECORD_BYTES = 16
+
+
+class HicError(RuntimeError):
+    pass
+
+
+class Geometry(ctypes.Structure):
+    _fields_ = [("h", c_int32), ("w", c_int32), ("hc", c_int32), ("wc", c_int32),
+                ("nby_l", c_int32), ("nbx_l", c_int32), ("nby_c", c_int32), ("nbx_c", c_int32),
+                ("nb_l", ctypes.c_int64), ("nb_c", ctypes.c_int64), ("blocks_per_image", ctypes.c_int64),
+                ("out_h", c_int32), ("out_w", c_int32)]
+
+
+#: every symbol include/hiccup_b200.h declares -> (restype, argtypes)
+SIGNATURES = {
+    "hic_version": (c_int, []),
+    "hic_last_error": (ctypes.c_char_p, []),
+    "hic_device_count": (c_int, [ctypes.POINTER(c_int)]),
+    "hic_set_device": (c_int, [c_int]),
+    "hic_device_name": (c_int, [ctypes.c_char_p, c_size_t]),
+    "hic_malloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
+    "hic_free": (c_int, [c_void_p]),
+    "hic_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
+    "hic_host_free": (c_int, [c_void_p]),
+    "hic_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hic_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hic_memset": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    "hic_stream_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "hic_stream_destroy": (c_int, [c_void_p]),
+    "hic_stream_sync": (c_int, [c_void_p]),
+    "hic_dct_geometry_of": (c_int, [c_int32, c_int32, ctypes.POINTER(Geometry)]),
+    "hic_dct_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
+    "hic_blocks_to_planes": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_planes_to_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_dct_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol (no CUDA call is made)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise HicError("libhiccup_b200.so is not built (%s); run `python -m hiccup_b200.build` -- "
+                           "there is no CPU fallback" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if the header and the library diverge
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().hic_last_error()
+        raise HicError("hiccup_b200 error %d: %s" % (rc, (msg or b"").decode("utf-8", "replace")))
+
+
+_device_ready = False
+
+
+def require_device():
+    """Fail loudly when there is no CUDA device (the product has no host path)."""
+    global _device_ready
+    if _device_ready:
+        return
+    lib = load()
+    n = c_int(0)
+    rc = lib.hic_device_count(ctypes.byref(n))
+    if rc != 0 or n.value < 1:
+        raise HicError("no CUDA device is available; hiccup_b200 has no CPU fallback (%s)"
+                       % (lib.hic_last_error() or b"").decode("utf-8", "replace"))
+    _device_ready = True
+
+
+def geometry(h, w):
+    g = Geometry()
+    check(load().hic_dct_geometry_of(int(h), int(w), ctypes.byref(g)))
+    return g
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (no torch involved)."""
+
+    def __init__(self, nbytes):
+        require_device()
+        self.nbytes = int(nbytes)
+        p = c_void_p()
+        check(load().hic_malloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def upload(self, array, stream=None):
+        a = np.ascontiguousarray(array)
+        assert a.nbytes <= self.nbytes
+        check(load().hic_memcpy_h2d(self.ptr, a.ctypes.data, a.nbytes, stream))
+        return a            # keep alive until the stream is synchronised
+
+    def download(self, dtype, count, stream=None, offset=0):
+        out = np.empty(int(count), dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        check(load().hic_memcpy_d2h(out.ctypes.data, self.ptr + offset, out.nbytes, stream))
+        check(load().hic_stream_sync(stream))
+        return out
+
+    def zero(self, stream=None):
+        check(load().hic_memset(self.ptr, 0, self.nbytes, stream))
+
+    def free(self):
+        if self.ptr:
+            load().hic_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sync(stream=None):
+    check(load().hic_stream_sync(stream))

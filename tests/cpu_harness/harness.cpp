@@ -1,0 +1,117 @@
+// CPU check harness: runs the kernels' shared __host__ __device__ arithmetic (hic_core.cuh) on the
+// host so it can be compared with the oracle without a GPU.  TEST INFRASTRUCTURE ONLY -- it is not
+// linked into libhiccup_b200.so and nothing under hiccup_b200/ loads it.
+// Build: g++ -O2 -ffp-contract=off -std=c++17 -shared -fPIC harness.cpp -o libhic_cpu_harness.so
+#include <string.h>
+#include "../../hiccup_b200/csrc/hic_core.cuh"
+
+using namespace hic;
+
+static const int LUM[64] = HIC_LUM_TABLE;
+static const int CHROMA[64] = HIC_CHROMA_TABLE;
+static const uint8_t ZZ[64] = HIC_ZIGZAG8;
+
+extern "C" {
+
+void hx_ducc_dct2(double* x, int n) { for (int i = 0; i < n; ++i) ducc_dct2_8(x + 8 * i); }
+void hx_ducc_dct3(double* x, int n) { for (int i = 0; i < n; ++i) ducc_dct3_8(x + 8 * i); }
+int hx_exact_coef(const int16_t* px, int u, int v, int q) { return exact_quantised_coef(px, u, v, q); }
+double hx_exact_sample(const int32_t* cq, int y, int x) { return exact_decoded_sample(cq, y, x); }
+
+// float32 forward path of K1's transform_block, restated on the host with the same primitives.
+// px: [nb][64] int16 (x-128, row major); out: [nb][64] int16 in scan order (float32 result, before
+// fix-up); mask: [nb] near-tie masks; ratio: [nb] max over AC coefficients of
+// |v32 - v64| * q / (4 * 2^-24 * E)  (the quantity HIC_TIE_KAPPA must bound).
+void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64_t* mask, double* ratio) {
+    const int* q = kind == 0 ? LUM : CHROMA;
+    float rq[64], qf[64];
+    for (int u = 0; u < 8; ++u)
+        for (int v = 0; v < 8; ++v) {
+            rq[8 * u + v] = (float)(4.0 * aan_g(u) * aan_g(v) / q[8 * u + v]);
+            qf[8 * u + v] = (float)q[8 * u + v];
+        }
+    const float MAGIC = 12582912.0f;
+    for (int b = 0; b < nb; ++b) {
+        float v[64];
+        float abs_sum = 0.f;
+        for (int i = 0; i < 64; ++i) { v[i] = (float)px[64 * b + i]; abs_sum += fabsf(v[i]); }
+        for (int r = 0; r < 8; ++r)
+            aan_forward8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
+        for (int c = 0; c < 8; ++c)
+            aan_forward8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
+        const float band = (float)(HIC_TIE_KAPPA * 4.0 / 16777216.0) * abs_sum;
+        // float64 truth for the ratio
+        double truth[64];
+        {
+            double a[64];
+            for (int i = 0; i < 8; ++i) {
+                double row[8];
+                for (int j = 0; j < 8; ++j) row[j] = px[64 * b + 8 * i + j];
+                ducc_dct2_8(row);
+                for (int j = 0; j < 8; ++j) a[8 * i + j] = row[j];
+            }
+            for (int j = 0; j < 8; ++j) {
+                double col[8];
+                for (int i = 0; i < 8; ++i) col[i] = a[8 * i + j];
+                ducc_dct2_8(col);
+                for (int i = 0; i < 8; ++i) truth[8 * i + j] = col[i];
+            }
+        }
+        uint64_t m = 0;
+        double worst = 0.0;
+        for (int k = 0; k < 64; ++k) {
+            const int nat = ZZ[k];
+            const float t = fmaf(v[nat], rq[nat], MAGIC);
+            int32_t bits;
+            memcpy(&bits, &t, 4);
+            out[64 * b + k] = (int16_t)(bits & 0xFFFF);
+            if (k != 0) {
+                const float d = fmaf(v[nat], rq[nat], MAGIC - t);
+                if ((0.5f - fabsf(d)) * qf[nat] <= band) m |= (1ull << k);
+                if (abs_sum > 0.f) {
+                    const double v32 = (double)v[nat] * (double)rq[nat];
+                    const double v64 = truth[nat] / q[nat];
+                    const double r = fabs(v32 - v64) * q[nat] / (4.0 / 16777216.0 * abs_sum);
+                    if (r > worst) worst = r;
+                }
+            }
+        }
+        mask[b] = m;
+        ratio[b] = worst;
+    }
+}
+
+// float32 inverse path of K7's inverse_block.  coef: [nb][64] int16 scan order; out [nb][64] uint8.
+void hx_inverse_blocks(const int16_t* coef, int nb, int kind, uint8_t* out) {
+    const int* q = kind == 0 ? LUM : CHROMA;
+    float dq[64];
+    for (int u = 0; u < 8; ++u)
+        for (int v = 0; v < 8; ++v) dq[8 * u + v] = (float)(q[8 * u + v] * aan_h(u) * aan_h(v) / 256.0);
+    for (int b = 0; b < nb; ++b) {
+        float v[64];
+        for (int k = 0; k < 64; ++k) v[ZZ[k]] = (float)coef[64 * b + k] * dq[ZZ[k]];
+        for (int r = 0; r < 8; ++r)
+            aan_inverse8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
+        for (int c = 0; c < 8; ++c)
+            aan_inverse8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
+        for (int i = 0; i < 64; ++i) out[64 * b + i] = (uint8_t)((int)(v[i] + 128.f) & 0xFF);
+    }
+}
+
+void hx_colour(const uint8_t* rgb, int n, uint8_t* ycrcb) {
+    for (int i = 0; i < n; ++i) {
+        int y, cr, cb;
+        rgb_to_ycrcb(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], y, cr, cb);
+        ycrcb[3 * i] = (uint8_t)y; ycrcb[3 * i + 1] = (uint8_t)cr; ycrcb[3 * i + 2] = (uint8_t)cb;
+    }
+}
+
+void hx_colour_inv(const uint8_t* ycrcb, int n, uint8_t* rgb) {
+    for (int i = 0; i < n; ++i) {
+        int r, g, b;
+        ycrcb_to_rgb(ycrcb[3 * i], ycrcb[3 * i + 1], ycrcb[3 * i + 2], r, g, b);
+        rgb[3 * i] = (uint8_t)r; rgb[3 * i + 1] = (uint8_t)g; rgb[3 * i + 2] = (uint8_t)b;
+    }
+}
+
+}  // extern "C"
