@@ -22,6 +22,11 @@ class HicError(RuntimeError):
     pass
 
 
+class StreamLayout(ctypes.Structure):
+    _fields_ = [("n_images", c_int32), ("skip_first", c_int32), ("blocks_per_image", ctypes.c_int64),
+                ("nb", ctypes.c_int64 * 3), ("block_off", ctypes.c_int64 * 3), ("len", ctypes.c_int64 * 3)]
+
+
 class Geometry(ctypes.Structure):
     _fields_ = [("h", c_int32), ("w", c_int32), ("hc", c_int32), ("wc", c_int32),
                 ("nby_l", c_int32), ("nbx_l", c_int32), ("nby_c", c_int32), ("nbx_c", c_int32),
@@ -50,7 +55,25 @@ SIGNATURES = {
     "hic_dct_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
     "hic_blocks_to_planes": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_planes_to_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    "hic_dct_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_dct_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_uint32, c_void_p, c_void_p]),
+    "hic_layout_dct": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(StreamLayout)]),
+    "hic_layout_flat": (c_int, [c_int32, ctypes.c_int64, ctypes.POINTER(StreamLayout)]),
+    "hic_entropy_plan_create": (c_int, [ctypes.POINTER(StreamLayout), c_int32, ctypes.POINTER(c_void_p)]),
+    "hic_entropy_plan_destroy": (c_int, [c_void_p]),
+    "hic_entropy_symbolize": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_build_codes": (c_int, [c_void_p, c_void_p]),
+    "hic_entropy_stream_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "hic_entropy_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hic_huffman_build_host": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p]),
+    "hic_entropy_symbol_buffers": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                           ctypes.POINTER(c_void_p)]),
+    "hic_decode_plan_create": (c_int, [ctypes.POINTER(StreamLayout), ctypes.POINTER(c_void_p)]),
+    "hic_decode_plan_destroy": (c_int, [c_void_p]),
+    "hic_decode_set_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_decode_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()
@@ -139,6 +162,18 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def layout_dct(n, h, w):
+    lay = StreamLayout()
+    check(load().hic_layout_dct(int(n), int(h), int(w), ctypes.byref(lay)))
+    return lay
+
+
+def layout_flat(n, length):
+    lay = StreamLayout()
+    check(load().hic_layout_flat(int(n), int(length), ctypes.byref(lay)))
+    return lay
 
 
 def sync(stream=None):

@@ -13,6 +13,7 @@ import numpy as np
 from hiccup_b200 import _lib, model, settings
 
 LAST_STATS = {}        #: tie statistics of the most recent jpeg_compression call
+LAST_INVERSE_STATS = {}  #: same for the most recent jpeg_decompression call
 
 
 def _as_rgb(rgb):
@@ -104,9 +105,14 @@ def jpeg_decompression(d: model.CompressedImage) -> np.ndarray:
     cr = _lib.DeviceBuffer(g.hc * g.wc)
     cb = _lib.DeviceBuffer(g.hc * g.wc)
     rgb = _lib.DeviceBuffer(g.out_h * g.out_w * 3)
-    _lib.check(lib.hic_dct_inverse(coef.ptr, 1, g.h, g.w, y.ptr, cr.ptr, cb.ptr, rgb.ptr, None))
+    ties = _lib.DeviceBuffer(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
+    stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+    _lib.check(lib.hic_dct_inverse(coef.ptr, 1, g.h, g.w, y.ptr, cr.ptr, cb.ptr, rgb.ptr, ties.ptr,
+                                   g.blocks_per_image, stats.ptr, None))
     out = rgb.download(np.uint8, g.out_h * g.out_w * 3).reshape(g.out_h, g.out_w, 3)
-    for b in (coef, y, cr, cb, rgb):
+    st = stats.download(np.uint32, _lib.TIE_STATS)
+    LAST_INVERSE_STATS.update(flagged_blocks=int(st[0]), reevaluated=int(st[1]), changed=int(st[2]))
+    for b in (coef, y, cr, cb, rgb, ties, stats):
         b.free()
     return out
 

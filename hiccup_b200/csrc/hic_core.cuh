@@ -331,5 +331,9 @@ HIC_HD double aan_h(int k) { return k == 0 ? 1.0 : 2.0 * cos(k * 3.1415926535897
 // the block.  (A first-order bound for the two AAN passes is ~14; tests/cpu_harness measures the
 // observed maximum, see DESIGN.md.)
 #define HIC_TIE_KAPPA 16.0
+// Same idea for the decode transform: a float32 sample p is trusted when its distance to the nearest
+// integer (where the reference's uint8 truncation steps) exceeds HIC_INV_KAPPA * 2^-24 * 4 * S / 256,
+// S = sum |coef * q| over the block.
+#define HIC_INV_KAPPA 16.0
 
 }  // namespace hic

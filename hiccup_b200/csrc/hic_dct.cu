@@ -363,11 +363,17 @@ fixup_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, 
 // K7: dequantise + IDCT + 128 + uint8 cast, one 8x8 block per thread
 // ------------------------------------------------------------------------------------------------
 namespace k7 {
+constexpr float MAGIC = 12582912.0f;
+
 template <int KIND>
 __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, uint8_t* __restrict__ plane, int ph,
-                                              int pw, int BY, int BX) {
+                                              int pw, int BY, int BX, uint32_t block_index,
+                                              hic_tie_record* __restrict__ ties, uint32_t tie_capacity,
+                                              uint32_t* __restrict__ stats) {
     constexpr uint8_t zz[64] = HIC_ZIGZAG8;
     float v[64];
+    float energy = 0.f;          // S = sum |coef * q|
+    int ac_bits = 0;
     const int4* in = reinterpret_cast<const int4*>(src);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -377,8 +383,12 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
         for (int e = 0; e < 4; ++e) {
             const int k0 = 8 * j + 2 * e;
             const int lo = (int)(short)(words[e] & 0xFFFF), hi = words[e] >> 16;
-            v[zz[k0]] = (float)lo * c_tab.dq[KIND][zz[k0]];
-            v[zz[k0 + 1]] = (float)hi * c_tab.dq[KIND][zz[k0 + 1]];
+            const float flo = (float)lo, fhi = (float)hi;
+            v[zz[k0]] = flo * c_tab.dq[KIND][zz[k0]];
+            v[zz[k0 + 1]] = fhi * c_tab.dq[KIND][zz[k0 + 1]];
+            energy = fmaf(fabsf(flo), c_tab.qf[KIND][zz[k0]], energy);
+            energy = fmaf(fabsf(fhi), c_tab.qf[KIND][zz[k0 + 1]], energy);
+            ac_bits |= k0 == 0 ? (words[e] & 0xFFFF0000) : words[e];
         }
     }
 #pragma unroll
@@ -389,13 +399,21 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
     for (int c = 0; c < 8; ++c)
         aan_inverse8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
     const int rows = min(8, ph - 8 * BY), cols = min(8, pw - 8 * BX);
+    // distance of every sample to the nearest integer, where the reference's uint8 truncation steps
+    float margin = 1e30f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        v[i] += 128.f;
+        const float r = (v[i] + MAGIC) - MAGIC;
+        margin = fminf(margin, fabsf(v[i] - r));
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         if (r >= rows) break;
         uint32_t w0 = 0, w1 = 0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint32_t b = (uint32_t)(__float2int_rz(v[8 * r + c] + 128.f)) & 0xFFu;   // truncate, wrap
+            const uint32_t b = (uint32_t)(__float2int_rz(v[8 * r + c])) & 0xFFu;   // truncate, wrap
             if (c < 4) w0 |= b << (8 * c); else w1 |= b << (8 * (c - 4));
         }
         uint8_t* dst = plane + (size_t)(8 * BY + r) * pw + 8 * BX;
@@ -405,11 +423,34 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
             for (int c = 0; c < cols; ++c) dst[c] = (uint8_t)((c < 4 ? w0 >> (8 * c) : w1 >> (8 * (c - 4))) & 0xFF);
         }
     }
+    // a DC-only block is exact in both float32 and float64 (no rounding happens at all)
+    const float band = (float)(HIC_INV_KAPPA * 4.0 / 16777216.0 / 256.0) * energy + 3.0517578125e-5f;
+    if (ac_bits != 0 && margin <= band) {
+        uint64_t mask = 0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const float r = (v[i] + MAGIC) - MAGIC;
+            if (fabsf(v[i] - r) <= band && (i >> 3) < rows && (i & 7) < cols) mask |= (1ull << i);
+        }
+        if (mask) {
+            const uint32_t slot = atomicAdd(&stats[0], 1u);
+            if (slot < tie_capacity) {
+                hic_tie_record rec;
+                rec.block = block_index;
+                rec.reserved = 0;
+                rec.mask = mask;
+                ties[slot] = rec;
+            } else {
+                atomicAdd(&stats[3], 1u);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128)
 inverse_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, int n, uint8_t* __restrict__ yp,
-               uint8_t* __restrict__ crp, uint8_t* __restrict__ cbp) {
+               uint8_t* __restrict__ crp, uint8_t* __restrict__ cbp, hic_tie_record* __restrict__ ties,
+               uint32_t tie_capacity, uint32_t* __restrict__ stats) {
     const int64_t total = (int64_t)n * g.blocks_per_image;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -417,13 +458,61 @@ inverse_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, int n, uint
     int64_t local = gid - img * g.blocks_per_image;
     const int16_t* src = coef + (size_t)gid * 64;
     if (local < g.nb_l) {
-        inverse_block<0>(src, yp + (size_t)img * g.h * g.w, g.h, g.w, (int)(local / g.nbx_l), (int)(local % g.nbx_l));
+        inverse_block<0>(src, yp + (size_t)img * g.h * g.w, g.h, g.w, (int)(local / g.nbx_l), (int)(local % g.nbx_l),
+                         (uint32_t)gid, ties, tie_capacity, stats);
     } else {
         local -= g.nb_l;
         const int plane = (int)(local / g.nb_c);
         local -= (int64_t)plane * g.nb_c;
         uint8_t* base = (plane == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
-        inverse_block<1>(src, base, g.hc, g.wc, (int)(local / g.nbx_c), (int)(local % g.nbx_c));
+        inverse_block<1>(src, base, g.hc, g.wc, (int)(local / g.nbx_c), (int)(local % g.nbx_c), (uint32_t)gid, ties,
+                         tie_capacity, stats);
+    }
+}
+
+// Float64 re-evaluation of every flagged sample with scipy's exact operation order.
+__global__ void __launch_bounds__(128)
+inverse_fixup_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, uint8_t* __restrict__ yp,
+                     uint8_t* __restrict__ crp, uint8_t* __restrict__ cbp, const hic_tie_record* __restrict__ ties,
+                     uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    const uint32_t n_rec = min(stats[0], tie_capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+        const hic_tie_record rec = ties[i];
+        const int64_t img = rec.block / g.blocks_per_image;
+        int64_t local = rec.block - img * g.blocks_per_image;
+        int kind = 0, ph = g.h, pw = g.w, nbx = g.nbx_l;
+        uint8_t* plane = yp + (size_t)img * g.h * g.w;
+        if (local >= g.nb_l) {
+            kind = 1;
+            local -= g.nb_l;
+            const int p = (int)(local / g.nb_c);
+            local -= (int64_t)p * g.nb_c;
+            ph = g.hc; pw = g.wc; nbx = g.nbx_c;
+            plane = (p == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
+        }
+        const int BY = (int)(local / nbx), BX = (int)(local % nbx);
+        const int16_t* blk = coef + (size_t)rec.block * 64;
+        int32_t cq[64];
+        for (int k = 0; k < 64; ++k) {
+            const int nat = c_zigzag[k];
+            cq[nat] = (int32_t)blk[k] * c_tab.qi[kind][nat];
+        }
+        uint64_t mask = rec.mask;
+        uint32_t evaluated = 0, changed = 0;
+        while (mask) {
+            const int s = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const int y = s >> 3, x = s & 7;
+            const uint8_t exact = wrap_u8(exact_decoded_sample(cq, y, x));
+            uint8_t* dst = plane + (size_t)(8 * BY + y) * pw + 8 * BX + x;
+            ++evaluated;
+            if (8 * BY + y < ph && 8 * BX + x < pw && *dst != exact) {
+                *dst = exact;
+                ++changed;
+            }
+        }
+        atomicAdd(&stats[1], evaluated);
+        if (changed) atomicAdd(&stats[2], changed);
     }
 }
 
@@ -599,19 +688,24 @@ int hic_planes_to_blocks(const int32_t* d_lum, const int32_t* d_cr, const int32_
 }
 
 int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint8_t* d_y, uint8_t* d_cr,
-                    uint8_t* d_cb, uint8_t* d_rgb_out, void* stream) {
+                    uint8_t* d_cb, uint8_t* d_rgb_out, hic_tie_record* d_ties, uint32_t tie_capacity,
+                    uint32_t* d_stats, void* stream) {
     using namespace hic;
-    HIC_REQUIRE(d_coef && d_y && d_cr && d_cb && d_rgb_out, "NULL device pointer");
+    HIC_REQUIRE(d_coef && d_y && d_cr && d_cb && d_rgb_out && d_ties && d_stats, "NULL device pointer");
     HIC_REQUIRE(n >= 1, "batch size must be positive");
     hic_dct_geometry g;
     int rc = geometry_of(h, w, &g);
     if (rc) return rc;
+    HIC_REQUIRE((int64_t)n * g.blocks_per_image < (1ll << 32), "batch too large: %lld blocks", (long long)n * g.blocks_per_image);
     rc = ensure_tables();
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
+    HIC_CUDA(cudaMemsetAsync(d_stats, 0, HIC_TIE_STATS * sizeof(uint32_t), st));
     const int64_t blocks = (int64_t)n * g.blocks_per_image;
-    k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb);
+    k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats);
     HIC_CHECK_LAUNCH("inverse_kernel");
+    k7::inverse_fixup_kernel<<<148 * 4, 128, 0, st>>>(d_coef, g, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats);
+    HIC_CHECK_LAUNCH("inverse_fixup_kernel");
     const int64_t quads = (int64_t)n * g.hc * g.wc;
     k7::upsample_colour_kernel<<<grid_for(quads, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out);
     HIC_CHECK_LAUNCH("upsample_colour_kernel");

@@ -1,0 +1,908 @@
+// hic_entropy.cu -- entropy encode stage: DC differences, run-length symbols, symbol histograms with
+// first-occurrence indices (E1), host Huffman construction (E2), bit packing (E3).
+//
+// Run-length coding as a map + scan.  Reference codec.run_length_coding (codec.py:55-99) walks the
+// whole channel with a Python reduce.  Restated per input position p of a channel stream, with
+// prev(p) = position of the last non-zero before p (-1 at the start) and last_nz = position of
+// the stream's last non-zero:
+//     non-zero at p                                   -> symbol ((p - prev - 1) mod 15, value)
+//     zero at p, (p - prev) mod 15 == 0, p < last_nz  -> filler (14, 0)
+//     after the last position, if last_nz != len - 1  -> one trailing (0, 0)
+// which emits exactly the reference's list (l // 15 fillers then (l - 15 (l // 15), value) for a
+// run of l zeros; trailing zeros collapse to (0, 0) and their count is dropped).  Every position
+// emits at most one symbol, so a tile of positions has a bounded output and the output index is an
+// exclusive prefix sum -- no serial dependency besides two small carries per tile.
+#include <algorithm>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "hic_core.cuh"
+#include "hic_huffman.cuh"
+#include "hic_runtime.cuh"
+
+namespace hic {
+
+constexpr int RLE_TB = 256;          // blocks (of 64 elements) per RLE tile = threads per CTA
+constexpr int PACK_SPT = 8;          // symbols per thread in the pack kernels
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_TILE = PACK_SPT * PACK_THREADS;      // 2048 symbols
+constexpr int PACK_WORDS = 4096;     // 2048 symbols * 58 bits max + slack, in 32-bit words
+constexpr int LEN_BINS = 16;
+constexpr uint32_t MAX_CODE_LEN = 58;
+
+struct Segment {     // summary of a run of positions: first/last non-zero and symbols within [first, last]
+    int first, last, count;
+};
+__host__ __device__ inline Segment seg_combine(const Segment& a, const Segment& b) {
+    if (b.first < 0) return a;
+    if (a.first < 0) return b;
+    Segment r;
+    r.first = a.first;
+    r.last = b.last;
+    r.count = a.count + b.count + (b.first - a.last - 1) / 15;
+    return r;
+}
+
+struct TileCarry {
+    int prev_last;          // last non-zero position before the tile (-1: none)
+    uint32_t sym_off;       // symbols emitted at positions before the tile
+};
+struct StreamTotals {
+    int last_nz;            // last non-zero position of the stream (-1: none)
+    uint32_t nsym;          // run-length symbols including the trailing (0, 0)
+};
+struct CompactEntry {
+    int32_t sym;
+    uint32_t count, first;
+};
+struct CompactIndex {
+    uint32_t offset, count;
+};
+
+struct Geom {               // kernel-side copy of the layout plus derived tile counts
+    hic_stream_layout L;
+    int tiles[3];
+    int tiles_per_image;
+    int ptiles[3][3];       // pack tiles per (channel, kind)
+    int ptiles_per_image;
+    int nb_bins;            // value bins
+};
+
+__host__ __device__ inline int64_t cs_block_base(const Geom& g, int img, int c) {
+    return (int64_t)img * g.L.blocks_per_image + g.L.block_off[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide helpers (256 threads)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Segment warp_reduce_segment(Segment s) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Segment o;
+        o.first = __shfl_down_sync(0xffffffffu, s.first, off);
+        o.last = __shfl_down_sync(0xffffffffu, s.last, off);
+        o.count = __shfl_down_sync(0xffffffffu, s.count, off);
+        if ((threadIdx.x & 31) + off < 32) s = seg_combine(s, o);
+    }
+    return s;
+}
+
+// exclusive scans over the CTA: running maximum (seeded with `seed`) and running sum
+template <int THREADS>
+__device__ __forceinline__ int block_excl_max(int v, int seed, int* smem /* THREADS/32 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc = max(inc, o);
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    int base = seed;
+    for (int w = 0; w < warp; ++w) base = max(base, smem[w]);
+    int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    ex = lane == 0 ? base : max(base, ex);
+    __syncthreads();
+    return ex;
+}
+
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* smem /* THREADS/32 */, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        if (w < warp) base += smem[w];
+        tot += smem[w];
+    }
+    if (total) *total = tot;
+    __syncthreads();
+    return base + inc - v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// E1: run-length symbols
+// ------------------------------------------------------------------------------------------------
+struct TileRef {
+    int img, c, tile;       // tile index inside its channel stream
+};
+__device__ __forceinline__ TileRef locate_tile(const Geom& g, int64_t t) {
+    TileRef r;
+    r.img = (int)(t / g.tiles_per_image);
+    int rem = (int)(t - (int64_t)r.img * g.tiles_per_image);
+    r.c = 0;
+    while (rem >= g.tiles[r.c]) {
+        rem -= g.tiles[r.c];
+        ++r.c;
+    }
+    r.tile = rem;
+    return r;
+}
+
+__device__ __forceinline__ void load_block(const int16_t* __restrict__ src, int (&w)[32]) {
+    const int4* p = reinterpret_cast<const int4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int4 v = __ldg(p + j);
+        w[4 * j + 0] = v.x;
+        w[4 * j + 1] = v.y;
+        w[4 * j + 2] = v.z;
+        w[4 * j + 3] = v.w;
+    }
+}
+#define HIC_ELEM(w, e) (((e) & 1) ? ((w)[(e) >> 1] >> 16) : (int)(short)((w)[(e) >> 1] & 0xFFFF))
+
+// pass A: per-tile segment summary
+template <bool SKIP>
+__global__ void __launch_bounds__(RLE_TB)
+rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __restrict__ tile_seg) {
+    __shared__ Segment warp_seg[RLE_TB / 32];
+    const TileRef tr = locate_tile(g, blockIdx.x);
+    const int64_t nb = g.L.nb[tr.c];
+    const int64_t b = (int64_t)tr.tile * RLE_TB + threadIdx.x;
+    Segment s{-1, -1, 0};
+    if (b < nb) {
+        int w[32];
+        load_block(coef + (cs_block_base(g, tr.img, tr.c) + b) * 64, w);
+        const int len = (int)g.L.len[tr.c];
+        const int base = SKIP ? (int)(63 * b) - 1 : (int)(64 * b);       // position of element e is base + e
+        int zmod = 0, pend = 0;
+#pragma unroll
+        for (int e = SKIP ? 1 : 0; e < 64; ++e) {
+            const int p = base + e;
+            const bool nz = HIC_ELEM(w, e) != 0 && (SKIP || p < len);
+            if (nz) {
+                if (s.first < 0) s.first = p;
+                s.last = p;
+                s.count += 1 + pend;
+                pend = 0;
+                zmod = 0;
+            } else if (s.first >= 0) {
+                if (++zmod == 15) {
+                    zmod = 0;
+                    ++pend;
+                }
+            }
+        }
+    }
+    s = warp_reduce_segment(s);
+    if ((threadIdx.x & 31) == 0) warp_seg[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Segment t = warp_seg[0];
+        for (int i = 1; i < RLE_TB / 32; ++i) t = seg_combine(t, warp_seg[i]);
+        tile_seg[blockIdx.x] = t;
+    }
+}
+
+// pass B: one thread per channel stream walks its tiles, producing the carries and stream totals,
+// and writes the trailing (0, 0) symbol (with its histogram contribution).
+__global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_seg, TileCarry* __restrict__ carry,
+                                       StreamTotals* __restrict__ totals, int16_t* __restrict__ values,
+                                       uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist,
+                                       uint32_t* __restrict__ first) {
+    const int cs = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cs >= g.L.n_images * 3) return;
+    const int img = cs / 3, c = cs % 3;
+    int64_t t0 = (int64_t)img * g.tiles_per_image;
+    for (int k = 0; k < c; ++k) t0 += g.tiles[k];
+    const int per_tile = RLE_TB * (g.L.skip_first ? 63 : 64);
+    Segment run{-1, -1, 0};          // a virtual non-zero at position -1 carrying no symbol
+    bool any = false;
+    for (int t = 0; t < g.tiles[c]; ++t) {
+        const int start = t * per_tile;
+        TileCarry tc;
+        tc.prev_last = run.last;
+        tc.sym_off = (uint32_t)(run.count + (start - 1 - run.last) / 15);
+        carry[t0 + t] = tc;
+        const Segment s = tile_seg[t0 + t];
+        if (s.first >= 0) {
+            run.count += s.count + (s.first - run.last - 1) / 15;
+            run.last = s.last;
+            any = true;
+        }
+    }
+    const int len = (int)g.L.len[c];
+    StreamTotals st;
+    st.last_nz = any ? run.last : -1;
+    uint32_t nsym = any ? (uint32_t)run.count : 0u;
+    if (st.last_nz != len - 1 || len == 0) {          // trailing zeros -> one (0, 0)
+        const int64_t sym_base = cs_block_base(g, img, c) * 64;
+        values[sym_base + nsym] = 0;
+        lengths[sym_base + nsym] = 0;
+        const size_t hv = ((size_t)cs * 3 + HIC_KIND_VALUE) * g.nb_bins + g.nb_bins / 2;
+        const size_t hl = ((size_t)cs * 3 + HIC_KIND_LENGTH) * g.nb_bins;
+        atomicAdd(&hist[hv], 1u);
+        atomicAdd(&hist[hl], 1u);
+        atomicMin(&first[hv], nsym);
+        atomicMin(&first[hl], nsym);
+        ++nsym;
+    }
+    st.nsym = nsym;
+    totals[cs] = st;
+}
+
+__device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t* __restrict__ first, size_t bin,
+                                         uint32_t index) {
+    atomicAdd(&hist[bin], 1u);
+    if (first[bin] > index) atomicMin(&first[bin], index);
+}
+
+// pass C: emit symbols, DC differences and histograms
+template <bool SKIP>
+__global__ void __launch_bounds__(RLE_TB)
+rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __restrict__ carry,
+                const StreamTotals* __restrict__ totals, int16_t* __restrict__ dc_out, int16_t* __restrict__ values,
+                uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
+                uint32_t* __restrict__ err) {
+    __shared__ int smax[RLE_TB / 32];
+    __shared__ uint32_t ssum[RLE_TB / 32];
+    const TileRef tr = locate_tile(g, blockIdx.x);
+    const int cs = tr.img * 3 + tr.c;
+    const int64_t nb = g.L.nb[tr.c];
+    const int64_t b = (int64_t)tr.tile * RLE_TB + threadIdx.x;
+    const int64_t block_base = cs_block_base(g, tr.img, tr.c);
+    const int len = (int)g.L.len[tr.c];
+    const int last_nz = totals[cs].last_nz;
+    const TileCarry tc = carry[blockIdx.x];
+    const int half = g.nb_bins / 2;
+    const size_t hbase = (size_t)cs * 3 * g.nb_bins;
+
+    int w[32];
+    const bool active = b < nb;
+    if (active) load_block(coef + (block_base + b) * 64, w);
+    const int base = SKIP ? (int)(63 * b) - 1 : (int)(64 * b);
+
+    // DC differences (codec.differential_coding): d[0] = DC[0], d[k] = DC[k] - DC[k-1]
+    if (SKIP && active) {
+        const int dc = HIC_ELEM(w, 0);
+        const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : 0;
+        const int diff = dc - prev;
+        dc_out[block_base + b] = (int16_t)diff;
+        const int bin = diff + half;
+        if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
+        else hist_add(hist, first, hbase + (size_t)HIC_KIND_DC * g.nb_bins + bin, (uint32_t)b);
+    }
+
+    // thread-local last non-zero
+    int my_last = -1;
+    if (active) {
+#pragma unroll
+        for (int e = SKIP ? 1 : 0; e < 64; ++e) {
+            const int p = base + e;
+            if (HIC_ELEM(w, e) != 0 && (SKIP || p < len)) my_last = p;
+        }
+    }
+    const int prev = block_excl_max<RLE_TB>(my_last, tc.prev_last, smax);
+
+    // count pass
+    const int zeros_before = base + (SKIP ? 1 : 0) - 1 - prev;       // zeros between prev and my first position
+    const int zmod0 = zeros_before % 15;
+    uint32_t cnt = 0;
+    if (active) {
+        int zmod = zmod0;
+#pragma unroll
+        for (int e = SKIP ? 1 : 0; e < 64; ++e) {
+            const int p = base + e;
+            const bool valid = SKIP || p < len;
+            const bool nz = HIC_ELEM(w, e) != 0 && valid;
+            if (nz) {
+                ++cnt;
+                zmod = 0;
+            } else if (valid) {
+                if (++zmod == 15) {
+                    zmod = 0;
+                    if (p < last_nz) ++cnt;
+                }
+            }
+        }
+    }
+    const uint32_t rank = block_excl_sum<RLE_TB>(cnt, ssum, nullptr);
+    if (!active || cnt == 0) return;
+
+    // emit pass
+    const int64_t sym_base = block_base * 64;
+    uint32_t idx = tc.sym_off + rank;
+    int zmod = zmod0;
+    const size_t hv = hbase + (size_t)HIC_KIND_VALUE * g.nb_bins, hl = hbase + (size_t)HIC_KIND_LENGTH * g.nb_bins;
+#pragma unroll
+    for (int e = SKIP ? 1 : 0; e < 64; ++e) {
+        const int p = base + e;
+        const bool valid = SKIP || p < len;
+        const int val = HIC_ELEM(w, e);
+        const bool nz = val != 0 && valid;
+        bool emit = false;
+        int sym_len = 14, sym_val = 0;
+        if (nz) {
+            emit = true;
+            sym_len = zmod;
+            sym_val = val;
+            zmod = 0;
+        } else if (valid) {
+            if (++zmod == 15) {
+                zmod = 0;
+                emit = p < last_nz;
+            }
+        }
+        if (emit) {
+            values[sym_base + idx] = (int16_t)sym_val;
+            lengths[sym_base + idx] = (uint8_t)sym_len;
+            const int bin = sym_val + half;
+            if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
+            else hist_add(hist, first, hv + bin, idx);
+            hist_add(hist, first, hl + sym_len, idx);
+            ++idx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// histogram compaction: one CTA per symbol stream
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+compact_kernel(Geom g, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ first,
+               CompactEntry* __restrict__ entries, CompactIndex* __restrict__ index, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t s_count, s_base, s_pos;
+    const int ss = blockIdx.x;
+    const int kind = ss % 3;
+    const int bins = kind == HIC_KIND_LENGTH ? LEN_BINS : g.nb_bins;
+    const size_t off = (size_t)ss * g.nb_bins;
+    if (threadIdx.x == 0) {
+        s_count = 0;
+        s_pos = 0;
+    }
+    __syncthreads();
+    uint32_t mine = 0;
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) mine += hist[off + i] != 0;
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_base = s_count ? atomicAdd(cursor, s_count) : 0;
+        index[ss] = CompactIndex{s_base, s_count};
+    }
+    __syncthreads();
+    const int bias = kind == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+        const uint32_t cnt = hist[off + i];
+        if (cnt) {
+            const uint32_t pos = s_base + atomicAdd(&s_pos, 1u);
+            entries[pos] = CompactEntry{i - bias, cnt, first[off + i]};
+        }
+    }
+}
+
+// scatter the code rows into the dense per-stream lookup table: lut[ss][bin] = len << 58 | code
+__global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, const uint64_t* __restrict__ row_code,
+                                   const uint32_t* __restrict__ row_stream, uint64_t n_rows, uint64_t* __restrict__ lut) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const uint32_t ss = row_stream[i];
+    const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
+    lut[(size_t)ss * g.nb_bins + row_sym[i] + bias] = row_code[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// E3: bit packing
+// ------------------------------------------------------------------------------------------------
+struct PackRef {
+    int ss, tile;
+    int64_t sym_base;       // element offset of the stream's symbols in its source array
+};
+__device__ __forceinline__ PackRef locate_pack_tile(const Geom& g, int64_t t) {
+    PackRef r;
+    const int img = (int)(t / g.ptiles_per_image);
+    int rem = (int)(t - (int64_t)img * g.ptiles_per_image);
+    int c = 0, k = 0;
+    while (rem >= g.ptiles[c][k]) {
+        rem -= g.ptiles[c][k];
+        if (++k == 3) {
+            k = 0;
+            ++c;
+        }
+    }
+    r.ss = (img * 3 + c) * 3 + k;
+    r.tile = rem;
+    const int64_t bb = cs_block_base(g, img, c);
+    r.sym_base = k == HIC_KIND_DC ? bb : bb * 64;
+    return r;
+}
+
+__device__ __forceinline__ uint64_t lookup_code(const Geom& g, const uint64_t* __restrict__ lut, int ss, int kind,
+                                                const int16_t* __restrict__ dc, const int16_t* __restrict__ values,
+                                                const uint8_t* __restrict__ lengths, int64_t pos) {
+    int bin;
+    if (kind == HIC_KIND_LENGTH) bin = lengths[pos];
+    else bin = (int)(kind == HIC_KIND_DC ? dc[pos] : values[pos]) + g.nb_bins / 2;
+    return __ldg(lut + (size_t)ss * g.nb_bins + bin);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_tile_bits_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __restrict__ ss_nsym,
+                      const int16_t* __restrict__ dc, const int16_t* __restrict__ values,
+                      const uint8_t* __restrict__ lengths, uint32_t* __restrict__ tile_bits) {
+    __shared__ uint32_t ssum[PACK_THREADS / 32];
+    const PackRef pr = locate_pack_tile(g, blockIdx.x);
+    const uint32_t nsym = ss_nsym[pr.ss];
+    const uint32_t start = (uint32_t)pr.tile * PACK_TILE + threadIdx.x * PACK_SPT;
+    uint32_t bits = 0;
+    const int kind = pr.ss % 3;
+#pragma unroll
+    for (int j = 0; j < PACK_SPT; ++j)
+        if (start + j < nsym)
+            bits += (uint32_t)(lookup_code(g, lut, pr.ss, kind, dc, values, lengths, pr.sym_base + start + j) >> 58);
+    uint32_t total;
+    block_excl_sum<PACK_THREADS>(bits, ssum, &total);
+    if (threadIdx.x == 0) tile_bits[blockIdx.x] = total;
+}
+
+__global__ void pack_stream_scan_kernel(Geom g, const uint32_t* __restrict__ tile_bits, uint64_t* __restrict__ tile_off) {
+    const int ss = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ss >= g.L.n_images * 9) return;
+    const int img = ss / 9, c = (ss % 9) / 3, k = ss % 3;
+    int64_t t0 = (int64_t)img * g.ptiles_per_image;
+    for (int cc = 0; cc < 3; ++cc)
+        for (int kk = 0; kk < 3; ++kk)
+            if (cc < c || (cc == c && kk < k)) t0 += g.ptiles[cc][kk];
+    uint64_t run = 8;           // the pad-count byte comes first (iohelper.py:41-46)
+    for (int t = 0; t < g.ptiles[c][k]; ++t) {
+        tile_off[t0 + t] = run;
+        run += tile_bits[t0 + t];
+    }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __restrict__ ss_nsym,
+                 const uint64_t* __restrict__ ss_nbits, const uint64_t* __restrict__ ss_byte_off,
+                 const uint64_t* __restrict__ tile_off, const int16_t* __restrict__ dc,
+                 const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths, uint8_t* __restrict__ out) {
+    __shared__ uint32_t buf[PACK_WORDS];
+    __shared__ uint32_t ssum[PACK_THREADS / 32];
+    const PackRef pr = locate_pack_tile(g, blockIdx.x);
+    const uint32_t nsym = ss_nsym[pr.ss];
+    const uint32_t tile_start = (uint32_t)pr.tile * PACK_TILE;
+    if (tile_start >= nsym) return;
+    const int kind = pr.ss % 3;
+    for (int i = threadIdx.x; i < PACK_WORDS; i += PACK_THREADS) buf[i] = 0;
+    uint64_t codes[PACK_SPT];
+    uint32_t bits = 0;
+    const uint32_t start = tile_start + threadIdx.x * PACK_SPT;
+#pragma unroll
+    for (int j = 0; j < PACK_SPT; ++j) {
+        codes[j] = start + j < nsym ? lookup_code(g, lut, pr.ss, kind, dc, values, lengths, pr.sym_base + start + j) : 0ull;
+        bits += (uint32_t)(codes[j] >> 58);
+    }
+    uint32_t total;
+    const uint32_t rank = block_excl_sum<PACK_THREADS>(bits, ssum, &total);      // also orders the zeroing of buf
+    const uint64_t g0 = tile_off[blockIdx.x];              // bit offset of the tile inside the stream's bytes
+    const uint32_t skew = (uint32_t)(g0 & 31);
+    uint32_t o = skew + rank;
+#pragma unroll
+    for (int j = 0; j < PACK_SPT; ++j) {
+        const uint32_t l = (uint32_t)(codes[j] >> 58);
+        if (l) {
+            const uint64_t left = (codes[j] & ((1ull << 58) - 1)) << (64 - l);     // code left-aligned in 64 bits
+            const uint32_t wi = o >> 5, sh = o & 31;
+            const uint32_t p0 = (uint32_t)(left >> (32 + sh));
+            const uint32_t p1 = (uint32_t)(left >> sh);
+            const uint32_t p2 = sh ? (uint32_t)(left << (32 - sh)) : 0u;
+            if (p0) atomicOr(&buf[wi], p0);
+            if (p1) atomicOr(&buf[wi + 1], p1);
+            if (p2) atomicOr(&buf[wi + 2], p2);
+            o += l;
+        }
+    }
+    if (pr.tile == 0 && threadIdx.x == 0) {                 // pad count p = 8 - (nbits mod 8) in byte 0
+        const uint32_t pad = 8u - (uint32_t)(ss_nbits[pr.ss] & 7);
+        atomicOr(&buf[0], pad << 24);
+    }
+    __syncthreads();
+    const uint32_t n_words = (skew + total + 31) >> 5;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ss_byte_off[pr.ss]) + (g0 >> 5);
+    for (uint32_t i = threadIdx.x; i < n_words; i += PACK_THREADS) {
+        const uint32_t v = __byte_perm(buf[i], 0, 0x0123);          // MSB-first bits -> byte order in memory
+        if (v == 0) continue;
+        if (i == 0 || i == n_words - 1) atomicOr(dst + i, v);       // words shared with a neighbouring tile
+        else dst[i] = v;
+    }
+}
+
+}  // namespace hic
+
+// ------------------------------------------------------------------------------------------------
+// plan object and C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace hic;
+
+struct hic_entropy_plan {
+    Geom g;
+    int64_t total_tiles = 0, total_ptiles = 0, total_blocks = 0;
+    int n_cs = 0, n_ss = 0;
+    // device
+    Segment* d_tile_seg = nullptr;
+    TileCarry* d_carry = nullptr;
+    StreamTotals* d_totals = nullptr;
+    int16_t* d_dc = nullptr;
+    int16_t* d_values = nullptr;
+    uint8_t* d_lengths = nullptr;
+    uint32_t* d_hist = nullptr;
+    uint32_t* d_first = nullptr;
+    uint32_t* d_err = nullptr;        // [0] error flags, [1] compaction cursor
+    CompactEntry* d_entries = nullptr;
+    CompactIndex* d_index = nullptr;
+    uint64_t* d_lut = nullptr;
+    int32_t* d_row_sym = nullptr;
+    uint64_t* d_row_code = nullptr;
+    uint32_t* d_row_stream = nullptr;
+    uint64_t row_capacity = 0;
+    uint32_t* d_ss_nsym = nullptr;
+    uint64_t* d_ss_nbits = nullptr;
+    uint64_t* d_ss_byte_off = nullptr;
+    uint32_t* d_ptile_bits = nullptr;
+    uint64_t* d_ptile_off = nullptr;
+    // host results
+    std::vector<uint32_t> rows, nsym;
+    std::vector<uint64_t> nbits, byte_off, byte_len, row_off;
+    std::vector<int32_t> t_sym;
+    std::vector<uint8_t> t_len;
+    std::vector<uint64_t> t_code;
+    uint64_t total_rows = 0, total_bytes = 0;
+    bool codes_ready = false;
+};
+
+static int fill_geom(const hic_stream_layout* L, int value_bins, Geom* g) {
+    HIC_REQUIRE(L != nullptr, "layout is NULL");
+    HIC_REQUIRE(L->n_images >= 1, "layout has no images");
+    HIC_REQUIRE(value_bins >= 64 && value_bins <= 65536 && (value_bins & (value_bins - 1)) == 0,
+                "value_bins must be a power of two in 64..65536 (got %d)", value_bins);
+    g->L = *L;
+    g->nb_bins = value_bins;
+    g->tiles_per_image = 0;
+    g->ptiles_per_image = 0;
+    for (int c = 0; c < 3; ++c) {
+        HIC_REQUIRE(L->nb[c] >= 1 && L->nb[c] * 64 < (1ll << 31), "channel stream too long (%lld blocks)", (long long)L->nb[c]);
+        HIC_REQUIRE(L->len[c] >= 0 && L->len[c] <= L->nb[c] * (L->skip_first ? 63 : 64), "bad stream length");
+        g->tiles[c] = (int)((L->nb[c] + RLE_TB - 1) / RLE_TB);
+        g->tiles_per_image += g->tiles[c];
+        for (int k = 0; k < 3; ++k) {
+            int64_t cap = k == HIC_KIND_DC ? (L->skip_first ? L->nb[c] : 0) : L->nb[c] * 64;
+            g->ptiles[c][k] = (int)((cap + PACK_TILE - 1) / PACK_TILE);
+            g->ptiles_per_image += g->ptiles[c][k];
+        }
+    }
+    return HIC_OK;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T));
+}
+
+extern "C" {
+
+int hic_layout_dct(int32_t n, int32_t h, int32_t w, hic_stream_layout* out) {
+    HIC_REQUIRE(out != nullptr, "layout output is NULL");
+    HIC_REQUIRE(n >= 1, "batch size must be positive");
+    hic_dct_geometry g;
+    int rc = hic_dct_geometry_of(h, w, &g);
+    if (rc) return rc;
+    out->n_images = n;
+    out->skip_first = 1;
+    out->blocks_per_image = g.blocks_per_image;
+    out->nb[0] = g.nb_l;
+    out->nb[1] = out->nb[2] = g.nb_c;
+    out->block_off[0] = 0;
+    out->block_off[1] = g.nb_l;
+    out->block_off[2] = g.nb_l + g.nb_c;
+    for (int c = 0; c < 3; ++c) out->len[c] = 63 * out->nb[c];
+    return HIC_OK;
+}
+
+int hic_layout_flat(int32_t n, int64_t len, hic_stream_layout* out) {
+    HIC_REQUIRE(out != nullptr, "layout output is NULL");
+    HIC_REQUIRE(n >= 1 && len >= 1, "batch size and length must be positive");
+    const int64_t nb = (len + 63) / 64;
+    out->n_images = n;
+    out->skip_first = 0;
+    out->blocks_per_image = 3 * nb;
+    for (int c = 0; c < 3; ++c) {
+        out->nb[c] = nb;
+        out->block_off[c] = c * nb;
+        out->len[c] = len;
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_plan_destroy(hic_entropy_plan* p) {
+    if (!p) return HIC_OK;
+    void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
+                    p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
+                    p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    delete p;
+    return HIC_OK;
+}
+
+int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins, hic_entropy_plan** out) {
+    HIC_REQUIRE(out != nullptr, "plan output is NULL");
+    *out = nullptr;
+    hic_entropy_plan* p = new hic_entropy_plan();
+    int rc = fill_geom(layout, value_bins, &p->g);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    const Geom& g = p->g;
+    p->n_cs = g.L.n_images * 3;
+    p->n_ss = g.L.n_images * 9;
+    p->total_tiles = (int64_t)g.L.n_images * g.tiles_per_image;
+    p->total_ptiles = (int64_t)g.L.n_images * g.ptiles_per_image;
+    p->total_blocks = (int64_t)g.L.n_images * g.L.blocks_per_image;
+    const size_t hist_n = (size_t)p->n_ss * g.nb_bins;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(dalloc(&p->d_tile_seg, p->total_tiles));
+    ok(dalloc(&p->d_carry, p->total_tiles));
+    ok(dalloc(&p->d_totals, p->n_cs));
+    ok(dalloc(&p->d_dc, p->total_blocks));
+    ok(dalloc(&p->d_values, p->total_blocks * 64 + 64));
+    ok(dalloc(&p->d_lengths, p->total_blocks * 64 + 64));
+    ok(dalloc(&p->d_hist, hist_n));
+    ok(dalloc(&p->d_first, hist_n));
+    ok(dalloc(&p->d_err, 4));
+    ok(dalloc(&p->d_entries, hist_n));
+    ok(dalloc(&p->d_index, p->n_ss));
+    ok(dalloc(&p->d_lut, hist_n));
+    ok(dalloc(&p->d_ss_nsym, p->n_ss));
+    ok(dalloc(&p->d_ss_nbits, p->n_ss));
+    ok(dalloc(&p->d_ss_byte_off, p->n_ss));
+    ok(dalloc(&p->d_ptile_bits, p->total_ptiles));
+    ok(dalloc(&p->d_ptile_off, p->total_ptiles));
+    if (e != cudaSuccess) {
+        hic_entropy_plan_destroy(p);
+        return hic::fail(HIC_ERR_CUDA, "entropy plan allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return HIC_OK;
+}
+
+int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stream) {
+    HIC_REQUIRE(p && d_coef, "NULL argument");
+    const Geom& g = p->g;
+    cudaStream_t st = as_stream(stream);
+    p->codes_ready = false;
+    const size_t hist_n = (size_t)p->n_ss * g.nb_bins;
+    HIC_CUDA(cudaMemsetAsync(p->d_hist, 0, hist_n * sizeof(uint32_t), st));
+    HIC_CUDA(cudaMemsetAsync(p->d_first, 0xFF, hist_n * sizeof(uint32_t), st));
+    HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
+    const unsigned tiles = (unsigned)p->total_tiles;
+    if (g.L.skip_first) rle_tile_summary_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg);
+    else rle_tile_summary_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg);
+    HIC_CHECK_LAUNCH("rle_tile_summary_kernel");
+    rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, p->d_carry, p->d_totals, p->d_values,
+                                                                 p->d_lengths, p->d_hist, p->d_first);
+    HIC_CHECK_LAUNCH("rle_stream_scan_kernel");
+    if (g.L.skip_first)
+        rle_emit_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
+                                                        p->d_lengths, p->d_hist, p->d_first, p->d_err);
+    else
+        rle_emit_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
+                                                         p->d_lengths, p->d_hist, p->d_first, p->d_err);
+    HIC_CHECK_LAUNCH("rle_emit_kernel");
+    compact_kernel<<<p->n_ss, 256, 0, st>>>(g, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1);
+    HIC_CHECK_LAUNCH("compact_kernel");
+    return HIC_OK;
+}
+
+int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    const Geom& g = p->g;
+    cudaStream_t st = as_stream(stream);
+    uint32_t flags[4];
+    HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    std::vector<CompactIndex> index(p->n_ss);
+    HIC_CUDA(cudaMemcpyAsync(index.data(), p->d_index, sizeof(CompactIndex) * p->n_ss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    if (flags[0]) return hic::fail(HIC_ERR_INVALID, "a symbol fell outside [-%d, %d): create the plan with more value_bins",
+                                   g.nb_bins / 2, g.nb_bins / 2);
+    const uint64_t n_entries = flags[1];
+    std::vector<CompactEntry> entries(n_entries);
+    if (n_entries) {
+        HIC_CUDA(cudaMemcpyAsync(entries.data(), p->d_entries, sizeof(CompactEntry) * n_entries, cudaMemcpyDeviceToHost, st));
+        HIC_CUDA(cudaStreamSynchronize(st));
+    }
+    const int nss = p->n_ss;
+    p->rows.assign(nss, 0);
+    p->nsym.assign(nss, 0);
+    p->nbits.assign(nss, 0);
+    p->byte_off.assign(nss, 0);
+    p->byte_len.assign(nss, 0);
+    p->row_off.assign(nss + 1, 0);
+    for (int s = 0; s < nss; ++s) {
+        p->rows[s] = index[s].count;
+        p->row_off[s + 1] = p->row_off[s] + index[s].count;
+    }
+    p->total_rows = p->row_off[nss];
+    p->t_sym.resize(p->total_rows);
+    p->t_len.resize(p->total_rows);
+    p->t_code.resize(p->total_rows);
+    std::vector<uint32_t> row_stream(p->total_rows);
+    std::vector<uint64_t> row_packed(p->total_rows);
+
+    // Huffman construction, one stream at a time per worker (the reference does this serially in Python)
+    unsigned hw = std::thread::hardware_concurrency();
+    const int workers = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+    std::vector<int> status(workers, 0);
+    auto work = [&](int wid) {
+        HeapqHuffman huff;
+        std::vector<CompactEntry> local;
+        std::vector<uint32_t> freqs;
+        std::vector<HuffCode> codes;
+        for (int s = wid; s < nss; s += workers) {
+            const CompactIndex ix = index[s];
+            if (!ix.count) continue;
+            local.assign(entries.begin() + ix.offset, entries.begin() + ix.offset + ix.count);
+            std::sort(local.begin(), local.end(), [](const CompactEntry& a, const CompactEntry& b) { return a.first < b.first; });
+            freqs.resize(ix.count);
+            for (uint32_t i = 0; i < ix.count; ++i) freqs[i] = local[i].count;
+            if (!huff.build(freqs.data(), ix.count, codes, MAX_CODE_LEN)) {
+                status[wid] = 1;
+                return;
+            }
+            uint64_t bits = 0, n = 0;
+            const uint64_t r0 = p->row_off[s];
+            for (uint32_t i = 0; i < ix.count; ++i) {
+                p->t_sym[r0 + i] = local[i].sym;
+                p->t_len[r0 + i] = (uint8_t)codes[i].len;
+                p->t_code[r0 + i] = codes[i].bits;
+                row_stream[r0 + i] = (uint32_t)s;
+                row_packed[r0 + i] = ((uint64_t)codes[i].len << 58) | codes[i].bits;
+                bits += (uint64_t)local[i].count * codes[i].len;
+                n += local[i].count;
+            }
+            p->nbits[s] = bits;
+            p->nsym[s] = (uint32_t)n;
+        }
+    };
+    if (workers == 1 || nss < 16) {
+        for (int wdx = 0; wdx < workers; ++wdx) work(wdx);
+    } else {
+        std::vector<std::thread> pool;
+        for (int wdx = 0; wdx < workers; ++wdx) pool.emplace_back(work, wdx);
+        for (auto& t : pool) t.join();
+    }
+    for (int wdx = 0; wdx < workers; ++wdx)
+        if (status[wdx]) return hic::fail(HIC_ERR_INVALID, "a Huffman code exceeds %u bits", MAX_CODE_LEN);
+
+    uint64_t off = 0;
+    for (int s = 0; s < nss; ++s) {
+        if (p->nsym[s] == 0) continue;                       // no such stream (DC in flat mode)
+        const uint64_t pad = 8 - (p->nbits[s] & 7);
+        p->byte_off[s] = off;
+        p->byte_len[s] = 1 + (p->nbits[s] + pad) / 8;
+        off += (p->byte_len[s] + 3) & ~3ull;
+    }
+    p->total_bytes = off;
+
+    if (p->total_rows > p->row_capacity) {
+        if (p->d_row_sym) cudaFree(p->d_row_sym);
+        if (p->d_row_code) cudaFree(p->d_row_code);
+        if (p->d_row_stream) cudaFree(p->d_row_stream);
+        p->d_row_sym = nullptr; p->d_row_code = nullptr; p->d_row_stream = nullptr;
+        p->row_capacity = p->total_rows + p->total_rows / 4 + 1024;
+        HIC_CUDA(dalloc(&p->d_row_sym, p->row_capacity));
+        HIC_CUDA(dalloc(&p->d_row_code, p->row_capacity));
+        HIC_CUDA(dalloc(&p->d_row_stream, p->row_capacity));
+    }
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_sym, p->t_sym.data(), sizeof(int32_t) * p->total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_code, row_packed.data(), sizeof(uint64_t) * p->total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_stream, row_stream.data(), sizeof(uint32_t) * p->total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_nsym, p->nsym.data(), sizeof(uint32_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_nbits, p->nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_off, p->byte_off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    if (p->total_rows) {
+        lut_scatter_kernel<<<(unsigned)((p->total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
+                                                                                   p->d_row_stream, p->total_rows, p->d_lut);
+        HIC_CHECK_LAUNCH("lut_scatter_kernel");
+    }
+    HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors above go out of scope
+    p->codes_ready = true;
+    return HIC_OK;
+}
+
+int hic_entropy_stream_info(const hic_entropy_plan* p, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
+                            uint64_t* h_byte_off, uint64_t* h_byte_len, uint64_t* total_rows, uint64_t* total_bytes) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    for (int s = 0; s < p->n_ss; ++s) {
+        if (h_rows) h_rows[s] = p->rows[s];
+        if (h_nsym) h_nsym[s] = p->nsym[s];
+        if (h_nbits) h_nbits[s] = p->nbits[s];
+        if (h_byte_off) h_byte_off[s] = p->byte_off[s];
+        if (h_byte_len) h_byte_len[s] = p->byte_len[s];
+    }
+    if (total_rows) *total_rows = p->total_rows;
+    if (total_bytes) *total_bytes = p->total_bytes;
+    return HIC_OK;
+}
+
+int hic_entropy_tables(const hic_entropy_plan* p, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    for (uint64_t i = 0; i < p->total_rows; ++i) {
+        if (h_symbols) h_symbols[i] = p->t_sym[i];
+        if (h_lens) h_lens[i] = p->t_len[i];
+        if (h_codes) h_codes[i] = p->t_code[i];
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_pack(hic_entropy_plan* p, uint8_t* d_out, void* stream) {
+    HIC_REQUIRE(p && d_out, "NULL argument");
+    HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    HIC_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3) == 0, "d_out must be 4-byte aligned");
+    const Geom& g = p->g;
+    cudaStream_t st = as_stream(stream);
+    HIC_CUDA(cudaMemsetAsync(d_out, 0, p->total_bytes, st));
+    const unsigned tiles = (unsigned)p->total_ptiles;
+    pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
+                                                         p->d_ptile_bits);
+    HIC_CHECK_LAUNCH("pack_tile_bits_kernel");
+    pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_ptile_off);
+    HIC_CHECK_LAUNCH("pack_stream_scan_kernel");
+    pack_emit_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off,
+                                                    p->d_ptile_off, p->d_dc, p->d_values, p->d_lengths, d_out);
+    HIC_CHECK_LAUNCH("pack_emit_kernel");
+    return HIC_OK;
+}
+
+int hic_huffman_build_host(const uint32_t* h_freqs, uint32_t n, uint8_t* h_lens, uint64_t* h_codes) {
+    HIC_REQUIRE(h_freqs && h_lens && h_codes, "NULL argument");
+    HeapqHuffman huff;
+    std::vector<HuffCode> codes;
+    if (!huff.build(h_freqs, n, codes, MAX_CODE_LEN)) return hic::fail(HIC_ERR_INVALID, "a Huffman code exceeds %u bits", MAX_CODE_LEN);
+    for (uint32_t i = 0; i < n; ++i) {
+        h_lens[i] = (uint8_t)codes[i].len;
+        h_codes[i] = codes[i].bits;
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_symbol_buffers(const hic_entropy_plan* p, const int16_t** d_dc, const int16_t** d_values,
+                               const uint8_t** d_lengths) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    if (d_dc) *d_dc = p->d_dc;
+    if (d_values) *d_values = p->d_values;
+    if (d_lengths) *d_lengths = p->d_lengths;
+    return HIC_OK;
+}
+
+}  // extern "C"

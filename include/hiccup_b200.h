@@ -105,10 +105,99 @@ int hic_planes_to_blocks(const int32_t* d_lum, const int32_t* d_cr, const int32_
  * coefficient * table, idct rows then columns, /256, +128, astype(uint8) (truncate, wrap),
  * cv2.pyrUp of both chroma planes, crop of the luminance plane, cv2.cvtColor YCrCb->RGB.
  * d_y (n*h*w), d_cr, d_cb (n*hc*wc each) are scratch planes; d_rgb_out is n*out_h*out_w*3.
- * float32 butterflies: pixels are within +-1 LSB of the reference's (or +-255 where its uint8 cast
- * wraps); tests count both. */
+ * float32 butterflies; every sample within the float32 error band of an integer (where the
+ * reference's uint8 truncation steps) is re-evaluated in float64 with scipy's exact operation
+ * order before the (integer) upsampling and colour conversion, so pixels equal the reference's.
+ * d_ties / tie_capacity / d_stats as for hic_dct_forward (mask bit i = sample 8*y + x). */
 int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint8_t* d_y,
-                    uint8_t* d_cr, uint8_t* d_cb, uint8_t* d_rgb_out, void* stream);
+                    uint8_t* d_cr, uint8_t* d_cb, uint8_t* d_rgb_out, hic_tie_record* d_ties,
+                    uint32_t tie_capacity, uint32_t* d_stats, void* stream);
+
+/* ---- entropy stage ---------------------------------------------------------------------------- */
+/* A batch is 3 n "channel streams" (image i, channel c in lum, cr, cb).  Each channel stream is a
+ * run of 64-element int16 blocks.  DCT mode (skip_first = 1): element 0 of every block is its DC
+ * term and the AC stream is elements 1..63 of all blocks in order (transform.ac_components,
+ * transform.py:260-266).  Flat mode (skip_first = 0, wavelet): the stream is simply the first
+ * len[c] elements (the ten zigzagged sub-bands concatenated, codec.py:123-126).
+ * Every channel stream yields symbol streams, indexed  s = (image * 3 + channel) * 3 + kind:
+ * kind 0 = DC differences (DCT mode only), 1 = run-length values, 2 = run-length zero counts. */
+typedef struct hic_stream_layout {
+    int32_t n_images;
+    int32_t skip_first;
+    int64_t blocks_per_image;
+    int64_t nb[3];            /* blocks per channel stream */
+    int64_t block_off[3];     /* first block of channel c inside an image */
+    int64_t len[3];           /* run-length input positions per channel stream */
+} hic_stream_layout;
+int hic_layout_dct(int32_t n, int32_t h, int32_t w, hic_stream_layout* out);
+int hic_layout_flat(int32_t n, int64_t len, hic_stream_layout* out);   /* blocks = ceil(len/64), same for all 3 */
+
+#define HIC_KIND_DC 0
+#define HIC_KIND_VALUE 1
+#define HIC_KIND_LENGTH 2
+
+typedef struct hic_entropy_plan hic_entropy_plan;      /* owns the device workspace of one batch shape */
+
+/* value_bins: power of two; symbols must lie in [-value_bins/2, value_bins/2).  8192 covers every
+ * value K1 / the wavelet kernels can produce; 65536 covers all of int16. */
+int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins, hic_entropy_plan** out);
+int hic_entropy_plan_destroy(hic_entropy_plan* plan);
+
+/* E1 (device) -- DC differences (codec.differential_coding, codec.py:47-52; utils.differences,
+ * utils.py:51-63), run-length symbols (codec.run_length_coding, codec.py:55-99: symbol = (zeros
+ * before, value); a run l >= 15 becomes l/15 fillers (14, 0) then (l mod 15, value); trailing
+ * zeros collapse to one (0, 0)), and per-stream symbol histograms with first-occurrence indices
+ * (utils.group_by, utils.py:83-96, via huffman.py:17-19). */
+int hic_entropy_symbolize(hic_entropy_plan* plan, const int16_t* d_coef, void* stream);
+
+/* E2 (host; synchronises `stream`) -- fetch the compacted histograms, build every Huffman code
+ * exactly as HuffmanTree._construct does (huffman.py:60-79, heapq replay), upload code tables. */
+int hic_entropy_build_codes(hic_entropy_plan* plan, void* stream);
+
+/* Results of E2, all host arrays indexed by symbol stream s (9 n entries; kind 0 entries are
+ * empty in flat mode).  rows[s]: table rows; nsym[s]: symbols; nbits[s]: Huffman-coded bits;
+ * byte_off[s] / byte_len[s]: where hic_entropy_pack puts the framed bytes of stream s. */
+int hic_entropy_stream_info(const hic_entropy_plan* plan, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
+                            uint64_t* h_byte_off, uint64_t* h_byte_len, uint64_t* total_rows, uint64_t* total_bytes);
+/* Table rows of all streams concatenated in s order, each stream's rows in first-occurrence order
+ * (what HuffmanTree.encode_table returns, huffman.py:144-147): symbol, code length, code bits
+ * (right aligned; first bit of the code string = most significant; '1' = left = first popped). */
+int hic_entropy_tables(const hic_entropy_plan* plan, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes);
+
+/* E3 (device) -- concatenate the codes of every symbol stream (HuffmanTree.encode_data,
+ * huffman.py:131-142) and frame them as iohelper.padded_bs_2_bytes does (iohelper.py:35-48):
+ * byte 0 = p = 8 - (nbits mod 8), then the bits MSB first, then p zero bits.  d_out must hold
+ * total_bytes; it is zeroed by the call. */
+int hic_entropy_pack(hic_entropy_plan* plan, uint8_t* d_out, void* stream);
+
+/* The host Huffman construction on its own (no CUDA call): leaf frequencies in first-occurrence
+ * order -> code length and bits per leaf.  Replaces HuffmanTree._construct + encode_table
+ * (huffman.py:60-79, 144-147).  Returns HIC_ERR_INVALID if a code would exceed 58 bits. */
+int hic_huffman_build_host(const uint32_t* h_freqs, uint32_t n, uint8_t* h_lens, uint64_t* h_codes);
+
+/* Device pointers into the plan's workspace (valid until the plan is destroyed), for tests and
+ * for the band-sharded path: DC differences (int16, indexed by global block), run-length values
+ * (int16) and zero counts (uint8) (channel stream cs starts at 64 * first block of cs). */
+int hic_entropy_symbol_buffers(const hic_entropy_plan* plan, const int16_t** d_dc, const int16_t** d_values,
+                               const uint8_t** d_lengths);
+
+/* ---- entropy decode --------------------------------------------------------------------------- */
+typedef struct hic_decode_plan hic_decode_plan;
+int hic_decode_plan_create(const hic_stream_layout* layout, hic_decode_plan** out);
+int hic_decode_plan_destroy(hic_decode_plan* plan);
+/* Code tables of every symbol stream (same layout as hic_entropy_tables) -- replaces
+ * HuffmanTree.construct_from_coding (huffman.py:30-58). */
+int hic_decode_set_tables(hic_decode_plan* plan, const uint32_t* h_rows, const int32_t* h_symbols,
+                          const uint8_t* h_lens, const uint64_t* h_codes, void* stream);
+/* D1-D3 (device) -- Huffman decode (HuffmanTree.decode_data, huffman.py:149-174), run-length
+ * expansion (codec.decode_run_length, codec.py:102-113), DC prefix sum (utils.invert_differences,
+ * utils.py:66-74) and de-zigzag into blocks (codec.py:415-425).  d_bytes holds the framed byte
+ * strings (each 4-byte aligned at h_byte_off[s], with 8 readable bytes after the last one);
+ * h_nbits[s] is the payload bit count of stream s (8 * (framed length - 1) - pad count, 0 for an
+ * absent stream).  d_coef receives zigzag blocks.  Synchronises `stream` and returns
+ * HIC_ERR_CORRUPT if a stream decodes to the wrong length. */
+int hic_decode_run(hic_decode_plan* plan, const uint8_t* d_bytes, const uint64_t* h_byte_off,
+                   const uint64_t* h_nbits, int16_t* d_coef, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,20 +81,47 @@ void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64
     }
 }
 
-// float32 inverse path of K7's inverse_block.  coef: [nb][64] int16 scan order; out [nb][64] uint8.
-void hx_inverse_blocks(const int16_t* coef, int nb, int kind, uint8_t* out) {
+// float32 inverse path of K7's inverse_block.  coef: [nb][64] int16 scan order; out [nb][64] uint8
+// (float32 result before fix-up); mask: samples within the near-integer band; ratio: max over
+// samples of |p32 - p64| / (2^-24 * 4 * S / 256), S = sum |coef * q| (what HIC_INV_KAPPA must bound);
+// exact: [nb][64] uint8 from the float64 emulation.
+void hx_inverse_blocks(const int16_t* coef, int nb, int kind, uint8_t* out, uint64_t* mask, double* ratio, uint8_t* exact) {
     const int* q = kind == 0 ? LUM : CHROMA;
     float dq[64];
     for (int u = 0; u < 8; ++u)
         for (int v = 0; v < 8; ++v) dq[8 * u + v] = (float)(q[8 * u + v] * aan_h(u) * aan_h(v) / 256.0);
     for (int b = 0; b < nb; ++b) {
         float v[64];
-        for (int k = 0; k < 64; ++k) v[ZZ[k]] = (float)coef[64 * b + k] * dq[ZZ[k]];
+        int32_t cq[64];
+        float S = 0.f;
+        bool ac = false;
+        for (int k = 0; k < 64; ++k) {
+            const int c = coef[64 * b + k];
+            v[ZZ[k]] = (float)c * dq[ZZ[k]];
+            cq[ZZ[k]] = c * q[ZZ[k]];
+            S += fabsf((float)c) * (float)q[ZZ[k]];
+            if (k && c) ac = true;
+        }
         for (int r = 0; r < 8; ++r)
             aan_inverse8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
         for (int c = 0; c < 8; ++c)
             aan_inverse8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
-        for (int i = 0; i < 64; ++i) out[64 * b + i] = (uint8_t)((int)(v[i] + 128.f) & 0xFF);
+        const float band = (float)(HIC_INV_KAPPA * 4.0 / 16777216.0 / 256.0) * S;
+        uint64_t m = 0;
+        double worst = 0.0;
+        for (int i = 0; i < 64; ++i) {
+            const float p = v[i] + 128.f;
+            out[64 * b + i] = (uint8_t)((int)p & 0xFF);
+            const double p64 = exact_decoded_sample(cq, i >> 3, i & 7);
+            exact[64 * b + i] = wrap_u8(p64);
+            if (ac && fabsf(p - rintf(p)) <= band) m |= (1ull << i);
+            if (S > 0.f) {
+                const double r = fabs((double)p - p64) / (4.0 / 16777216.0 / 256.0 * S);
+                if (r > worst) worst = r;
+            }
+        }
+        mask[b] = m;
+        ratio[b] = worst;
     }
 }
 

@@ -1,0 +1,126 @@
+"""GPU parity of the entropy stage (E1-E3, D1-D3) against the reference goldens and the oracle."""
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import hiccup_oracle as orc
+from tests.conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+JPEG_GOLDENS = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                      if not os.path.basename(f).startswith("w_"))
+
+
+def _golden_comp(g):
+    from hiccup_b200 import model
+    return model.CompressedImage(g["coef_lum"], g["coef_cr"], g["coef_cb"])
+
+
+@pytest.mark.parametrize("name", JPEG_GOLDENS)
+def test_jpeg_encode_bytes_equal_reference(name):
+    """codec.jpeg_encode(...).byte_stream() is byte-identical to the reference's .hic payload list."""
+    from hiccup_b200 import codec
+    g = load_golden(name)
+    want = pickle.loads(g["hic"].tobytes())
+    got = codec.jpeg_encode(_golden_comp(g)).byte_stream()
+    assert len(got) == len(want) == 21
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, "%s: payload %d differs (%d vs %d bytes)" % (name, i, len(a), len(b))
+
+
+@pytest.mark.parametrize("name", JPEG_GOLDENS)
+def test_full_encode_pipeline_bytes_equal_reference(name):
+    """rgb -> jpeg_compression -> jpeg_encode -> bytes: the whole encode path, bit-exact .hic."""
+    from hiccup_b200 import codec, compression
+    g = load_golden(name)
+    want = pickle.loads(g["hic"].tobytes())
+    got = codec.jpeg_encode(compression.jpeg_compression(g["rgb"])).byte_stream()
+    assert got == want
+
+
+@pytest.mark.parametrize("name", JPEG_GOLDENS)
+def test_jpeg_decode_of_reference_file(name):
+    from hiccup_b200 import codec, hicimage
+    g = load_golden(name)
+    hi = hicimage.HicImage.from_bytes(pickle.loads(g["hic"].tobytes()))
+    dec = codec.jpeg_decode(hi)
+    for ch, arr in dec.as_dict.items():
+        assert arr.dtype == np.float64
+        assert np.array_equal(arr, g["coef_" + ch]), "%s %s" % (name, ch)
+
+
+@pytest.mark.parametrize("shape,seed", [((426, 640), 41), ((1080, 1920), 42), ((40, 24), 43), ((136, 264), 44)])
+def test_symbol_streams_match_oracle(shape, seed):
+    from hiccup_b200 import _lib, compression, entropy, model
+    rgb = orc.synthetic_image(shape[0], shape[1], seed)
+    planes = orc.jpeg_compression(rgb)
+    want = orc.jpeg_streams(planes)
+    coef, g = compression.planes_to_device_blocks(model.CompressedImage(planes["lum"], planes["cr"], planes["cb"]))
+    layout = _lib.layout_dct(1, shape[0], shape[1])
+    enc = entropy.EntropyEncoder(layout)
+    res = enc.encode(coef.ptr)
+    dc, val, ln = enc.symbol_arrays()
+    for c, ch in enumerate(orc.CHANNELS):
+        b0 = int(layout.block_off[c])
+        nb = int(layout.nb[c])
+        assert np.array_equal(dc[b0:b0 + nb], want["dc"][ch])
+        n = int(res.nsym[c * 3 + 1])
+        assert n == len(want["ac_value"][ch]) == int(res.nsym[c * 3 + 2])
+        assert np.array_equal(val[b0 * 64:b0 * 64 + n], want["ac_value"][ch])
+        assert np.array_equal(ln[b0 * 64:b0 * 64 + n], want["ac_length"][ch])
+    # tables and bits against the oracle's Huffman stage
+    enc_o = orc.jpeg_encode(planes)
+    for kind in range(3):
+        for c in range(3):
+            i = kind * 3 + c
+            s = c * 3 + kind
+            assert res.table(s) == [(int(a), b) for a, b in enc_o["tables"][i]]
+            assert res.framed(s) == orc.padded_bits_to_bytes(enc_o["bits"][i])
+    enc.close()
+    coef.free()
+
+
+def test_rle_edge_cases():
+    """All-zero planes, a single trailing non-zero, runs of exactly 15/16/30 zeros across blocks."""
+    from hiccup_b200 import codec, model
+    rng = np.random.default_rng(3)
+    cases = []
+    z = np.zeros((32, 32), np.int32)
+    cases.append((z, z[:16, :16], z[:16, :16]))
+    a = z.copy(); a[31, 31] = 7                       # last scan position of the last block
+    cases.append((a, z[:16, :16], z[:16, :16]))
+    b = z.copy(); b[0, 0] = -5; b[8, 1] = 3           # DC only + one AC far away
+    cases.append((b, z[:16, :16], z[:16, :16]))
+    c = (rng.integers(-3, 4, (32, 32)) * (rng.random((32, 32)) < 0.05)).astype(np.int32)
+    cases.append((c, c[:16, :16].copy(), c[16:, 16:].copy()))
+    d = (rng.integers(-300, 300, (64, 48)) * (rng.random((64, 48)) < 0.01)).astype(np.int32)
+    cases.append((d, d[:32, :24].copy(), d[32:, 24:].copy()))
+    for lum, cr, cb in cases:
+        planes = {"lum": lum, "cr": cr, "cb": cb}
+        want = orc.jpeg_encode(planes)
+        hi = codec.jpeg_encode(model.CompressedImage(lum, cr, cb))
+        for i in range(9):
+            assert [(int(a_), b_) for a_, b_ in hi.payloads[i].rows] == [(int(a_), b_) for a_, b_ in want["tables"][i]]
+            assert hi.payloads[9 + i].byte_stream == orc.padded_bits_to_bytes(want["bits"][i])
+        back = codec.jpeg_decode(hi)
+        assert np.array_equal(back.luminance_component, lum)
+        assert np.array_equal(back.red_chrominance_component, cr)
+        assert np.array_equal(back.blue_chrominance_component, cb)
+
+
+@pytest.mark.parametrize("shape,seed", [((426, 640), 51), ((250, 130), 52), ((1080, 1920), 53)])
+def test_round_trip_through_both_stages(shape, seed):
+    from hiccup_b200 import codec, compression, hicimage
+    rgb = orc.synthetic_image(shape[0], shape[1], seed)
+    comp = compression.jpeg_compression(rgb)
+    stream = codec.jpeg_encode(comp).byte_stream()
+    back = codec.jpeg_decode(hicimage.HicImage.from_bytes(stream))
+    assert back == comp
+    out = compression.jpeg_decompression(back)
+    want = orc.jpeg_decompression(orc.jpeg_compression(rgb))
+    assert out.shape == want.shape
+    assert np.array_equal(out, want)

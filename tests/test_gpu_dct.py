@@ -50,7 +50,9 @@ def test_forward_noise_and_extremes():
 
 
 @pytest.mark.parametrize("name", [n for n in JPEG_GOLDENS])
-def test_inverse_within_one_lsb_of_reference(name):
+def test_inverse_equals_reference_pixels(name):
+    """north_star allows +-1 LSB; with the float64 fix-up the decoded pixels are in fact identical.
+    Discrepancies are counted and reported rather than hidden."""
     from hiccup_b200 import compression, model
     g = load_golden(name)
     if str(g["decode_error"]):
@@ -60,18 +62,32 @@ def test_inverse_within_one_lsb_of_reference(name):
     want = g["rgb_out"].astype(np.int64)
     assert got.shape == want.shape
     diff = np.abs(got - want)
-    n_off = int((diff > 0).sum())
-    # tolerance stated by north_star: +-1 LSB; uint8 wrap cases (+-255) are counted separately
-    wraps = int((diff > 1).sum())
-    assert wraps <= max(3, diff.size // 100000), "%d samples differ by more than 1 LSB" % wraps
-    print("%s: %d of %d samples differ by 1 LSB, %d wrap cases" % (name, n_off - wraps, diff.size, wraps))
+    print("%s: %d of %d samples differ (max %d); fix-up stats %r" % (name, int((diff > 0).sum()), diff.size,
+                                                                     int(diff.max()), compression.LAST_INVERSE_STATS))
+    assert int(diff.max()) <= 1, "tolerance stated by north_star: +-1 LSB"
+    assert int((diff > 0).sum()) == 0
 
 
-def test_inverse_matches_oracle_odd_shape():
+@pytest.mark.parametrize("shape,seed", [((70, 90), 31), ((426, 640), 32), ((1080, 1920), 33), ((34, 18), 34)])
+def test_inverse_matches_oracle(shape, seed):
     from hiccup_b200 import compression, model
-    rgb = orc.synthetic_image(70, 90, 31)
+    rgb = orc.synthetic_image(shape[0], shape[1], seed)
     planes = orc.jpeg_compression(rgb)
-    want = orc.jpeg_decompression(planes).astype(np.int64)
-    got = compression.jpeg_decompression(model.CompressedImage(planes["lum"], planes["cr"], planes["cb"])).astype(np.int64)
+    want = orc.jpeg_decompression(planes)
+    got = compression.jpeg_decompression(model.CompressedImage(planes["lum"], planes["cr"], planes["cb"]))
     assert got.shape == want.shape
-    assert (np.abs(got - want) > 1).sum() <= 3
+    assert np.array_equal(got, want), "%d samples differ" % int((got != want).sum())
+
+
+def test_inverse_wrap_cases_match():
+    """Coefficients that drive samples below 0 / above 255: the reference's uint8 cast wraps."""
+    from hiccup_b200 import compression, model
+    rng = np.random.default_rng(77)
+    lum = (rng.integers(-40, 40, (32, 48)) * (rng.random((32, 48)) < 0.2)).astype(np.int32)
+    lum[::8, ::8] = rng.integers(-1200, 1200, (4, 6))
+    cr = (rng.integers(-20, 20, (16, 24)) * (rng.random((16, 24)) < 0.2)).astype(np.int32)
+    cb = cr[::-1].copy()
+    planes = {"lum": lum, "cr": cr, "cb": cb}
+    want = orc.jpeg_decompression(planes)
+    got = compression.jpeg_decompression(model.CompressedImage(lum, cr, cb))
+    assert np.array_equal(got, want)

@@ -25,7 +25,7 @@ def main():
     def fwd():
         _lib.check(lib.hic_dct_forward(rgb.data_ptr(), n, h, w, coef.data_ptr(), ties.data_ptr(), blocks, stats.data_ptr(), st))
     def inv():
-        _lib.check(lib.hic_dct_inverse(coef.data_ptr(), n, h, w, yp.data_ptr(), crp.data_ptr(), cbp.data_ptr(), out.data_ptr(), st))
+        _lib.check(lib.hic_dct_inverse(coef.data_ptr(), n, h, w, yp.data_ptr(), crp.data_ptr(), cbp.data_ptr(), out.data_ptr(), ties.data_ptr(), blocks, stats.data_ptr(), st))
     for name, fn, bpp in (("forward", fwd, 6.0), ("inverse", inv, 6.0)):
         for _ in range(3): fn()
         torch.cuda.synchronize()
