@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode megapixels/sec of the hiccup DCT hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images n --height h --width w]
+
+A step = one full pass of the hot path over one batch of synthetic images: encode (K1 fused
+colour/pyrDown/DCT/quantise/zigzag + float64 tie fix-up, E1 run-length symbols + histograms, E2 host
+Huffman construction, E3 bit packing) followed by decode (D1 Huffman decode, D2 run-length expand,
+D3 DC prefix sum, K7 dequantise/IDCT + fix-up, K8 pyrUp/colour).  Default workload: BASELINE.json
+configs[1], a batch of 1024 synthetic 640x426 RGB images on one B200.  With N GPUs every rank
+processes its own batch (images are independent; no data-path collective) -> weak scaling.
+
+`value`  = whole-job MP/s with the batch resident in HBM when the timed region starts.
+`e2e`    = the same metric through the public host API (DctBatchCodec.encode / .decode) with the
+           batch in pinned host memory: host->device and device->host copies inside the timed region.
+`--impl reference` times the reference's CPU path (the oracle port: the reference itself cannot
+finish one 640x426 image's entropy stage in minutes) on all host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encode+decode megapixels/sec"
+UNIT = "MP/s"
+
+
+def synthetic_image(h, w, seed):
+    """uint8 noise at 1/16 resolution, bicubic upsample, + N(0, 4), clipped."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    small = rng.integers(0, 256, size=(max(2, h // 16), max(2, w // 16), 3), dtype=np.uint8)
+    big = cv2.resize(small, (w, h), interpolation=cv2.INTER_CUBIC).astype(np.float32)
+    big += rng.normal(0.0, 4.0, size=big.shape).astype(np.float32)
+    return np.clip(np.rint(big), 0, 255).astype(np.uint8)
+
+
+def synthetic_batch(n, h, w, seed0, out=None):
+    out = np.empty((n, h, w, 3), np.uint8) if out is None else out
+    for i in range(n):
+        out[i] = synthetic_image(h, w, seed0 + i)
+    return out
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 <= t <= t1:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:          # region shorter than the sampling period: use every sample we have
+            for t, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_array(lib_mod, shape, dtype=np.uint8):
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    lib_mod.check(lib_mod.load().hic_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def kernel_bytes(name, P, B, s_ac, bits_bytes):
+    """Algorithmic bytes one launch of `name` moves: P pixels, B 64-element
+    blocks, s_ac run-length symbols, bits_bytes Huffman-coded payload bytes."""
+    coef = 128.0 * B
+    sym = 3.0 * s_ac + 2.0 * B
+    table = {
+        "forward_kernel": 6.0 * P,
+        "rle_tile_summary_kernel": coef,
+        "rle_emit_kernel": coef + sym,
+        "pack_tile_bits_kernel": sym,
+        "pack_emit_kernel": sym + bits_bytes,
+        "huffman_decode_kernel": bits_bytes + sym,
+        "expand_tile_sum_kernel": 1.0 * s_ac,
+        "expand_scatter_kernel": 3.0 * s_ac + 2.0 * s_ac,
+        "dc_tile_sum_kernel": 2.0 * B,
+        "dc_write_kernel": 4.0 * B,
+        "inverse_kernel": coef + 1.5 * P,
+        "upsample_colour_kernel": 4.5 * P,
+    }
+    return table.get(name)
+
+
+def cpu_baseline_sample(h, w, n_images, seed0):
+    """The oracle port (numpy restatement of the reference) on one host core."""
+    from oracle import hiccup_oracle as orc
+    imgs = [synthetic_image(h, w, seed0 + i) for i in range(n_images)]
+    t0 = time.perf_counter()
+    for rgb in imgs:
+        planes = orc.jpeg_compression(rgb)
+        enc = orc.jpeg_encode(planes)
+        dec = orc.jpeg_decode(enc)
+        orc.jpeg_decompression(dec)
+    dt = time.perf_counter() - t0
+    return n_images * h * w / 1e6 / dt, dt
+
+
+def _ref_worker(args):
+    h, w, seed = args
+    from oracle import hiccup_oracle as orc
+    rgb = synthetic_image(h, w, seed)
+    planes = orc.jpeg_compression(rgb)
+    enc = orc.jpeg_encode(planes)
+    dec = orc.jpeg_decode(enc)
+    out = orc.jpeg_decompression(dec)
+    return int(out[0, 0, 0])
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    h, w = args.height, args.width
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for i in range(args.warmup):
+            pool.map(_ref_worker, [(h, w, 5000 + i * per_step + j) for j in range(per_step)])
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pool.map(_ref_worker, [(h, w, 9000 + i * per_step + j) for j in range(per_step)])
+        dt = time.perf_counter() - t0
+    value = args.steps * per_step * h * w / 1e6 / dt
+    sample = "%d synthetic %dx%d images per step (of the %d-image batch), oracle port, one process per core" % (
+        per_step, w, h, args.images)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batch of %d synthetic %dx%d RGB images, DCT mode encode+decode" % (args.images, w, h),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images", type=int, default=1024)
+    ap.add_argument("--height", type=int, default=426)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from hiccup_b200 import _lib
+    from hiccup_b200.batch import DctBatchCodec
+    _lib.check(_lib.load().hic_set_device(local_rank))
+    n, h, w = args.images, args.height, args.width
+    codec = DctBatchCodec(n, h, w, stream=None)
+    host_rgb, _keep_in = pinned_array(_lib, (n, h, w, 3))
+    synthetic_batch(n, h, w, 1000 * 2 + rank * n, out=host_rgb)
+    codec.upload(host_rgb)
+    _lib.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        codec.encode_device()
+        codec.decode_device()
+
+    # ---- device-resident arm (value) -------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    t_end = time.time()
+    ms_total = e0.elapsed_time(e1)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    clocks = sampler.stop(t_start, t_end)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pixels = n * h * w
+    value = world * pixels / 1e6 / (ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    enc = codec.encoder
+    s_ac = float(sum(int(enc.nsym[s]) for s in range(1, len(enc.nsym), 3)))
+    bits_bytes = float(enc.total_bytes)
+    B = float(codec.blocks)
+    peak, peak_src = measured_peak()
+    kernels = {}
+    for name, (ms, launches) in prof.items():
+        per = ms / max(launches, 1)
+        ab = kernel_bytes(name, float(pixels), B, s_ac, bits_bytes)
+        kernels[name] = {"ms_per_launch": round(per, 4), "launches_per_step": launches / args.steps,
+                         "share_of_step": round(ms / ms_total, 4) if ms_total else None,
+                         "algorithmic_gbs": round(ab / per / 1e6, 1) if ab and per > 0 else None,
+                         "frac_of_peak": round(ab / per / 1e6 / peak, 4) if ab and per > 0 else None}
+    dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+    roofline = None
+    if dominant:
+        k = kernels[dominant]
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": k["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": k["share_of_step"]}
+    gpu_launches = int(sum(v[1] for v in prof.values()))
+
+    # ---- end-to-end arm (host buffers, copies inside the timed region) ---------------------
+    enc_res = None
+    for _ in range(2):
+        enc_res = codec.encode(host_rgb)
+        out = codec.decode(enc_res)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    t_e2e = time.perf_counter()
+    for _ in range(args.steps):
+        enc_res = codec.encode(host_rgb)
+        out = codec.decode(enc_res)
+    e3.record()
+    barrier()
+    wall_e2e = time.perf_counter() - t_e2e
+    ms_e2e = max(e2.elapsed_time(e3), wall_e2e * 1e3)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * pixels / 1e6 / (ms_e2e / args.steps / 1e3)
+    table_bytes = int(enc_res.symbols.nbytes + enc_res.lens.nbytes + enc_res.codes.nbytes)
+    h2d = int(host_rgb.nbytes + enc_res.data.nbytes + table_bytes)
+    d2h = int(enc_res.data.nbytes + table_bytes + out.nbytes)
+    parity = {"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),
+                               "changed": int(codec.forward_stats[2])},
+              "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
+                               "changed": int(codec.inverse_stats[2])}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = 16
+        v, dt = cpu_baseline_sample(h, w, n_cpu, 2000)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d of the batch's %d synthetic %dx%d images, full encode+decode through the oracle port "
+                         "(numpy restatement of the reference, %.1f s)" % (n_cpu, n, w, h, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "batch of %d synthetic %dx%d RGB images per GPU, DCT mode encode+decode" % (n, w, h),
+                       "images_per_gpu": n, "height": h, "width": w, "parallelism": "by image, %d GPU(s), no collective" % world,
+                       "l2": "inputs larger than L2 (%.0f MB RGB per batch), no flush" % (host_rgb.nbytes / 1e6),
+                       "compressed_bytes_per_batch": int(enc.total_bytes), "symbols_per_batch": int(s_ac)},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": gpu_launches, "parity": parity,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

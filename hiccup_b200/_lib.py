@@ -51,6 +51,8 @@ SIGNATURES = {
     "hic_stream_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "hic_stream_destroy": (c_int, [c_void_p]),
     "hic_stream_sync": (c_int, [c_void_p]),
+    "hic_profile_enable": (c_int, [c_int]),
+    "hic_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_dct_geometry_of": (c_int, [c_int32, c_int32, ctypes.POINTER(Geometry)]),
     "hic_dct_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
     "hic_blocks_to_planes": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -63,6 +65,10 @@ SIGNATURES = {
     "hic_entropy_plan_destroy": (c_int, [c_void_p]),
     "hic_entropy_symbolize": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hic_entropy_build_codes": (c_int, [c_void_p, c_void_p]),
+    "hic_entropy_build_codes_device": (c_int, [c_void_p, c_void_p]),
+    "hic_entropy_device_tables": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                          ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "hic_decode_set_tables_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_entropy_stream_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "hic_entropy_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -174,6 +180,18 @@ def layout_flat(n, length):
     lay = StreamLayout()
     check(load().hic_layout_flat(int(n), int(length), ctypes.byref(lay)))
     return lay
+
+
+def profile_enable(on=True):
+    check(load().hic_profile_enable(1 if on else 0))
+
+
+def profile_report():
+    """{"kernel name": (total_ms, launches)} since the last report."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().hic_profile_report(buf, len(buf)))
+    return {k: (v[0], v[1]) for k, v in json.loads(buf.value.decode()).items()}
 
 
 def sync(stream=None):

@@ -1,0 +1,125 @@
+"""Batched, device-resident DCT-mode pipeline (an additive entry point: the reference API is one
+image per call).
+
+    codec = DctBatchCodec(n, h, w)
+    enc = codec.encode(rgb_batch)          # host uint8 (n, h, w, 3) -> EncodedStreams (tables + framed bits)
+    rgb = codec.decode(enc)                # -> host uint8 (n, 2*(h//2), 2*(w//2), 3)
+    images = codec.hic_images(enc)         # -> list of HicImage, byte-identical to the reference's
+
+All buffers and both entropy plans are allocated once for the shape; a step launches the same
+kernels as the single-image drop-in functions (compression.py / codec.py), just over n images.
+"""
+import numpy as np
+
+from hiccup_b200 import _lib, entropy, hicimage
+
+
+class DctBatchCodec:
+    def __init__(self, n, h, w, value_bins=entropy.DEFAULT_VALUE_BINS, device=None, stream=None, device_codes=True):
+        _lib.require_device()
+        self.lib = _lib.load()
+        if device is not None:
+            _lib.check(self.lib.hic_set_device(int(device)))
+        self.n, self.h, self.w = int(n), int(h), int(w)
+        self.stream = stream
+        self.device_codes = bool(device_codes) and value_bins <= 8192      # E2 on the GPU (same codes, no PCIe)
+        g = self.g = _lib.geometry(h, w)
+        self.blocks = self.n * g.blocks_per_image
+        self.layout = _lib.layout_dct(self.n, h, w)
+        self.d_rgb = _lib.DeviceBuffer(self.n * h * w * 3)
+        self.d_coef = _lib.DeviceBuffer(self.blocks * 128)
+        self.d_coef_dec = _lib.DeviceBuffer(self.blocks * 128)
+        self.d_ties = _lib.DeviceBuffer(self.blocks * _lib.TIE_RECORD_BYTES)
+        self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+        self.d_y = _lib.DeviceBuffer(self.n * h * w)
+        self.d_cr = _lib.DeviceBuffer(self.n * g.hc * g.wc)
+        self.d_cb = _lib.DeviceBuffer(self.n * g.hc * g.wc)
+        self.d_out = _lib.DeviceBuffer(self.n * g.out_h * g.out_w * 3)
+        self.encoder = entropy.EntropyEncoder(self.layout, value_bins)
+        self.decoder = entropy.EntropyDecoder(self.layout)
+        self.forward_stats = np.zeros(4, np.uint32)
+        self.inverse_stats = np.zeros(4, np.uint32)
+
+    # ---- sizes -------------------------------------------------------------------------------
+    @property
+    def pixels(self):
+        return self.n * self.h * self.w
+
+    @property
+    def out_shape(self):
+        return (self.n, self.g.out_h, self.g.out_w, 3)
+
+    # ---- device-resident steps ---------------------------------------------------------------
+    def upload(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.shape == (self.n, self.h, self.w, 3), rgb.shape
+        self.d_rgb.upload(rgb, self.stream)
+
+    def encode_device(self):
+        """K1 + fix-up, E1, E2 (host trees), E3.  Inputs and outputs stay in HBM."""
+        lib, st = self.lib, self.stream
+        _lib.check(lib.hic_dct_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.d_ties.ptr,
+                                       self.blocks, self.d_stats.ptr, st))
+        self.encoder.symbolize(self.d_coef.ptr, st)
+        self.encoder.build_codes(st, on_device=self.device_codes)
+        return self.encoder.pack(st)
+
+    def decode_device(self):
+        """D1-D3, K7 + fix-up, K8, from the encoder's own device-resident output (tables and bits
+        are handed over device-to-device)."""
+        lib, st = self.lib, self.stream
+        enc = self.encoder
+        d_index, d_row_sym, d_row_packed, _, _ = enc.device_tables()
+        self.decoder.set_tables_device(d_index, d_row_sym, d_row_packed, st)
+        self.decoder.run(enc._out.ptr, enc.byte_off, enc.nbits, self.d_coef_dec.ptr, st)
+        _lib.check(lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
+                                       self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks, self.d_stats.ptr, st))
+
+    # ---- host-to-host entry points -----------------------------------------------------------
+    def encode(self, rgb):
+        self.upload(rgb)
+        out = self.encode_device()
+        enc = self.encoder
+        data = out.download(np.uint8, int(enc.total_bytes), self.stream)
+        sym, lens, codes = enc.tables()
+        self.forward_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
+        return entropy.EncodedStreams(self.layout, enc.rows.copy(), enc.nsym.copy(), enc.nbits.copy(),
+                                      enc.byte_off.copy(), enc.byte_len.copy(), sym, lens, codes, data)
+
+    def decode(self, enc):
+        data = np.concatenate([np.asarray(enc.data, np.uint8), np.zeros(16, np.uint8)])
+        self.decoder.decode(enc.rows, enc.symbols, enc.lens, enc.codes, data, enc.byte_off, enc.nbits,
+                            self.d_coef_dec.ptr, self.stream)
+        _lib.check(self.lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
+                                            self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks,
+                                            self.d_stats.ptr, self.stream))
+        out = self.d_out.download(np.uint8, self.n * self.g.out_h * self.g.out_w * 3, self.stream)
+        self.inverse_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
+        return out.reshape(self.out_shape)
+
+    def coefficients(self):
+        """Download the quantised zigzag blocks of the last encode: (n, blocks_per_image, 64) int16."""
+        c = self.d_coef.download(np.int16, self.blocks * 64, self.stream)
+        return c.reshape(self.n, self.g.blocks_per_image, 64)
+
+    def hic_images(self, enc):
+        """Materialise the reference's container objects (codec.jpeg_encode's return value) per image."""
+        g = self.g
+        out = []
+        for i in range(self.n):
+            tables, bits = [], []
+            for kind in range(3):
+                for c in range(3):
+                    s = (i * 3 + c) * 3 + kind
+                    conv = np.int32 if kind == entropy.KIND_DC else int
+                    tables.append(hicimage.PayloadStringP.from_rows([(conv(a), b) for a, b in enc.table(s)]))
+                    bits.append(hicimage.BitStringP.from_framed(enc.framed(s)))
+            out.append(hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(g.h, g.w), hicimage.TupP(g.hc, g.wc)]))
+        return out
+
+    def close(self):
+        self.encoder.close()
+        self.decoder.close()
+        for b in (self.d_rgb, self.d_coef, self.d_coef_dec, self.d_ties, self.d_stats, self.d_y, self.d_cr, self.d_cb,
+                  self.d_out):
+            b.free()

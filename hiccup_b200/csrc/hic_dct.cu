@@ -652,10 +652,8 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
         if (dev < 64) attr_set[dev] = true;
     }
-    k1::forward_kernel<<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats);
-    HIC_CHECK_LAUNCH("forward_kernel");
-    k1::fixup_kernel<<<148 * 4, 128, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats);
-    HIC_CHECK_LAUNCH("fixup_kernel");
+    HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 4, 128, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     return HIC_OK;
 }
 
@@ -668,8 +666,8 @@ int hic_blocks_to_planes(const int16_t* d_coef, int32_t n, int32_t h, int32_t w,
     int rc = geometry_of(h, w, &g);
     if (rc) return rc;
     const int64_t items = (int64_t)n * g.blocks_per_image * 64;
-    blocks_to_planes_kernel<<<grid_for(items, 256), 256, 0, as_stream(stream)>>>(d_coef, g, n, d_lum, d_cr, d_cb);
-    HIC_CHECK_LAUNCH("blocks_to_planes_kernel");
+    cudaStream_t st = as_stream(stream);
+    HIC_LAUNCH("blocks_to_planes_kernel", st, blocks_to_planes_kernel<<<grid_for(items, 256), 256, 0, st>>>(d_coef, g, n, d_lum, d_cr, d_cb));
     return HIC_OK;
 }
 
@@ -682,8 +680,8 @@ int hic_planes_to_blocks(const int32_t* d_lum, const int32_t* d_cr, const int32_
     int rc = geometry_of(h, w, &g);
     if (rc) return rc;
     const int64_t items = (int64_t)n * g.blocks_per_image * 64;
-    planes_to_blocks_kernel<<<grid_for(items, 256), 256, 0, as_stream(stream)>>>(d_lum, d_cr, d_cb, g, n, d_coef);
-    HIC_CHECK_LAUNCH("planes_to_blocks_kernel");
+    cudaStream_t st = as_stream(stream);
+    HIC_LAUNCH("planes_to_blocks_kernel", st, planes_to_blocks_kernel<<<grid_for(items, 256), 256, 0, st>>>(d_lum, d_cr, d_cb, g, n, d_coef));
     return HIC_OK;
 }
 
@@ -702,13 +700,10 @@ int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint
     cudaStream_t st = as_stream(stream);
     HIC_CUDA(cudaMemsetAsync(d_stats, 0, HIC_TIE_STATS * sizeof(uint32_t), st));
     const int64_t blocks = (int64_t)n * g.blocks_per_image;
-    k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats);
-    HIC_CHECK_LAUNCH("inverse_kernel");
-    k7::inverse_fixup_kernel<<<148 * 4, 128, 0, st>>>(d_coef, g, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats);
-    HIC_CHECK_LAUNCH("inverse_fixup_kernel");
+    HIC_LAUNCH("inverse_kernel", st, k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
+    HIC_LAUNCH("inverse_fixup_kernel", st, k7::inverse_fixup_kernel<<<148 * 4, 128, 0, st>>>(d_coef, g, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
     const int64_t quads = (int64_t)n * g.hc * g.wc;
-    k7::upsample_colour_kernel<<<grid_for(quads, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out);
-    HIC_CHECK_LAUNCH("upsample_colour_kernel");
+    HIC_LAUNCH("upsample_colour_kernel", st, k7::upsample_colour_kernel<<<grid_for(quads, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out));
     return HIC_OK;
 }
 

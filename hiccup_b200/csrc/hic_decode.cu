@@ -1,10 +1,9 @@
 // hic_decode.cu -- entropy decode stage: Huffman decode (D1), run-length expansion (D2), DC prefix
 // sum and de-zigzag into blocks (D3).
 //
-// The `.hic` format carries no restart offsets (codec.py:319-334), so a bit stream can only be
-// entered at its first bit.  D1 decodes each of the 9 n symbol streams with a lookup table on the
-// first LUT_BITS bits of the window (codes longer than that fall back to a search of the stream's
-// long rows); D2 and D3 are tile scans over the decoded symbols.
+// The `.hic` format carries no restart offsets (codec.py:319-334); D1 recovers parallelism inside a
+// stream from the self-synchronising property of Huffman codes.  D2 and D3 are tile scans over the
+// decoded symbols.
 #include <algorithm>
 #include <vector>
 #include "hic_core.cuh"
@@ -13,16 +12,12 @@
 namespace hic {
 namespace dec {
 
-constexpr int LUT_BITS = 11;
-constexpr int LUT_SIZE = 1 << LUT_BITS;
 constexpr int XT = 2048;             // symbols per expand tile
 constexpr int XTHREADS = 256;
 constexpr int XSPT = XT / XTHREADS;
 
-struct LongRow {
-    uint64_t code;      // left aligned in 64 bits
-    int32_t sym;
-    uint32_t len;
+struct RowIndex {       // rows of one symbol stream inside the row arrays (same layout as the encoder's index)
+    uint32_t offset, count;
 };
 
 struct Geom {
@@ -37,111 +32,349 @@ __host__ __device__ inline int64_t cs_block_base(const Geom& g, int img, int c) 
     return (int64_t)img * g.L.blocks_per_image + g.L.block_off[c];
 }
 
-// lut[ss][prefix] = sym << 8 | len  (len == 0: no code of <= LUT_BITS bits has this prefix)
+// ------------------------------------------------------------------------------------------------
+// D1: parallel Huffman decode by self-synchronisation.
+//
+// The format has no restart offsets, but Huffman codes self-synchronise: a decoder started at an
+// arbitrary bit falls onto true codeword boundaries after a few symbols.  Each stream is cut into
+// subsequences of SUB_BITS bits, one thread each; a CTA owns SUB_PER_CTA consecutive subsequences.
+//   sync kernel   every thread decodes from its nominal start until it crosses its upper boundary
+//                 and records where it stopped; then, in a loop inside the CTA, thread t restarts
+//                 from where thread t-1 stopped until nothing changes (shared memory only);
+//   resync kernel the same, seeded with the stop position of the previous CTA's last thread;
+//                 relaunched until no CTA's last stop position changes (usually once);
+//   count scan    symbols per CTA -> output offsets (per-stream scan);
+//   write kernel  final pass from the now-correct starts, writing symbols at their offsets.
+// Code lookup: a 12-bit first-level table in shared memory; prefixes of longer codes point into a
+// per-stream second-level table (codes up to 20 bits); anything longer is found by binary search
+// over the stream's long rows sorted by left-aligned code.
+// ------------------------------------------------------------------------------------------------
+constexpr int L1_BITS = 12;
+constexpr int L1_SIZE = 1 << L1_BITS;
+constexpr int L2_MAX_EXTRA = 8;
+constexpr int L2_CAP = 4096;                 // second-level entries per stream
+constexpr int SUB_BITS = 128;
+constexpr int SUB_PER_CTA = 256;
+constexpr int CHUNK_WORDS = SUB_BITS * SUB_PER_CTA / 32;      // 1024 words of bit stream per CTA
+constexpr int CHUNK_SLACK = 4;                                // a code may run 58 bits past the last boundary
+constexpr int L1_FALLBACK = 0xFF;
+
+struct SyncTile {
+    uint32_t ss;            // symbol stream
+    uint32_t sub0;          // first subsequence of the tile inside its stream
+    uint64_t sub_base;      // global index of that subsequence
+};
+
+// one CTA per symbol stream: first- and second-level tables from the code rows
 __global__ void __launch_bounds__(256)
-build_lut_kernel(const uint64_t* __restrict__ row_off, const int32_t* __restrict__ row_sym,
-                 const uint8_t* __restrict__ row_len, const uint64_t* __restrict__ row_code, int32_t* __restrict__ lut) {
+build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restrict__ row_sym,
+                    const uint64_t* __restrict__ row_packed, int32_t* __restrict__ lut1, int32_t* __restrict__ lut2) {
+    __shared__ uint32_t extra[L1_SIZE];          // max (len - 12) under each 12-bit prefix
+    __shared__ uint32_t offs[L1_SIZE];
+    __shared__ uint32_t wsum[8];
     const int ss = blockIdx.x;
-    int32_t* my = lut + (size_t)ss * LUT_SIZE;
-    for (int i = threadIdx.x; i < LUT_SIZE; i += blockDim.x) my[i] = 0;
+    int32_t* my1 = lut1 + (size_t)ss * L1_SIZE;
+    int32_t* my2 = lut2 + (size_t)ss * L2_CAP;
+    for (int i = threadIdx.x; i < L1_SIZE; i += blockDim.x) {
+        my1[i] = 0;
+        extra[i] = 0;
+    }
+    for (int i = threadIdx.x; i < L2_CAP; i += blockDim.x) my2[i] = 0;
     __syncthreads();
-    const uint64_t r0 = row_off[ss], r1 = row_off[ss + 1];
+    const uint64_t r0 = index[ss].offset, r1 = r0 + index[ss].count;
+    constexpr uint64_t CODE_MASK = (1ull << 58) - 1;
     for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-        const uint32_t len = row_len[r];
-        if (len == 0 || len > LUT_BITS) continue;
-        const uint32_t base = (uint32_t)(row_code[r] << (LUT_BITS - len));
+        const uint32_t len = (uint32_t)(row_packed[r] >> 58);
+        const uint64_t code = row_packed[r] & CODE_MASK;
+        if (len == 0) continue;
+        if (len <= L1_BITS) {
+            const uint32_t base = (uint32_t)(code << (L1_BITS - len));
+            const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
+            for (uint32_t j = 0; j < (1u << (L1_BITS - len)); ++j) my1[base + j] = entry;
+        } else {
+            atomicMax(&extra[(uint32_t)(code >> (len - L1_BITS))], len - L1_BITS);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the second-level sizes over the 4096 prefixes (16 per thread)
+    uint32_t local[16], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t e = extra[threadIdx.x * 16 + j];
+        local[j] = (e && e <= L2_MAX_EXTRA) ? (1u << e) : 0u;
+        sum += local[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += wsum[w];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int pfx = threadIdx.x * 16 + j;
+        const uint32_t e = extra[pfx];
+        if (e) {
+            if (local[j] && run + local[j] <= (uint32_t)L2_CAP) {
+                offs[pfx] = run;
+                my1[pfx] = (int32_t)((run << 8) | 0x80u | e);
+                run += local[j];
+            } else {
+                offs[pfx] = 0xFFFFFFFFu;
+                my1[pfx] = L1_FALLBACK;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        const uint32_t len = (uint32_t)(row_packed[r] >> 58);
+        const uint64_t code = row_packed[r] & CODE_MASK;
+        if (len <= L1_BITS) continue;
+        const uint32_t pfx = (uint32_t)(code >> (len - L1_BITS));
+        if (offs[pfx] == 0xFFFFFFFFu) continue;
+        const uint32_t e = extra[pfx], x = len - L1_BITS;
+        const uint32_t sub = (uint32_t)(code & ((1ull << x) - 1));
+        const uint32_t base = offs[pfx] + (sub << (e - x));
         const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
-        for (uint32_t j = 0; j < (1u << (LUT_BITS - len)); ++j) my[base + j] = entry;
+        for (uint32_t j = 0; j < (1u << (e - x)); ++j) my2[base + j] = entry;
     }
 }
 
-// D1: one thread per symbol stream.  Threads are ordered (channel, kind) major, image minor, so the
-// lanes of a warp decode streams of similar length.
-__global__ void __launch_bounds__(32)
-huffman_decode_kernel(Geom g, const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ byte_off,
-                      const uint64_t* __restrict__ nbits_arr, const int32_t* __restrict__ lut,
-                      const LongRow* __restrict__ long_rows, const uint32_t* __restrict__ long_off,
-                      int16_t* __restrict__ dc, int16_t* __restrict__ values, uint8_t* __restrict__ lengths,
-                      uint32_t* __restrict__ nsym_out, uint32_t* __restrict__ err) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = g.L.n_images;
-    if (t >= n * 9) return;
-    const int grp = t / n, img = t - grp * n;
-    const int c = grp / 3, kind = grp % 3;
-    const int ss = (img * 3 + c) * 3 + kind;
-    const uint64_t nbits = nbits_arr[ss];
-    const int64_t bb = cs_block_base(g, img, c);
-    const uint32_t cap = (uint32_t)(kind == HIC_KIND_DC ? g.L.nb[c] : g.L.nb[c] * 64);
-    int16_t* out16 = kind == HIC_KIND_DC ? dc + bb : values + bb * 64;
-    uint8_t* out8 = lengths + bb * 64;
-    const int32_t* my_lut = lut + (size_t)ss * LUT_SIZE;
-    const LongRow* lr = long_rows + long_off[ss];
-    const uint32_t n_long = long_off[ss + 1] - long_off[ss];
+struct BitReader {
+    const uint32_t* words;      // shared-memory copy of the CTA's chunk (already in MSB-first order)
+    __device__ __forceinline__ uint64_t window(uint32_t rel_bit) const {
+        const uint32_t wi = rel_bit >> 5, sh = rel_bit & 31;
+        const uint64_t hi = ((uint64_t)words[wi] << 32) | words[wi + 1];
+        return sh ? (hi << sh) | (words[wi + 2] >> (32 - sh)) : hi;
+    }
+};
 
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(bytes + byte_off[ss]);    // 4-byte aligned by contract
-    uint64_t buf = (uint64_t)__byte_perm(__ldg(words), 0, 0x0123) << 40;                // drop the pad-count byte
-    int avail = 24;
-    uint32_t next_word = 1;
-    uint64_t consumed = 0;
-    uint32_t count = 0;
-    bool bad = false;
-    while (consumed < nbits) {
-        if (avail <= 32) {
-            buf |= (uint64_t)__byte_perm(__ldg(words + next_word), 0, 0x0123) << (32 - avail);
-            ++next_word;
-            avail += 32;
-        }
-        const int32_t e = __ldg(my_lut + (uint32_t)(buf >> (64 - LUT_BITS)));
-        int32_t sym;
-        uint32_t len = (uint32_t)(e & 0xFF);
-        if (len) {
-            sym = e >> 8;
-        } else {
-            // long code: make sure the window holds up to 58 bits, then search the long rows
-            if (avail <= 32) {     // (cannot happen right after the refill above, kept for clarity)
-                buf |= (uint64_t)__byte_perm(__ldg(words + next_word), 0, 0x0123) << (32 - avail);
-                ++next_word;
-                avail += 32;
-            }
-            uint64_t window = buf;
-            if (avail < 58) {      // peek one more word without consuming it
-                window |= (uint64_t)__byte_perm(__ldg(words + next_word), 0, 0x0123) >> (avail - 32);
-            }
-            sym = 0;
-            for (uint32_t i = 0; i < n_long; ++i) {
-                const LongRow r = lr[i];
-                if ((window >> (64 - r.len)) == (r.code >> (64 - r.len))) {
-                    sym = r.sym;
-                    len = r.len;
-                    break;
-                }
-            }
-            if (!len) {
-                bad = true;
-                break;
-            }
-        }
-        if (consumed + len > nbits || count >= cap) {
-            bad = true;
-            break;
-        }
-        if (kind == HIC_KIND_LENGTH) out8[count] = (uint8_t)sym;
-        else out16[count] = (int16_t)sym;
-        ++count;
-        consumed += len;
-        if (len > (uint32_t)avail) {       // a long code that used the peeked word
-            buf = (uint64_t)__byte_perm(__ldg(words + next_word), 0, 0x0123) << 32;
-            ++next_word;
-            const uint32_t extra = len - avail;
-            buf <<= extra;
-            avail = 32 - (int)extra;
-        } else {
-            buf <<= len;
-            avail -= (int)len;
+// decode one code at the 64-bit window; returns its length (0 = no valid code) and the symbol
+__device__ __forceinline__ uint32_t decode_one(uint64_t w, const int32_t* __restrict__ l1, const int32_t* __restrict__ l2,
+                                               const int32_t* __restrict__ row_sym, const uint64_t* __restrict__ row_packed,
+                                               uint32_t n_rows, int32_t& sym) {
+    int32_t e = l1[(uint32_t)(w >> (64 - L1_BITS))];
+    if (!(e & 0x80)) {
+        sym = e >> 8;
+        return (uint32_t)(e & 0x7F);
+    }
+    const uint32_t nb2 = (uint32_t)(e & 0x7F);
+    if (nb2 != 0x7F) {
+        const uint32_t idx = ((uint32_t)e >> 8) + (uint32_t)((w >> (64 - L1_BITS - nb2)) & ((1u << nb2) - 1));
+        e = __ldg(l2 + idx);
+        sym = e >> 8;
+        return (uint32_t)(e & 0xFF);
+    }
+    // codes longer than 20 bits (or a crowded second level): scan the stream's rows -- prefix-free
+    // codes have exactly one match.  Practically never taken for image data.
+    for (uint32_t i = 0; i < n_rows; ++i) {
+        const uint64_t packed = __ldg(row_packed + i);
+        const uint32_t len = (uint32_t)(packed >> 58);
+        if (len > L1_BITS && (w >> (64 - len)) == (packed & ((1ull << 58) - 1))) {
+            sym = __ldg(row_sym + i);
+            return len;
         }
     }
-    nsym_out[ss] = count;
-    if (bad) atomicOr(err, 1u);
+    return 0;
+}
+
+// Decode from `pos` until the position reaches `limit` (the thread's upper boundary) or `end`.
+// Positions are bits from the stream's first byte; `chunk0` is the bit position of smem word 0.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t decode_span(const BitReader& br, uint32_t chunk0, uint32_t pos, uint32_t limit,
+                                                uint32_t end, const int32_t* __restrict__ l1,
+                                                const int32_t* __restrict__ l2, const int32_t* __restrict__ row_sym,
+                                                const uint64_t* __restrict__ row_packed, uint32_t n_rows, uint32_t& count, int16_t* __restrict__ out16,
+                                                uint8_t* __restrict__ out8, uint32_t out_idx, bool& bad) {
+    count = 0;
+    const uint32_t stop = limit < end ? limit : end;
+    while (pos < stop) {
+        int32_t sym = 0;
+        const uint32_t len = decode_one(br.window(pos - chunk0), l1, l2, row_sym, row_packed, n_rows, sym);
+        if (len == 0 || pos + len > end) {
+            bad = true;
+            return stop;          // not a codeword boundary (or a corrupt stream): give up on this span
+        }
+        if (WRITE) {
+            if (out8) out8[out_idx + count] = (uint8_t)sym; else out16[out_idx + count] = (int16_t)sym;
+        }
+        ++count;
+        pos += len;
+    }
+    return pos;
+}
+
+struct SyncArgs {
+    const uint8_t* bytes;
+    const uint64_t* byte_off;
+    const uint64_t* nbits;
+    const int32_t* lut1;
+    const int32_t* lut2;
+    const RowIndex* index;
+    const int32_t* row_sym;
+    const uint64_t* row_packed;
+    const SyncTile* tiles;
+    uint32_t* sub_end;          // per subsequence: where its decoder stopped
+    uint16_t* sub_cnt;          // per subsequence: symbols decoded
+    uint32_t* tile_start;       // per tile: the start its first thread used
+    uint32_t* tile_cnt;         // per tile: symbols
+    uint32_t* changed;          // set when a tile's last stop position moved
+};
+
+__device__ __forceinline__ void stage_chunk(const SyncArgs& a, const SyncTile& t, uint32_t* s_words, int32_t* s_l1) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.bytes + a.byte_off[t.ss]) + (size_t)t.sub0 * (SUB_BITS / 32);
+    const uint64_t total_bits = 8 + a.nbits[t.ss];
+    const uint32_t total_words = (uint32_t)((total_bits + 31) >> 5);
+    const uint32_t w0 = t.sub0 * (SUB_BITS / 32);
+    for (int i = threadIdx.x; i < CHUNK_WORDS + CHUNK_SLACK; i += blockDim.x)
+        s_words[i] = (w0 + i < total_words) ? __byte_perm(__ldg(src + i), 0, 0x0123) : 0u;
+    const int32_t* l1 = a.lut1 + (size_t)t.ss * L1_SIZE;
+    for (int i = threadIdx.x; i < L1_SIZE; i += blockDim.x) s_l1[i] = __ldg(l1 + i);
+}
+
+template <bool RESYNC>
+__global__ void __launch_bounds__(SUB_PER_CTA)
+huffman_sync_kernel(SyncArgs a) {
+    __shared__ uint32_t s_words[CHUNK_WORDS + CHUNK_SLACK];
+    __shared__ int32_t s_l1[L1_SIZE];
+    __shared__ uint32_t s_end[SUB_PER_CTA];
+    __shared__ uint32_t s_red[SUB_PER_CTA / 32];
+    const SyncTile t = a.tiles[blockIdx.x];
+    const uint32_t end = (uint32_t)(8 + a.nbits[t.ss]);
+    const uint32_t n_sub = (end + SUB_BITS - 1) / SUB_BITS;
+    const uint32_t sub = t.sub0 + threadIdx.x;
+    const bool active = sub < n_sub;
+    const uint64_t g = t.sub_base + threadIdx.x;
+    const uint32_t chunk0 = t.sub0 * SUB_BITS;
+    const uint32_t limit = (sub + 1) * SUB_BITS;
+    const uint32_t tile_true_start = t.sub0 == 0 ? 8u : (RESYNC ? a.sub_end[t.sub_base - 1] : chunk0);
+    if (RESYNC) {
+        if (tile_true_start == a.tile_start[blockIdx.x]) return;      // nothing upstream moved
+    }
+    stage_chunk(a, t, s_words, s_l1);
+    const BitReader br{s_words};
+    const int32_t* l2 = a.lut2 + (size_t)t.ss * L2_CAP;
+    const int32_t* rsym = a.row_sym + a.index[t.ss].offset;
+    const uint64_t* rpk = a.row_packed + a.index[t.ss].offset;
+    const uint32_t n_rows = a.index[t.ss].count;
+    __syncthreads();
+
+    uint32_t start, my_end = 0, cnt = 0, old_last_end = 0;
+    bool bad = false;
+    if (!RESYNC) {
+        start = threadIdx.x == 0 ? tile_true_start : sub * SUB_BITS;
+        if (active) my_end = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, rsym, rpk, n_rows, cnt, nullptr, nullptr, 0, bad);
+    } else {
+        // previous state: my stop position and count; my start was my left neighbour's stop
+        my_end = active ? a.sub_end[g] : 0;
+        cnt = active ? a.sub_cnt[g] : 0;
+        start = threadIdx.x == 0 ? a.tile_start[blockIdx.x] : (active ? a.sub_end[g - 1] : 0);
+        if (threadIdx.x == blockDim.x - 1 || sub == n_sub - 1) old_last_end = my_end;
+    }
+    s_end[threadIdx.x] = my_end;
+    // intra-CTA synchronisation: restart from the left neighbour's stop until nothing changes
+    for (int iter = 0; iter <= SUB_PER_CTA; ++iter) {
+        __syncthreads();
+        const uint32_t want = threadIdx.x == 0 ? tile_true_start : s_end[threadIdx.x - 1];
+        const bool redo = active && want != start;
+        __syncthreads();
+        bool moved = false;
+        if (redo) {
+            start = want;
+            bad = false;
+            const uint32_t e = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, rsym, rpk, n_rows, cnt, nullptr, nullptr, 0, bad);
+            moved = e != my_end;
+            my_end = e;
+            s_end[threadIdx.x] = e;
+        }
+        if (!__syncthreads_or(moved)) break;
+    }
+    if (active) {
+        a.sub_end[g] = my_end;
+        a.sub_cnt[g] = (uint16_t)cnt;
+    }
+    // tile totals
+    uint32_t v = active ? cnt : 0;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < SUB_PER_CTA / 32; ++w) tot += s_red[w];
+        a.tile_cnt[blockIdx.x] = tot;
+        a.tile_start[blockIdx.x] = tile_true_start;
+    }
+    if (RESYNC && active && (threadIdx.x == blockDim.x - 1 || sub == n_sub - 1) && my_end != old_last_end)
+        atomicOr(a.changed, 1u);
+}
+
+// per-stream exclusive scan of the tile symbol counts (tiles of a stream are consecutive)
+__global__ void sync_tile_scan_kernel(int n_ss, const uint32_t* __restrict__ ss_tile0, const uint32_t* __restrict__ tile_cnt,
+                                      uint32_t* __restrict__ tile_off, uint32_t* __restrict__ nsym_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_ss) return;
+    uint32_t run = 0;
+    for (uint32_t t = ss_tile0[s]; t < ss_tile0[s + 1]; ++t) {
+        tile_off[t] = run;
+        run += tile_cnt[t];
+    }
+    nsym_out[s] = run;
+}
+
+__global__ void __launch_bounds__(SUB_PER_CTA)
+huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, int16_t* __restrict__ dc,
+                     int16_t* __restrict__ values, uint8_t* __restrict__ lengths, uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_words[CHUNK_WORDS + CHUNK_SLACK];
+    __shared__ int32_t s_l1[L1_SIZE];
+    __shared__ uint32_t s_sum[SUB_PER_CTA / 32];
+    const SyncTile t = a.tiles[blockIdx.x];
+    const uint32_t end = (uint32_t)(8 + a.nbits[t.ss]);
+    const uint32_t n_sub = (end + SUB_BITS - 1) / SUB_BITS;
+    const uint32_t sub = t.sub0 + threadIdx.x;
+    const bool active = sub < n_sub;
+    const uint64_t gi = t.sub_base + threadIdx.x;
+    const uint32_t chunk0 = t.sub0 * SUB_BITS;
+    stage_chunk(a, t, s_words, s_l1);
+    const BitReader br{s_words};
+    const int32_t* l2 = a.lut2 + (size_t)t.ss * L2_CAP;
+    const int32_t* rsym = a.row_sym + a.index[t.ss].offset;
+    const uint64_t* rpk = a.row_packed + a.index[t.ss].offset;
+    const uint32_t n_rows = a.index[t.ss].count;
+    const uint32_t cnt = active ? a.sub_cnt[gi] : 0;
+    // exclusive scan of the counts inside the CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) s_sum[warp] = inc;
+    __syncthreads();            // also orders stage_chunk before the decode below
+    uint32_t rank = inc - cnt;
+    for (int w = 0; w < warp; ++w) rank += s_sum[w];
+    if (!active) return;
+    const int img = t.ss / 9, c = (t.ss % 9) / 3, kind = t.ss % 3;
+    const int64_t bb = cs_block_base(g, img, c);
+    const uint32_t cap = (uint32_t)(kind == HIC_KIND_DC ? g.L.nb[c] : g.L.nb[c] * 64);
+    const uint32_t out_idx = tile_off[blockIdx.x] + rank;
+    if (out_idx + cnt > cap) {
+        atomicOr(err, 1u);
+        return;
+    }
+    const uint32_t start = sub == 0 ? 8u : a.sub_end[gi - 1];
+    uint32_t got = 0;
+    bool bad = false;
+    const uint32_t e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, rsym, rpk, n_rows, got,
+                                         kind == HIC_KIND_DC ? dc + bb : values + bb * 64,
+                                         kind == HIC_KIND_LENGTH ? lengths + bb * 64 : nullptr, out_idx, bad);
+    if (bad || got != cnt || e != a.sub_end[gi] || (sub == n_sub - 1 && e != end)) atomicOr(err, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,15 +571,24 @@ struct hic_decode_plan {
     int16_t* d_dc = nullptr;
     int16_t* d_values = nullptr;
     uint8_t* d_lengths = nullptr;
-    int32_t* d_lut = nullptr;
-    LongRow* d_long = nullptr;
-    uint64_t long_capacity = 0;
-    uint32_t* d_long_off = nullptr;
-    uint64_t* d_row_off = nullptr;
-    int32_t* d_row_sym = nullptr;
-    uint8_t* d_row_len = nullptr;
-    uint64_t* d_row_code = nullptr;
+    int32_t* d_lut1 = nullptr;
+    int32_t* d_lut2 = nullptr;
+    SyncTile* d_tiles = nullptr;
+    uint64_t tile_capacity = 0;
+    uint32_t* d_ss_tile0 = nullptr;
+    uint32_t* d_sub_end = nullptr;
+    uint16_t* d_sub_cnt = nullptr;
+    uint64_t sub_capacity = 0;
+    uint32_t* d_tile_start = nullptr;
+    uint32_t* d_tile_cnt = nullptr;
+    uint32_t* d_tile_symoff = nullptr;
+    RowIndex* d_index_own = nullptr;            // tables uploaded from the host live in the plan ...
+    int32_t* d_row_sym_own = nullptr;
+    uint64_t* d_row_packed_own = nullptr;
     uint64_t row_capacity = 0;
+    const RowIndex* d_index = nullptr;          // ... tables handed over on the device are only referenced
+    const int32_t* d_row_sym = nullptr;
+    const uint64_t* d_row_packed = nullptr;
     uint64_t* d_byte_off = nullptr;
     uint64_t* d_nbits = nullptr;
     uint32_t* d_nsym = nullptr;
@@ -366,8 +608,9 @@ extern "C" {
 
 int hic_decode_plan_destroy(hic_decode_plan* p) {
     if (!p) return HIC_OK;
-    void* ptrs[] = {p->d_dc, p->d_values, p->d_lengths, p->d_lut, p->d_long, p->d_long_off, p->d_row_off, p->d_row_sym,
-                    p->d_row_len, p->d_row_code, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
+    void* ptrs[] = {p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
+                    p->d_sub_cnt, p->d_tile_start, p->d_tile_cnt, p->d_tile_symoff, p->d_index_own, p->d_row_sym_own,
+                    p->d_row_packed_own, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
                     p->d_tile_off, p->d_stream_total};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -402,9 +645,10 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
     ok(dalloc2(&p->d_dc, p->total_blocks));
     ok(dalloc2(&p->d_values, p->total_blocks * 64 + 64));
     ok(dalloc2(&p->d_lengths, p->total_blocks * 64 + 64));
-    ok(dalloc2(&p->d_lut, (size_t)p->n_ss * LUT_SIZE));
-    ok(dalloc2(&p->d_long_off, p->n_ss + 1));
-    ok(dalloc2(&p->d_row_off, p->n_ss + 1));
+    ok(dalloc2(&p->d_lut1, (size_t)p->n_ss * L1_SIZE));
+    ok(dalloc2(&p->d_lut2, (size_t)p->n_ss * L2_CAP));
+    ok(dalloc2(&p->d_ss_tile0, p->n_ss + 1));
+    ok(dalloc2(&p->d_index_own, p->n_ss));
     ok(dalloc2(&p->d_byte_off, p->n_ss));
     ok(dalloc2(&p->d_nbits, p->n_ss));
     ok(dalloc2(&p->d_nsym, p->n_ss));
@@ -420,56 +664,53 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
     return HIC_OK;
 }
 
+int hic_decode_set_tables_device(hic_decode_plan* p, const void* d_index, const int32_t* d_row_sym,
+                                 const uint64_t* d_row_packed, void* stream) {
+    HIC_REQUIRE(p && d_index && d_row_sym && d_row_packed, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    p->d_index = static_cast<const RowIndex*>(d_index);
+    p->d_row_sym = d_row_sym;
+    p->d_row_packed = d_row_packed;
+    HIC_LAUNCH("build_tables_kernel", st, build_tables_kernel<<<p->n_ss, 256, 0, st>>>(p->d_index, p->d_row_sym, p->d_row_packed, p->d_lut1, p->d_lut2));
+    p->tables_ready = true;
+    return HIC_OK;
+}
+
 int hic_decode_set_tables(hic_decode_plan* p, const uint32_t* h_rows, const int32_t* h_symbols, const uint8_t* h_lens,
                           const uint64_t* h_codes, void* stream) {
     HIC_REQUIRE(p && h_rows && h_symbols && h_lens && h_codes, "NULL argument");
     cudaStream_t st = as_stream(stream);
     const int nss = p->n_ss;
-    std::vector<uint64_t> row_off(nss + 1, 0);
-    for (int s = 0; s < nss; ++s) row_off[s + 1] = row_off[s] + h_rows[s];
-    const uint64_t total = row_off[nss];
-    std::vector<LongRow> longs;
-    std::vector<uint32_t> long_off(nss + 1, 0);
+    std::vector<RowIndex> index(nss);
+    uint64_t total = 0;
     for (int s = 0; s < nss; ++s) {
-        long_off[s] = (uint32_t)longs.size();
-        const size_t begin = longs.size();
-        for (uint64_t r = row_off[s]; r < row_off[s + 1]; ++r) {
-            const uint32_t len = h_lens[r];
-            HIC_REQUIRE(len >= 1 && len <= 58, "code length %u out of range in stream %d", len, s);
-            if (len > (uint32_t)LUT_BITS) longs.push_back(LongRow{h_codes[r] << (64 - len), h_symbols[r], len});
-        }
-        std::sort(longs.begin() + begin, longs.end(), [](const LongRow& a, const LongRow& b) { return a.len < b.len; });
+        HIC_REQUIRE(total + h_rows[s] < (1ull << 32), "too many table rows");
+        index[s] = RowIndex{(uint32_t)total, h_rows[s]};
+        total += h_rows[s];
     }
-    long_off[nss] = (uint32_t)longs.size();
+    std::vector<uint64_t> packed(total);
+    for (uint64_t r = 0; r < total; ++r) {
+        HIC_REQUIRE(h_lens[r] >= 1 && h_lens[r] <= 58, "code length %u out of range in row %llu", (unsigned)h_lens[r],
+                    (unsigned long long)r);
+        packed[r] = ((uint64_t)h_lens[r] << 58) | (h_codes[r] & ((1ull << 58) - 1));
+    }
     if (total > p->row_capacity) {
-        if (p->d_row_sym) cudaFree(p->d_row_sym);
-        if (p->d_row_len) cudaFree(p->d_row_len);
-        if (p->d_row_code) cudaFree(p->d_row_code);
-        p->d_row_sym = nullptr; p->d_row_len = nullptr; p->d_row_code = nullptr;
+        if (p->d_row_sym_own) cudaFree(p->d_row_sym_own);
+        if (p->d_row_packed_own) cudaFree(p->d_row_packed_own);
+        p->d_row_sym_own = nullptr; p->d_row_packed_own = nullptr;
         p->row_capacity = total + total / 4 + 1024;
-        HIC_CUDA(dalloc2(&p->d_row_sym, p->row_capacity));
-        HIC_CUDA(dalloc2(&p->d_row_len, p->row_capacity));
-        HIC_CUDA(dalloc2(&p->d_row_code, p->row_capacity));
+        HIC_CUDA(dalloc2(&p->d_row_sym_own, p->row_capacity));
+        HIC_CUDA(dalloc2(&p->d_row_packed_own, p->row_capacity));
     }
-    if (longs.size() > p->long_capacity) {
-        if (p->d_long) cudaFree(p->d_long);
-        p->d_long = nullptr;
-        p->long_capacity = longs.size() + longs.size() / 4 + 1024;
-        HIC_CUDA(dalloc2(&p->d_long, p->long_capacity));
-    }
-    HIC_CUDA(cudaMemcpyAsync(p->d_row_off, row_off.data(), sizeof(uint64_t) * (nss + 1), cudaMemcpyHostToDevice, st));
-    HIC_CUDA(cudaMemcpyAsync(p->d_long_off, long_off.data(), sizeof(uint32_t) * (nss + 1), cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_index_own, index.data(), sizeof(RowIndex) * nss, cudaMemcpyHostToDevice, st));
     if (total) {
-        HIC_CUDA(cudaMemcpyAsync(p->d_row_sym, h_symbols, sizeof(int32_t) * total, cudaMemcpyHostToDevice, st));
-        HIC_CUDA(cudaMemcpyAsync(p->d_row_len, h_lens, sizeof(uint8_t) * total, cudaMemcpyHostToDevice, st));
-        HIC_CUDA(cudaMemcpyAsync(p->d_row_code, h_codes, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
+        HIC_CUDA(cudaMemcpyAsync(p->d_row_sym_own, h_symbols, sizeof(int32_t) * total, cudaMemcpyHostToDevice, st));
+        HIC_CUDA(cudaMemcpyAsync(p->d_row_packed_own, packed.data(), sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
     }
-    if (!longs.empty())
-        HIC_CUDA(cudaMemcpyAsync(p->d_long, longs.data(), sizeof(LongRow) * longs.size(), cudaMemcpyHostToDevice, st));
-    build_lut_kernel<<<nss, 256, 0, st>>>(p->d_row_off, p->d_row_sym, p->d_row_len, p->d_row_code, p->d_lut);
-    HIC_CHECK_LAUNCH("build_lut_kernel");
-    HIC_CUDA(cudaStreamSynchronize(st));
-    p->tables_ready = true;
+    int rc = hic_decode_set_tables_device(p, p->d_index_own, p->d_row_sym_own ? p->d_row_sym_own : (const int32_t*)p->d_index_own,
+                                          p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, stream);
+    if (rc) return rc;
+    HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors go out of scope
     return HIC_OK;
 }
 
@@ -488,30 +729,72 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     HIC_CUDA(cudaMemcpyAsync(p->d_nbits, nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
     HIC_CUDA(cudaMemsetAsync(d_coef, 0, (size_t)p->total_blocks * 128, st));
-    huffman_decode_kernel<<<(nss + 31) / 32, 32, 0, st>>>(g, d_bytes, p->d_byte_off, p->d_nbits, p->d_lut, p->d_long,
-                                                         p->d_long_off, p->d_dc, p->d_values, p->d_lengths, p->d_nsym,
-                                                         p->d_err);
-    HIC_CHECK_LAUNCH("huffman_decode_kernel");
-    expand_tile_sum_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum);
-    HIC_CHECK_LAUNCH("expand_tile_sum_kernel");
-    stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
+    // ---- D1: tiles of SUB_PER_CTA subsequences, streams in order ----
+    std::vector<SyncTile> tiles;
+    std::vector<uint32_t> ss_tile0(nss + 1, 0);
+    uint64_t n_sub_total = 0;
+    for (int s = 0; s < nss; ++s) {
+        ss_tile0[s] = (uint32_t)tiles.size();
+        if (nbits[s] == 0) continue;
+        HIC_REQUIRE(nbits[s] + 8 < (1ull << 32), "stream %d too long", s);
+        const uint64_t n_sub = (8 + nbits[s] + SUB_BITS - 1) / SUB_BITS;
+        for (uint64_t sub0 = 0; sub0 < n_sub; sub0 += SUB_PER_CTA)
+            tiles.push_back(SyncTile{(uint32_t)s, (uint32_t)sub0, n_sub_total + sub0});
+        n_sub_total += n_sub;
+    }
+    ss_tile0[nss] = (uint32_t)tiles.size();
+    const uint64_t n_tiles = tiles.size();
+    if (n_tiles > p->tile_capacity) {
+        for (void* q : {(void*)p->d_tiles, (void*)p->d_tile_start, (void*)p->d_tile_cnt, (void*)p->d_tile_symoff})
+            if (q) cudaFree(q);
+        p->d_tiles = nullptr; p->d_tile_start = nullptr; p->d_tile_cnt = nullptr; p->d_tile_symoff = nullptr;
+        p->tile_capacity = n_tiles + n_tiles / 4 + 64;
+        HIC_CUDA(dalloc2(&p->d_tiles, p->tile_capacity));
+        HIC_CUDA(dalloc2(&p->d_tile_start, p->tile_capacity));
+        HIC_CUDA(dalloc2(&p->d_tile_cnt, p->tile_capacity));
+        HIC_CUDA(dalloc2(&p->d_tile_symoff, p->tile_capacity));
+    }
+    if (n_sub_total > p->sub_capacity) {
+        if (p->d_sub_end) cudaFree(p->d_sub_end);
+        if (p->d_sub_cnt) cudaFree(p->d_sub_cnt);
+        p->d_sub_end = nullptr; p->d_sub_cnt = nullptr;
+        p->sub_capacity = n_sub_total + n_sub_total / 4 + 1024;
+        HIC_CUDA(dalloc2(&p->d_sub_end, p->sub_capacity));
+        HIC_CUDA(dalloc2(&p->d_sub_cnt, p->sub_capacity));
+    }
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_tile0, ss_tile0.data(), sizeof(uint32_t) * (nss + 1), cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemsetAsync(p->d_nsym, 0, sizeof(uint32_t) * nss, st));
+    if (n_tiles) {
+        HIC_CUDA(cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(SyncTile) * n_tiles, cudaMemcpyHostToDevice, st));
+        SyncArgs a;
+        a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2;
+        a.index = p->d_index; a.row_sym = p->d_row_sym; a.row_packed = p->d_row_packed; a.tiles = p->d_tiles; a.sub_end = p->d_sub_end;
+        a.sub_cnt = p->d_sub_cnt; a.tile_start = p->d_tile_start; a.tile_cnt = p->d_tile_cnt; a.changed = p->d_err + 1;
+        HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
+        for (int round = 0; round < 1024; ++round) {
+            HIC_CUDA(cudaMemsetAsync(p->d_err + 1, 0, sizeof(uint32_t), st));
+            HIC_LAUNCH("huffman_resync_kernel", st, huffman_sync_kernel<true><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
+            uint32_t changed = 0;
+            HIC_CUDA(cudaMemcpyAsync(&changed, p->d_err + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            HIC_CUDA(cudaStreamSynchronize(st));
+            if (!changed) break;
+        }
+        HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
+        HIC_LAUNCH("huffman_write_kernel", st, huffman_write_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a, g, p->d_tile_symoff, p->d_dc, p->d_values, p->d_lengths, p->d_err));
+    }
+    HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum));
+    HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
                                                                g.xtiles_per_image, p->d_tile_sum, p->d_tile_off,
-                                                               p->d_stream_total);
-    HIC_CHECK_LAUNCH("stream_scan64_kernel");
-    expand_scatter_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym,
-                                                                         p->d_tile_off, d_coef, p->d_err);
-    HIC_CHECK_LAUNCH("expand_scatter_kernel");
-    validate_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym, p->d_stream_total, p->d_err);
-    HIC_CHECK_LAUNCH("validate_kernel");
+                                                               p->d_stream_total));
+    HIC_LAUNCH("expand_scatter_kernel", st, expand_scatter_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym,
+                                                                         p->d_tile_off, d_coef, p->d_err));
+    HIC_LAUNCH("validate_kernel", st, validate_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym, p->d_stream_total, p->d_err));
     if (g.L.skip_first) {
-        dc_tile_sum_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_sum);
-        HIC_CHECK_LAUNCH("dc_tile_sum_kernel");
-        stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.dtiles[0], g.dtiles[1], g.dtiles[2],
+        HIC_LAUNCH("dc_tile_sum_kernel", st, dc_tile_sum_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_sum));
+        HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.dtiles[0], g.dtiles[1], g.dtiles[2],
                                                                    g.dtiles_per_image, p->d_tile_sum, p->d_tile_off,
-                                                                   p->d_stream_total);
-        HIC_CHECK_LAUNCH("stream_scan64_kernel");
-        dc_write_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_off, d_coef);
-        HIC_CHECK_LAUNCH("dc_write_kernel");
+                                                                   p->d_stream_total));
+        HIC_LAUNCH("dc_write_kernel", st, dc_write_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_off, d_coef));
     }
     uint32_t flags[4];
     HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));

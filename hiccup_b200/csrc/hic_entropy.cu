@@ -256,15 +256,30 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t* 
     if (first[bin] > index) atomicMin(&first[bin], index);
 }
 
-// pass C: emit symbols, DC differences and histograms
+// pass C: emit symbols, DC differences and histograms.
+// Symbols of the tile are staged in shared memory and written out coalesced (the tile's output is
+// one contiguous run).  Histogram updates are aggregated per warp with match.any and accumulated in
+// shared memory for the central value bins and all zero-count bins; one flush per tile.
+constexpr int EMIT_CENTRAL = 256;            // value bins [-128, 128) are privatised in shared memory
+constexpr int EMIT_CAP = RLE_TB * 64;        // a position emits at most one symbol
+
+struct EmitSmem {
+    int16_t val[EMIT_CAP];
+    uint8_t len[EMIT_CAP];
+    uint32_t hist_v[EMIT_CENTRAL], first_v[EMIT_CENTRAL];
+    uint32_t hist_l[LEN_BINS], first_l[LEN_BINS];
+    int smax[RLE_TB / 32];
+    uint32_t ssum[RLE_TB / 32];
+};
+
 template <bool SKIP>
 __global__ void __launch_bounds__(RLE_TB)
 rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __restrict__ carry,
                 const StreamTotals* __restrict__ totals, int16_t* __restrict__ dc_out, int16_t* __restrict__ values,
                 uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
                 uint32_t* __restrict__ err) {
-    __shared__ int smax[RLE_TB / 32];
-    __shared__ uint32_t ssum[RLE_TB / 32];
+    extern __shared__ __align__(16) uint8_t emit_raw[];
+    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_raw);
     const TileRef tr = locate_tile(g, blockIdx.x);
     const int cs = tr.img * 3 + tr.c;
     const int64_t nb = g.L.nb[tr.c];
@@ -276,9 +291,22 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
     const int half = g.nb_bins / 2;
     const size_t hbase = (size_t)cs * 3 * g.nb_bins;
 
+    for (int i = threadIdx.x; i < EMIT_CENTRAL; i += RLE_TB) {
+        sm.hist_v[i] = 0;
+        sm.first_v[i] = 0xFFFFFFFFu;
+    }
+    if (threadIdx.x < LEN_BINS) {
+        sm.hist_l[threadIdx.x] = 0;
+        sm.first_l[threadIdx.x] = 0xFFFFFFFFu;
+    }
+
     int w[32];
     const bool active = b < nb;
     if (active) load_block(coef + (block_base + b) * 64, w);
+    else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = 0;
+    }
     const int base = SKIP ? (int)(63 * b) - 1 : (int)(64 * b);
 
     // DC differences (codec.differential_coding): d[0] = DC[0], d[k] = DC[k] - DC[k-1]
@@ -301,11 +329,11 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
             if (HIC_ELEM(w, e) != 0 && (SKIP || p < len)) my_last = p;
         }
     }
-    const int prev = block_excl_max<RLE_TB>(my_last, tc.prev_last, smax);
+    const int prev = block_excl_max<RLE_TB>(my_last, tc.prev_last, sm.smax);
 
     // count pass
     const int zeros_before = base + (SKIP ? 1 : 0) - 1 - prev;       // zeros between prev and my first position
-    const int zmod0 = zeros_before % 15;
+    const int zmod0 = active ? zeros_before % 15 : 0;
     uint32_t cnt = 0;
     if (active) {
         int zmod = zmod0;
@@ -325,18 +353,18 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
             }
         }
     }
-    const uint32_t rank = block_excl_sum<RLE_TB>(cnt, ssum, nullptr);
-    if (!active || cnt == 0) return;
+    uint32_t tile_total;
+    const uint32_t rank = block_excl_sum<RLE_TB>(cnt, sm.ssum, &tile_total);
 
-    // emit pass
-    const int64_t sym_base = block_base * 64;
-    uint32_t idx = tc.sym_off + rank;
+    // emit pass (every lane runs the loop so that the warp votes below are convergent)
+    uint32_t local = rank;
     int zmod = zmod0;
-    const size_t hv = hbase + (size_t)HIC_KIND_VALUE * g.nb_bins, hl = hbase + (size_t)HIC_KIND_LENGTH * g.nb_bins;
+    const size_t hv = hbase + (size_t)HIC_KIND_VALUE * g.nb_bins;
+    const unsigned lane = threadIdx.x & 31;
 #pragma unroll
     for (int e = SKIP ? 1 : 0; e < 64; ++e) {
         const int p = base + e;
-        const bool valid = SKIP || p < len;
+        const bool valid = active && (SKIP || p < len);
         const int val = HIC_ELEM(w, e);
         const bool nz = val != 0 && valid;
         bool emit = false;
@@ -352,14 +380,63 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
                 emit = p < last_nz;
             }
         }
+        const unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (em == 0) continue;
         if (emit) {
-            values[sym_base + idx] = (int16_t)sym_val;
-            lengths[sym_base + idx] = (uint8_t)sym_len;
-            const int bin = sym_val + half;
-            if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
-            else hist_add(hist, first, hv + bin, idx);
-            hist_add(hist, first, hl + sym_len, idx);
-            ++idx;
+            sm.val[local] = (int16_t)sym_val;
+            sm.len[local] = (uint8_t)sym_len;
+            const uint32_t idx = tc.sym_off + local;
+            // zero-count histogram: aggregate lanes with the same bin; the lowest lane has the lowest index
+            const unsigned gl = __match_any_sync(em, sym_len);
+            if (lane == (unsigned)(__ffs(gl) - 1)) {
+                atomicAdd(&sm.hist_l[sym_len], (uint32_t)__popc(gl));
+                atomicMin(&sm.first_l[sym_len], idx);
+            }
+            const unsigned gv = __match_any_sync(em, sym_val);
+            if (lane == (unsigned)(__ffs(gv) - 1)) {
+                const int central = sym_val + EMIT_CENTRAL / 2;
+                if (central >= 0 && central < EMIT_CENTRAL) {
+                    atomicAdd(&sm.hist_v[central], (uint32_t)__popc(gv));
+                    atomicMin(&sm.first_v[central], idx);
+                } else {
+                    const int bin = sym_val + half;
+                    if (bin < 0 || bin >= g.nb_bins) {
+                        atomicOr(err, 1u);
+                    } else {
+                        atomicAdd(&hist[hv + bin], (uint32_t)__popc(gv));
+                        if (first[hv + bin] > idx) atomicMin(&first[hv + bin], idx);
+                    }
+                }
+            }
+            ++local;
+        }
+    }
+    __syncthreads();
+    // coalesced write-out of the tile's symbols
+    const int64_t sym_base = block_base * 64 + tc.sym_off;
+    for (uint32_t i = threadIdx.x; i < tile_total; i += RLE_TB) {
+        values[sym_base + i] = sm.val[i];
+        lengths[sym_base + i] = sm.len[i];
+    }
+    // flush the privatised histograms
+    for (int i = threadIdx.x; i < EMIT_CENTRAL; i += RLE_TB) {
+        const uint32_t c = sm.hist_v[i];
+        if (c) {
+            const int bin = i - EMIT_CENTRAL / 2 + half;
+            if (bin < 0 || bin >= g.nb_bins) {
+                atomicOr(err, 1u);
+            } else {
+                atomicAdd(&hist[hv + bin], c);
+                if (first[hv + bin] > sm.first_v[i]) atomicMin(&first[hv + bin], sm.first_v[i]);
+            }
+        }
+    }
+    if (threadIdx.x < LEN_BINS) {
+        const uint32_t c = sm.hist_l[threadIdx.x];
+        const size_t hl = hbase + (size_t)HIC_KIND_LENGTH * g.nb_bins + threadIdx.x;
+        if (c) {
+            atomicAdd(&hist[hl], c);
+            if (first[hl] > sm.first_l[threadIdx.x]) atomicMin(&first[hl], sm.first_l[threadIdx.x]);
         }
     }
 }
@@ -407,6 +484,238 @@ __global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, 
     const uint32_t ss = row_stream[i];
     const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
     lut[(size_t)ss * g.nb_bins + row_sym[i] + bias] = row_code[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// E2 on the device: the same heapq replay as csrc/hic_huffman.cuh, one CTA per symbol stream, all
+// state in shared memory.  (a) load the stream's compacted histogram entries, (b) bitonic sort by
+// first-occurrence index = the reference's leaf order, (c) one thread replays heapify / heappop /
+// heappush with frequency-only comparisons, (d) every leaf walks its parent chain to read off its
+// code (left = first popped = '1'), (e) rows, code lookup table and stream totals are written.
+// Two instantiations share the work by alphabet size so that small alphabets keep many CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct BuildSmem {
+    uint64_t heap[N];         // heap entries packed as freq << 16 | node, compared on freq only
+    uint32_t freq[N];         // leaf frequencies (internal nodes live only inside heap entries)
+    uint32_t key[N];          // first-occurrence index (sort key); dead after the sort
+    uint16_t bin[N];          // histogram bin of each leaf
+    uint16_t parent[2 * N];   // bit 15: this node is its parent's left child
+};
+
+// NLO < n <= N is handled by this instantiation
+template <int N, int NLO, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const CompactIndex* __restrict__ index,
+                     int32_t* __restrict__ row_sym, uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut,
+                     uint32_t* __restrict__ ss_nsym, uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t build_raw[];
+    BuildSmem<N>& sm = *reinterpret_cast<BuildSmem<N>*>(build_raw);
+    __shared__ int s_root;
+    __shared__ unsigned long long s_bits;
+    __shared__ uint32_t s_nsym;
+    const int ss = blockIdx.x;
+    const CompactIndex ix = index[ss];
+    const int n = (int)ix.count;
+    if (n == 0) {
+        if (NLO == 0 && threadIdx.x == 0) {
+            ss_nsym[ss] = 0;
+            ss_nbits[ss] = 0;
+        }
+        return;
+    }
+    if (n <= NLO || n > N) {
+        if (n > 8192 && NLO == 0 && threadIdx.x == 0) atomicOr(err, 2u);
+        return;
+    }
+    const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += THREADS) {
+        if (i < n) {
+            sm.key[i] = entries[ix.offset + i].first;
+            sm.bin[i] = (uint16_t)i;              // entry index while sorting; becomes the bin below
+        } else {
+            sm.key[i] = 0xFFFFFFFFu;
+            sm.bin[i] = 0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        s_bits = 0;
+        s_nsym = 0;
+    }
+    __syncthreads();
+    // (b) bitonic sort of (key, entry index) by key
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t a = sm.key[i], b = sm.key[l];
+                    if ((a > b) == up) {
+                        sm.key[i] = b;
+                        sm.key[l] = a;
+                        const uint16_t t = sm.bin[i];
+                        sm.bin[i] = sm.bin[l];
+                        sm.bin[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        const CompactEntry e = entries[ix.offset + sm.bin[i]];
+        sm.freq[i] = e.count;
+        sm.bin[i] = (uint16_t)(e.sym + bias);
+        sm.heap[i] = ((uint64_t)e.count << 16) | (uint64_t)i;
+    }
+    __syncthreads();
+    // (c) heapq replay (CPython Lib/heapq.py), comparisons on the frequency field only
+    if (threadIdx.x == 0) {
+        if (n == 1) {
+            s_root = -1;
+        } else {
+            int size = n;
+            uint64_t* heap = sm.heap;
+            auto lt = [](uint64_t a, uint64_t b) { return (a >> 16) < (b >> 16); };
+            auto siftdown = [&](int startpos, int pos) {
+                const uint64_t newitem = heap[pos];
+                while (pos > startpos) {
+                    const int parentpos = (pos - 1) >> 1;
+                    const uint64_t par = heap[parentpos];
+                    if (lt(newitem, par)) {
+                        heap[pos] = par;
+                        pos = parentpos;
+                        continue;
+                    }
+                    break;
+                }
+                heap[pos] = newitem;
+            };
+            auto siftup = [&](int pos) {
+                const int endpos = size, startpos = pos;
+                const uint64_t newitem = heap[pos];
+                int childpos = 2 * pos + 1;
+                while (childpos < endpos) {
+                    const int rightpos = childpos + 1;
+                    uint64_t child = heap[childpos];
+                    if (rightpos < endpos) {
+                        const uint64_t right = heap[rightpos];
+                        if (!lt(child, right)) {
+                            child = right;
+                            childpos = rightpos;
+                        }
+                    }
+                    heap[pos] = child;
+                    pos = childpos;
+                    childpos = 2 * pos + 1;
+                }
+                heap[pos] = newitem;
+                siftdown(startpos, pos);
+            };
+            auto pop = [&]() {
+                const uint64_t lastelt = heap[--size];
+                if (size > 0) {
+                    const uint64_t ret = heap[0];
+                    heap[0] = lastelt;
+                    siftup(0);
+                    return ret;
+                }
+                return lastelt;
+            };
+            for (int i = n / 2 - 1; i >= 0; --i) siftup(i);
+            int next = n;
+            while (size > 1) {
+                const uint64_t l = pop();
+                const uint64_t r = pop();
+                sm.parent[(int)(l & 0xFFFF)] = (uint16_t)(next | 0x8000);
+                sm.parent[(int)(r & 0xFFFF)] = (uint16_t)next;
+                heap[size++] = (((l >> 16) + (r >> 16)) << 16) | (uint64_t)next;
+                siftdown(0, size - 1);
+                ++next;
+            }
+            s_root = (int)(heap[0] & 0xFFFF);
+        }
+    }
+    __syncthreads();
+    // (d, e) codes, rows, lookup table, totals
+    const int root = s_root;
+    unsigned long long bits_sum = 0;
+    uint32_t sym_sum = 0;
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        uint64_t code = 0;
+        uint32_t len = 0;
+        if (root < 0) {
+            code = 1;
+            len = 1;
+        } else {
+            int node = i;
+            while (node != root && len < 64) {
+                const uint32_t p = sm.parent[node];
+                code |= (uint64_t)(p >> 15) << len;
+                ++len;
+                node = (int)(p & 0x7FFF);
+            }
+        }
+        if (len > MAX_CODE_LEN) {
+            atomicOr(err, 4u);
+            len = MAX_CODE_LEN;
+            code &= (1ull << MAX_CODE_LEN) - 1;
+        }
+        const uint64_t packed = ((uint64_t)len << 58) | code;
+        const int b = sm.bin[i];
+        row_sym[ix.offset + i] = b - bias;
+        row_code[ix.offset + i] = packed;
+        lut[(size_t)ss * g.nb_bins + b] = packed;
+        bits_sum += (unsigned long long)sm.freq[i] * len;
+        sym_sum += sm.freq[i];
+    }
+    atomicAdd(&s_bits, bits_sum);
+    atomicAdd(&s_nsym, sym_sum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ss_nsym[ss] = s_nsym;
+        ss_nbits[ss] = s_bits;
+    }
+}
+
+// byte layout of the framed payloads: exclusive scan over the streams (single CTA)
+__global__ void __launch_bounds__(1024)
+payload_layout_kernel(int n_ss, const uint32_t* __restrict__ ss_nsym, const uint64_t* __restrict__ ss_nbits,
+                      uint64_t* __restrict__ byte_off, uint64_t* __restrict__ byte_len, unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_ss; base += 1024) {
+        const int s = base + threadIdx.x;
+        unsigned long long len = 0;
+        if (s < n_ss && ss_nsym[s]) {
+            const unsigned long long nb = ss_nbits[s];
+            len = 1 + (nb + (8 - (nb & 7))) / 8;
+        }
+        const unsigned long long al = (len + 3) & ~3ull;
+        unsigned long long inc = al;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (int w2 = 0; w2 < warp; ++w2) pre += s_warp[w2];
+        if (s < n_ss) {
+            byte_off[s] = len ? pre + inc - al : 0;
+            byte_len[s] = len;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[0] = s_carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,9 +876,14 @@ struct hic_entropy_plan {
     uint64_t* d_ss_byte_off = nullptr;
     uint32_t* d_ptile_bits = nullptr;
     uint64_t* d_ptile_off = nullptr;
+    uint64_t* d_ss_byte_len = nullptr;
+    unsigned long long* d_pay_totals = nullptr; // [0] total payload bytes
+    bool device_built = false;                  // codes came from hic_entropy_build_codes_device
+    bool host_info_valid = false;               // rows/nsym/nbits/byte_off/byte_len mirror the device
+    bool host_tables_valid = false;
     // host results
     std::vector<uint32_t> rows, nsym;
-    std::vector<uint64_t> nbits, byte_off, byte_len, row_off;
+    std::vector<uint64_t> nbits, byte_off, byte_len, row_off, dev_row_start;
     std::vector<int32_t> t_sym;
     std::vector<uint8_t> t_len;
     std::vector<uint64_t> t_code;
@@ -644,7 +958,8 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     if (!p) return HIC_OK;
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
-                    p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off};
+                    p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
+                    p->d_pay_totals};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     delete p;
@@ -686,6 +1001,8 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_ss_byte_off, p->n_ss));
     ok(dalloc(&p->d_ptile_bits, p->total_ptiles));
     ok(dalloc(&p->d_ptile_off, p->total_ptiles));
+    ok(dalloc(&p->d_ss_byte_len, p->n_ss));
+    ok(dalloc(&p->d_pay_totals, 2));
     if (e != cudaSuccess) {
         hic_entropy_plan_destroy(p);
         return hic::fail(HIC_ERR_CUDA, "entropy plan allocation failed: %s", cudaGetErrorString(e));
@@ -704,21 +1021,29 @@ int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stre
     HIC_CUDA(cudaMemsetAsync(p->d_first, 0xFF, hist_n * sizeof(uint32_t), st));
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
     const unsigned tiles = (unsigned)p->total_tiles;
-    if (g.L.skip_first) rle_tile_summary_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg);
-    else rle_tile_summary_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg);
-    HIC_CHECK_LAUNCH("rle_tile_summary_kernel");
-    rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, p->d_carry, p->d_totals, p->d_values,
-                                                                 p->d_lengths, p->d_hist, p->d_first);
-    HIC_CHECK_LAUNCH("rle_stream_scan_kernel");
     if (g.L.skip_first)
-        rle_emit_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
-                                                        p->d_lengths, p->d_hist, p->d_first, p->d_err);
+        HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
     else
-        rle_emit_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
-                                                         p->d_lengths, p->d_hist, p->d_first, p->d_err);
-    HIC_CHECK_LAUNCH("rle_emit_kernel");
-    compact_kernel<<<p->n_ss, 256, 0, st>>>(g, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1);
-    HIC_CHECK_LAUNCH("compact_kernel");
+        HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
+    HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, p->d_carry, p->d_totals, p->d_values,
+                                                                 p->d_lengths, p->d_hist, p->d_first));
+    {
+        static bool emit_attr[64] = {false};
+        int dev = 0;
+        HIC_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !emit_attr[dev]) {
+            HIC_CUDA(cudaFuncSetAttribute(rle_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
+            HIC_CUDA(cudaFuncSetAttribute(rle_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
+            if (dev < 64) emit_attr[dev] = true;
+        }
+    }
+    if (g.L.skip_first)
+        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<true><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
+                                                        p->d_lengths, p->d_hist, p->d_first, p->d_err));
+    else
+        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
+                                                         p->d_lengths, p->d_hist, p->d_first, p->d_err));
+    HIC_LAUNCH("compact_kernel", st, compact_kernel<<<p->n_ss, 256, 0, st>>>(g, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
     return HIC_OK;
 }
 
@@ -829,19 +1154,136 @@ int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
     HIC_CUDA(cudaMemcpyAsync(p->d_ss_nbits, p->nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_off, p->byte_off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     if (p->total_rows) {
-        lut_scatter_kernel<<<(unsigned)((p->total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
-                                                                                   p->d_row_stream, p->total_rows, p->d_lut);
-        HIC_CHECK_LAUNCH("lut_scatter_kernel");
+        HIC_LAUNCH("lut_scatter_kernel", st, lut_scatter_kernel<<<(unsigned)((p->total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
+                                                                                   p->d_row_stream, p->total_rows, p->d_lut));
     }
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_len, p->byte_len.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    // rows were uploaded in stream order: make the device index describe that layout
+    std::vector<CompactIndex> row_index(nss);
+    for (int s = 0; s < nss; ++s) row_index[s] = CompactIndex{(uint32_t)p->row_off[s], p->rows[s]};
+    HIC_CUDA(cudaMemcpyAsync(p->d_index, row_index.data(), sizeof(CompactIndex) * nss, cudaMemcpyHostToDevice, st));
     HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors above go out of scope
     p->codes_ready = true;
+    p->device_built = false;
+    p->host_info_valid = true;
+    p->host_tables_valid = true;
     return HIC_OK;
 }
 
-int hic_entropy_stream_info(const hic_entropy_plan* p, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
+static int ensure_row_capacity(hic_entropy_plan* p, uint64_t rows) {
+    if (rows <= p->row_capacity) return HIC_OK;
+    if (p->d_row_sym) cudaFree(p->d_row_sym);
+    if (p->d_row_code) cudaFree(p->d_row_code);
+    if (p->d_row_stream) cudaFree(p->d_row_stream);
+    p->d_row_sym = nullptr; p->d_row_code = nullptr; p->d_row_stream = nullptr;
+    p->row_capacity = rows;
+    HIC_CUDA(dalloc(&p->d_row_sym, p->row_capacity));
+    HIC_CUDA(dalloc(&p->d_row_code, p->row_capacity));
+    HIC_CUDA(dalloc(&p->d_row_stream, p->row_capacity));
+    return HIC_OK;
+}
+
+// mirror the per-stream results of a device build on the host (small: 32 bytes per stream)
+static int fetch_host_info(hic_entropy_plan* p, cudaStream_t st) {
+    if (p->host_info_valid) return HIC_OK;
+    const int nss = p->n_ss;
+    std::vector<CompactIndex> index(nss);
+    p->rows.assign(nss, 0); p->nsym.assign(nss, 0); p->nbits.assign(nss, 0);
+    p->byte_off.assign(nss, 0); p->byte_len.assign(nss, 0); p->row_off.assign(nss + 1, 0);
+    HIC_CUDA(cudaMemcpyAsync(index.data(), p->d_index, sizeof(CompactIndex) * nss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(p->nsym.data(), p->d_ss_nsym, sizeof(uint32_t) * nss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(p->nbits.data(), p->d_ss_nbits, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(p->byte_off.data(), p->d_ss_byte_off, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(p->byte_len.data(), p->d_ss_byte_len, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    // rows of a device build sit at the compaction offsets, which are not in stream order
+    p->dev_row_start.assign(nss, 0);
+    for (int s = 0; s < nss; ++s) {
+        p->rows[s] = index[s].count;
+        p->dev_row_start[s] = index[s].offset;
+        p->row_off[s + 1] = p->row_off[s] + index[s].count;
+    }
+    p->host_info_valid = true;
+    return HIC_OK;
+}
+
+static int fetch_host_tables(hic_entropy_plan* p, cudaStream_t st) {
+    if (p->host_tables_valid) return HIC_OK;
+    int rc = fetch_host_info(p, st);
+    if (rc) return rc;
+    std::vector<int32_t> sym(p->total_rows);
+    std::vector<uint64_t> code(p->total_rows);
+    if (p->total_rows) {
+        HIC_CUDA(cudaMemcpyAsync(sym.data(), p->d_row_sym, sizeof(int32_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
+        HIC_CUDA(cudaMemcpyAsync(code.data(), p->d_row_code, sizeof(uint64_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
+        HIC_CUDA(cudaStreamSynchronize(st));
+    }
+    p->t_sym.resize(p->total_rows); p->t_len.resize(p->total_rows); p->t_code.resize(p->total_rows);
+    for (int s = 0; s < p->n_ss; ++s) {
+        const uint64_t src = p->dev_row_start[s], dst = p->row_off[s];
+        for (uint32_t i = 0; i < p->rows[s]; ++i) {
+            p->t_sym[dst + i] = sym[src + i];
+            p->t_len[dst + i] = (uint8_t)(code[src + i] >> 58);
+            p->t_code[dst + i] = code[src + i] & ((1ull << 58) - 1);
+        }
+    }
+    p->host_tables_valid = true;
+    return HIC_OK;
+}
+
+extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    const Geom& g = p->g;
+    HIC_REQUIRE(g.nb_bins <= 8192, "the device Huffman builder handles up to 8192 value bins; use hic_entropy_build_codes");
+    cudaStream_t st = as_stream(stream);
+    int rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    HIC_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<2048, 1024, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(BuildSmem<2048>)));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<8192, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(BuildSmem<8192>)));
+        if (dev < 64) attr_set[dev] = true;
+    }
+#define HIC_BUILD_TIER(N, NLO, T, label)                                                                              \
+    HIC_LAUNCH(label, st, huffman_build_kernel<N, NLO, T><<<p->n_ss, T, sizeof(BuildSmem<N>), st>>>(                    \
+        g, p->d_entries, p->d_index, p->d_row_sym, p->d_row_code, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_err))
+    HIC_BUILD_TIER(256, 0, 64, "huffman_build_256_kernel");
+    HIC_BUILD_TIER(1024, 256, 128, "huffman_build_1024_kernel");
+    HIC_BUILD_TIER(2048, 1024, 128, "huffman_build_2048_kernel");
+    HIC_BUILD_TIER(8192, 2048, 256, "huffman_build_8192_kernel");
+#undef HIC_BUILD_TIER
+    HIC_LAUNCH("payload_layout_kernel", st, payload_layout_kernel<<<1, 1024, 0, st>>>(p->n_ss, p->d_ss_nsym, p->d_ss_nbits,
+        p->d_ss_byte_off, p->d_ss_byte_len, p->d_pay_totals));
+    unsigned long long totals[2] = {0, 0};
+    uint32_t flags[4];
+    HIC_CUDA(cudaMemcpyAsync(totals, p->d_pay_totals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    if (flags[0] & 1u) return hic::fail(HIC_ERR_INVALID, "a symbol fell outside [-%d, %d): create the plan with more value_bins",
+                                        g.nb_bins / 2, g.nb_bins / 2);
+    if (flags[0] & 2u) return hic::fail(HIC_ERR_INVALID, "an alphabet exceeds 8192 symbols; use hic_entropy_build_codes");
+    if (flags[0] & 4u) return hic::fail(HIC_ERR_INVALID, "a Huffman code exceeds %u bits", MAX_CODE_LEN);
+    p->total_bytes = totals[0];
+    p->total_rows = flags[1];
+    p->codes_ready = true;
+    p->device_built = true;
+    p->host_info_valid = false;
+    p->host_tables_valid = false;
+    return HIC_OK;
+}
+
+int hic_entropy_stream_info(hic_entropy_plan* p, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
                             uint64_t* h_byte_off, uint64_t* h_byte_len, uint64_t* total_rows, uint64_t* total_bytes) {
     HIC_REQUIRE(p != nullptr, "plan is NULL");
     HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    {
+        int rc = fetch_host_info(p, nullptr);
+        if (rc) return rc;
+    }
     for (int s = 0; s < p->n_ss; ++s) {
         if (h_rows) h_rows[s] = p->rows[s];
         if (h_nsym) h_nsym[s] = p->nsym[s];
@@ -854,9 +1296,13 @@ int hic_entropy_stream_info(const hic_entropy_plan* p, uint32_t* h_rows, uint32_
     return HIC_OK;
 }
 
-int hic_entropy_tables(const hic_entropy_plan* p, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes) {
+int hic_entropy_tables(hic_entropy_plan* p, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes) {
     HIC_REQUIRE(p != nullptr, "plan is NULL");
     HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    {
+        int rc = fetch_host_tables(p, nullptr);
+        if (rc) return rc;
+    }
     for (uint64_t i = 0; i < p->total_rows; ++i) {
         if (h_symbols) h_symbols[i] = p->t_sym[i];
         if (h_lens) h_lens[i] = p->t_len[i];
@@ -873,14 +1319,23 @@ int hic_entropy_pack(hic_entropy_plan* p, uint8_t* d_out, void* stream) {
     cudaStream_t st = as_stream(stream);
     HIC_CUDA(cudaMemsetAsync(d_out, 0, p->total_bytes, st));
     const unsigned tiles = (unsigned)p->total_ptiles;
-    pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
-                                                         p->d_ptile_bits);
-    HIC_CHECK_LAUNCH("pack_tile_bits_kernel");
-    pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_ptile_off);
-    HIC_CHECK_LAUNCH("pack_stream_scan_kernel");
-    pack_emit_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off,
-                                                    p->d_ptile_off, p->d_dc, p->d_values, p->d_lengths, d_out);
-    HIC_CHECK_LAUNCH("pack_emit_kernel");
+    HIC_LAUNCH("pack_tile_bits_kernel", st, pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
+                                                         p->d_ptile_bits));
+    HIC_LAUNCH("pack_stream_scan_kernel", st, pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_ptile_off));
+    HIC_LAUNCH("pack_emit_kernel", st, pack_emit_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off,
+                                                    p->d_ptile_off, p->d_dc, p->d_values, p->d_lengths, d_out));
+    return HIC_OK;
+}
+
+int hic_entropy_device_tables(const hic_entropy_plan* p, const void** d_index, const int32_t** d_row_sym,
+                              const uint64_t** d_row_packed, const uint64_t** d_byte_off, const uint64_t** d_nbits) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    HIC_REQUIRE(p->codes_ready, "no codes have been built");
+    if (d_index) *d_index = p->d_index;
+    if (d_row_sym) *d_row_sym = p->d_row_sym;
+    if (d_row_packed) *d_row_packed = p->d_row_code;
+    if (d_byte_off) *d_byte_off = p->d_ss_byte_off;
+    if (d_nbits) *d_nbits = p->d_ss_nbits;
     return HIC_OK;
 }
 

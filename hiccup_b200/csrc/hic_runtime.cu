@@ -1,5 +1,9 @@
 // hic_runtime.cu -- device/stream/memory plumbing of the C ABI (include/hiccup_b200.h).
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include "hic_runtime.cuh"
 
 namespace hic {
@@ -17,9 +21,80 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+namespace {
+struct ProfSpan {
+    const char* name;
+    cudaEvent_t a, b;
+};
+bool g_prof_on = false;
+std::vector<ProfSpan> g_spans;
+std::vector<cudaEvent_t> g_free_events;
+std::mutex g_prof_mu;
+cudaEvent_t take_event() {
+    if (!g_free_events.empty()) {
+        cudaEvent_t e = g_free_events.back();
+        g_free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void prof_begin(const char* name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfSpan sp{name, take_event(), take_event()};
+    cudaEventRecord(sp.a, st);
+    g_spans.push_back(sp);
+}
+
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (!g_spans.empty()) cudaEventRecord(g_spans.back().b, st);
+}
+
 }  // namespace hic
 
 extern "C" {
+
+int hic_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(hic::g_prof_mu);
+    hic::g_prof_on = on != 0;
+    return HIC_OK;
+}
+
+int hic_profile_report(char* buf, size_t buflen) {
+    HIC_REQUIRE(buf != nullptr && buflen > 2, "buf is NULL");
+    std::lock_guard<std::mutex> lock(hic::g_prof_mu);
+    std::map<std::string, std::pair<double, int>> agg;
+    for (auto& sp : hic::g_spans) {
+        cudaEventSynchronize(sp.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            auto& e = agg[sp.name];
+            e.first += ms;
+            e.second += 1;
+        }
+        hic::g_free_events.push_back(sp.a);
+        hic::g_free_events.push_back(sp.b);
+    }
+    hic::g_spans.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char item[256];
+        snprintf(item, sizeof(item), "%s\"%s\": [%.6f, %d]", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += item;
+        first = false;
+    }
+    out += "}";
+    if (out.size() + 1 > buflen) return hic::fail(HIC_ERR_CAPACITY, "profile report needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return HIC_OK;
+}
 
 int hic_version(void) { return 100; }
 

@@ -12,6 +12,10 @@ int fail(int code, const char* fmt, ...);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// optional per-kernel timing with CUDA events on the launching stream (hic_profile_* in the ABI)
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
 }  // namespace hic
 
 #define HIC_CUDA(expr)                                                                        \
@@ -28,6 +32,14 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
         if (_e != cudaSuccess)                                                                \
             return hic::fail(HIC_ERR_CUDA, "launch of %s failed: %s", name,                   \
                              cudaGetErrorString(_e));                                         \
+    } while (0)
+
+#define HIC_LAUNCH(name, st, ...)                                                             \
+    do {                                                                                      \
+        hic::prof_begin(name, st);                                                            \
+        __VA_ARGS__;                                                                          \
+        hic::prof_end(st);                                                                    \
+        HIC_CHECK_LAUNCH(name);                                                               \
     } while (0)
 
 #define HIC_REQUIRE(cond, ...)                                                                \

@@ -68,8 +68,13 @@ class EntropyEncoder:
     def symbolize(self, d_coef, stream=None):
         _lib.check(self.lib.hic_entropy_symbolize(self.plan, d_coef, stream))
 
-    def build_codes(self, stream=None):
-        _lib.check(self.lib.hic_entropy_build_codes(self.plan, stream))
+    def build_codes(self, stream=None, on_device=False):
+        """E2.  on_device=False: host heapq replay (reference-faithful default, any alphabet size);
+        on_device=True: the same replay by one CTA per stream on the GPU (alphabets <= 8192)."""
+        if on_device:
+            _lib.check(self.lib.hic_entropy_build_codes_device(self.plan, stream))
+        else:
+            _lib.check(self.lib.hic_entropy_build_codes(self.plan, stream))
         n = self.n_streams
         self.rows = np.zeros(n, np.uint32)
         self.nsym = np.zeros(n, np.uint32)
@@ -99,10 +104,16 @@ class EntropyEncoder:
         _lib.check(self.lib.hic_entropy_pack(self.plan, self._out.ptr, stream))
         return self._out
 
-    def encode(self, d_coef, stream=None, download=True):
+    def device_tables(self):
+        """Device pointers (index, row symbols, packed rows) for EntropyDecoder.set_tables_device."""
+        ptrs = [ctypes.c_void_p() for _ in range(5)]
+        _lib.check(self.lib.hic_entropy_device_tables(self.plan, *[ctypes.byref(q) for q in ptrs]))
+        return tuple(q.value for q in ptrs)
+
+    def encode(self, d_coef, stream=None, download=True, on_device=False):
         """Full entropy encode of device-resident zigzag blocks."""
         self.symbolize(d_coef, stream)
-        self.build_codes(stream)
+        self.build_codes(stream, on_device=on_device)
         out = self.pack(stream)
         if not download:
             _lib.sync(stream)
@@ -153,6 +164,14 @@ class EntropyDecoder:
             self.close()
         except Exception:
             pass
+
+    def set_tables_device(self, d_index, d_row_sym, d_row_packed, stream=None):
+        _lib.check(self.lib.hic_decode_set_tables_device(self.plan, d_index, d_row_sym, d_row_packed, stream))
+
+    def run(self, d_data, byte_off, nbits, d_coef, stream=None):
+        byte_off = np.ascontiguousarray(byte_off, np.uint64)
+        nbits = np.ascontiguousarray(nbits, np.uint64)
+        _lib.check(self.lib.hic_decode_run(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, d_coef, stream))
 
     def decode(self, rows, symbols, lens, codes, data, byte_off, nbits, d_coef, stream=None, d_data=None):
         """rows/symbols/lens/codes: concatenated code tables; data: uint8 host array holding every

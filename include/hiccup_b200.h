@@ -58,6 +58,12 @@ int hic_stream_create(void** stream);
 int hic_stream_destroy(void* stream);
 int hic_stream_sync(void* stream);                       /* blocks the host */
 
+/* Per-kernel timing with CUDA events recorded on the launching stream around every kernel this
+ * library launches.  hic_profile_report synchronises, writes {"kernel": [total_ms, launches], ...}
+ * as JSON into buf and clears the record. */
+int hic_profile_enable(int on);
+int hic_profile_report(char* buf, size_t buflen);
+
 /* ---- DCT-mode geometry ----------------------------------------------------------------------- */
 typedef struct hic_dct_geometry {
     int32_t h, w;             /* luminance plane = image */
@@ -154,21 +160,33 @@ int hic_entropy_symbolize(hic_entropy_plan* plan, const int16_t* d_coef, void* s
  * exactly as HuffmanTree._construct does (huffman.py:60-79, heapq replay), upload code tables. */
 int hic_entropy_build_codes(hic_entropy_plan* plan, void* stream);
 
+/* E2 on the device -- the same heapq replay run by one CTA per symbol stream in shared memory
+ * (alphabets up to 8192 symbols); nothing but 32 bytes of totals crosses PCIe.  Produces exactly
+ * the codes of hic_entropy_build_codes (tests/test_gpu_codec.py compares them).  The per-stream
+ * results and tables are downloaded lazily by the two query functions below. */
+int hic_entropy_build_codes_device(hic_entropy_plan* plan, void* stream);
+
 /* Results of E2, all host arrays indexed by symbol stream s (9 n entries; kind 0 entries are
  * empty in flat mode).  rows[s]: table rows; nsym[s]: symbols; nbits[s]: Huffman-coded bits;
  * byte_off[s] / byte_len[s]: where hic_entropy_pack puts the framed bytes of stream s. */
-int hic_entropy_stream_info(const hic_entropy_plan* plan, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
+int hic_entropy_stream_info(hic_entropy_plan* plan, uint32_t* h_rows, uint32_t* h_nsym, uint64_t* h_nbits,
                             uint64_t* h_byte_off, uint64_t* h_byte_len, uint64_t* total_rows, uint64_t* total_bytes);
 /* Table rows of all streams concatenated in s order, each stream's rows in first-occurrence order
  * (what HuffmanTree.encode_table returns, huffman.py:144-147): symbol, code length, code bits
  * (right aligned; first bit of the code string = most significant; '1' = left = first popped). */
-int hic_entropy_tables(const hic_entropy_plan* plan, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes);
+int hic_entropy_tables(hic_entropy_plan* plan, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes);
 
 /* E3 (device) -- concatenate the codes of every symbol stream (HuffmanTree.encode_data,
  * huffman.py:131-142) and frame them as iohelper.padded_bs_2_bytes does (iohelper.py:35-48):
  * byte 0 = p = 8 - (nbits mod 8), then the bits MSB first, then p zero bits.  d_out must hold
  * total_bytes; it is zeroed by the call. */
 int hic_entropy_pack(hic_entropy_plan* plan, uint8_t* d_out, void* stream);
+
+/* Device-resident code tables of the last build (either flavour), for handing straight to
+ * hic_decode_set_tables_device: per-stream {uint32 offset, uint32 count} index, row symbols, and
+ * rows packed as (length << 58 | code bits). */
+int hic_entropy_device_tables(const hic_entropy_plan* plan, const void** d_index, const int32_t** d_row_sym,
+                              const uint64_t** d_row_packed, const uint64_t** d_byte_off, const uint64_t** d_nbits);
 
 /* The host Huffman construction on its own (no CUDA call): leaf frequencies in first-occurrence
  * order -> code length and bits per leaf.  Replaces HuffmanTree._construct + encode_table
@@ -189,6 +207,10 @@ int hic_decode_plan_destroy(hic_decode_plan* plan);
  * HuffmanTree.construct_from_coding (huffman.py:30-58). */
 int hic_decode_set_tables(hic_decode_plan* plan, const uint32_t* h_rows, const int32_t* h_symbols,
                           const uint8_t* h_lens, const uint64_t* h_codes, void* stream);
+/* The same from device-resident tables (hic_entropy_device_tables); the arrays are referenced, not
+ * copied, and must stay valid until decoding is done.  Asynchronous. */
+int hic_decode_set_tables_device(hic_decode_plan* plan, const void* d_index, const int32_t* d_row_sym,
+                                 const uint64_t* d_row_packed, void* stream);
 /* D1-D3 (device) -- Huffman decode (HuffmanTree.decode_data, huffman.py:149-174), run-length
  * expansion (codec.decode_run_length, codec.py:102-113), DC prefix sum (utils.invert_differences,
  * utils.py:66-74) and de-zigzag into blocks (codec.py:415-425).  d_bytes holds the framed byte

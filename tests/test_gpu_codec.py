@@ -124,3 +124,40 @@ def test_round_trip_through_both_stages(shape, seed):
     want = orc.jpeg_decompression(orc.jpeg_compression(rgb))
     assert out.shape == want.shape
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("shape,seed,n", [((426, 640), 61, 3), ((64, 64), 62, 5), ((1080, 1920), 63, 1)])
+def test_device_huffman_builder_equals_host(shape, seed, n):
+    """E2 on the GPU (one CTA per stream replaying heapq) produces the host replay's tables and bits."""
+    from hiccup_b200.batch import DctBatchCodec
+    rgb = np.stack([orc.synthetic_image(shape[0], shape[1], seed + i) for i in range(n)])
+    a = DctBatchCodec(n, shape[0], shape[1], device_codes=True)
+    b = DctBatchCodec(n, shape[0], shape[1], device_codes=False)
+    ea, eb = a.encode(rgb), b.encode(rgb)
+    assert np.array_equal(ea.rows, eb.rows) and np.array_equal(ea.nsym, eb.nsym) and np.array_equal(ea.nbits, eb.nbits)
+    for s in range(9 * n):
+        assert ea.table(s) == eb.table(s), "stream %d" % s
+        assert ea.framed(s) == eb.framed(s), "stream %d" % s
+    a.close()
+    b.close()
+
+
+def test_batch_codec_matches_single_image_path():
+    from hiccup_b200 import codec, compression
+    from hiccup_b200.batch import DctBatchCodec
+    n, h, w = 4, 72, 104
+    rgb = np.stack([orc.synthetic_image(h, w, 70 + i) for i in range(n)])
+    bc = DctBatchCodec(n, h, w)
+    enc = bc.encode(rgb)
+    images = bc.hic_images(enc)
+    out = bc.decode(enc)
+    for i in range(n):
+        single = codec.jpeg_encode(compression.jpeg_compression(rgb[i]))
+        assert images[i].byte_stream() == single.byte_stream()
+        want = orc.jpeg_decompression(orc.jpeg_compression(rgb[i]))
+        assert np.array_equal(out[i], want)
+    bc.encode_device()
+    bc.decode_device()
+    dev = bc.d_out.download(np.uint8, out.size).reshape(out.shape)
+    assert np.array_equal(dev, out)
+    bc.close()
