@@ -4,8 +4,12 @@
 // Data layout in HBM (see include/hiccup_b200.h): RGB u8 interleaved in; coefficients as int16
 // "zigzag blocks" (one 128-byte line per 8x8 block) out.  HBM-bound by design: 3 B/pixel read,
 // 3 B/pixel written (1.5 samples/pixel x 2 B) = 6 algorithmic bytes per pixel for K1.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include "hic_core.cuh"
+#include "hic_f32x2.cuh"
 #include "hic_runtime.cuh"
 
 namespace hic {
@@ -17,6 +21,7 @@ struct DctTables {
     float rq[2][64];     // [0 = luminance, 1 = chroma][natural index]: 4 g_u g_v / q  (forward)
     float qf[2][64];     // q as float
     float dq[2][64];     // q h_u h_v / 256 (inverse)
+    float rcpq[2][64];   // 1 / q
     int qi[2][64];       // q
 };
 __constant__ DctTables c_tab;
@@ -42,6 +47,7 @@ static int ensure_tables() {
                 t.qf[kind][8 * u + v] = (float)q;
                 t.dq[kind][8 * u + v] = (float)(q * aan_h(u) * aan_h(v) / 256.0);
                 t.qi[kind][8 * u + v] = q;
+                t.rcpq[kind][8 * u + v] = (float)(1.0 / q);
             }
     HIC_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
     if (dev < 64) done[dev] = true;
@@ -77,22 +83,33 @@ static int geometry_of(int h, int w, hic_dct_geometry* g) {
 // K1: fused encode transform
 // ------------------------------------------------------------------------------------------------
 namespace k1 {
-constexpr int TW = 128;               // luminance tile, pixels
+// Tile: 128 x 64 luminance pixels = 16 x 8 Y blocks + 8 x 4 Cr blocks + 8 x 4 Cb blocks = 192
+// blocks, one thread each in the transform stage.  The staged RGB region covers image columns
+// x0-16 .. x0+132 and rows y0-2 .. y0+64 (pyrDown needs columns x0-2 .. x0+128 and rows
+// y0-2 .. y0+64).  The 16-pixel lead is what TMA demands: the innermost start offset of a box must
+// be a multiple of 16 bytes (a 12-byte-aligned start faults with "illegal instruction"; probed in
+// tools/scratch/tma_test.cu), and 3 * (x0 - lead) is a multiple of 16 only for lead = 0 mod 16.
+constexpr int TW = 128;
 constexpr int TH = 64;
-constexpr int RW = TW + 3;            // staged region: columns/rows -2 .. +T (pyrDown halo)
-constexpr int RH = TH + 3;
-constexpr int RGB_PITCH = 396;        // RW * 3 = 393, rounded up to a multiple of 4
-constexpr int C_PITCH = 132;          // chroma staging pitch
+constexpr int RH = TH + 3;            // staged rows
+constexpr int RWORDS = 112;           // staged row pitch in 32-bit words (448 bytes = 149 pixels)
+constexpr int RPIX = 136;             // pixels converted per staged row (34 groups of 4)
+constexpr int RGROUPS = RPIX / 4;
+constexpr int LEAD = 16;              // staged pixel q <-> image column x0 - LEAD + q
+constexpr int SKIP = 12;              // converted pixel p = q - SKIP <-> image column x0 - 4 + p
+constexpr int SPIX = RWORDS * 4 / 3;  // whole pixels in a staged row
+constexpr int C_PITCH = 144;          // Cr/Cb staging pitch (bytes), indexed by region pixel
 constexpr int CW = TW / 2;            // chroma tile
 constexpr int CH = TH / 2;
 constexpr int NY_BLOCKS = (TW / 8) * (TH / 8);       // 128
 constexpr int NC_BLOCKS = (CW / 8) * (CH / 8);       // 32
-constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // 192: one thread per 8x8 block
+constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // 192
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
+constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
 
 struct Smem {
-    union alignas(16) {
-        uint8_t rgb[RH * RGB_PITCH];                 // stage 0/1
+    union alignas(128) {
+        uint32_t rgb[RH * RWORDS];                   // stage 0/1 (TMA destination)
         uint16_t hpass[2][RH][CW];                   // stage 2 (rgb is dead by then)
     };
     alignas(16) uint8_t y[TH][TW];
@@ -100,65 +117,114 @@ struct Smem {
     alignas(16) uint8_t cb[RH][C_PITCH];
     alignas(16) uint8_t crd[CH][CW];
     alignas(16) uint8_t cbd[CH][CW];
+    alignas(16) uint8_t lut_cr[512];                 // Cr as a function of R - Y + 255
+    alignas(16) uint8_t lut_cb[512];                 // Cb as a function of B - Y + 255
+    alignas(8) unsigned long long bar;
 };
 
-// 8x8 block in registers -> quantised zigzag int16, with the near-tie mask.
-// KIND: 0 luminance table, 1 chroma table.  v[8*r + c] holds x - 128 (0 where padded).
-// umax/vmax: coefficients with u >= umax or v >= vmax lie outside the unpadded plane -> 0.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// inverse of the scan order: natural index -> scan position
+struct InverseZigzag {
+    uint8_t pos[64];
+    constexpr InverseZigzag() : pos() {
+        constexpr uint8_t zz[64] = HIC_ZIGZAG8;
+        for (int k = 0; k < 64; ++k) pos[zz[k]] = (uint8_t)k;
+    }
+};
+
+// 8x8 block (as 16 words of bytes, rows of 8) -> quantised zigzag int16 + near-tie mask.
+// Two rows (then two columns) ride in each f32x2 register pair.
 template <int KIND>
-__device__ __forceinline__ void transform_block(float (&v)[64], float abs_sum, int umax, int vmax,
+__device__ __forceinline__ void transform_block(const uint32_t (&wv)[16], int umax, int vmax,
                                                 int16_t* __restrict__ dst, uint32_t block_index,
                                                 hic_tie_record* __restrict__ ties, uint32_t tie_capacity,
                                                 uint32_t* __restrict__ stats) {
+    // sum |x| over the block (exact, integer) for the error band
+    uint32_t abs_sum = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-        aan_forward8(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5],
-                     v[8 * r + 6], v[8 * r + 7]);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        aan_forward8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+    for (int i = 0; i < 16; ++i) abs_sum = __vsadu4(wv[i], 0x80808080u) + abs_sum;
+    const float band = (float)(HIC_TIE_KAPPA * 4.0 / 16777216.0) * (float)abs_sum;
 
-    constexpr uint8_t zz[64] = HIC_ZIGZAG8;
-    const float band = (float)(HIC_TIE_KAPPA * 4.0 / 16777216.0) * abs_sum;     // in units of C = q * v
-    int bits[64];
-    float margin = 1e30f;
+    // row pass: rows (2 rp, 2 rp + 1) together; bytes become floats by splicing them into 2^23
+    const f2 shift(-(8388608.0f + 128.0f));
+    f2 a[32];
 #pragma unroll
-    for (int k = 0; k < 64; ++k) {
-        const int nat = zz[k];
-        const float t = fmaf(v[nat], c_tab.rq[KIND][nat], MAGIC);
-        bits[k] = __float_as_int(t);
-        if (k != 0) {     // DC = 4*sum(x)/q is exact in float32 and cannot land in a wrong tie
-            const float d = fmaf(v[nat], c_tab.rq[KIND][nat], MAGIC - t);
-            margin = fminf(margin, (0.5f - fabsf(d)) * c_tab.qf[KIND][nat]);
+    for (int rp = 0; rp < 4; ++rp) {
+        f2 d[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t top = wv[4 * rp + (c >> 2)], bot = wv[4 * rp + 2 + (c >> 2)];
+            const float ft = __uint_as_float(__byte_perm(top, 0x4B000000u, 0x7540 + (c & 3)));
+            const float fb = __uint_as_float(__byte_perm(bot, 0x4B000000u, 0x7540 + (c & 3)));
+            d[c] = f2(ft, fb) + shift;
         }
+        aan_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[rp * 8 + c] = d[c];
+    }
+    // column pass: columns (2 cp, 2 cp + 1) together
+    f2 b[32];        // b[r * 4 + cp] = natural (8 r + 2 cp, 8 r + 2 cp + 1)
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+        f2 d[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const f2 left = a[(r >> 1) * 8 + 2 * cp], right = a[(r >> 1) * 8 + 2 * cp + 1];
+            d[r] = (r & 1) ? f2(left.hi(), right.hi()) : f2(left.lo(), right.lo());
+        }
+        aan_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) b[r * 4 + cp] = d[r];
+    }
+    // quantise: t = RN(v * rq + MAGIC) holds round-half-even(v * rq) in its low mantissa bits;
+    // d = v * rq - round(v * rq); near a tie when |d| + band / q >= 1/2
+    int bits[64];
+    float worst = 0.f;
+    const f2 magic2(MAGIC);
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const int n0 = (p >> 2) * 8 + 2 * (p & 3);
+        const f2 rq(c_tab.rq[KIND][n0], c_tab.rq[KIND][n0 + 1]);
+        const f2 t = fma2(b[p], rq, magic2);
+        const f2 d = fma2(b[p], rq, magic2 - t);
+        bits[n0] = __float_as_int(t.lo());
+        bits[n0 + 1] = __float_as_int(t.hi());
+        if (p != 0) worst = fmaxf(worst, fmaf(band, c_tab.rcpq[KIND][n0], fabsf(d.lo())));   // DC is exact
+        worst = fmaxf(worst, fmaf(band, c_tab.rcpq[KIND][n0 + 1], fabsf(d.hi())));
     }
     const bool cropped = (umax < 8) | (vmax < 8);
     if (cropped) {
 #pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            const int nat = zz[k];
-            if ((nat >> 3) >= umax || (nat & 7) >= vmax) bits[k] = __float_as_int(MAGIC);
-        }
+        for (int nat = 0; nat < 64; ++nat)
+            if ((nat >> 3) >= umax || (nat & 7) >= vmax) bits[nat] = __float_as_int(MAGIC);
     }
+    constexpr uint8_t zz[64] = HIC_ZIGZAG8;
     int4* out = reinterpret_cast<int4*>(dst);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int4 w;
-        w.x = __byte_perm(bits[8 * j + 0], bits[8 * j + 1], 0x5410);
-        w.y = __byte_perm(bits[8 * j + 2], bits[8 * j + 3], 0x5410);
-        w.z = __byte_perm(bits[8 * j + 4], bits[8 * j + 5], 0x5410);
-        w.w = __byte_perm(bits[8 * j + 6], bits[8 * j + 7], 0x5410);
+        w.x = __byte_perm(bits[zz[8 * j + 0]], bits[zz[8 * j + 1]], 0x5410);
+        w.y = __byte_perm(bits[zz[8 * j + 2]], bits[zz[8 * j + 3]], 0x5410);
+        w.z = __byte_perm(bits[zz[8 * j + 4]], bits[zz[8 * j + 5]], 0x5410);
+        w.w = __byte_perm(bits[zz[8 * j + 6]], bits[zz[8 * j + 7]], 0x5410);
         out[j] = w;
     }
-    if (margin <= band) {       // rare: find which scan positions are inside the band
+    if (worst >= 0.5f) {        // rare: find which scan positions are inside the band
+        constexpr InverseZigzag izz{};
         uint64_t mask = 0;
 #pragma unroll
-        for (int k = 1; k < 64; ++k) {
-            const int nat = zz[k];
-            const float t = fmaf(v[nat], c_tab.rq[KIND][nat], MAGIC);
-            const float d = fmaf(v[nat], c_tab.rq[KIND][nat], MAGIC - t);
-            const bool inside = (nat >> 3) < umax && (nat & 7) < vmax;
-            if (inside && (0.5f - fabsf(d)) * c_tab.qf[KIND][nat] <= band) mask |= (1ull << k);
+        for (int p = 0; p < 32; ++p) {
+            const int n0 = (p >> 2) * 8 + 2 * (p & 3);
+            const f2 rq(c_tab.rq[KIND][n0], c_tab.rq[KIND][n0 + 1]);
+            const f2 t = fma2(b[p], rq, magic2);
+            const f2 d = fma2(b[p], rq, magic2 - t);
+            if (p != 0 && (n0 >> 3) < umax && (n0 & 7) < vmax &&
+                fmaf(band, c_tab.rcpq[KIND][n0], fabsf(d.lo())) >= 0.5f)
+                mask |= 1ull << izz.pos[n0];
+            if (((n0 + 1) >> 3) < umax && ((n0 + 1) & 7) < vmax &&
+                fmaf(band, c_tab.rcpq[KIND][n0 + 1], fabsf(d.hi())) >= 0.5f)
+                mask |= 1ull << izz.pos[n0 + 1];
         }
         if (mask) {
             const uint32_t slot = atomicAdd(&stats[0], 1u);
@@ -175,67 +241,169 @@ __device__ __forceinline__ void transform_block(float (&v)[64], float abs_sum, i
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 3)
-forward_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, int16_t* __restrict__ coef,
-               hic_tie_record* __restrict__ ties, uint32_t tie_capacity, uint32_t* __restrict__ stats) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+// keep the first `cols` bytes of each row word pair and the first `rows` rows; the rest become 128
+// (x - 128 = 0: the reference zero-pads after the level shift, transform.py:186-188)
+__device__ __forceinline__ void mask_block(uint32_t (&wv)[16], int rows, int cols) {
+    const uint32_t keep_lo = cols >= 4 ? 0xFFFFFFFFu : ((1u << (8 * cols)) - 1u);
+    const uint32_t keep_hi = cols >= 8 ? 0xFFFFFFFFu : (cols > 4 ? ((1u << (8 * (cols - 4))) - 1u) : 0u);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const bool row_ok = r < rows;
+        wv[2 * r] = row_ok ? ((wv[2 * r] & keep_lo) | (0x80808080u & ~keep_lo)) : 0x80808080u;
+        wv[2 * r + 1] = row_ok ? ((wv[2 * r + 1] & keep_hi) | (0x80808080u & ~keep_hi)) : 0x80808080u;
+    }
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(THREADS, 2)
+forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
+               hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
+               uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const uint8_t* src = rgb + (size_t)img * h * w * 3;
 
-    // stage 0: stage the RGB region (with BORDER_REFLECT_101 at the image edges) in shared memory
-    for (int i = tid; i < RH * RW; i += THREADS) {
-        const int ry = i / RW, rx = i - ry * RW;
-        const int gy = reflect101(y0 - 2 + ry, h), gx = reflect101(x0 - 2 + rx, w);
-        const uint8_t* p = src + ((size_t)gy * w + gx) * 3;
-        uint8_t* q = &s.rgb[ry * RGB_PITCH + rx * 3];
-        q[0] = p[0];
-        q[1] = p[1];
-        q[2] = p[2];
+    // ---- stage 0: RGB region -> shared memory ----
+    if (USE_TMA) {
+        if (tid == 0) {
+            const uint32_t bar = smem_u32(&s.bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TILE_BYTES) : "memory");
+            const int c0 = (3 * x0 - 3 * LEAD) / 4, c1 = y0 - 2, c2 = img;
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(smem_u32(s.rgb)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                : "memory");
+        }
+    }
+    // chroma lookup tables (cv2's fixed point, compression.py:21): index = difference + 255
+    for (int i = tid; i < 511; i += THREADS) {
+        const int d = i - 255;
+        s.lut_cr[i] = (uint8_t)clamp_u8((d * 11682 + (128 << 14) + 8192) >> 14);
+        s.lut_cb[i] = (uint8_t)clamp_u8((d * 9241 + (128 << 14) + 8192) >> 14);
+    }
+    if (!USE_TMA) {
+        // generic loader (row pitch not a multiple of 16 bytes): bytes with the border rule applied
+        const uint8_t* src = rgb + (size_t)img * h * w * 3;
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(s.rgb);
+        for (int i = tid; i < RH * RPIX; i += THREADS) {
+            const int ry = i / RPIX, p = SKIP + (i - ry * RPIX);
+            const int gy = reflect101(y0 - 2 + ry, h), gx = reflect101(x0 - LEAD + p, w);
+            const uint8_t* q = src + ((size_t)gy * w + gx) * 3;
+            uint8_t* o = dst8 + ry * (RWORDS * 4) + p * 3;
+            o[0] = q[0];
+            o[1] = q[1];
+            o[2] = q[2];
+        }
+    }
+    __syncthreads();           // barrier initialised / generic load + tables visible
+    if (USE_TMA) {
+        const uint32_t bar = smem_u32(&s.bar);
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar)
+            : "memory");
+        // TMA zero-fills outside the image; cv2.pyrDown wants BORDER_REFLECT_101 there.  Only the
+        // two pixels next to each edge are ever read by a valid output: patch them in place.
+        uint8_t* r8 = reinterpret_cast<uint8_t*>(s.rgb);
+        const bool left = x0 == 0, right = x0 - LEAD + SPIX > w, top = y0 == 0, bottom = y0 - 2 + RH > h;
+        if (left | right) {
+            for (int i = tid; i < RH * 4; i += THREADS) {
+                const int ry = i >> 2, k = i & 3;
+                // k = 0, 1: image columns -2, -1; k = 2, 3: image columns w, w + 1
+                const int col = k < 2 ? k - 2 : w + (k - 2);
+                if ((k < 2 && !left) || (k >= 2 && !right)) continue;
+                const int p = col - x0 + LEAD, ps = reflect101(col, w) - x0 + LEAD;
+                if (p < 0 || p >= SPIX || ps < 0 || ps >= SPIX) continue;
+                uint8_t* o = r8 + ry * (RWORDS * 4);
+                o[3 * p] = o[3 * ps];
+                o[3 * p + 1] = o[3 * ps + 1];
+                o[3 * p + 2] = o[3 * ps + 2];
+            }
+            __syncthreads();
+        }
+        if (top | bottom) {
+            for (int i = tid; i < 4 * RWORDS; i += THREADS) {
+                const int k = i / RWORDS, wd = i - k * RWORDS;
+                const int row = k < 2 ? k - 2 : h + (k - 2);
+                if ((k < 2 && !top) || (k >= 2 && !bottom)) continue;
+                const int ry = row - y0 + 2, rs = reflect101(row, h) - y0 + 2;
+                if (ry < 0 || ry >= RH || rs < 0 || rs >= RH) continue;
+                s.rgb[ry * RWORDS + wd] = s.rgb[rs * RWORDS + wd];
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- stage 1: colour conversion, four pixels (three words) at a time ----
+    // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes
+    for (int i = tid; i < RH * RGROUPS; i += THREADS) {
+        const int ry = i / RGROUPS, gx = i - ry * RGROUPS;
+        const uint32_t* rw = s.rgb + ry * RWORDS + 3 * (gx + SKIP / 4);
+        const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+        const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
+        uint32_t yv[4], crv[4], cbv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = __dp4a(px[k], 0x004C9123u, 8192u);
+            const uint32_t hi = __dp4a(px[k], 0x00072513u, 0u);
+            const uint32_t yy = (lo + (hi << 8)) >> 14;
+            yv[k] = yy;
+            crv[k] = s.lut_cr[(px[k] & 0xFFu) + 255u - yy];
+            cbv[k] = s.lut_cb[((px[k] >> 16) & 0xFFu) + 255u - yy];
+        }
+        const uint32_t crw = crv[0] | (crv[1] << 8) | (crv[2] << 16) | (crv[3] << 24);
+        const uint32_t cbw = cbv[0] | (cbv[1] << 8) | (cbv[2] << 16) | (cbv[3] << 24);
+        *reinterpret_cast<uint32_t*>(&s.cr[ry][4 * gx]) = crw;
+        *reinterpret_cast<uint32_t*>(&s.cb[ry][4 * gx]) = cbw;
+        if (ry >= 2 && ry < 2 + TH && gx >= 1 && gx <= TW / 4)
+            *reinterpret_cast<uint32_t*>(&s.y[ry - 2][4 * (gx - 1)]) = yv[0] | (yv[1] << 8) | (yv[2] << 16) | (yv[3] << 24);
     }
     __syncthreads();
 
-    // stage 1: RGB -> Y (tile interior), Cr, Cb (tile + halo)
-    for (int i = tid; i < RH * RW; i += THREADS) {
-        const int ry = i / RW, rx = i - ry * RW;
-        const uint8_t* q = &s.rgb[ry * RGB_PITCH + rx * 3];
-        int yy, cr, cb;
-        rgb_to_ycrcb(q[0], q[1], q[2], yy, cr, cb);
-        s.cr[ry][rx] = (uint8_t)cr;
-        s.cb[ry][rx] = (uint8_t)cb;
-        const int ty = ry - 2, tx = rx - 2;
-        if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) s.y[ty][tx] = (uint8_t)yy;
+    // ---- stage 2a: horizontal [1 4 6 4 1] at stride 2; chroma column cx reads region pixels 2 cx + 2 .. 2 cx + 6 ----
+    for (int i = tid; i < 2 * RH * (CW / 4); i += THREADS) {
+        const int ch = i / (RH * (CW / 4));
+        const int rem = i - ch * (RH * (CW / 4));
+        const int ry = rem / (CW / 4), j = rem - ry * (CW / 4);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
+        const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
+        const uint32_t o0 = __dp4a(wb, 0x00010406u, __dp4a(wa, 0x04010000u, 0u));
+        const uint32_t o1 = __dp4a(wc, 0x00000001u, __dp4a(wb, 0x04060401u, 0u));
+        const uint32_t o2 = __dp4a(wc, 0x00010406u, __dp4a(wb, 0x04010000u, 0u));
+        const uint32_t o3 = __dp4a(wd, 0x00000001u, __dp4a(wc, 0x04060401u, 0u));
+        *reinterpret_cast<uint2*>(&s.hpass[ch][ry][4 * j]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    }
+    __syncthreads();
+    // ---- stage 2b: vertical on two 16-bit lanes per word (sums stay below 2^16), (sum + 128) >> 8 ----
+    for (int i = tid; i < 2 * CH * (CW / 4); i += THREADS) {
+        const int ch = i / (CH * (CW / 4));
+        const int rem = i - ch * (CH * (CW / 4));
+        const int cy = rem / (CW / 4), j = rem - cy * (CW / 4);
+        uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint2 t = *reinterpret_cast<const uint2*>(&s.hpass[ch][2 * cy + k][4 * j]);
+            const uint32_t wt = k == 2 ? 6u : ((k == 1 || k == 3) ? 4u : 1u);
+            v0 += wt * t.x;
+            v1 += wt * t.y;
+        }
+        const uint32_t packed = __byte_perm(v0, v1, 0x7531);       // the high byte of each 16-bit lane
+        *reinterpret_cast<uint32_t*>(ch == 0 ? &s.crd[cy][4 * j] : &s.cbd[cy][4 * j]) = packed;
     }
     __syncthreads();
 
-    // stage 2a: horizontal [1 4 6 4 1] at stride 2 (region column 2*cx + k <-> image column 2*(cx0+cx) - 2 + k)
-    for (int i = tid; i < 2 * RH * CW; i += THREADS) {
-        const int ch = i / (RH * CW);
-        const int rem = i - ch * (RH * CW);
-        const int ry = rem / CW, cx = rem - ry * CW;
-        const uint8_t* row = ch == 0 ? s.cr[ry] : s.cb[ry];
-        const int b = 2 * cx;
-        s.hpass[ch][ry][cx] = (uint16_t)(row[b] + 4 * row[b + 1] + 6 * row[b + 2] + 4 * row[b + 3] + row[b + 4]);
-    }
-    __syncthreads();
-    // stage 2b: vertical, (sum + 128) >> 8
-    for (int i = tid; i < 2 * CH * CW; i += THREADS) {
-        const int ch = i / (CH * CW);
-        const int rem = i - ch * (CH * CW);
-        const int cy = rem / CW, cx = rem - cy * CW;
-        const int b = 2 * cy;
-        const int sum = s.hpass[ch][b][cx] + 4 * s.hpass[ch][b + 1][cx] + 6 * s.hpass[ch][b + 2][cx] +
-                        4 * s.hpass[ch][b + 3][cx] + s.hpass[ch][b + 4][cx];
-        const uint8_t val = (uint8_t)((sum + 128) >> 8);
-        if (ch == 0) s.crd[cy][cx] = val; else s.cbd[cy][cx] = val;
-    }
-    __syncthreads();
-
-    // stage 3: one 8x8 block per thread
-    float v[64];
-    float abs_sum = 0.f;
+    // ---- stage 3: one 8x8 block per thread ----
+    uint32_t wv[16];
     if (tid < NY_BLOCKS) {
         const int by = tid / (TW / 8), bx = tid % (TW / 8);
         const int BY = blockIdx.y * (TH / 8) + by, BX = blockIdx.x * (TW / 8) + bx;
@@ -243,19 +411,13 @@ forward_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g
         const int rows = min(8, h - 8 * BY), cols = min(8, w - 8 * BX);      // valid pixels
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const uint2 word = *reinterpret_cast<const uint2*>(&s.y[8 * by + r][8 * bx]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t wv = c < 4 ? word.x : word.y;
-                float x = (float)(int)((wv >> (8 * (c & 3))) & 0xFF) - 128.f;
-                if (r >= rows || c >= cols) x = 0.f;
-                v[8 * r + c] = x;
-                abs_sum += fabsf(x);
-            }
+            const uint2 t = *reinterpret_cast<const uint2*>(&s.y[8 * by + r][8 * bx]);
+            wv[2 * r] = t.x;
+            wv[2 * r + 1] = t.y;
         }
+        if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
         const uint32_t block_index = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
-        transform_block<0>(v, abs_sum, rows, cols, coef + (size_t)block_index * 64, block_index, ties,
-                           tie_capacity, stats);
+        transform_block<0>(wv, rows, cols, coef + (size_t)block_index * 64, block_index, ties, tie_capacity, stats);
     } else {
         const int plane = (tid - NY_BLOCKS) / NC_BLOCKS;          // 0 = Cr, 1 = Cb
         const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
@@ -266,20 +428,14 @@ forward_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g
         const uint8_t (*pl)[CW] = plane == 0 ? s.crd : s.cbd;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const uint2 word = *reinterpret_cast<const uint2*>(&pl[8 * by + r][8 * bx]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t wv = c < 4 ? word.x : word.y;
-                float x = (float)(int)((wv >> (8 * (c & 3))) & 0xFF) - 128.f;
-                if (r >= rows || c >= cols) x = 0.f;
-                v[8 * r + c] = x;
-                abs_sum += fabsf(x);
-            }
+            const uint2 t = *reinterpret_cast<const uint2*>(&pl[8 * by + r][8 * bx]);
+            wv[2 * r] = t.x;
+            wv[2 * r + 1] = t.y;
         }
+        if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
         const uint32_t block_index = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c +
                                                 (int64_t)BY * g.nbx_c + BX);
-        transform_block<1>(v, abs_sum, rows, cols, coef + (size_t)block_index * 64, block_index, ties,
-                           tie_capacity, stats);
+        transform_block<1>(wv, rows, cols, coef + (size_t)block_index * 64, block_index, ties, tie_capacity, stats);
     }
 }
 
@@ -649,10 +805,40 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
     int dev = 0;
     HIC_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
         if (dev < 64) attr_set[dev] = true;
     }
-    HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    // TMA path: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool use_tma = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0) && getenv("HIC_NO_TMA") == nullptr;
+    if (use_tma) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            HIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (qres != cudaDriverEntryPointSuccess || !fn) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+            encode = reinterpret_cast<EncodeFn>(fn);
+        }
+        const cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
+        const cuuint32_t box[3] = {(cuuint32_t)k1::RWORDS, (cuuint32_t)k1::RH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(d_rgb), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) use_tma = false;       // fall back to the generic loader
+        if (getenv("HIC_DEBUG")) fprintf(stderr, "[hic] tensor map encode -> %d (use_tma=%d)\n", (int)r, (int)use_tma);
+    }
+    if (use_tma)
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    else
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 4, 128, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     return HIC_OK;
 }
