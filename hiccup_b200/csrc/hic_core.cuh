@@ -220,6 +220,54 @@ HIC_HD int32_t exact_quantised_coef(const int16_t* px, int u, int v, int q) {
     return round_half_even(ddiv(col[u], (double)q));
 }
 
+// The whole quantised block exactly as the reference computes it (16 eight-point transforms).
+// px: x - 128, zero padded, row major; q: the table, row major; out: natural order.
+HIC_HD void exact_quantised_block(const int16_t* px, const int* q, int32_t* out) {
+    double a[64];
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        double row[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = (double)px[8 * i + j];
+        ducc_dct2_8(row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[8 * i + j] = row[j];
+    }
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        double col[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) col[i] = a[8 * i + j];
+        ducc_dct2_8(col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[8 * i + j] = round_half_even(ddiv(col[i], (double)q[8 * i + j]));
+    }
+}
+
+// The whole decoded block exactly as the reference computes it.  cq: coef * table, natural order;
+// out: the float64 samples before the uint8 cast, row major.
+HIC_HD void exact_decoded_block(const int32_t* cq, double* out) {
+    double a[64];
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        double row[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = (double)cq[8 * i + j];
+        ducc_dct3_8(row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[8 * i + j] = row[j];
+    }
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        double col[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) col[i] = a[8 * i + j];
+        ducc_dct3_8(col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[8 * i + j] = dadd(ddiv(col[i], 256.0), 128.0);
+    }
+}
+
 // One decoded sample exactly as the reference computes it (transform.py:169-179, 87-103):
 // coef*table, idct rows then columns, /256, +128, astype(uint8) = truncate toward zero, wrap.
 // cq: the dequantised 8x8 block (coef * table), row major.  Returns the float64 value before the

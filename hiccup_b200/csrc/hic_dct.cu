@@ -124,15 +124,6 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// inverse of the scan order: natural index -> scan position
-struct InverseZigzag {
-    uint8_t pos[64];
-    constexpr InverseZigzag() : pos() {
-        constexpr uint8_t zz[64] = HIC_ZIGZAG8;
-        for (int k = 0; k < 64; ++k) pos[zz[k]] = (uint8_t)k;
-    }
-};
-
 // 8x8 block (as 16 words of bytes, rows of 8) -> quantised zigzag int16 + near-tie mask.
 // Two rows (then two columns) ride in each f32x2 register pair.
 template <int KIND>
@@ -210,33 +201,16 @@ __device__ __forceinline__ void transform_block(const uint32_t (&wv)[16], int um
         w.w = __byte_perm(bits[zz[8 * j + 6]], bits[zz[8 * j + 7]], 0x5410);
         out[j] = w;
     }
-    if (worst >= 0.5f) {        // rare: find which scan positions are inside the band
-        constexpr InverseZigzag izz{};
-        uint64_t mask = 0;
-#pragma unroll
-        for (int p = 0; p < 32; ++p) {
-            const int n0 = (p >> 2) * 8 + 2 * (p & 3);
-            const f2 rq(c_tab.rq[KIND][n0], c_tab.rq[KIND][n0 + 1]);
-            const f2 t = fma2(b[p], rq, magic2);
-            const f2 d = fma2(b[p], rq, magic2 - t);
-            if (p != 0 && (n0 >> 3) < umax && (n0 & 7) < vmax &&
-                fmaf(band, c_tab.rcpq[KIND][n0], fabsf(d.lo())) >= 0.5f)
-                mask |= 1ull << izz.pos[n0];
-            if (((n0 + 1) >> 3) < umax && ((n0 + 1) & 7) < vmax &&
-                fmaf(band, c_tab.rcpq[KIND][n0 + 1], fabsf(d.hi())) >= 0.5f)
-                mask |= 1ull << izz.pos[n0 + 1];
-        }
-        if (mask) {
-            const uint32_t slot = atomicAdd(&stats[0], 1u);
-            if (slot < tie_capacity) {
-                hic_tie_record rec;
-                rec.block = block_index;
-                rec.reserved = 0;
-                rec.mask = mask;
-                ties[slot] = rec;
-            } else {
-                atomicAdd(&stats[3], 1u);
-            }
+    if (worst >= 0.5f) {        // some coefficient is within the float32 error band of a rounding tie:
+        const uint32_t slot = atomicAdd(&stats[0], 1u);     // the fix-up kernel redoes this block in float64
+        if (slot < tie_capacity) {
+            hic_tie_record rec;
+            rec.block = block_index;
+            rec.reserved = 0;
+            rec.mask = ~0ull;
+            ties[slot] = rec;
+        } else {
+            atomicAdd(&stats[3], 1u);
         }
     }
 }
@@ -346,8 +320,12 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
 
     // ---- stage 1: colour conversion, four pixels (three words) at a time ----
     // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes
-    for (int i = tid; i < RH * RGROUPS; i += THREADS) {
-        const int ry = i / RGROUPS, gx = i - ry * RGROUPS;
+    static_assert(THREADS == 5 * RGROUPS + 22, "index stepping below assumes 192 = 5 * 34 + 22");
+    for (int ry = tid / RGROUPS, gx = tid % RGROUPS; ry < RH; ry += 5, gx += 22) {
+        if (gx >= RGROUPS) {
+            gx -= RGROUPS;
+            if (++ry >= RH) break;
+        }
         const uint32_t* rw = s.rgb + ry * RWORDS + 3 * (gx + SKIP / 4);
         const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
         const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
@@ -358,8 +336,9 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
             const uint32_t hi = __dp4a(px[k], 0x00072513u, 0u);
             const uint32_t yy = (lo + (hi << 8)) >> 14;
             yv[k] = yy;
-            crv[k] = s.lut_cr[(px[k] & 0xFFu) + 255u - yy];
-            cbv[k] = s.lut_cb[((px[k] >> 16) & 0xFFu) + 255u - yy];
+            const uint32_t bias = 255u - yy;
+            crv[k] = s.lut_cr[__dp4a(px[k], 0x00000001u, bias)];        // R - Y + 255
+            cbv[k] = s.lut_cb[__dp4a(px[k], 0x00010000u, bias)];        // B - Y + 255
         }
         const uint32_t crw = crv[0] | (crv[1] << 8) | (crv[2] << 16) | (crv[3] << 24);
         const uint32_t cbw = cbv[0] | (cbv[1] << 8) | (cbv[2] << 16) | (cbv[3] << 24);
@@ -371,10 +350,10 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     __syncthreads();
 
     // ---- stage 2a: horizontal [1 4 6 4 1] at stride 2; chroma column cx reads region pixels 2 cx + 2 .. 2 cx + 6 ----
-    for (int i = tid; i < 2 * RH * (CW / 4); i += THREADS) {
-        const int ch = i / (RH * (CW / 4));
-        const int rem = i - ch * (RH * (CW / 4));
-        const int ry = rem / (CW / 4), j = rem - ry * (CW / 4);
+    // 16 four-output groups per row: the 192 threads cover 6 (channel, row) pairs x 2 channels per step
+    for (int rr = tid >> 4; rr < 2 * RH; rr += THREADS / 16) {
+        const int j = tid & 15;
+        const int ch = rr >= RH ? 1 : 0, ry = rr - ch * RH;
         const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
         const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
         const uint32_t o0 = __dp4a(wb, 0x00010406u, __dp4a(wa, 0x04010000u, 0u));
@@ -385,10 +364,9 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     }
     __syncthreads();
     // ---- stage 2b: vertical on two 16-bit lanes per word (sums stay below 2^16), (sum + 128) >> 8 ----
-    for (int i = tid; i < 2 * CH * (CW / 4); i += THREADS) {
-        const int ch = i / (CH * (CW / 4));
-        const int rem = i - ch * (CH * (CW / 4));
-        const int cy = rem / (CW / 4), j = rem - cy * (CW / 4);
+    for (int rr = tid >> 4; rr < 2 * CH; rr += THREADS / 16) {
+        const int j = tid & 15;
+        const int ch = rr >= CH ? 1 : 0, cy = rr - ch * CH;
         uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -496,20 +474,29 @@ fixup_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, 
                 }
         }
         int16_t* blk = coef + (size_t)rec.block * 64;
-        uint64_t mask = rec.mask;
-        uint32_t evaluated = 0, changed = 0;
-        while (mask) {
-            const int k = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
+        int32_t exact[64];
+        exact_quantised_block(px, c_tab.qi[kind], exact);
+        // coefficients outside the unpadded plane stay zero (transform.py:63, codec.py:288)
+        int ph, pw, BY2, BX2;
+        if (kind == 0) {
+            ph = h; pw = w;
+            const int64_t l2 = rec.block - img * g.blocks_per_image;
+            BY2 = (int)(l2 / g.nbx_l); BX2 = (int)(l2 % g.nbx_l);
+        } else {
+            ph = g.hc; pw = g.wc;
+            BY2 = (int)(local / g.nbx_c); BX2 = (int)(local % g.nbx_c);
+        }
+        uint32_t changed = 0;
+        for (int k = 1; k < 64; ++k) {
             const int nat = c_zigzag[k];
-            const int32_t exact = exact_quantised_coef(px, nat >> 3, nat & 7, c_tab.qi[kind][nat]);
-            ++evaluated;
-            if ((int32_t)blk[k] != exact) {
-                blk[k] = (int16_t)exact;
+            int32_t v = exact[nat];
+            if (8 * BY2 + (nat >> 3) >= ph || 8 * BX2 + (nat & 7) >= pw) v = 0;
+            if ((int32_t)blk[k] != v) {
+                blk[k] = (int16_t)v;
                 ++changed;
             }
         }
-        atomicAdd(&stats[1], evaluated);
+        atomicAdd(&stats[1], 63u);
         if (changed) atomicAdd(&stats[2], changed);
     }
 }
@@ -582,23 +569,15 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
     // a DC-only block is exact in both float32 and float64 (no rounding happens at all)
     const float band = (float)(HIC_INV_KAPPA * 4.0 / 16777216.0 / 256.0) * energy + 3.0517578125e-5f;
     if (ac_bits != 0 && margin <= band) {
-        uint64_t mask = 0;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            const float r = (v[i] + MAGIC) - MAGIC;
-            if (fabsf(v[i] - r) <= band && (i >> 3) < rows && (i & 7) < cols) mask |= (1ull << i);
-        }
-        if (mask) {
-            const uint32_t slot = atomicAdd(&stats[0], 1u);
-            if (slot < tie_capacity) {
-                hic_tie_record rec;
-                rec.block = block_index;
-                rec.reserved = 0;
-                rec.mask = mask;
-                ties[slot] = rec;
-            } else {
-                atomicAdd(&stats[3], 1u);
-            }
+        const uint32_t slot = atomicAdd(&stats[0], 1u);
+        if (slot < tie_capacity) {
+            hic_tie_record rec;
+            rec.block = block_index;
+            rec.reserved = 0;
+            rec.mask = ~0ull;
+            ties[slot] = rec;
+        } else {
+            atomicAdd(&stats[3], 1u);
         }
     }
 }
@@ -653,21 +632,20 @@ inverse_fixup_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, uint8
             const int nat = c_zigzag[k];
             cq[nat] = (int32_t)blk[k] * c_tab.qi[kind][nat];
         }
-        uint64_t mask = rec.mask;
-        uint32_t evaluated = 0, changed = 0;
-        while (mask) {
-            const int s = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            const int y = s >> 3, x = s & 7;
-            const uint8_t exact = wrap_u8(exact_decoded_sample(cq, y, x));
-            uint8_t* dst = plane + (size_t)(8 * BY + y) * pw + 8 * BX + x;
-            ++evaluated;
-            if (8 * BY + y < ph && 8 * BX + x < pw && *dst != exact) {
-                *dst = exact;
-                ++changed;
+        double exact[64];
+        exact_decoded_block(cq, exact);
+        uint32_t changed = 0;
+        for (int y = 0; y < 8; ++y)
+            for (int x = 0; x < 8; ++x) {
+                if (8 * BY + y >= ph || 8 * BX + x >= pw) continue;
+                const uint8_t v = wrap_u8(exact[8 * y + x]);
+                uint8_t* dst = plane + (size_t)(8 * BY + y) * pw + 8 * BX + x;
+                if (*dst != v) {
+                    *dst = v;
+                    ++changed;
+                }
             }
-        }
-        atomicAdd(&stats[1], evaluated);
+        atomicAdd(&stats[1], 64u);
         if (changed) atomicAdd(&stats[2], changed);
     }
 }

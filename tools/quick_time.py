@@ -10,9 +10,10 @@ def main():
     lib = _lib.load(); _lib.require_device()
     g = _lib.geometry(h, w)
     dev = torch.device("cuda:0")
-    rgb = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev)
-    # smooth it a bit so it is not pure noise: average with shifted copies
-    rgb = ((rgb.float() + rgb.roll(1, 1).float() + rgb.roll(1, 2).float() + rgb.roll(2, 2).float()) / 4).to(torch.uint8).contiguous()
+    import bench
+    base = bench.synthetic_batch(min(n, 16), h, w, 2000)
+    reps = (n + len(base) - 1) // len(base)
+    rgb = torch.from_numpy(np.concatenate([base] * reps)[:n].copy()).to(dev).contiguous()
     blocks = n * g.blocks_per_image
     coef = torch.empty(blocks * 64, dtype=torch.int16, device=dev)
     ties = torch.empty(blocks * 16, dtype=torch.uint8, device=dev)
