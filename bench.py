@@ -310,8 +310,11 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     t_e2e = time.perf_counter()
+    t_enc = 0.0
     for _ in range(args.steps):
+        t_a = time.perf_counter()
         enc_res = codec.encode(host_rgb)
+        t_enc += time.perf_counter() - t_a
         out = codec.decode(enc_res)
     e3.record()
     barrier()
@@ -349,7 +352,8 @@ def main():
                        "compressed_bytes_per_batch": int(enc.total_bytes), "symbols_per_batch": int(s_ac)},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "encode_ms_per_step": t_enc / args.steps * 1e3,
+                    "decode_ms_per_step": (wall_e2e - t_enc) / args.steps * 1e3},
             "gpu_launches": gpu_launches, "parity": parity,
         }
         print(json.dumps(line))

@@ -148,8 +148,10 @@ class DeviceBuffer:
         check(load().hic_memcpy_h2d(self.ptr, a.ctypes.data, a.nbytes, stream))
         return a            # keep alive until the stream is synchronised
 
-    def download(self, dtype, count, stream=None, offset=0):
-        out = np.empty(int(count), dtype=dtype)
+    def download(self, dtype, count, stream=None, offset=0, out=None):
+        """Device -> host.  `out`: a preallocated (ideally pinned) array to fill instead of a new one."""
+        out = np.empty(int(count), dtype=dtype) if out is None else out
+        assert out.dtype == np.dtype(dtype) and out.size == int(count) and out.flags.c_contiguous
         assert offset + out.nbytes <= self.nbytes
         check(load().hic_memcpy_d2h(out.ctypes.data, self.ptr + offset, out.nbytes, stream))
         check(load().hic_stream_sync(stream))
@@ -161,6 +163,36 @@ class DeviceBuffer:
     def free(self):
         if self.ptr:
             load().hic_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory owned through the C ABI; `array(dtype, count)` views it as numpy."""
+
+    def __init__(self, nbytes):
+        require_device()
+        self.nbytes = int(nbytes)
+        p = c_void_p()
+        check(load().hic_host_alloc(ctypes.byref(p), max(self.nbytes, 1)))
+        self.ptr = p.value
+        self._raw = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+
+    def array(self, dtype=np.uint8, count=None, offset=0):
+        item = np.dtype(dtype).itemsize
+        count = (self.nbytes - offset) // item if count is None else int(count)
+        assert offset + count * item <= self.nbytes
+        return np.frombuffer(self._raw, dtype=dtype, count=count, offset=offset)
+
+    def free(self):
+        if self.ptr:
+            self._raw = None
+            load().hic_host_free(self.ptr)
             self.ptr = None
 
     def __del__(self):

@@ -39,6 +39,9 @@ class DctBatchCodec:
         self.decoder = entropy.EntropyDecoder(self.layout)
         self.forward_stats = np.zeros(4, np.uint32)
         self.inverse_stats = np.zeros(4, np.uint32)
+        # page-locked staging for the host-to-host entry points (grown on demand, reused every call)
+        self._h_data = None
+        self._h_out = None
 
     # ---- sizes -------------------------------------------------------------------------------
     @property
@@ -80,20 +83,29 @@ class DctBatchCodec:
         self.upload(rgb)
         out = self.encode_device()
         enc = self.encoder
-        data = out.download(np.uint8, int(enc.total_bytes), self.stream)
+        nbytes = int(enc.total_bytes)
+        if self._h_data is None or self._h_data.nbytes < nbytes:
+            if self._h_data is not None:
+                self._h_data.free()
+            self._h_data = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
+        # the returned arrays view this codec's pinned staging: valid until the next encode()
+        data = out.download(np.uint8, nbytes, self.stream, out=self._h_data.array(np.uint8, nbytes))
         sym, lens, codes = enc.tables()
         self.forward_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
         return entropy.EncodedStreams(self.layout, enc.rows.copy(), enc.nsym.copy(), enc.nbits.copy(),
                                       enc.byte_off.copy(), enc.byte_len.copy(), sym, lens, codes, data)
 
     def decode(self, enc):
-        data = np.concatenate([np.asarray(enc.data, np.uint8), np.zeros(16, np.uint8)])
-        self.decoder.decode(enc.rows, enc.symbols, enc.lens, enc.codes, data, enc.byte_off, enc.nbits,
+        self.decoder.decode(enc.rows, enc.symbols, enc.lens, enc.codes, enc.data, enc.byte_off, enc.nbits,
                             self.d_coef_dec.ptr, self.stream)
         _lib.check(self.lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
                                             self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks,
                                             self.d_stats.ptr, self.stream))
-        out = self.d_out.download(np.uint8, self.n * self.g.out_h * self.g.out_w * 3, self.stream)
+        count = self.n * self.g.out_h * self.g.out_w * 3
+        if self._h_out is None:
+            self._h_out = _lib.PinnedBuffer(count)
+        # a view of the codec's pinned staging: valid until the next decode()
+        out = self.d_out.download(np.uint8, count, self.stream, out=self._h_out.array(np.uint8, count))
         self.inverse_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
         return out.reshape(self.out_shape)
 
@@ -121,5 +133,6 @@ class DctBatchCodec:
         self.encoder.close()
         self.decoder.close()
         for b in (self.d_rgb, self.d_coef, self.d_coef_dec, self.d_ties, self.d_stats, self.d_y, self.d_cr, self.d_cb,
-                  self.d_out):
-            b.free()
+                  self.d_out, self._h_data, self._h_out):
+            if b is not None:
+                b.free()

@@ -494,13 +494,19 @@ __global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, 
 // code (left = first popped = '1'), (e) rows, code lookup table and stream totals are written.
 // Two instantiations share the work by alphabet size so that small alphabets keep many CTAs per SM.
 // ------------------------------------------------------------------------------------------------
+// Shared-memory footprint per stream is 14 bytes per leaf, so that one wave of CTAs covers a whole
+// batch (the replay is a serial dependent chain per stream: concurrency = streams resident per SM):
+//   slot[n + 2]   heap entries {node, freq} as uint2; heap index i lives in slot i + 1, which puts the
+//                 children 2p+1, 2p+2 of p in the 16-byte aligned slot pair (2p+2, 2p+3) -> one LDS.128
+//   parent[2n]    uint16, bit 15: this node is its parent's left child
+//   order[n]      entry index of leaf i (leaves sorted by first occurrence)
+// The sort keys (4 bytes per padded leaf) alias the heap slots, which are only filled after the sort.
 template <int N>
-struct BuildSmem {
-    uint64_t heap[N];         // heap entries packed as freq << 16 | node, compared on freq only
-    uint32_t freq[N];         // leaf frequencies (internal nodes live only inside heap entries)
-    uint32_t key[N];          // first-occurrence index (sort key); dead after the sort
-    uint16_t bin[N];          // histogram bin of each leaf
-    uint16_t parent[2 * N];   // bit 15: this node is its parent's left child
+struct BuildLayout {
+    static constexpr int HEAP_BYTES = 8 * (N + 2);
+    static constexpr int PARENT_OFF = HEAP_BYTES;
+    static constexpr int ORDER_OFF = PARENT_OFF + 2 * (2 * N);
+    static constexpr int BYTES = ORDER_OFF + 2 * N;
 };
 
 // NLO < n <= N is handled by this instantiation
@@ -510,7 +516,10 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
                      int32_t* __restrict__ row_sym, uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut,
                      uint32_t* __restrict__ ss_nsym, uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t build_raw[];
-    BuildSmem<N>& sm = *reinterpret_cast<BuildSmem<N>*>(build_raw);
+    uint2* slot = reinterpret_cast<uint2*>(build_raw);
+    uint32_t* key = reinterpret_cast<uint32_t*>(build_raw);                       // aliases slot (dead after the sort)
+    uint16_t* parent = reinterpret_cast<uint16_t*>(build_raw + BuildLayout<N>::PARENT_OFF);
+    uint16_t* order = reinterpret_cast<uint16_t*>(build_raw + BuildLayout<N>::ORDER_OFF);
     __shared__ int s_root;
     __shared__ unsigned long long s_bits;
     __shared__ uint32_t s_nsym;
@@ -529,16 +538,12 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
         return;
     }
     const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
+    const CompactEntry* my = entries + ix.offset;
     int P = 1;
     while (P < n) P <<= 1;
     for (int i = threadIdx.x; i < P; i += THREADS) {
-        if (i < n) {
-            sm.key[i] = entries[ix.offset + i].first;
-            sm.bin[i] = (uint16_t)i;              // entry index while sorting; becomes the bin below
-        } else {
-            sm.key[i] = 0xFFFFFFFFu;
-            sm.bin[i] = 0;
-        }
+        key[i] = i < n ? my[i].first : 0xFFFFFFFFu;
+        order[i] = (uint16_t)(i < n ? i : 0);
     }
     if (threadIdx.x == 0) {
         s_bits = 0;
@@ -552,23 +557,30 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
                 const int l = i ^ j;
                 if (l > i) {
                     const bool up = (i & k) == 0;
-                    const uint32_t a = sm.key[i], b = sm.key[l];
+                    const uint32_t a = key[i], b = key[l];
                     if ((a > b) == up) {
-                        sm.key[i] = b;
-                        sm.key[l] = a;
-                        const uint16_t t = sm.bin[i];
-                        sm.bin[i] = sm.bin[l];
-                        sm.bin[l] = t;
+                        key[i] = b;
+                        key[l] = a;
+                        const uint16_t t = order[i];
+                        order[i] = order[l];
+                        order[l] = t;
                     }
                 }
             }
             __syncthreads();
         }
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-        const CompactEntry e = entries[ix.offset + sm.bin[i]];
-        sm.freq[i] = e.count;
-        sm.bin[i] = (uint16_t)(e.sym + bias);
-        sm.heap[i] = ((uint64_t)e.count << 16) | (uint64_t)i;
+    // leaves into the heap array in first-occurrence order (the keys die here)
+    uint32_t my_freq[(N + THREADS - 1) / THREADS];
+#pragma unroll
+    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
+        const int i = threadIdx.x + r * THREADS;
+        my_freq[r] = i < n ? my[order[i]].count : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
+        const int i = threadIdx.x + r * THREADS;
+        if (i < n) slot[i + 1] = make_uint2((uint32_t)i, my_freq[r]);
     }
     __syncthreads();
     // (c) heapq replay (CPython Lib/heapq.py), comparisons on the frequency field only
@@ -577,65 +589,57 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
             s_root = -1;
         } else {
             int size = n;
-            uint64_t* heap = sm.heap;
-            auto lt = [](uint64_t a, uint64_t b) { return (a >> 16) < (b >> 16); };
-            auto siftdown = [&](int startpos, int pos) {
-                const uint64_t newitem = heap[pos];
+            // heapq._siftdown(heap, startpos, pos) with the item already in a register
+            auto siftdown = [&](int startpos, int pos, uint2 newitem) {
                 while (pos > startpos) {
                     const int parentpos = (pos - 1) >> 1;
-                    const uint64_t par = heap[parentpos];
-                    if (lt(newitem, par)) {
-                        heap[pos] = par;
+                    const uint2 par = slot[parentpos + 1];
+                    if (newitem.y < par.y) {
+                        slot[pos + 1] = par;
                         pos = parentpos;
                         continue;
                     }
                     break;
                 }
-                heap[pos] = newitem;
+                slot[pos + 1] = newitem;
             };
-            auto siftup = [&](int pos) {
+            // heapq._siftup(heap, pos): both children arrive in one 16-byte load
+            auto siftup = [&](int pos, uint2 newitem) {
                 const int endpos = size, startpos = pos;
-                const uint64_t newitem = heap[pos];
                 int childpos = 2 * pos + 1;
                 while (childpos < endpos) {
-                    const int rightpos = childpos + 1;
-                    uint64_t child = heap[childpos];
-                    if (rightpos < endpos) {
-                        const uint64_t right = heap[rightpos];
-                        if (!lt(child, right)) {
-                            child = right;
-                            childpos = rightpos;
-                        }
-                    }
-                    heap[pos] = child;
+                    const uint4 c = *reinterpret_cast<const uint4*>(&slot[childpos + 1]);
+                    const bool take_right = (childpos + 1 < endpos) && !(c.y < c.w);
+                    const uint2 child = take_right ? make_uint2(c.z, c.w) : make_uint2(c.x, c.y);
+                    childpos += take_right ? 1 : 0;
+                    slot[pos + 1] = child;
                     pos = childpos;
                     childpos = 2 * pos + 1;
                 }
-                heap[pos] = newitem;
-                siftdown(startpos, pos);
+                siftdown(startpos, pos, newitem);
             };
             auto pop = [&]() {
-                const uint64_t lastelt = heap[--size];
+                const uint2 lastelt = slot[size];          // heap[size - 1]
+                --size;
                 if (size > 0) {
-                    const uint64_t ret = heap[0];
-                    heap[0] = lastelt;
-                    siftup(0);
+                    const uint2 ret = slot[1];
+                    siftup(0, lastelt);
                     return ret;
                 }
                 return lastelt;
             };
-            for (int i = n / 2 - 1; i >= 0; --i) siftup(i);
+            for (int i = n / 2 - 1; i >= 0; --i) siftup(i, slot[i + 1]);
             int next = n;
             while (size > 1) {
-                const uint64_t l = pop();
-                const uint64_t r = pop();
-                sm.parent[(int)(l & 0xFFFF)] = (uint16_t)(next | 0x8000);
-                sm.parent[(int)(r & 0xFFFF)] = (uint16_t)next;
-                heap[size++] = (((l >> 16) + (r >> 16)) << 16) | (uint64_t)next;
-                siftdown(0, size - 1);
+                const uint2 l = pop();
+                const uint2 r = pop();
+                parent[l.x] = (uint16_t)(next | 0x8000);
+                parent[r.x] = (uint16_t)next;
+                ++size;
+                siftdown(0, size - 1, make_uint2((uint32_t)next, l.y + r.y));
                 ++next;
             }
-            s_root = (int)(heap[0] & 0xFFFF);
+            s_root = (int)slot[1].x;
         }
     }
     __syncthreads();
@@ -643,7 +647,10 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
     const int root = s_root;
     unsigned long long bits_sum = 0;
     uint32_t sym_sum = 0;
-    for (int i = threadIdx.x; i < n; i += THREADS) {
+#pragma unroll
+    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
+        const int i = threadIdx.x + r * THREADS;
+        if (i >= n) break;
         uint64_t code = 0;
         uint32_t len = 0;
         if (root < 0) {
@@ -652,7 +659,7 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
         } else {
             int node = i;
             while (node != root && len < 64) {
-                const uint32_t p = sm.parent[node];
+                const uint32_t p = parent[node];
                 code |= (uint64_t)(p >> 15) << len;
                 ++len;
                 node = (int)(p & 0x7FFF);
@@ -664,12 +671,12 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
             code &= (1ull << MAX_CODE_LEN) - 1;
         }
         const uint64_t packed = ((uint64_t)len << 58) | code;
-        const int b = sm.bin[i];
+        const int b = my[order[i]].sym + bias;
         row_sym[ix.offset + i] = b - bias;
         row_code[ix.offset + i] = packed;
         lut[(size_t)ss * g.nb_bins + b] = packed;
-        bits_sum += (unsigned long long)sm.freq[i] * len;
-        sym_sum += sm.freq[i];
+        bits_sum += (unsigned long long)my_freq[r] * len;
+        sym_sum += my_freq[r];
     }
     atomicAdd(&s_bits, bits_sum);
     atomicAdd(&s_nsym, sym_sum);
@@ -889,6 +896,11 @@ struct hic_entropy_plan {
     std::vector<uint64_t> t_code;
     uint64_t total_rows = 0, total_bytes = 0;
     bool codes_ready = false;
+    // fork/join plumbing of the device Huffman builder
+    static constexpr int N_AUX = 3;
+    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
 };
 
 static int fill_geom(const hic_stream_layout* L, int value_bins, Geom* g) {
@@ -962,6 +974,11 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
                     p->d_pay_totals};
     for (void* q : ptrs)
         if (q) cudaFree(q);
+    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
+        if (p->aux[a]) cudaStreamDestroy(p->aux[a]);
+        if (p->ev_join[a]) cudaEventDestroy(p->ev_join[a]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     return HIC_OK;
 }
@@ -1003,6 +1020,11 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_ptile_off, p->total_ptiles));
     ok(dalloc(&p->d_ss_byte_len, p->n_ss));
     ok(dalloc(&p->d_pay_totals, 2));
+    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
+        ok(cudaStreamCreateWithFlags(&p->aux[a], cudaStreamNonBlocking));
+        ok(cudaEventCreateWithFlags(&p->ev_join[a], cudaEventDisableTiming));
+    }
+    ok(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     if (e != cudaSuccess) {
         hic_entropy_plan_destroy(p);
         return hic::fail(HIC_ERR_CUDA, "entropy plan allocation failed: %s", cudaGetErrorString(e));
@@ -1242,20 +1264,30 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     int dev = 0;
     HIC_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<2048, 1024, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(BuildSmem<2048>)));
-        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<8192, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(BuildSmem<8192>)));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<4096, 2048, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      BuildLayout<4096>::BYTES));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<8192, 4096, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      BuildLayout<8192>::BYTES));
         if (dev < 64) attr_set[dev] = true;
     }
-#define HIC_BUILD_TIER(N, NLO, T, label)                                                                              \
-    HIC_LAUNCH(label, st, huffman_build_kernel<N, NLO, T><<<p->n_ss, T, sizeof(BuildSmem<N>), st>>>(                    \
+    // The replay is latency-bound (one dependent chain per stream), so the tiers run side by side on
+    // the plan's auxiliary streams: fork after the compaction, join before the payload layout.
+    HIC_CUDA(cudaEventRecord(p->ev_fork, st));
+    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
+#define HIC_BUILD_TIER(N, NLO, T, label, sx)                                                                          \
+    HIC_LAUNCH(label, sx, huffman_build_kernel<N, NLO, T><<<p->n_ss, T, BuildLayout<N>::BYTES, sx>>>(                   \
         g, p->d_entries, p->d_index, p->d_row_sym, p->d_row_code, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_err))
-    HIC_BUILD_TIER(256, 0, 64, "huffman_build_256_kernel");
-    HIC_BUILD_TIER(1024, 256, 128, "huffman_build_1024_kernel");
-    HIC_BUILD_TIER(2048, 1024, 128, "huffman_build_2048_kernel");
-    HIC_BUILD_TIER(8192, 2048, 256, "huffman_build_8192_kernel");
+    HIC_BUILD_TIER(2048, 1024, 64, "huffman_build_2048_kernel", st);
+    HIC_BUILD_TIER(1024, 512, 64, "huffman_build_1024_kernel", p->aux[0]);
+    HIC_BUILD_TIER(512, 256, 64, "huffman_build_512_kernel", p->aux[1]);
+    HIC_BUILD_TIER(256, 0, 32, "huffman_build_256_kernel", p->aux[2]);
+    HIC_BUILD_TIER(4096, 2048, 128, "huffman_build_4096_kernel", p->aux[1]);
+    HIC_BUILD_TIER(8192, 4096, 256, "huffman_build_8192_kernel", p->aux[2]);
 #undef HIC_BUILD_TIER
+    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
+        HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
+        HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
+    }
     HIC_LAUNCH("payload_layout_kernel", st, payload_layout_kernel<<<1, 1024, 0, st>>>(p->n_ss, p->d_ss_nsym, p->d_ss_nbits,
         p->d_ss_byte_off, p->d_ss_byte_len, p->d_pay_totals));
     unsigned long long totals[2] = {0, 0};
