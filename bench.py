@@ -325,7 +325,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = world * pixels / 1e6 / (ms_e2e / args.steps / 1e3)
-    table_bytes = int(enc_res.symbols.nbytes + enc_res.lens.nbytes + enc_res.codes.nbytes)
+    table_bytes = int(enc_res.symbols.nbytes + enc_res.packed.nbytes + enc_res.index.nbytes)
     h2d = int(host_rgb.nbytes + enc_res.data.nbytes + table_bytes)
     d2h = int(enc_res.data.nbytes + table_bytes + out.nbytes)
     parity = {"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),

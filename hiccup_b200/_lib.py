@@ -72,6 +72,7 @@ SIGNATURES = {
     "hic_entropy_stream_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "hic_entropy_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_tables_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_entropy_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hic_huffman_build_host": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p]),
     "hic_entropy_symbol_buffers": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "hic_decode_plan_create": (c_int, [ctypes.POINTER(StreamLayout), ctypes.POINTER(c_void_p)]),
     "hic_decode_plan_destroy": (c_int, [c_void_p]),
     "hic_decode_set_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_decode_set_tables_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_decode_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

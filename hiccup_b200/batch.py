@@ -42,6 +42,8 @@ class DctBatchCodec:
         # page-locked staging for the host-to-host entry points (grown on demand, reused every call)
         self._h_data = None
         self._h_out = None
+        self._h_tab = None
+        self._h_tab_mem = []
 
     # ---- sizes -------------------------------------------------------------------------------
     @property
@@ -90,14 +92,19 @@ class DctBatchCodec:
             self._h_data = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
         # the returned arrays view this codec's pinned staging: valid until the next encode()
         data = out.download(np.uint8, nbytes, self.stream, out=self._h_data.array(np.uint8, nbytes))
-        sym, lens, codes = enc.tables()
+        rows = int(enc.total_rows)
+        if self._h_tab is None or self._h_tab[1].size < rows:
+            cap = rows + rows // 4 + 1024
+            self._h_tab_mem = [_lib.PinnedBuffer(8 * enc.n_streams), _lib.PinnedBuffer(4 * cap), _lib.PinnedBuffer(8 * cap)]
+            self._h_tab = (self._h_tab_mem[0].array(np.uint32), self._h_tab_mem[1].array(np.int32),
+                           self._h_tab_mem[2].array(np.uint64))
+        index, sym, packed = enc.tables_packed(self.stream, out=self._h_tab)
         self.forward_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
-        return entropy.EncodedStreams(self.layout, enc.rows.copy(), enc.nsym.copy(), enc.nbits.copy(),
-                                      enc.byte_off.copy(), enc.byte_len.copy(), sym, lens, codes, data)
+        return entropy.EncodedStreams(self.layout, index, enc.nsym.copy(), enc.nbits.copy(),
+                                      enc.byte_off.copy(), enc.byte_len.copy(), sym, packed, data)
 
     def decode(self, enc):
-        self.decoder.decode(enc.rows, enc.symbols, enc.lens, enc.codes, enc.data, enc.byte_off, enc.nbits,
-                            self.d_coef_dec.ptr, self.stream)
+        self.decoder.decode_streams(enc, self.d_coef_dec.ptr, self.stream)
         _lib.check(self.lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
                                             self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks,
                                             self.d_stats.ptr, self.stream))
@@ -133,6 +140,7 @@ class DctBatchCodec:
         self.encoder.close()
         self.decoder.close()
         for b in (self.d_rgb, self.d_coef, self.d_coef_dec, self.d_ties, self.d_stats, self.d_y, self.d_cr, self.d_cb,
-                  self.d_out, self._h_data, self._h_out):
+                  self.d_out, self._h_data, self._h_out, *self._h_tab_mem):
             if b is not None:
                 b.free()
+        self._h_tab, self._h_tab_mem = None, []

@@ -676,6 +676,32 @@ int hic_decode_set_tables_device(hic_decode_plan* p, const void* d_index, const 
     return HIC_OK;
 }
 
+int hic_decode_set_tables_packed(hic_decode_plan* p, const uint32_t* h_index, const int32_t* h_row_sym,
+                                 const uint64_t* h_row_packed, uint64_t total, void* stream) {
+    HIC_REQUIRE(p && h_index && h_row_sym && h_row_packed, "NULL argument");
+    HIC_REQUIRE(total < (1ull << 32), "too many table rows");
+    cudaStream_t st = as_stream(stream);
+    for (int s = 0; s < p->n_ss; ++s)
+        HIC_REQUIRE((uint64_t)h_index[2 * s] + h_index[2 * s + 1] <= total, "stream %d: rows [%u, +%u) exceed %llu", s,
+                    h_index[2 * s], h_index[2 * s + 1], (unsigned long long)total);
+    if (total > p->row_capacity) {
+        if (p->d_row_sym_own) cudaFree(p->d_row_sym_own);
+        if (p->d_row_packed_own) cudaFree(p->d_row_packed_own);
+        p->d_row_sym_own = nullptr; p->d_row_packed_own = nullptr;
+        p->row_capacity = total + total / 4 + 1024;
+        HIC_CUDA(dalloc2(&p->d_row_sym_own, p->row_capacity));
+        HIC_CUDA(dalloc2(&p->d_row_packed_own, p->row_capacity));
+    }
+    static_assert(sizeof(RowIndex) == 2 * sizeof(uint32_t), "index layout");
+    HIC_CUDA(cudaMemcpyAsync(p->d_index_own, h_index, sizeof(RowIndex) * p->n_ss, cudaMemcpyHostToDevice, st));
+    if (total) {
+        HIC_CUDA(cudaMemcpyAsync(p->d_row_sym_own, h_row_sym, sizeof(int32_t) * total, cudaMemcpyHostToDevice, st));
+        HIC_CUDA(cudaMemcpyAsync(p->d_row_packed_own, h_row_packed, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
+    }
+    return hic_decode_set_tables_device(p, p->d_index_own, p->d_row_sym_own ? p->d_row_sym_own : (const int32_t*)p->d_index_own,
+                                        p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, stream);
+}
+
 int hic_decode_set_tables(hic_decode_plan* p, const uint32_t* h_rows, const int32_t* h_symbols, const uint8_t* h_lens,
                           const uint64_t* h_codes, void* stream) {
     HIC_REQUIRE(p && h_rows && h_symbols && h_lens && h_codes, "NULL argument");

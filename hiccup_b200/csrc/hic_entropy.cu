@@ -487,73 +487,58 @@ __global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// E2 on the device: the same heapq replay as csrc/hic_huffman.cuh, one CTA per symbol stream, all
-// state in shared memory.  (a) load the stream's compacted histogram entries, (b) bitonic sort by
-// first-occurrence index = the reference's leaf order, (c) one thread replays heapify / heappop /
-// heappush with frequency-only comparisons, (d) every leaf walks its parent chain to read off its
-// code (left = first popped = '1'), (e) rows, code lookup table and stream totals are written.
-// Two instantiations share the work by alphabet size so that small alphabets keep many CTAs per SM.
+// E2 on the device: the same heapq replay as csrc/hic_huffman.cuh, in three kernels.
+//   huffman_sort_kernel    one CTA per symbol stream: bitonic sort of the stream's compacted histogram
+//                          entries by first-occurrence index (= the reference's leaf order); writes the
+//                          leaf frequencies and the table's symbol column, and files the stream in a
+//                          size tier.
+//   huffman_replay_kernel  the serial part.  heapify / heappop / heappush with frequency-only
+//                          comparisons is one dependent chain per stream, so its throughput is set by
+//                          (streams resident per SM) / (latency of one heap level).  One LANE per
+//                          stream, every stream's heap in shared memory at 8 bytes per leaf: a warp
+//                          carries as many streams as fit in its shared-memory budget, lanes diverge
+//                          freely, and the issue slots are shared instead of one warp per stream.
+//                          Heap index i lives in slot i + 1, so the children 2p+1, 2p+2 of p are the
+//                          16-byte aligned slot pair (2p+2, 2p+3): one LDS.128 per level.
+//   huffman_codes_kernel   one CTA per stream: every leaf walks its parent chain to read off its code
+//                          (left = first popped = '1'); rows, code lookup table and stream totals.
+// Scratch: leaf frequencies reuse the first-occurrence array and parent links (uint16, bit 15 = "I am
+// my parent's left child") reuse the histogram array; both are dead once the entries are compacted.
 // ------------------------------------------------------------------------------------------------
-// Shared-memory footprint per stream is 14 bytes per leaf, so that one wave of CTAs covers a whole
-// batch (the replay is a serial dependent chain per stream: concurrency = streams resident per SM):
-//   slot[n + 2]   heap entries {node, freq} as uint2; heap index i lives in slot i + 1, which puts the
-//                 children 2p+1, 2p+2 of p in the 16-byte aligned slot pair (2p+2, 2p+3) -> one LDS.128
-//   parent[2n]    uint16, bit 15: this node is its parent's left child
-//   order[n]      entry index of leaf i (leaves sorted by first occurrence)
-// The sort keys (4 bytes per padded leaf) alias the heap slots, which are only filled after the sort.
-template <int N>
-struct BuildLayout {
-    static constexpr int HEAP_BYTES = 8 * (N + 2);
-    static constexpr int PARENT_OFF = HEAP_BYTES;
-    static constexpr int ORDER_OFF = PARENT_OFF + 2 * (2 * N);
-    static constexpr int BYTES = ORDER_OFF + 2 * N;
-};
+constexpr int N_TIERS = 21;
+__constant__ int c_tier_bound[N_TIERS] = {16, 32, 64, 128, 192, 256, 384, 512, 640, 768, 896,
+                                          1024, 1280, 1536, 1792, 2048, 2560, 3072, 4096, 6144, 8192};
+static const int h_tier_bound[N_TIERS] = {16, 32, 64, 128, 192, 256, 384, 512, 640, 768, 896,
+                                          1024, 1280, 1536, 1792, 2048, 2560, 3072, 4096, 6144, 8192};
+constexpr int SORT_THREADS = 256;
+constexpr int REPLAY_SMEM_BUDGET = 48 * 1024;
 
-// NLO < n <= N is handled by this instantiation
-template <int N, int NLO, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const CompactIndex* __restrict__ index,
-                     int32_t* __restrict__ row_sym, uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut,
-                     uint32_t* __restrict__ ss_nsym, uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t build_raw[];
-    uint2* slot = reinterpret_cast<uint2*>(build_raw);
-    uint32_t* key = reinterpret_cast<uint32_t*>(build_raw);                       // aliases slot (dead after the sort)
-    uint16_t* parent = reinterpret_cast<uint16_t*>(build_raw + BuildLayout<N>::PARENT_OFF);
-    uint16_t* order = reinterpret_cast<uint16_t*>(build_raw + BuildLayout<N>::ORDER_OFF);
-    __shared__ int s_root;
-    __shared__ unsigned long long s_bits;
-    __shared__ uint32_t s_nsym;
+__global__ void __launch_bounds__(SORT_THREADS)
+huffman_sort_kernel(Geom g, const CompactEntry* __restrict__ entries, const CompactIndex* __restrict__ index,
+                    uint32_t* __restrict__ leaf_freq, int32_t* __restrict__ row_sym, uint32_t* __restrict__ tier_count,
+                    uint32_t* __restrict__ tier_list, int n_ss, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t sort_raw[];
     const int ss = blockIdx.x;
     const CompactIndex ix = index[ss];
     const int n = (int)ix.count;
-    if (n == 0) {
-        if (NLO == 0 && threadIdx.x == 0) {
-            ss_nsym[ss] = 0;
-            ss_nbits[ss] = 0;
-        }
+    if (n == 0) return;
+    if (n > 8192) {
+        if (threadIdx.x == 0) atomicOr(err, 2u);
         return;
     }
-    if (n <= NLO || n > N) {
-        if (n > 8192 && NLO == 0 && threadIdx.x == 0) atomicOr(err, 2u);
-        return;
-    }
-    const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
-    const CompactEntry* my = entries + ix.offset;
     int P = 1;
     while (P < n) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += THREADS) {
+    uint32_t* key = reinterpret_cast<uint32_t*>(sort_raw);
+    uint16_t* order = reinterpret_cast<uint16_t*>(sort_raw + 4 * P);
+    const CompactEntry* my = entries + ix.offset;
+    for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
         key[i] = i < n ? my[i].first : 0xFFFFFFFFu;
         order[i] = (uint16_t)(i < n ? i : 0);
     }
-    if (threadIdx.x == 0) {
-        s_bits = 0;
-        s_nsym = 0;
-    }
     __syncthreads();
-    // (b) bitonic sort of (key, entry index) by key
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += THREADS) {
+            for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
                 const int l = i ^ j;
                 if (l > i) {
                     const bool up = (i & k) == 0;
@@ -569,97 +554,136 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
             }
             __syncthreads();
         }
-    // leaves into the heap array in first-occurrence order (the keys die here)
-    uint32_t my_freq[(N + THREADS - 1) / THREADS];
-#pragma unroll
-    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
-        const int i = threadIdx.x + r * THREADS;
-        my_freq[r] = i < n ? my[order[i]].count : 0u;
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+        const CompactEntry e = my[order[i]];
+        leaf_freq[ix.offset + i] = e.count;
+        row_sym[ix.offset + i] = e.sym;
     }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
-        const int i = threadIdx.x + r * THREADS;
-        if (i < n) slot[i + 1] = make_uint2((uint32_t)i, my_freq[r]);
+    if (threadIdx.x == 0 && n >= 2) {
+        int t = 0;
+        while (c_tier_bound[t] < n) ++t;
+        const uint32_t pos = atomicAdd(&tier_count[t], 1u);
+        tier_list[(size_t)t * n_ss + pos] = (uint32_t)ss;
     }
-    __syncthreads();
-    // (c) heapq replay (CPython Lib/heapq.py), comparisons on the frequency field only
-    if (threadIdx.x == 0) {
-        if (n == 1) {
-            s_root = -1;
-        } else {
-            int size = n;
-            // heapq._siftdown(heap, startpos, pos) with the item already in a register
-            auto siftdown = [&](int startpos, int pos, uint2 newitem) {
-                while (pos > startpos) {
-                    const int parentpos = (pos - 1) >> 1;
-                    const uint2 par = slot[parentpos + 1];
-                    if (newitem.y < par.y) {
-                        slot[pos + 1] = par;
-                        pos = parentpos;
-                        continue;
-                    }
-                    break;
-                }
-                slot[pos + 1] = newitem;
-            };
-            // heapq._siftup(heap, pos): both children arrive in one 16-byte load
-            auto siftup = [&](int pos, uint2 newitem) {
-                const int endpos = size, startpos = pos;
-                int childpos = 2 * pos + 1;
-                while (childpos < endpos) {
-                    const uint4 c = *reinterpret_cast<const uint4*>(&slot[childpos + 1]);
-                    const bool take_right = (childpos + 1 < endpos) && !(c.y < c.w);
-                    const uint2 child = take_right ? make_uint2(c.z, c.w) : make_uint2(c.x, c.y);
-                    childpos += take_right ? 1 : 0;
-                    slot[pos + 1] = child;
-                    pos = childpos;
-                    childpos = 2 * pos + 1;
-                }
-                siftdown(startpos, pos, newitem);
-            };
-            auto pop = [&]() {
-                const uint2 lastelt = slot[size];          // heap[size - 1]
-                --size;
-                if (size > 0) {
-                    const uint2 ret = slot[1];
-                    siftup(0, lastelt);
-                    return ret;
-                }
-                return lastelt;
-            };
-            for (int i = n / 2 - 1; i >= 0; --i) siftup(i, slot[i + 1]);
-            int next = n;
-            while (size > 1) {
-                const uint2 l = pop();
-                const uint2 r = pop();
-                parent[l.x] = (uint16_t)(next | 0x8000);
-                parent[r.x] = (uint16_t)next;
-                ++size;
-                siftdown(0, size - 1, make_uint2((uint32_t)next, l.y + r.y));
-                ++next;
-            }
-            s_root = (int)slot[1].x;
+}
+
+__global__ void __launch_bounds__(32)
+huffman_replay_kernel(int tier, int G, int stride_slots, int n_ss, const CompactIndex* __restrict__ index,
+                      const uint32_t* __restrict__ leaf_freq, const uint32_t* __restrict__ tier_count,
+                      const uint32_t* __restrict__ tier_list, uint16_t* __restrict__ parent) {
+    extern __shared__ __align__(16) uint8_t replay_raw[];
+    const uint32_t count = tier_count[tier];
+    const uint32_t first = blockIdx.x * (uint32_t)G;
+    if (first >= count) return;
+    const int lane = threadIdx.x;
+    const int mine = (int)min((uint32_t)G, count - first);
+    // this lane's stream
+    uint32_t my_off = 0;
+    int my_n = 0;
+    if (lane < mine) {
+        const CompactIndex ix = index[tier_list[(size_t)tier * n_ss + first + lane]];
+        my_off = ix.offset;
+        my_n = (int)ix.count;
+    }
+    // all lanes fill the heaps: leaves in first-occurrence order
+    for (int k = 0; k < mine; ++k) {
+        const uint32_t off = __shfl_sync(0xffffffffu, my_off, k);
+        const int n = __shfl_sync(0xffffffffu, my_n, k);
+        uint2* slot = reinterpret_cast<uint2*>(replay_raw) + (size_t)k * stride_slots;
+        for (int i = lane; i < n; i += 32) slot[i + 1] = make_uint2((uint32_t)i, leaf_freq[off + i]);
+    }
+    __syncwarp();
+    if (lane >= mine) return;
+    uint2* slot = reinterpret_cast<uint2*>(replay_raw) + (size_t)lane * stride_slots;
+    const uint4* slot_pair = reinterpret_cast<const uint4*>(slot);       // pair k = slots (2k, 2k+1)
+    uint16_t* par = parent + 2 * (size_t)my_off;
+    const int n = my_n;
+    int size = n;
+    // heapq._siftdown(heap, startpos, pos) with the item already in a register
+    auto siftdown = [&](int startpos, int pos, uint2 newitem) {
+        while (pos > startpos) {
+            const int parentpos = (pos - 1) >> 1;
+            const uint2 p = slot[parentpos + 1];
+            if (!(newitem.y < p.y)) break;
+            slot[pos + 1] = p;
+            pos = parentpos;
         }
+        slot[pos + 1] = newitem;
+    };
+    // heapq._siftup(heap, pos): the smaller child moves up until a leaf is reached, then the item
+    // bubbles back up (CPython's order of comparisons; ties go to the right child)
+    auto siftup = [&](int pos, uint2 newitem) {
+        const int endpos = size, startpos = pos;
+        int childpos = 2 * pos + 1;
+        while (childpos < endpos) {
+            const uint4 c = slot_pair[pos + 1];                       // slots 2 pos + 2, 2 pos + 3
+            const bool take_right = (childpos + 1 < endpos) && !(c.y < c.w);
+            slot[pos + 1] = take_right ? make_uint2(c.z, c.w) : make_uint2(c.x, c.y);
+            pos = childpos + (take_right ? 1 : 0);
+            childpos = 2 * pos + 1;
+        }
+        siftdown(startpos, pos, newitem);
+    };
+    auto pop = [&]() {
+        const uint2 lastelt = slot[size];          // heap[size - 1]
+        --size;
+        if (size > 0) {
+            const uint2 ret = slot[1];
+            siftup(0, lastelt);
+            return ret;
+        }
+        return lastelt;
+    };
+    for (int i = n / 2 - 1; i >= 0; --i) siftup(i, slot[i + 1]);     // heapq.heapify
+    int next = n;
+    while (size > 1) {
+        const uint2 l = pop();
+        const uint2 r = pop();
+        par[l.x] = (uint16_t)(next | 0x8000);
+        par[r.x] = (uint16_t)next;
+        ++size;
+        siftdown(0, size - 1, make_uint2((uint32_t)next, l.y + r.y));      // heapq.heappush
+        ++next;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+huffman_codes_kernel(Geom g, const CompactIndex* __restrict__ index, const uint32_t* __restrict__ leaf_freq,
+                     const uint16_t* __restrict__ parent, const int32_t* __restrict__ row_sym,
+                     uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut, uint32_t* __restrict__ ss_nsym,
+                     uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
+    __shared__ unsigned long long s_bits;
+    __shared__ uint32_t s_nsym;
+    const int ss = blockIdx.x;
+    const CompactIndex ix = index[ss];
+    const int n = (int)ix.count;
+    if (n == 0 || n > 8192) {
+        if (threadIdx.x == 0) {
+            ss_nsym[ss] = 0;
+            ss_nbits[ss] = 0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_bits = 0;
+        s_nsym = 0;
     }
     __syncthreads();
-    // (d, e) codes, rows, lookup table, totals
-    const int root = s_root;
+    const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
+    const uint16_t* par = parent + 2 * (size_t)ix.offset;
+    const int root = 2 * n - 2;                    // the last node created (a single leaf has no tree)
     unsigned long long bits_sum = 0;
     uint32_t sym_sum = 0;
-#pragma unroll
-    for (int r = 0; r < (N + THREADS - 1) / THREADS; ++r) {
-        const int i = threadIdx.x + r * THREADS;
-        if (i >= n) break;
+    for (int i = threadIdx.x; i < n; i += 128) {
         uint64_t code = 0;
         uint32_t len = 0;
-        if (root < 0) {
-            code = 1;
+        if (n == 1) {
+            code = 1;                              // huffman.py:66-67,181-182: the lone leaf hangs on the left
             len = 1;
         } else {
             int node = i;
             while (node != root && len < 64) {
-                const uint32_t p = parent[node];
+                const uint32_t p = par[node];
                 code |= (uint64_t)(p >> 15) << len;
                 ++len;
                 node = (int)(p & 0x7FFF);
@@ -671,12 +695,11 @@ huffman_build_kernel(Geom g, const CompactEntry* __restrict__ entries, const Com
             code &= (1ull << MAX_CODE_LEN) - 1;
         }
         const uint64_t packed = ((uint64_t)len << 58) | code;
-        const int b = my[order[i]].sym + bias;
-        row_sym[ix.offset + i] = b - bias;
+        const uint32_t f = leaf_freq[ix.offset + i];
         row_code[ix.offset + i] = packed;
-        lut[(size_t)ss * g.nb_bins + b] = packed;
-        bits_sum += (unsigned long long)my_freq[r] * len;
-        sym_sum += my_freq[r];
+        lut[(size_t)ss * g.nb_bins + row_sym[ix.offset + i] + bias] = packed;
+        bits_sum += (unsigned long long)f * len;
+        sym_sum += f;
     }
     atomicAdd(&s_bits, bits_sum);
     atomicAdd(&s_nsym, sym_sum);
@@ -885,6 +908,8 @@ struct hic_entropy_plan {
     uint64_t* d_ptile_off = nullptr;
     uint64_t* d_ss_byte_len = nullptr;
     unsigned long long* d_pay_totals = nullptr; // [0] total payload bytes
+    uint32_t* d_tier_count = nullptr;           // device Huffman builder: streams per size tier
+    uint32_t* d_tier_list = nullptr;            // [tier][n_ss] stream ids
     bool device_built = false;                  // codes came from hic_entropy_build_codes_device
     bool host_info_valid = false;               // rows/nsym/nbits/byte_off/byte_len mirror the device
     bool host_tables_valid = false;
@@ -971,7 +996,7 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
                     p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
-                    p->d_pay_totals};
+                    p->d_pay_totals, p->d_tier_count, p->d_tier_list};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
@@ -1020,6 +1045,8 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_ptile_off, p->total_ptiles));
     ok(dalloc(&p->d_ss_byte_len, p->n_ss));
     ok(dalloc(&p->d_pay_totals, 2));
+    ok(dalloc(&p->d_tier_count, N_TIERS));
+    ok(dalloc(&p->d_tier_list, (size_t)N_TIERS * p->n_ss));
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
         ok(cudaStreamCreateWithFlags(&p->aux[a], cudaStreamNonBlocking));
         ok(cudaEventCreateWithFlags(&p->ev_join[a], cudaEventDisableTiming));
@@ -1263,31 +1290,35 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     static bool attr_set[64] = {false};
     int dev = 0;
     HIC_CUDA(cudaGetDevice(&dev));
+    const int max_stride = 8 * (h_tier_bound[N_TIERS - 1] + 2);
     if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<4096, 2048, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      BuildLayout<4096>::BYTES));
-        HIC_CUDA(cudaFuncSetAttribute(huffman_build_kernel<8192, 4096, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      BuildLayout<8192>::BYTES));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
         if (dev < 64) attr_set[dev] = true;
     }
-    // The replay is latency-bound (one dependent chain per stream), so the tiers run side by side on
-    // the plan's auxiliary streams: fork after the compaction, join before the payload layout.
+    uint32_t* leaf_freq = p->d_first;                                    // dead after the compaction
+    uint16_t* parent = reinterpret_cast<uint16_t*>(p->d_hist);           // likewise (2 links per entry = 4 bytes)
+    HIC_CUDA(cudaMemsetAsync(p->d_tier_count, 0, N_TIERS * sizeof(uint32_t), st));
+    HIC_LAUNCH("huffman_sort_kernel", st, huffman_sort_kernel<<<p->n_ss, SORT_THREADS, 6 * 8192, st>>>(
+        g, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
+    // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams:
+    // fork after the sort, join before the code read-out.
     HIC_CUDA(cudaEventRecord(p->ev_fork, st));
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
-#define HIC_BUILD_TIER(N, NLO, T, label, sx)                                                                          \
-    HIC_LAUNCH(label, sx, huffman_build_kernel<N, NLO, T><<<p->n_ss, T, BuildLayout<N>::BYTES, sx>>>(                   \
-        g, p->d_entries, p->d_index, p->d_row_sym, p->d_row_code, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_err))
-    HIC_BUILD_TIER(2048, 1024, 64, "huffman_build_2048_kernel", st);
-    HIC_BUILD_TIER(1024, 512, 64, "huffman_build_1024_kernel", p->aux[0]);
-    HIC_BUILD_TIER(512, 256, 64, "huffman_build_512_kernel", p->aux[1]);
-    HIC_BUILD_TIER(256, 0, 32, "huffman_build_256_kernel", p->aux[2]);
-    HIC_BUILD_TIER(4096, 2048, 128, "huffman_build_4096_kernel", p->aux[1]);
-    HIC_BUILD_TIER(8192, 4096, 256, "huffman_build_8192_kernel", p->aux[2]);
-#undef HIC_BUILD_TIER
+    for (int t = N_TIERS - 1; t >= 0; --t) {                             // longest chains first
+        const int stride_slots = h_tier_bound[t] + 2;
+        const int stride = 8 * stride_slots;
+        const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
+        const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
+        cudaStream_t sx = (t % (hic_entropy_plan::N_AUX + 1)) == 0 ? st : p->aux[(t % (hic_entropy_plan::N_AUX + 1)) - 1];
+        HIC_LAUNCH("huffman_replay_kernel", sx, huffman_replay_kernel<<<grid, 32, (size_t)G * stride, sx>>>(
+            t, G, stride_slots, p->n_ss, p->d_index, leaf_freq, p->d_tier_count, p->d_tier_list, parent));
+    }
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
         HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
         HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
     }
+    HIC_LAUNCH("huffman_codes_kernel", st, huffman_codes_kernel<<<p->n_ss, 128, 0, st>>>(
+        g, p->d_index, leaf_freq, parent, p->d_row_sym, p->d_row_code, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_err));
     HIC_LAUNCH("payload_layout_kernel", st, payload_layout_kernel<<<1, 1024, 0, st>>>(p->n_ss, p->d_ss_nsym, p->d_ss_nbits,
         p->d_ss_byte_off, p->d_ss_byte_len, p->d_pay_totals));
     unsigned long long totals[2] = {0, 0};
@@ -1339,6 +1370,20 @@ int hic_entropy_tables(hic_entropy_plan* p, int32_t* h_symbols, uint8_t* h_lens,
         if (h_symbols) h_symbols[i] = p->t_sym[i];
         if (h_lens) h_lens[i] = p->t_len[i];
         if (h_codes) h_codes[i] = p->t_code[i];
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_tables_packed(hic_entropy_plan* p, uint32_t* h_index, int32_t* h_row_sym, uint64_t* h_row_packed,
+                              void* stream) {
+    HIC_REQUIRE(p && h_index && h_row_sym && h_row_packed, "NULL argument");
+    HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
+    cudaStream_t st = as_stream(stream);
+    static_assert(sizeof(CompactIndex) == 2 * sizeof(uint32_t), "index layout");
+    HIC_CUDA(cudaMemcpyAsync(h_index, p->d_index, sizeof(CompactIndex) * p->n_ss, cudaMemcpyDeviceToHost, st));
+    if (p->total_rows) {
+        HIC_CUDA(cudaMemcpyAsync(h_row_sym, p->d_row_sym, sizeof(int32_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
+        HIC_CUDA(cudaMemcpyAsync(h_row_packed, p->d_row_code, sizeof(uint64_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
     }
     return HIC_OK;
 }

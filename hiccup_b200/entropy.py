@@ -14,22 +14,52 @@ KIND_DC, KIND_VALUE, KIND_LENGTH = 0, 1, 2
 DEFAULT_VALUE_BINS = 8192
 
 
-class EncodedStreams:
-    """Host-side result of the entropy encoder for a batch: code tables and framed bit payloads."""
+CODE_MASK = np.uint64((1 << 58) - 1)
 
-    def __init__(self, layout, rows, nsym, nbits, byte_off, byte_len, symbols, lens, codes, data):
+
+class EncodedStreams:
+    """Host-side result of the entropy encoder for a batch: code tables and framed bit payloads.
+
+    Tables are kept in the packed layout of hic_entropy_tables_packed: `index[s] = (first row, rows)`
+    of symbol stream s, `symbols[r]`, `packed[r] = length << 58 | code bits`; a stream's rows are
+    contiguous and in first-occurrence order."""
+
+    def __init__(self, layout, index, nsym, nbits, byte_off, byte_len, symbols, packed, data):
         self.layout = layout
-        self.rows, self.nsym, self.nbits = rows, nsym, nbits
+        self.index = np.asarray(index, np.uint32).reshape(-1, 2)
+        self.nsym, self.nbits = nsym, nbits
         self.byte_off, self.byte_len = byte_off, byte_len
-        self.symbols, self.lens, self.codes = symbols, lens, codes
+        self.symbols, self.packed = symbols, packed
         self.data = data                                   # uint8, all framed payloads, 4-byte aligned each
-        self.row_off = np.concatenate(([0], np.cumsum(rows, dtype=np.int64)))
+
+    @classmethod
+    def from_tables(cls, layout, rows, nsym, nbits, byte_off, byte_len, symbols, lens, codes, data):
+        """From per-stream row counts and concatenated (symbol, length, code) arrays in stream order."""
+        rows = np.asarray(rows, np.uint32)
+        start = np.concatenate(([0], np.cumsum(rows, dtype=np.uint64)[:-1])).astype(np.uint32)
+        packed = (np.asarray(lens, np.uint64) << np.uint64(58)) | (np.asarray(codes, np.uint64) & CODE_MASK)
+        return cls(layout, np.stack([start, rows], axis=1), nsym, nbits, byte_off, byte_len,
+                   np.asarray(symbols, np.int32), packed, data)
+
+    @property
+    def rows(self):
+        return self.index[:, 1]
+
+    @property
+    def total_rows(self):
+        return int(self.index[:, 1].sum(dtype=np.uint64))
+
+    def stream_rows(self, s):
+        """(symbols, lengths, codes) of symbol stream s in first-occurrence order."""
+        a = int(self.index[s, 0])
+        b = a + int(self.index[s, 1])
+        pk = self.packed[a:b]
+        return self.symbols[a:b], (pk >> np.uint64(58)).astype(np.uint8), pk & CODE_MASK
 
     def table(self, s):
         """[(symbol, code string)] of symbol stream s in first-occurrence order."""
-        a, b = int(self.row_off[s]), int(self.row_off[s + 1])
-        return [(int(sym), format(int(code), "0%db" % int(ln)))
-                for sym, ln, code in zip(self.symbols[a:b], self.lens[a:b], self.codes[a:b])]
+        sym, lens, codes = self.stream_rows(s)
+        return [(int(v), format(int(code), "0%db" % int(ln))) for v, ln, code in zip(sym, lens, codes)]
 
     def framed(self, s):
         """The framed bytes of symbol stream s (what iohelper.padded_bs_2_bytes returns)."""
@@ -94,6 +124,19 @@ class EntropyEncoder:
         _lib.check(self.lib.hic_entropy_tables(self.plan, sym.ctypes.data, lens.ctypes.data, codes.ctypes.data))
         return sym, lens, codes
 
+    def tables_packed(self, stream=None, out=None):
+        """(index, symbols, packed) as EncodedStreams wants them.  `out`: preallocated (pinned) arrays
+        (index uint32[2 n_streams], symbols int32[>= total_rows], packed uint64[>= total_rows]).
+        Synchronises `stream`."""
+        n = int(self.total_rows)
+        if out is None:
+            out = (np.empty(2 * self.n_streams, np.uint32), np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.uint64))
+        index, sym, packed = out
+        assert index.size >= 2 * self.n_streams and sym.size >= n and packed.size >= n
+        _lib.check(self.lib.hic_entropy_tables_packed(self.plan, index.ctypes.data, sym.ctypes.data, packed.ctypes.data, stream))
+        _lib.sync(stream)
+        return index[:2 * self.n_streams].reshape(-1, 2), sym[:n], packed[:n]
+
     def pack(self, stream=None):
         """Returns the device buffer holding all framed payloads (valid until the next pack)."""
         need = int(self.total_bytes) + 16
@@ -119,9 +162,8 @@ class EntropyEncoder:
             _lib.sync(stream)
             return None
         data = out.download(np.uint8, int(self.total_bytes), stream)
-        sym, lens, codes = self.tables()
-        return EncodedStreams(self.layout, self.rows, self.nsym, self.nbits, self.byte_off, self.byte_len,
-                              sym, lens, codes, data)
+        index, sym, packed = self.tables_packed(stream)
+        return EncodedStreams(self.layout, index, self.nsym, self.nbits, self.byte_off, self.byte_len, sym, packed, data)
 
     def symbol_arrays(self, stream=None):
         """Download DC differences and run-length symbols (tests / band stitching)."""
@@ -172,6 +214,23 @@ class EntropyDecoder:
         byte_off = np.ascontiguousarray(byte_off, np.uint64)
         nbits = np.ascontiguousarray(nbits, np.uint64)
         _lib.check(self.lib.hic_decode_run(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, d_coef, stream))
+
+    def decode_streams(self, enc, d_coef, stream=None):
+        """Decode an EncodedStreams (packed tables; no per-row host work)."""
+        index = np.ascontiguousarray(enc.index, np.uint32)
+        symbols = np.ascontiguousarray(enc.symbols, np.int32)
+        packed = np.ascontiguousarray(enc.packed, np.uint64)
+        total = int(symbols.size)
+        _lib.check(self.lib.hic_decode_set_tables_packed(self.plan, index.ctypes.data, symbols.ctypes.data,
+                                                         packed.ctypes.data, total, stream))
+        data = np.ascontiguousarray(enc.data, np.uint8)
+        need = data.nbytes + 16
+        if self._in is None or self._in.nbytes < need:
+            if self._in is not None:
+                self._in.free()
+            self._in = _lib.DeviceBuffer(need + need // 4)
+        self._in.upload(data, stream)
+        self.run(self._in.ptr, enc.byte_off, enc.nbits, d_coef, stream)      # synchronises: host arrays may go
 
     def decode(self, rows, symbols, lens, codes, data, byte_off, nbits, d_coef, stream=None, d_data=None):
         """rows/symbols/lens/codes: concatenated code tables; data: uint8 host array holding every

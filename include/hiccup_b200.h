@@ -176,6 +176,15 @@ int hic_entropy_stream_info(hic_entropy_plan* plan, uint32_t* h_rows, uint32_t* 
  * (right aligned; first bit of the code string = most significant; '1' = left = first popped). */
 int hic_entropy_tables(hic_entropy_plan* plan, int32_t* h_symbols, uint8_t* h_lens, uint64_t* h_codes);
 
+/* The same tables without any host-side reshaping, for the batched path: the rows exactly as they
+ * sit on the device (each stream's rows contiguous and in first-occurrence order, streams in no
+ * particular order), rows packed as (length << 58 | code bits), and h_index[2 s], h_index[2 s + 1] =
+ * first row and row count of stream s.  Asynchronous device-to-host copies on `stream` into the
+ * caller's (ideally pinned) arrays of hic_entropy_stream_info's total_rows entries; synchronise
+ * `stream` before reading them. */
+int hic_entropy_tables_packed(hic_entropy_plan* plan, uint32_t* h_index, int32_t* h_row_sym, uint64_t* h_row_packed,
+                              void* stream);
+
 /* E3 (device) -- concatenate the codes of every symbol stream (HuffmanTree.encode_data,
  * huffman.py:131-142) and frame them as iohelper.padded_bs_2_bytes does (iohelper.py:35-48):
  * byte 0 = p = 8 - (nbits mod 8), then the bits MSB first, then p zero bits.  d_out must hold
@@ -207,6 +216,10 @@ int hic_decode_plan_destroy(hic_decode_plan* plan);
  * HuffmanTree.construct_from_coding (huffman.py:30-58). */
 int hic_decode_set_tables(hic_decode_plan* plan, const uint32_t* h_rows, const int32_t* h_symbols,
                           const uint8_t* h_lens, const uint64_t* h_codes, void* stream);
+/* The same from the packed host layout of hic_entropy_tables_packed.  Asynchronous: the host arrays
+ * must stay valid until `stream` has been synchronised. */
+int hic_decode_set_tables_packed(hic_decode_plan* plan, const uint32_t* h_index, const int32_t* h_row_sym,
+                                 const uint64_t* h_row_packed, uint64_t total_rows, void* stream);
 /* The same from device-resident tables (hic_entropy_device_tables); the arrays are referenced, not
  * copied, and must stay valid until decoding is done.  Asynchronous. */
 int hic_decode_set_tables_device(hic_decode_plan* plan, const void* d_index, const int32_t* d_row_sym,
