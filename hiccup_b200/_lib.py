@@ -34,6 +34,11 @@ class Geometry(ctypes.Structure):
                 ("out_h", c_int32), ("out_w", c_int32)]
 
 
+class WaveletGeometry(ctypes.Structure):
+    _fields_ = [("h", c_int32), ("w", c_int32), ("lh", c_int32 * 4), ("lw", c_int32 * 4),
+                ("band_off", ctypes.c_int64 * 10), ("len", ctypes.c_int64)]
+
+
 #: every symbol include/hiccup_b200.h declares -> (restype, argtypes)
 SIGNATURES = {
     "hic_version": (c_int, []),
@@ -59,6 +64,11 @@ SIGNATURES = {
     "hic_planes_to_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hic_dct_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_uint32, c_void_p, c_void_p]),
+    "hic_wavelet_geometry_of": (c_int, [c_int32, c_int32, ctypes.POINTER(WaveletGeometry)]),
+    "hic_wavelet_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_wavelet_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_wavelet_flat_to_bands": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_wavelet_bands_to_flat": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hic_layout_dct": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(StreamLayout)]),
     "hic_layout_flat": (c_int, [c_int32, ctypes.c_int64, ctypes.POINTER(StreamLayout)]),
     "hic_entropy_plan_create": (c_int, [ctypes.POINTER(StreamLayout), c_int32, ctypes.POINTER(c_void_p)]),
@@ -202,6 +212,12 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def wavelet_geometry(h, w):
+    g = WaveletGeometry()
+    check(load().hic_wavelet_geometry_of(int(h), int(w), ctypes.byref(g)))
+    return g
 
 
 def layout_dct(n, h, w):

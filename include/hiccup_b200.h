@@ -119,6 +119,35 @@ int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint
                     uint8_t* d_cr, uint8_t* d_cb, uint8_t* d_rgb_out, hic_tie_record* d_ties,
                     uint32_t tie_capacity, uint32_t* d_stats, void* stream);
 
+/* ---- wavelet ("HIC") mode --------------------------------------------------------------------- */
+/* Sub-band geometry of pywt.wavedec2(channel, "db1", level=3) (transform.py:196-209): level sizes
+ * ceil(n / 2) per level; ten sub-bands per channel in the order [cA3, cH3, cV3, cD3, cH2, cV2, cD2,
+ * cH1, cV1, cD1]; band_off[b] = first element of band b in the channel's concatenated stream. */
+typedef struct hic_wavelet_geometry {
+    int32_t h, w;
+    int32_t lh[4], lw[4];     /* [0] = image, [l] = sub-band shape at level l */
+    int64_t band_off[10];
+    int64_t len;              /* coefficients per channel */
+} hic_wavelet_geometry;
+int hic_wavelet_geometry_of(int32_t h, int32_t w, hic_wavelet_geometry* out);
+
+/* K9 -- fused wavelet encode transform.  Replaces compression.wavelet_compression
+ * (compression.py:59-85: cvtColor, x - 256, pywt.wavedec2 db1 level 3, subband_quantize
+ * (quantization.py:60-69: cA rounded, detail level i = 0 (coarsest) .. 2 divided by i*i + 1, np.round),
+ * threshold |v| < 5 -> 0 (transform.py:227-239)) plus the zigzag of every whole sub-band and their
+ * concatenation (codec.wavelet_encode, codec.py:123-126).  float64, PyWavelets' operation order.
+ * d_flat: the flat-mode stream of hic_layout_flat(n, geometry.len): channel stream (image, c) starts at
+ * element 64 * ceil(len / 64) * (3 image + c). */
+int hic_wavelet_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16_t* d_flat, void* stream);
+/* K10 -- fused wavelet decode transform.  Replaces codec.wavelet_decode_pull_subbands (codec.py:166-179)
+ * and compression.wavelet_decompression (compression.py:88-100).  h and w must be multiples of 8 (the
+ * reference's decoder assumes exact doubling between levels, codec.py:182-189). */
+int hic_wavelet_inverse(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, uint8_t* d_rgb_out, void* stream);
+/* Flat stream <-> the reference's CompressedImage sub-bands (model.py:38-74): per image and channel the
+ * ten raster int32 sub-bands concatenated in band order (geometry.len values). */
+int hic_wavelet_flat_to_bands(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, int32_t* d_bands, void* stream);
+int hic_wavelet_bands_to_flat(const int32_t* d_bands, int32_t n, int32_t h, int32_t w, int16_t* d_flat, void* stream);
+
 /* ---- entropy stage ---------------------------------------------------------------------------- */
 /* A batch is 3 n "channel streams" (image i, channel c in lum, cr, cb).  Each channel stream is a
  * run of 64-element int16 blocks.  DCT mode (skip_first = 1): element 0 of every block is its DC
