@@ -121,51 +121,88 @@ def pinned_array(lib_mod, shape, dtype=np.uint8):
     return arr, p
 
 
-def kernel_bytes(name, P, B, s_ac, bits_bytes):
+def kernel_bytes(name, P, B, s_ac, bits_bytes, rows, n_ss, bins, mode):
     """Algorithmic bytes one launch of `name` moves: P pixels, B 64-element
-    blocks, s_ac run-length symbols, bits_bytes Huffman-coded payload bytes."""
+    blocks, s_ac run-length symbols, bits_bytes Huffman-coded payload bytes, rows code-table rows,
+    n_ss symbol streams, bins histogram bins per stream."""
     coef = 128.0 * B
-    sym = 3.0 * s_ac + 2.0 * B
+    n_dc = B if mode == "dct" else 0.0
+    sym = 3.0 * s_ac + 2.0 * n_dc
     table = {
-        "forward_kernel": 6.0 * P,
+        "forward_kernel": 6.0 * P,                      # 3 B/pixel RGB in, 1.5 samples x int16 out
+        "wavelet_forward_kernel": 9.0 * P,              # 3 B/pixel in, 3 samples x int16 out
+        "wavelet_inverse_kernel": 9.0 * P,
         "rle_tile_summary_kernel": coef,
         "rle_emit_kernel": coef + sym,
+        "compact_kernel": 8.0 * n_ss * bins + 12.0 * rows,
+        "huffman_sort_kernel": 20.0 * rows,
+        "huffman_replay_kernel": 8.0 * rows / 21.0,     # 21 tier launches share the rows
+        "huffman_codes_kernel": 28.0 * rows,
         "pack_tile_bits_kernel": sym,
         "pack_emit_kernel": sym + bits_bytes,
-        "huffman_decode_kernel": bits_bytes + sym,
+        "build_tables_kernel": 12.0 * rows + 32768.0 * n_ss,
+        "huffman_sync_kernel": bits_bytes,
+        "huffman_resync_kernel": bits_bytes,
+        "huffman_write_kernel": bits_bytes + sym,
         "expand_tile_sum_kernel": 1.0 * s_ac,
         "expand_scatter_kernel": 3.0 * s_ac + 2.0 * s_ac,
-        "dc_tile_sum_kernel": 2.0 * B,
-        "dc_write_kernel": 4.0 * B,
+        "dc_tile_sum_kernel": 2.0 * n_dc,
+        "dc_write_kernel": 4.0 * n_dc,
         "inverse_kernel": coef + 1.5 * P,
         "upsample_colour_kernel": 4.5 * P,
     }
     return table.get(name)
 
 
-def cpu_baseline_sample(h, w, n_images, seed0):
-    """The oracle port (numpy restatement of the reference) on one host core."""
+CONFIGS = {
+    # BASELINE.json configs[1..3]; c5 (16384^2 band-sharded over 8 GPUs) is bench_bands.py
+    "c2": dict(mode="dct", images=1024, height=426, width=640, label="batch of %d synthetic 640x426 RGB images per GPU, DCT mode encode+decode"),
+    "c3": dict(mode="dct", images=256, height=2160, width=3840, label="batch of %d synthetic 4K (3840x2160) RGB images per GPU, DCT + Huffman encode+decode"),
+    "c4": dict(mode="wavelet", images=1, height=4320, width=7680, label="%d synthetic 8K (7680x4320) RGB image per GPU, wavelet mode encode+decode"),
+}
+
+
+def _oracle_round_trip(rgb, mode):
     from oracle import hiccup_oracle as orc
+    if mode == "dct":
+        return orc.jpeg_decompression(orc.jpeg_decode(orc.jpeg_encode(orc.jpeg_compression(rgb))))
+    return orc.wavelet_decompression(orc.wavelet_decode(orc.wavelet_encode(orc.wavelet_compression(rgb))))
+
+
+def cpu_baseline_sample(h, w, n_images, seed0, mode):
+    """The oracle port (numpy restatement of the reference) on one host core."""
     imgs = [synthetic_image(h, w, seed0 + i) for i in range(n_images)]
     t0 = time.perf_counter()
     for rgb in imgs:
-        planes = orc.jpeg_compression(rgb)
-        enc = orc.jpeg_encode(planes)
-        dec = orc.jpeg_decode(enc)
-        orc.jpeg_decompression(dec)
+        _oracle_round_trip(rgb, mode)
     dt = time.perf_counter() - t0
     return n_images * h * w / 1e6 / dt, dt
 
 
 def _ref_worker(args):
-    h, w, seed = args
-    from oracle import hiccup_oracle as orc
-    rgb = synthetic_image(h, w, seed)
-    planes = orc.jpeg_compression(rgb)
-    enc = orc.jpeg_encode(planes)
-    dec = orc.jpeg_decode(enc)
-    out = orc.jpeg_decompression(dec)
+    h, w, seed, mode = args
+    out = _oracle_round_trip(synthetic_image(h, w, seed), mode)
     return int(out[0, 0, 0])
+
+
+def resolve_config(args):
+    cfg = dict(CONFIGS[args.config])
+    for key in ("images", "height", "width", "mode"):
+        if getattr(args, key) is not None:
+            cfg[key] = getattr(args, key)
+    cfg["workload"] = cfg["label"] % cfg["images"] if "%d" in cfg["label"] else cfg["label"]
+    if any(getattr(args, k) is not None for k in ("images", "height", "width", "mode")):
+        cfg["workload"] = "%d synthetic %dx%d RGB image(s) per GPU, %s mode encode+decode" % (
+            cfg["images"], cfg["width"], cfg["height"], cfg["mode"])
+    return cfg
+
+
+def cpu_sample_shape(h, w):
+    """A bounded CPU sample: whole images up to ~1 MP, else a 1024x1024 corner crop (multiple of 16)."""
+    if h * w <= (1 << 20):
+        return h, w, "whole %dx%d images" % (w, h)
+    ch, cw = min(h, 1024), min(w, 1024)
+    return ch, cw, "%dx%d corner crops of the %dx%d images" % (cw, ch, w, h)
 
 
 def run_reference(args):
@@ -174,26 +211,25 @@ def run_reference(args):
     if rank != 0:
         return 0
     import multiprocessing as mp
+    cfg = resolve_config(args)
     cores = os.cpu_count() or 1
     per_step = max(cores, 8)
-    h, w = args.height, args.width
+    h, w, what = cpu_sample_shape(cfg["height"], cfg["width"])
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for i in range(args.warmup):
-            pool.map(_ref_worker, [(h, w, 5000 + i * per_step + j) for j in range(per_step)])
+            pool.map(_ref_worker, [(h, w, 5000 + i * per_step + j, cfg["mode"]) for j in range(per_step)])
         t0 = time.perf_counter()
         for i in range(args.steps):
-            pool.map(_ref_worker, [(h, w, 9000 + i * per_step + j) for j in range(per_step)])
+            pool.map(_ref_worker, [(h, w, 9000 + i * per_step + j, cfg["mode"]) for j in range(per_step)])
         dt = time.perf_counter() - t0
     value = args.steps * per_step * h * w / 1e6 / dt
-    sample = "%d synthetic %dx%d images per step (of the %d-image batch), oracle port, one process per core" % (
-        per_step, w, h, args.images)
+    sample = "%d per step, %s, oracle port (numpy restatement of the reference), one process per core" % (per_step, what)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batch of %d synthetic %dx%d RGB images, DCT mode encode+decode" % (args.images, w, h),
-                   "sample": sample},
+        "config": {"workload": cfg["workload"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -208,15 +244,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=1024)
-    ap.add_argument("--height", type=int, default=426)
-    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default=None, choices=["dct", "wavelet"])
+    ap.add_argument("--images", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    cfg = resolve_config(args)
+    mode = cfg["mode"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,12 +270,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from hiccup_b200 import _lib
-    from hiccup_b200.batch import DctBatchCodec
+    from hiccup_b200.batch import DctBatchCodec, WaveletBatchCodec
     _lib.check(_lib.load().hic_set_device(local_rank))
-    n, h, w = args.images, args.height, args.width
-    codec = DctBatchCodec(n, h, w, stream=None)
+    n, h, w = cfg["images"], cfg["height"], cfg["width"]
+    codec = (DctBatchCodec if mode == "dct" else WaveletBatchCodec)(n, h, w, stream=None)
     host_rgb, _keep_in = pinned_array(_lib, (n, h, w, 3))
-    synthetic_batch(n, h, w, 1000 * 2 + rank * n, out=host_rgb)
+    distinct = n if n * h * w <= 300e6 else min(n, 16)       # big batches repeat a few distinct images
+    synthetic_batch(distinct, h, w, 1000 * 2 + rank * n, out=host_rgb[:distinct])
+    for i in range(distinct, n):
+        host_rgb[i] = host_rgb[i % distinct]
     codec.upload(host_rgb)
     _lib.sync()
 
@@ -257,16 +300,32 @@ def main():
     time.sleep(0.25)
     _lib.profile_enable(True)
     _lib.profile_report()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Working sets below ~2x L2 (126 MB) get an L2 flush (a 256 MB device fill) before every timed step,
+    # timed step by step so the flush itself stays outside the measurement.
+    need_flush = host_rgb.nbytes < 256e6
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
     barrier()
     t_start = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
+    if need_flush:
+        pairs = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            step_device()
+            eb.record()
+            pairs.append((ea, eb))
+        barrier()
+        ms_total = sum(a.elapsed_time(b) for a, b in pairs)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_device()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
     t_end = time.time()
-    ms_total = e0.elapsed_time(e1)
     prof = _lib.profile_report()
     _lib.profile_enable(False)
     clocks = sampler.stop(t_start, t_end)
@@ -282,12 +341,13 @@ def main():
     enc = codec.encoder
     s_ac = float(sum(int(enc.nsym[s]) for s in range(1, len(enc.nsym), 3)))
     bits_bytes = float(enc.total_bytes)
-    B = float(codec.blocks)
+    B = float(codec.layout.n_images * codec.layout.blocks_per_image)
+    rows, n_ss, bins = float(enc.total_rows), float(enc.n_streams), float(enc.value_bins)
     peak, peak_src = measured_peak()
     kernels = {}
     for name, (ms, launches) in prof.items():
         per = ms / max(launches, 1)
-        ab = kernel_bytes(name, float(pixels), B, s_ac, bits_bytes)
+        ab = kernel_bytes(name, float(pixels), B, s_ac, bits_bytes, rows, n_ss, bins, mode)
         kernels[name] = {"ms_per_launch": round(per, 4), "launches_per_step": launches / args.steps,
                          "share_of_step": round(ms / ms_total, 4) if ms_total else None,
                          "algorithmic_gbs": round(ab / per / 1e6, 1) if ab and per > 0 else None,
@@ -328,27 +388,30 @@ def main():
     table_bytes = int(enc_res.symbols.nbytes + enc_res.packed.nbytes + enc_res.index.nbytes)
     h2d = int(host_rgb.nbytes + enc_res.data.nbytes + table_bytes)
     d2h = int(enc_res.data.nbytes + table_bytes + out.nbytes)
-    parity = {"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),
-                               "changed": int(codec.forward_stats[2])},
-              "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
-                               "changed": int(codec.inverse_stats[2])}}
+    parity = None
+    if mode == "dct":
+        parity = {"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),
+                                   "changed": int(codec.forward_stats[2])},
+                  "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
+                                   "changed": int(codec.inverse_stats[2])}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = 16
-        v, dt = cpu_baseline_sample(h, w, n_cpu, 2000)
+        ch_, cw_, what = cpu_sample_shape(h, w)
+        n_cpu = max(1, min(16, int(4.5e6 // (ch_ * cw_))))
+        v, dt = cpu_baseline_sample(ch_, cw_, n_cpu, 2000, mode)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d of the batch's %d synthetic %dx%d images, full encode+decode through the oracle port "
-                         "(numpy restatement of the reference, %.1f s)" % (n_cpu, n, w, h, dt)}
+               "sample": "%d x %s of this workload, full encode+decode through the oracle port "
+                         "(numpy restatement of the reference, %.1f s)" % (n_cpu, what, dt)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "batch of %d synthetic %dx%d RGB images per GPU, DCT mode encode+decode" % (n, w, h),
-                       "images_per_gpu": n, "height": h, "width": w, "parallelism": "by image, %d GPU(s), no collective" % world,
-                       "l2": "inputs larger than L2 (%.0f MB RGB per batch), no flush" % (host_rgb.nbytes / 1e6),
+            "config": {"workload": cfg["workload"], "mode": mode, "images_per_gpu": n, "distinct_images": distinct, "height": h, "width": w, "parallelism": "by image, %d GPU(s), no collective" % world,
+                       "l2": ("L2 flushed (256 MB device fill) before every timed step; steps timed individually"
+                              if need_flush else "inputs larger than L2 (%.0f MB RGB per batch), no flush" % (host_rgb.nbytes / 1e6)),
                        "compressed_bytes_per_batch": int(enc.total_bytes), "symbols_per_batch": int(s_ac)},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

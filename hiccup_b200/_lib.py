@@ -78,7 +78,7 @@ SIGNATURES = {
     "hic_entropy_build_codes_device": (c_int, [c_void_p, c_void_p]),
     "hic_entropy_device_tables": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                           ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
-    "hic_decode_set_tables_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_decode_set_tables_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_entropy_stream_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "hic_entropy_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,44 +1,38 @@
-"""Batched, device-resident DCT-mode pipeline (an additive entry point: the reference API is one
-image per call).
+"""Batched, device-resident pipelines (additive entry points: the reference API is one image per
+call).
 
-    codec = DctBatchCodec(n, h, w)
+    codec = DctBatchCodec(n, h, w)         # or WaveletBatchCodec(n, h, w)
     enc = codec.encode(rgb_batch)          # host uint8 (n, h, w, 3) -> EncodedStreams (tables + framed bits)
-    rgb = codec.decode(enc)                # -> host uint8 (n, 2*(h//2), 2*(w//2), 3)
+    rgb = codec.decode(enc)                # -> host uint8 (n, out_h, out_w, 3)
     images = codec.hic_images(enc)         # -> list of HicImage, byte-identical to the reference's
 
 All buffers and both entropy plans are allocated once for the shape; a step launches the same
-kernels as the single-image drop-in functions (compression.py / codec.py), just over n images.
+kernels as the single-image drop-in functions (compression.py / codec.py / wavelet.py), just over n
+images.  Host-side results are views of page-locked staging owned by the codec (valid until the next
+call of the same method).
 """
 import numpy as np
 
 from hiccup_b200 import _lib, entropy, hicimage
 
 
-class DctBatchCodec:
-    def __init__(self, n, h, w, value_bins=entropy.DEFAULT_VALUE_BINS, device=None, stream=None, device_codes=True):
-        _lib.require_device()
+class _BatchCodec:
+    """Shared plumbing: buffers, entropy plans, pinned staging.  Subclasses provide the transform."""
+
+    def __init__(self, n, h, w, layout, coef_bytes, out_hw, value_bins, device, stream, device_codes):
         self.lib = _lib.load()
-        if device is not None:
-            _lib.check(self.lib.hic_set_device(int(device)))
         self.n, self.h, self.w = int(n), int(h), int(w)
         self.stream = stream
         self.device_codes = bool(device_codes) and value_bins <= 8192      # E2 on the GPU (same codes, no PCIe)
-        g = self.g = _lib.geometry(h, w)
-        self.blocks = self.n * g.blocks_per_image
-        self.layout = _lib.layout_dct(self.n, h, w)
+        self.layout = layout
+        self.out_h, self.out_w = out_hw
         self.d_rgb = _lib.DeviceBuffer(self.n * h * w * 3)
-        self.d_coef = _lib.DeviceBuffer(self.blocks * 128)
-        self.d_coef_dec = _lib.DeviceBuffer(self.blocks * 128)
-        self.d_ties = _lib.DeviceBuffer(self.blocks * _lib.TIE_RECORD_BYTES)
-        self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
-        self.d_y = _lib.DeviceBuffer(self.n * h * w)
-        self.d_cr = _lib.DeviceBuffer(self.n * g.hc * g.wc)
-        self.d_cb = _lib.DeviceBuffer(self.n * g.hc * g.wc)
-        self.d_out = _lib.DeviceBuffer(self.n * g.out_h * g.out_w * 3)
+        self.d_coef = _lib.DeviceBuffer(coef_bytes)
+        self.d_coef_dec = _lib.DeviceBuffer(coef_bytes)
+        self.d_out = _lib.DeviceBuffer(self.n * self.out_h * self.out_w * 3)
         self.encoder = entropy.EntropyEncoder(self.layout, value_bins)
         self.decoder = entropy.EntropyDecoder(self.layout)
-        self.forward_stats = np.zeros(4, np.uint32)
-        self.inverse_stats = np.zeros(4, np.uint32)
+        self._buffers = [self.d_rgb, self.d_coef, self.d_coef_dec, self.d_out]
         # page-locked staging for the host-to-host entry points (grown on demand, reused every call)
         self._h_data = None
         self._h_out = None
@@ -52,7 +46,14 @@ class DctBatchCodec:
 
     @property
     def out_shape(self):
-        return (self.n, self.g.out_h, self.g.out_w, 3)
+        return (self.n, self.out_h, self.out_w, 3)
+
+    # ---- transform hooks ---------------------------------------------------------------------
+    def _forward(self):
+        raise NotImplementedError
+
+    def _inverse(self):
+        raise NotImplementedError
 
     # ---- device-resident steps ---------------------------------------------------------------
     def upload(self, rgb):
@@ -61,24 +62,22 @@ class DctBatchCodec:
         self.d_rgb.upload(rgb, self.stream)
 
     def encode_device(self):
-        """K1 + fix-up, E1, E2 (host trees), E3.  Inputs and outputs stay in HBM."""
-        lib, st = self.lib, self.stream
-        _lib.check(lib.hic_dct_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.d_ties.ptr,
-                                       self.blocks, self.d_stats.ptr, st))
+        """Transform, E1 (symbols + histograms), E2 (Huffman codes), E3 (bit packing); all in HBM."""
+        st = self.stream
+        self._forward()
         self.encoder.symbolize(self.d_coef.ptr, st)
         self.encoder.build_codes(st, on_device=self.device_codes)
         return self.encoder.pack(st)
 
     def decode_device(self):
-        """D1-D3, K7 + fix-up, K8, from the encoder's own device-resident output (tables and bits
-        are handed over device-to-device)."""
-        lib, st = self.lib, self.stream
+        """D1-D3 and the inverse transform from the encoder's own device-resident output (tables
+        and bits are handed over device-to-device)."""
+        st = self.stream
         enc = self.encoder
         d_index, d_row_sym, d_row_packed, _, _ = enc.device_tables()
-        self.decoder.set_tables_device(d_index, d_row_sym, d_row_packed, st)
+        self.decoder.set_tables_device(d_index, d_row_sym, d_row_packed, enc.total_rows, st)
         self.decoder.run(enc._out.ptr, enc.byte_off, enc.nbits, self.d_coef_dec.ptr, st)
-        _lib.check(lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
-                                       self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks, self.d_stats.ptr, st))
+        self._inverse()
 
     # ---- host-to-host entry points -----------------------------------------------------------
     def encode(self, rgb):
@@ -90,31 +89,79 @@ class DctBatchCodec:
             if self._h_data is not None:
                 self._h_data.free()
             self._h_data = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
-        # the returned arrays view this codec's pinned staging: valid until the next encode()
         data = out.download(np.uint8, nbytes, self.stream, out=self._h_data.array(np.uint8, nbytes))
         rows = int(enc.total_rows)
         if self._h_tab is None or self._h_tab[1].size < rows:
+            for b in self._h_tab_mem:
+                b.free()
             cap = rows + rows // 4 + 1024
             self._h_tab_mem = [_lib.PinnedBuffer(8 * enc.n_streams), _lib.PinnedBuffer(4 * cap), _lib.PinnedBuffer(8 * cap)]
             self._h_tab = (self._h_tab_mem[0].array(np.uint32), self._h_tab_mem[1].array(np.int32),
                            self._h_tab_mem[2].array(np.uint64))
         index, sym, packed = enc.tables_packed(self.stream, out=self._h_tab)
-        self.forward_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
+        self._after_encode()
         return entropy.EncodedStreams(self.layout, index, enc.nsym.copy(), enc.nbits.copy(),
                                       enc.byte_off.copy(), enc.byte_len.copy(), sym, packed, data)
 
     def decode(self, enc):
         self.decoder.decode_streams(enc, self.d_coef_dec.ptr, self.stream)
+        self._inverse()
+        count = self.n * self.out_h * self.out_w * 3
+        if self._h_out is None:
+            self._h_out = _lib.PinnedBuffer(count)
+        out = self.d_out.download(np.uint8, count, self.stream, out=self._h_out.array(np.uint8, count))
+        self._after_decode()
+        return out.reshape(self.out_shape)
+
+    def _after_encode(self):
+        pass
+
+    def _after_decode(self):
+        pass
+
+    def close(self):
+        self.encoder.close()
+        self.decoder.close()
+        for b in self._buffers + [self._h_data, self._h_out] + self._h_tab_mem:
+            if b is not None:
+                b.free()
+        self._buffers, self._h_data, self._h_out, self._h_tab, self._h_tab_mem = [], None, None, None, []
+
+
+class DctBatchCodec(_BatchCodec):
+    """DCT ("JPEG") mode: K1 + fix-up -> entropy stage -> K7 + fix-up, K8."""
+
+    def __init__(self, n, h, w, value_bins=entropy.DEFAULT_VALUE_BINS, device=None, stream=None, device_codes=True):
+        _lib.require_device()
+        if device is not None:
+            _lib.check(_lib.load().hic_set_device(int(device)))
+        g = self.g = _lib.geometry(h, w)
+        self.blocks = int(n) * g.blocks_per_image
+        super().__init__(n, h, w, _lib.layout_dct(int(n), h, w), self.blocks * 128, (g.out_h, g.out_w), value_bins,
+                         device, stream, device_codes)
+        self.d_ties = _lib.DeviceBuffer(self.blocks * _lib.TIE_RECORD_BYTES)
+        self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+        self.d_y = _lib.DeviceBuffer(self.n * h * w)
+        self.d_cr = _lib.DeviceBuffer(self.n * g.hc * g.wc)
+        self.d_cb = _lib.DeviceBuffer(self.n * g.hc * g.wc)
+        self._buffers += [self.d_ties, self.d_stats, self.d_y, self.d_cr, self.d_cb]
+        self.forward_stats = np.zeros(4, np.uint32)
+        self.inverse_stats = np.zeros(4, np.uint32)
+
+    def _forward(self):
+        _lib.check(self.lib.hic_dct_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.d_ties.ptr,
+                                            self.blocks, self.d_stats.ptr, self.stream))
+
+    def _inverse(self):
         _lib.check(self.lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,
                                             self.d_cb.ptr, self.d_out.ptr, self.d_ties.ptr, self.blocks,
                                             self.d_stats.ptr, self.stream))
-        count = self.n * self.g.out_h * self.g.out_w * 3
-        if self._h_out is None:
-            self._h_out = _lib.PinnedBuffer(count)
-        # a view of the codec's pinned staging: valid until the next decode()
-        out = self.d_out.download(np.uint8, count, self.stream, out=self._h_out.array(np.uint8, count))
+
+    def _after_encode(self):
+        self.forward_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
+
+    def _after_decode(self):
         self.inverse_stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, self.stream)
-        return out.reshape(self.out_shape)
 
     def coefficients(self):
         """Download the quantised zigzag blocks of the last encode: (n, blocks_per_image, 64) int16."""
@@ -136,11 +183,26 @@ class DctBatchCodec:
             out.append(hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(g.h, g.w), hicimage.TupP(g.hc, g.wc)]))
         return out
 
-    def close(self):
-        self.encoder.close()
-        self.decoder.close()
-        for b in (self.d_rgb, self.d_coef, self.d_coef_dec, self.d_ties, self.d_stats, self.d_y, self.d_cr, self.d_cb,
-                  self.d_out, self._h_data, self._h_out, *self._h_tab_mem):
-            if b is not None:
-                b.free()
-        self._h_tab, self._h_tab_mem = None, []
+
+class WaveletBatchCodec(_BatchCodec):
+    """Wavelet ("HIC") mode: K9 -> flat-mode entropy stage -> K10.  h and w must be multiples of 8
+    to decode (the reference's decoder needs exact halvings, codec.py:182-189)."""
+
+    def __init__(self, n, h, w, value_bins=entropy.DEFAULT_VALUE_BINS, device=None, stream=None, device_codes=True):
+        _lib.require_device()
+        if device is not None:
+            _lib.check(_lib.load().hic_set_device(int(device)))
+        g = self.g = _lib.wavelet_geometry(h, w)
+        self.chan_elems = 64 * ((int(g.len) + 63) // 64)
+        super().__init__(n, h, w, _lib.layout_flat(int(n), int(g.len)), 2 * self.chan_elems * 3 * int(n), (h, w),
+                         value_bins, device, stream, device_codes)
+
+    def _forward(self):
+        _lib.check(self.lib.hic_wavelet_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.stream))
+
+    def _inverse(self):
+        _lib.check(self.lib.hic_wavelet_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_out.ptr, self.stream))
+
+    def hic_images(self, enc):
+        from hiccup_b200 import wavelet
+        return [wavelet.encode_streams_to_hic(enc, self.g, image=i) for i in range(self.n)]

@@ -46,13 +46,16 @@ __host__ __device__ inline int64_t cs_block_base(const Geom& g, int img, int c) 
 //   count scan    symbols per CTA -> output offsets (per-stream scan);
 //   write kernel  final pass from the now-correct starts, writing symbols at their offsets.
 // Code lookup: a 12-bit first-level table in shared memory; prefixes of longer codes point into a
-// per-stream second-level table (codes up to 20 bits); anything longer is found by binary search
-// over the stream's long rows sorted by left-aligned code.
+// per-stream second-level table of up to 8 more bits; a code that runs past 20 bits (or a prefix
+// the second level had no room for) is found by predecessor search over the stream's rows sorted by
+// left-aligned code -- prefix-free codes are disjoint intervals of the 64-bit window space.
 // ------------------------------------------------------------------------------------------------
 constexpr int L1_BITS = 12;
 constexpr int L1_SIZE = 1 << L1_BITS;
 constexpr int L2_MAX_EXTRA = 8;
-constexpr int L2_CAP = 4096;                 // second-level entries per stream
+constexpr int L2_CAP_MIN = 4096;             // second-level entries per stream: the plan picks a power of two
+constexpr int L2_CAP_MAX = 65536;            // in this range from a budget of 2^28 entries per plan
+constexpr int L2_LONG = 0xFF;                // second-level length field: the code runs past 20 bits
 constexpr int SUB_BITS = 128;
 constexpr int SUB_PER_CTA = 256;
 constexpr int CHUNK_WORDS = SUB_BITS * SUB_PER_CTA / 32;      // 1024 words of bit stream per CTA
@@ -65,21 +68,25 @@ struct SyncTile {
     uint64_t sub_base;      // global index of that subsequence
 };
 
-// one CTA per symbol stream: first- and second-level tables from the code rows
+// one CTA per symbol stream: first- and second-level tables from the code rows; streams that own a
+// code longer than 20 bits (or overflow the second level) also get their rows sorted by
+// left-aligned code for the predecessor search.
 __global__ void __launch_bounds__(256)
 build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restrict__ row_sym,
-                    const uint64_t* __restrict__ row_packed, int32_t* __restrict__ lut1, int32_t* __restrict__ lut2) {
+                    const uint64_t* __restrict__ row_packed, int32_t* __restrict__ lut1, int32_t* __restrict__ lut2,
+                    int l2_cap, uint64_t* __restrict__ sorted_left, uint32_t* __restrict__ sorted_row) {
     __shared__ uint32_t extra[L1_SIZE];          // max (len - 12) under each 12-bit prefix
     __shared__ uint32_t offs[L1_SIZE];
     __shared__ uint32_t wsum[8];
+    __shared__ int s_need_sort;
     const int ss = blockIdx.x;
     int32_t* my1 = lut1 + (size_t)ss * L1_SIZE;
-    int32_t* my2 = lut2 + (size_t)ss * L2_CAP;
+    int32_t* my2 = lut2 + (size_t)ss * l2_cap;
     for (int i = threadIdx.x; i < L1_SIZE; i += blockDim.x) {
         my1[i] = 0;
         extra[i] = 0;
     }
-    for (int i = threadIdx.x; i < L2_CAP; i += blockDim.x) my2[i] = 0;
+    if (threadIdx.x == 0) s_need_sort = 0;
     __syncthreads();
     const uint64_t r0 = index[ss].offset, r1 = r0 + index[ss].count;
     constexpr uint64_t CODE_MASK = (1ull << 58) - 1;
@@ -92,7 +99,8 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
             const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
             for (uint32_t j = 0; j < (1u << (L1_BITS - len)); ++j) my1[base + j] = entry;
         } else {
-            atomicMax(&extra[(uint32_t)(code >> (len - L1_BITS))], len - L1_BITS);
+            atomicMax(&extra[(uint32_t)(code >> (len - L1_BITS))], min(len - L1_BITS, (uint32_t)L2_MAX_EXTRA));
+            if (len > L1_BITS + L2_MAX_EXTRA) s_need_sort = 1;
         }
     }
     __syncthreads();
@@ -101,7 +109,7 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const uint32_t e = extra[threadIdx.x * 16 + j];
-        local[j] = (e && e <= L2_MAX_EXTRA) ? (1u << e) : 0u;
+        local[j] = e ? (1u << e) : 0u;
         sum += local[j];
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,16 +128,20 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
         const int pfx = threadIdx.x * 16 + j;
         const uint32_t e = extra[pfx];
         if (e) {
-            if (local[j] && run + local[j] <= (uint32_t)L2_CAP) {
+            if (run + local[j] <= (uint32_t)l2_cap) {
                 offs[pfx] = run;
                 my1[pfx] = (int32_t)((run << 8) | 0x80u | e);
-                run += local[j];
             } else {
-                offs[pfx] = 0xFFFFFFFFu;
+                offs[pfx] = 0xFFFFFFFFu;          // no room: the whole prefix goes to the search
                 my1[pfx] = L1_FALLBACK;
+                s_need_sort = 1;
             }
+            run += local[j];
         }
     }
+    if (threadIdx.x == blockDim.x - 1) wsum[0] = min(run, (uint32_t)l2_cap);      // second-level entries in use
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < wsum[0]; i += blockDim.x) my2[i] = 0;       // (incomplete code sets leave holes)
     __syncthreads();
     for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         const uint32_t len = (uint32_t)(row_packed[r] >> 58);
@@ -138,11 +150,55 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
         const uint32_t pfx = (uint32_t)(code >> (len - L1_BITS));
         if (offs[pfx] == 0xFFFFFFFFu) continue;
         const uint32_t e = extra[pfx], x = len - L1_BITS;
-        const uint32_t sub = (uint32_t)(code & ((1ull << x) - 1));
-        const uint32_t base = offs[pfx] + (sub << (e - x));
-        const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
-        for (uint32_t j = 0; j < (1u << (e - x)); ++j) my2[base + j] = entry;
+        if (x <= e) {
+            const uint32_t sub = (uint32_t)(code & ((1ull << x) - 1));
+            const uint32_t base = offs[pfx] + (sub << (e - x));
+            const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
+            for (uint32_t j = 0; j < (1u << (e - x)); ++j) my2[base + j] = entry;
+        } else {                                   // longer than the second level reaches: mark its slot
+            const uint32_t sub = (uint32_t)((code >> (x - e)) & ((1ull << e) - 1));
+            my2[offs[pfx] + sub] = L2_LONG;
+        }
     }
+    if (!s_need_sort) return;
+    // rows sorted by left-aligned code (bitonic, in global memory: only big alphabets come here)
+    const uint32_t n = index[ss].count;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    uint64_t* key = sorted_left + 2 * r0;          // room for the padded power of two
+    uint32_t* row = sorted_row + 2 * r0;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        if (i < n) {
+            const uint64_t pk = row_packed[r0 + i];
+            const uint32_t len = (uint32_t)(pk >> 58);
+            key[i] = len ? (pk & CODE_MASK) << (64 - len) : ~0ull;
+            row[i] = i;
+        } else {
+            key[i] = ~0ull;
+            row[i] = 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint64_t ka = key[i], kb = key[l];
+                    const uint32_t ra = row[i], rb = row[l];
+                    // ties only among the padding; order them by row to keep the sort deterministic
+                    const bool gt = ka > kb || (ka == kb && ra > rb);
+                    if (gt == up) {
+                        key[i] = kb;
+                        key[l] = ka;
+                        row[i] = rb;
+                        row[l] = ra;
+                    }
+                }
+            }
+            __syncthreads();
+        }
 }
 
 struct BitReader {
@@ -154,10 +210,35 @@ struct BitReader {
     }
 };
 
+struct LongSearch {            // per-stream view for the predecessor search
+    const uint64_t* left;      // rows' left-aligned codes, ascending
+    const uint32_t* row;       // row index (inside the stream) of each sorted entry
+    const int32_t* row_sym;
+    const uint64_t* row_packed;
+    uint32_t n_rows;
+};
+
+// the row whose code is a prefix of the window, by predecessor search (prefix-free codes are disjoint
+// intervals [code << (64 - len), (code + 1) << (64 - len)) of the window space)
+__device__ __noinline__ uint32_t decode_long(uint64_t w, const LongSearch& ls, int32_t& sym) {
+    if (ls.n_rows == 0) return 0;
+    uint32_t lo = 0, hi = ls.n_rows;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ls.left + mid) <= w) lo = mid; else hi = mid;
+    }
+    const uint32_t r = __ldg(ls.row + lo);
+    if (r >= ls.n_rows) return 0;
+    const uint64_t packed = __ldg(ls.row_packed + r);
+    const uint32_t len = (uint32_t)(packed >> 58);
+    if (len == 0 || (w >> (64 - len)) != (packed & ((1ull << 58) - 1))) return 0;
+    sym = __ldg(ls.row_sym + r);
+    return len;
+}
+
 // decode one code at the 64-bit window; returns its length (0 = no valid code) and the symbol
 __device__ __forceinline__ uint32_t decode_one(uint64_t w, const int32_t* __restrict__ l1, const int32_t* __restrict__ l2,
-                                               const int32_t* __restrict__ row_sym, const uint64_t* __restrict__ row_packed,
-                                               uint32_t n_rows, int32_t& sym) {
+                                               const LongSearch& ls, int32_t& sym) {
     int32_t e = l1[(uint32_t)(w >> (64 - L1_BITS))];
     if (!(e & 0x80)) {
         sym = e >> 8;
@@ -167,20 +248,12 @@ __device__ __forceinline__ uint32_t decode_one(uint64_t w, const int32_t* __rest
     if (nb2 != 0x7F) {
         const uint32_t idx = ((uint32_t)e >> 8) + (uint32_t)((w >> (64 - L1_BITS - nb2)) & ((1u << nb2) - 1));
         e = __ldg(l2 + idx);
-        sym = e >> 8;
-        return (uint32_t)(e & 0xFF);
-    }
-    // codes longer than 20 bits (or a crowded second level): scan the stream's rows -- prefix-free
-    // codes have exactly one match.  Practically never taken for image data.
-    for (uint32_t i = 0; i < n_rows; ++i) {
-        const uint64_t packed = __ldg(row_packed + i);
-        const uint32_t len = (uint32_t)(packed >> 58);
-        if (len > L1_BITS && (w >> (64 - len)) == (packed & ((1ull << 58) - 1))) {
-            sym = __ldg(row_sym + i);
-            return len;
+        if ((e & 0xFF) != L2_LONG) {
+            sym = e >> 8;
+            return (uint32_t)(e & 0xFF);
         }
     }
-    return 0;
+    return decode_long(w, ls, sym);
 }
 
 // Decode from `pos` until the position reaches `limit` (the thread's upper boundary) or `end`.
@@ -188,14 +261,13 @@ __device__ __forceinline__ uint32_t decode_one(uint64_t w, const int32_t* __rest
 template <bool WRITE>
 __device__ __forceinline__ uint32_t decode_span(const BitReader& br, uint32_t chunk0, uint32_t pos, uint32_t limit,
                                                 uint32_t end, const int32_t* __restrict__ l1,
-                                                const int32_t* __restrict__ l2, const int32_t* __restrict__ row_sym,
-                                                const uint64_t* __restrict__ row_packed, uint32_t n_rows, uint32_t& count, int16_t* __restrict__ out16,
+                                                const int32_t* __restrict__ l2, const LongSearch& ls, uint32_t& count, int16_t* __restrict__ out16,
                                                 uint8_t* __restrict__ out8, uint32_t out_idx, bool& bad) {
     count = 0;
     const uint32_t stop = limit < end ? limit : end;
     while (pos < stop) {
         int32_t sym = 0;
-        const uint32_t len = decode_one(br.window(pos - chunk0), l1, l2, row_sym, row_packed, n_rows, sym);
+        const uint32_t len = decode_one(br.window(pos - chunk0), l1, l2, ls, sym);
         if (len == 0 || pos + len > end) {
             bad = true;
             return stop;          // not a codeword boundary (or a corrupt stream): give up on this span
@@ -215,6 +287,9 @@ struct SyncArgs {
     const uint64_t* nbits;
     const int32_t* lut1;
     const int32_t* lut2;
+    int l2_cap;
+    const uint64_t* sorted_left;
+    const uint32_t* sorted_row;
     const RowIndex* index;
     const int32_t* row_sym;
     const uint64_t* row_packed;
@@ -258,17 +333,17 @@ huffman_sync_kernel(SyncArgs a) {
     }
     stage_chunk(a, t, s_words, s_l1);
     const BitReader br{s_words};
-    const int32_t* l2 = a.lut2 + (size_t)t.ss * L2_CAP;
-    const int32_t* rsym = a.row_sym + a.index[t.ss].offset;
-    const uint64_t* rpk = a.row_packed + a.index[t.ss].offset;
-    const uint32_t n_rows = a.index[t.ss].count;
+    const int32_t* l2 = a.lut2 + (size_t)t.ss * a.l2_cap;
+    const RowIndex ridx = a.index[t.ss];
+    const LongSearch ls{a.sorted_left + 2 * (size_t)ridx.offset, a.sorted_row + 2 * (size_t)ridx.offset,
+                        a.row_sym + ridx.offset, a.row_packed + ridx.offset, ridx.count};
     __syncthreads();
 
     uint32_t start, my_end = 0, cnt = 0, old_last_end = 0;
     bool bad = false;
     if (!RESYNC) {
         start = threadIdx.x == 0 ? tile_true_start : sub * SUB_BITS;
-        if (active) my_end = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, rsym, rpk, n_rows, cnt, nullptr, nullptr, 0, bad);
+        if (active) my_end = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, ls, cnt, nullptr, nullptr, 0, bad);
     } else {
         // previous state: my stop position and count; my start was my left neighbour's stop
         my_end = active ? a.sub_end[g] : 0;
@@ -287,7 +362,7 @@ huffman_sync_kernel(SyncArgs a) {
         if (redo) {
             start = want;
             bad = false;
-            const uint32_t e = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, rsym, rpk, n_rows, cnt, nullptr, nullptr, 0, bad);
+            const uint32_t e = decode_span<false>(br, chunk0, start, limit, end, s_l1, l2, ls, cnt, nullptr, nullptr, 0, bad);
             moved = e != my_end;
             my_end = e;
             s_end[threadIdx.x] = e;
@@ -342,10 +417,10 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     const uint32_t chunk0 = t.sub0 * SUB_BITS;
     stage_chunk(a, t, s_words, s_l1);
     const BitReader br{s_words};
-    const int32_t* l2 = a.lut2 + (size_t)t.ss * L2_CAP;
-    const int32_t* rsym = a.row_sym + a.index[t.ss].offset;
-    const uint64_t* rpk = a.row_packed + a.index[t.ss].offset;
-    const uint32_t n_rows = a.index[t.ss].count;
+    const int32_t* l2 = a.lut2 + (size_t)t.ss * a.l2_cap;
+    const RowIndex ridx = a.index[t.ss];
+    const LongSearch ls{a.sorted_left + 2 * (size_t)ridx.offset, a.sorted_row + 2 * (size_t)ridx.offset,
+                        a.row_sym + ridx.offset, a.row_packed + ridx.offset, ridx.count};
     const uint32_t cnt = active ? a.sub_cnt[gi] : 0;
     // exclusive scan of the counts inside the CTA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -371,7 +446,7 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     const uint32_t start = sub == 0 ? 8u : a.sub_end[gi - 1];
     uint32_t got = 0;
     bool bad = false;
-    const uint32_t e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, rsym, rpk, n_rows, got,
+    const uint32_t e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got,
                                          kind == HIC_KIND_DC ? dc + bb : values + bb * 64,
                                          kind == HIC_KIND_LENGTH ? lengths + bb * 64 : nullptr, out_idx, bad);
     if (bad || got != cnt || e != a.sub_end[gi] || (sub == n_sub - 1 && e != end)) atomicOr(err, 1u);
@@ -573,6 +648,10 @@ struct hic_decode_plan {
     uint8_t* d_lengths = nullptr;
     int32_t* d_lut1 = nullptr;
     int32_t* d_lut2 = nullptr;
+    int l2_cap = L2_CAP_MIN;
+    uint64_t* d_sorted_left = nullptr;          // 2 x row capacity (bitonic padding)
+    uint32_t* d_sorted_row = nullptr;
+    uint64_t sorted_capacity = 0;
     SyncTile* d_tiles = nullptr;
     uint64_t tile_capacity = 0;
     uint32_t* d_ss_tile0 = nullptr;
@@ -608,7 +687,7 @@ extern "C" {
 
 int hic_decode_plan_destroy(hic_decode_plan* p) {
     if (!p) return HIC_OK;
-    void* ptrs[] = {p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
+    void* ptrs[] = {p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
                     p->d_sub_cnt, p->d_tile_start, p->d_tile_cnt, p->d_tile_symoff, p->d_index_own, p->d_row_sym_own,
                     p->d_row_packed_own, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
                     p->d_tile_off, p->d_stream_total};
@@ -646,7 +725,12 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
     ok(dalloc2(&p->d_values, p->total_blocks * 64 + 64));
     ok(dalloc2(&p->d_lengths, p->total_blocks * 64 + 64));
     ok(dalloc2(&p->d_lut1, (size_t)p->n_ss * L1_SIZE));
-    ok(dalloc2(&p->d_lut2, (size_t)p->n_ss * L2_CAP));
+    {
+        int cap = L2_CAP_MAX;
+        while (cap > L2_CAP_MIN && (size_t)cap * p->n_ss > ((size_t)1 << 28)) cap >>= 1;
+        p->l2_cap = cap;
+    }
+    ok(dalloc2(&p->d_lut2, (size_t)p->n_ss * p->l2_cap));
     ok(dalloc2(&p->d_ss_tile0, p->n_ss + 1));
     ok(dalloc2(&p->d_index_own, p->n_ss));
     ok(dalloc2(&p->d_byte_off, p->n_ss));
@@ -665,13 +749,23 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
 }
 
 int hic_decode_set_tables_device(hic_decode_plan* p, const void* d_index, const int32_t* d_row_sym,
-                                 const uint64_t* d_row_packed, void* stream) {
+                                 const uint64_t* d_row_packed, uint64_t total_rows, void* stream) {
     HIC_REQUIRE(p && d_index && d_row_sym && d_row_packed, "NULL argument");
     cudaStream_t st = as_stream(stream);
     p->d_index = static_cast<const RowIndex*>(d_index);
     p->d_row_sym = d_row_sym;
     p->d_row_packed = d_row_packed;
-    HIC_LAUNCH("build_tables_kernel", st, build_tables_kernel<<<p->n_ss, 256, 0, st>>>(p->d_index, p->d_row_sym, p->d_row_packed, p->d_lut1, p->d_lut2));
+    if (total_rows > p->sorted_capacity) {          // scratch for the long-code search (2x: bitonic padding)
+        HIC_CUDA(cudaStreamSynchronize(st));
+        if (p->d_sorted_left) cudaFree(p->d_sorted_left);
+        if (p->d_sorted_row) cudaFree(p->d_sorted_row);
+        p->d_sorted_left = nullptr; p->d_sorted_row = nullptr;
+        p->sorted_capacity = total_rows + total_rows / 4 + 1024;
+        HIC_CUDA(dalloc2(&p->d_sorted_left, 2 * p->sorted_capacity));
+        HIC_CUDA(dalloc2(&p->d_sorted_row, 2 * p->sorted_capacity));
+    }
+    HIC_LAUNCH("build_tables_kernel", st, build_tables_kernel<<<p->n_ss, 256, 0, st>>>(p->d_index, p->d_row_sym, p->d_row_packed, p->d_lut1, p->d_lut2,
+                                                                                         p->l2_cap, p->d_sorted_left, p->d_sorted_row));
     p->tables_ready = true;
     return HIC_OK;
 }
@@ -699,7 +793,7 @@ int hic_decode_set_tables_packed(hic_decode_plan* p, const uint32_t* h_index, co
         HIC_CUDA(cudaMemcpyAsync(p->d_row_packed_own, h_row_packed, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
     }
     return hic_decode_set_tables_device(p, p->d_index_own, p->d_row_sym_own ? p->d_row_sym_own : (const int32_t*)p->d_index_own,
-                                        p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, stream);
+                                        p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, total, stream);
 }
 
 int hic_decode_set_tables(hic_decode_plan* p, const uint32_t* h_rows, const int32_t* h_symbols, const uint8_t* h_lens,
@@ -734,7 +828,7 @@ int hic_decode_set_tables(hic_decode_plan* p, const uint32_t* h_rows, const int3
         HIC_CUDA(cudaMemcpyAsync(p->d_row_packed_own, packed.data(), sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
     }
     int rc = hic_decode_set_tables_device(p, p->d_index_own, p->d_row_sym_own ? p->d_row_sym_own : (const int32_t*)p->d_index_own,
-                                          p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, stream);
+                                          p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, total, stream);
     if (rc) return rc;
     HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors go out of scope
     return HIC_OK;
@@ -793,7 +887,7 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     if (n_tiles) {
         HIC_CUDA(cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(SyncTile) * n_tiles, cudaMemcpyHostToDevice, st));
         SyncArgs a;
-        a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2;
+        a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2; a.l2_cap = p->l2_cap; a.sorted_left = p->d_sorted_left; a.sorted_row = p->d_sorted_row;
         a.index = p->d_index; a.row_sym = p->d_row_sym; a.row_packed = p->d_row_packed; a.tiles = p->d_tiles; a.sub_end = p->d_sub_end;
         a.sub_cnt = p->d_sub_cnt; a.tile_start = p->d_tile_start; a.tile_cnt = p->d_tile_cnt; a.changed = p->d_err + 1;
         HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));

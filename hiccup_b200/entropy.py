@@ -207,8 +207,8 @@ class EntropyDecoder:
         except Exception:
             pass
 
-    def set_tables_device(self, d_index, d_row_sym, d_row_packed, stream=None):
-        _lib.check(self.lib.hic_decode_set_tables_device(self.plan, d_index, d_row_sym, d_row_packed, stream))
+    def set_tables_device(self, d_index, d_row_sym, d_row_packed, total_rows, stream=None):
+        _lib.check(self.lib.hic_decode_set_tables_device(self.plan, d_index, d_row_sym, d_row_packed, int(total_rows), stream))
 
     def run(self, d_data, byte_off, nbits, d_coef, stream=None):
         byte_off = np.ascontiguousarray(byte_off, np.uint64)

@@ -250,9 +250,10 @@ int hic_decode_set_tables(hic_decode_plan* plan, const uint32_t* h_rows, const i
 int hic_decode_set_tables_packed(hic_decode_plan* plan, const uint32_t* h_index, const int32_t* h_row_sym,
                                  const uint64_t* h_row_packed, uint64_t total_rows, void* stream);
 /* The same from device-resident tables (hic_entropy_device_tables); the arrays are referenced, not
- * copied, and must stay valid until decoding is done.  Asynchronous. */
+ * copied, and must stay valid until decoding is done.  total_rows: an upper bound on first row + row
+ * count over the streams (hic_entropy_stream_info's total_rows).  Asynchronous. */
 int hic_decode_set_tables_device(hic_decode_plan* plan, const void* d_index, const int32_t* d_row_sym,
-                                 const uint64_t* d_row_packed, void* stream);
+                                 const uint64_t* d_row_packed, uint64_t total_rows, void* stream);
 /* D1-D3 (device) -- Huffman decode (HuffmanTree.decode_data, huffman.py:149-174), run-length
  * expansion (codec.decode_run_length, codec.py:102-113), DC prefix sum (utils.invert_differences,
  * utils.py:66-74) and de-zigzag into blocks (codec.py:415-425).  d_bytes holds the framed byte

@@ -121,3 +121,35 @@ def test_wavelet_decode_rejects_shapes_the_reference_cannot_read():
     hi = codec.wavelet_encode(compression.wavelet_compression(rgb))     # encoding works for any shape
     with pytest.raises(ValueError):
         codec.wavelet_decode(hi)
+
+
+def test_long_huffman_codes_round_trip():
+    """Fibonacci symbol frequencies give codes far longer than the decoder's 20-bit table levels (the
+    predecessor-search path of D1); the coded bits must still equal the oracle's and decode back."""
+    from hiccup_b200 import codec, hicimage, model
+    h = w = 512
+    shapes = [(64, 64)] * 4 + [(128, 128)] * 3 + [(256, 256)] * 3
+    total = sum(a * b for a, b in shapes)
+    fib = [1, 1]
+    while sum(fib) + fib[-1] + fib[-2] <= total:
+        fib.append(fib[-1] + fib[-2])
+    fib[-1] += total - sum(fib)              # no zeros at all: nothing but the Fibonacci chain in the tree
+    rng = np.random.default_rng(11)
+    planes = {}
+    for ci, ch in enumerate(CH):
+        vals = np.concatenate([np.full(f, 7 + k + ci, np.int32) for k, f in enumerate(fib)])
+        stream = rng.permutation(vals)
+        bands, off = [], 0
+        for (bh, bw) in shapes:
+            bands.append(stream[off:off + bh * bw].reshape(bh, bw).copy())
+            off += bh * bw
+        planes[ch] = bands
+    enc = orc.wavelet_encode(planes)
+    assert max(len(c) for _, c in enc["tables"][0]) > 22, "the test must produce codes past the table levels"
+    hi = codec.wavelet_encode(model.CompressedImage.from_dict(planes))
+    stream_bytes = hi.byte_stream()
+    for i in range(6):
+        assert [(int(a), b) for a, b in hi.payloads[i].rows] == [(int(a), b) for a, b in enc["tables"][i]], "table %d" % i
+        assert stream_bytes[7 + i] == orc.padded_bits_to_bytes(enc["bits"][i]), "bit string %d" % i
+    back = codec.wavelet_decode(hicimage.HicImage.from_bytes(stream_bytes))
+    assert _same_bands(back.as_dict, planes)

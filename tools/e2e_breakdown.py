@@ -54,7 +54,7 @@ def main():
         _lib.check(codec.lib.hic_dct_inverse(codec.d_coef_dec.ptr, n, h, w, codec.d_y.ptr, codec.d_cr.ptr, codec.d_cb.ptr,
                                              codec.d_out.ptr, codec.d_ties.ptr, codec.blocks, codec.d_stats.ptr, None)); tick("dec.inverse", t)
         t = time.perf_counter()
-        count = n * codec.g.out_h * codec.g.out_w * 3
+        count = n * codec.out_h * codec.out_w * 3
         if codec._h_out is None:
             codec._h_out = _lib.PinnedBuffer(count)
         codec.d_out.download(np.uint8, count, None, out=codec._h_out.array(np.uint8, count)); tick("dec.d2h_rgb", t)
