@@ -244,5 +244,18 @@ def profile_report():
     return {k: (v[0], v[1]) for k, v in json.loads(buf.value.decode()).items()}
 
 
+def stream_create():
+    """A new non-blocking CUDA stream (as the integer handle the C ABI takes)."""
+    require_device()
+    st = c_void_p()
+    check(load().hic_stream_create(ctypes.byref(st)))
+    return st.value
+
+
+def stream_destroy(stream):
+    if stream:
+        load().hic_stream_destroy(stream)
+
+
 def sync(stream=None):
     check(load().hic_stream_sync(stream))

@@ -82,6 +82,10 @@ class _BatchCodec:
     # ---- host-to-host entry points -----------------------------------------------------------
     def encode(self, rgb):
         self.upload(rgb)
+        return self.encode_resident()
+
+    def encode_resident(self):
+        """Encode the batch already uploaded with upload(); returns the host-side EncodedStreams."""
         out = self.encode_device()
         enc = self.encoder
         nbytes = int(enc.total_bytes)
@@ -103,13 +107,27 @@ class _BatchCodec:
         return entropy.EncodedStreams(self.layout, index, enc.nsym.copy(), enc.nbits.copy(),
                                       enc.byte_off.copy(), enc.byte_len.copy(), sym, packed, data)
 
-    def decode(self, enc):
+    def decode(self, enc, out=None):
+        """out: optional preallocated uint8 array of out_shape (ideally page-locked) to receive the pixels."""
+        self.decode_resident(enc)
+        return self.fetch(out)
+
+    def decode_resident(self, enc):
+        """Entropy-decode and inverse-transform an EncodedStreams; the pixels stay on the device."""
         self.decoder.decode_streams(enc, self.d_coef_dec.ptr, self.stream)
         self._inverse()
+
+    def fetch(self, out=None):
+        """Download the pixels of the last decode_resident()."""
         count = self.n * self.out_h * self.out_w * 3
-        if self._h_out is None:
-            self._h_out = _lib.PinnedBuffer(count)
-        out = self.d_out.download(np.uint8, count, self.stream, out=self._h_out.array(np.uint8, count))
+        if out is None:
+            if self._h_out is None:
+                self._h_out = _lib.PinnedBuffer(count)
+            out = self._h_out.array(np.uint8, count)
+        else:
+            assert out.dtype == np.uint8 and out.size == count and out.flags.c_contiguous
+            out = out.reshape(-1)
+        out = self.d_out.download(np.uint8, count, self.stream, out=out)
         self._after_decode()
         return out.reshape(self.out_shape)
 
@@ -206,3 +224,84 @@ class WaveletBatchCodec(_BatchCodec):
     def hic_images(self, enc):
         from hiccup_b200 import wavelet
         return [wavelet.encode_streams_to_hic(enc, self.g, image=i) for i in range(self.n)]
+
+
+class PipelinedCodec:
+    """A big batch as a pipeline of chunks over a few concurrent slots (each slot = one codec on its own
+    CUDA stream, driven by its own host thread): the host->device copy of one chunk, the kernels of
+    another and the device->host copy of a third overlap, so the host-to-host rate approaches
+    max(PCIe, kernels) instead of their sum.  Results are identical to the unchunked codecs (images are
+    independent).
+
+        pipe = PipelinedCodec(1024, 426, 640, chunk=128, slots=3)            # mode="dct" | "wavelet"
+        pipe.round_trip(rgb, out, on_encoded=lambda first_image, enc: ...)  # enc: EncodedStreams of a chunk
+    """
+
+    def __init__(self, n, h, w, chunk=128, slots=3, mode="dct", device=None, **kw):
+        _lib.require_device()
+        if device is not None:
+            _lib.check(_lib.load().hic_set_device(int(device)))
+        self.device = device
+        self.n, self.h, self.w = int(n), int(h), int(w)
+        self.chunk = max(1, min(int(chunk), self.n))
+        if self.n % self.chunk:
+            raise ValueError("batch of %d is not a whole number of %d-image chunks" % (self.n, self.chunk))
+        self.n_chunks = self.n // self.chunk
+        self.slots = max(1, min(int(slots), self.n_chunks))
+        cls = DctBatchCodec if mode == "dct" else WaveletBatchCodec
+        self.streams = [_lib.stream_create() for _ in range(self.slots)]
+        self.codecs = [cls(self.chunk, h, w, stream=st, **kw) for st in self.streams]
+        self.out_shape = (self.n,) + self.codecs[0].out_shape[1:]
+
+    def round_trip(self, rgb, out, on_encoded=None, repeat=1):
+        """Encode then decode every chunk of `rgb` (n, h, w, 3) into `out` (out_shape); both should be
+        page-locked for the copies to overlap.  `repeat` > 1 streams the same batch through that many
+        times without draining the pipeline in between (a stream of batches).  Returns the compressed
+        payload bytes of one pass.
+
+        Two gates keep the slots out of lockstep: one chunk at a time owns the bulk host->device copy
+        and one the bulk device->host copy, so copies queue first-in first-out at full PCIe rate while
+        the other slots are in their kernel phases."""
+        import threading
+        assert rgb.shape == (self.n, self.h, self.w, 3) and out.shape == self.out_shape
+        totals = [0] * self.slots
+        errors = []
+        gate_in, gate_out = threading.Lock(), threading.Lock()
+
+        def work(slot):
+            try:
+                if self.device is not None:
+                    _lib.check(_lib.load().hic_set_device(int(self.device)))
+                codec = self.codecs[slot]
+                for v in range(slot, repeat * self.n_chunks, self.slots):
+                    c = v % self.n_chunks
+                    a, b = c * self.chunk, (c + 1) * self.chunk
+                    with gate_in:
+                        codec.upload(rgb[a:b])
+                        _lib.sync(codec.stream)
+                    enc = codec.encode_resident()
+                    if v < self.n_chunks:
+                        totals[slot] += int(enc.data.nbytes)
+                    if on_encoded is not None:
+                        on_encoded(a, enc)
+                    codec.decode_resident(enc)
+                    with gate_out:
+                        codec.fetch(out[a:b])
+            except Exception as e:      # surfaced to the caller below
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(s,)) for s in range(self.slots)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return sum(totals)
+
+    def close(self):
+        for c in self.codecs:
+            c.close()
+        for st in self.streams:
+            _lib.stream_destroy(st)
+        self.codecs, self.streams = [], []

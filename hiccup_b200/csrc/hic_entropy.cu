@@ -611,16 +611,26 @@ huffman_replay_kernel(int tier, int G, int stride_slots, int n_ss, const Compact
         slot[pos + 1] = newitem;
     };
     // heapq._siftup(heap, pos): the smaller child moves up until a leaf is reached, then the item
-    // bubbles back up (CPython's order of comparisons; ties go to the right child)
+    // bubbles back up (CPython's order of comparisons; ties go to the right child).  Both child pairs
+    // one level further down are requested before the comparison that picks between them, so the
+    // shared-memory latency overlaps the decision chain (indices are clamped, not predicated: a pair
+    // past the end is loaded from a valid slot and never used).
+    const int pair_lim = (n + 1) >> 1;                                // last pair index inside the lane's slots
     auto siftup = [&](int pos, uint2 newitem) {
         const int endpos = size, startpos = pos;
         int childpos = 2 * pos + 1;
-        while (childpos < endpos) {
-            const uint4 c = slot_pair[pos + 1];                       // slots 2 pos + 2, 2 pos + 3
-            const bool take_right = (childpos + 1 < endpos) && !(c.y < c.w);
-            slot[pos + 1] = take_right ? make_uint2(c.z, c.w) : make_uint2(c.x, c.y);
-            pos = childpos + (take_right ? 1 : 0);
-            childpos = 2 * pos + 1;
+        if (childpos < endpos) {
+            uint4 c = slot_pair[pos + 1];                             // slots 2 pos + 2, 2 pos + 3
+            while (true) {
+                const uint4 gl = slot_pair[min(childpos + 1, pair_lim)];       // children of childpos
+                const uint4 gr = slot_pair[min(childpos + 2, pair_lim)];       // children of childpos + 1
+                const bool take_right = (childpos + 1 < endpos) && !(c.y < c.w);
+                slot[pos + 1] = take_right ? make_uint2(c.z, c.w) : make_uint2(c.x, c.y);
+                pos = childpos + (take_right ? 1 : 0);
+                childpos = 2 * pos + 1;
+                if (childpos >= endpos) break;
+                c = take_right ? gr : gl;
+            }
         }
         siftdown(startpos, pos, newitem);
     };
@@ -921,11 +931,12 @@ struct hic_entropy_plan {
     std::vector<uint64_t> t_code;
     uint64_t total_rows = 0, total_bytes = 0;
     bool codes_ready = false;
+    cudaStream_t last_stream = nullptr;         // stream of the last code build (the lazy host mirrors use it)
     // fork/join plumbing of the device Huffman builder
-    static constexpr int N_AUX = 3;
-    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr};
+    static constexpr int N_AUX = 7;
+    cudaStream_t aux[N_AUX] = {};
     cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[N_AUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[N_AUX] = {};
 };
 
 static int fill_geom(const hic_stream_layout* L, int value_bins, Geom* g) {
@@ -1100,6 +1111,7 @@ int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
     HIC_REQUIRE(p != nullptr, "plan is NULL");
     const Geom& g = p->g;
     cudaStream_t st = as_stream(stream);
+    p->last_stream = st;
     uint32_t flags[4];
     HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
     std::vector<CompactIndex> index(p->n_ss);
@@ -1285,6 +1297,7 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     const Geom& g = p->g;
     HIC_REQUIRE(g.nb_bins <= 8192, "the device Huffman builder handles up to 8192 value bins; use hic_entropy_build_codes");
     cudaStream_t st = as_stream(stream);
+    p->last_stream = st;
     int rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
     if (rc) return rc;
     static bool attr_set[64] = {false};
@@ -1344,7 +1357,7 @@ int hic_entropy_stream_info(hic_entropy_plan* p, uint32_t* h_rows, uint32_t* h_n
     HIC_REQUIRE(p != nullptr, "plan is NULL");
     HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
     {
-        int rc = fetch_host_info(p, nullptr);
+        int rc = fetch_host_info(p, p->last_stream);
         if (rc) return rc;
     }
     for (int s = 0; s < p->n_ss; ++s) {
@@ -1363,7 +1376,7 @@ int hic_entropy_tables(hic_entropy_plan* p, int32_t* h_symbols, uint8_t* h_lens,
     HIC_REQUIRE(p != nullptr, "plan is NULL");
     HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
     {
-        int rc = fetch_host_tables(p, nullptr);
+        int rc = fetch_host_tables(p, p->last_stream);
         if (rc) return rc;
     }
     for (uint64_t i = 0; i < p->total_rows; ++i) {
