@@ -34,6 +34,10 @@ class Geometry(ctypes.Structure):
                 ("out_h", c_int32), ("out_w", c_int32)]
 
 
+class BandCarry(ctypes.Structure):
+    _fields_ = [("carry_zeros", c_int32), ("prev_dc", c_int32), ("more_after", c_int32), ("closes_stream", c_int32)]
+
+
 class WaveletGeometry(ctypes.Structure):
     _fields_ = [("h", c_int32), ("w", c_int32), ("lh", c_int32 * 4), ("lw", c_int32 * 4),
                 ("band_off", ctypes.c_int64 * 10), ("len", ctypes.c_int64)]
@@ -74,6 +78,12 @@ SIGNATURES = {
     "hic_entropy_plan_create": (c_int, [ctypes.POINTER(StreamLayout), c_int32, ctypes.POINTER(c_void_p)]),
     "hic_entropy_plan_destroy": (c_int, [c_void_p]),
     "hic_entropy_symbolize": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_scan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_emit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_entropy_histograms": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64),
+                                       c_void_p, c_void_p]),
+    "hic_entropy_set_codes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "hic_entropy_build_codes": (c_int, [c_void_p, c_void_p]),
     "hic_entropy_build_codes_device": (c_int, [c_void_p, c_void_p]),
     "hic_entropy_device_tables": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),

@@ -1,0 +1,365 @@
+"""Row-band sharding of one large image's DCT-mode encode (BASELINE config 5).
+
+The image is cut into bands of rows (multiples of 16, so luminance and chroma blocks align); every
+band runs the transform and entropy kernels on its own GPU, and only small metadata crosses between
+them -- there is no data-path collective:
+
+    1. every band: K1 on its rows (plus 16 rows of halo each side for the chroma pyramid), E1 pass 1
+       -> first / last non-zero position per channel, last DC value per channel
+    2. all-gather of those few integers; every band derives its seam state (zero run carried in, previous
+       DC, whether a later band holds a non-zero, whether it closes the stream)
+    3. every band: E1 pass 2 with the seam state -> exactly its slice of the whole image's symbol lists,
+       and their histograms with first-occurrence indices
+    4. all-gather of the histograms; every band merges them (counts add, first occurrences offset by the
+       symbols of the bands above), replays the reference's heapq Huffman construction once (host) and
+       gets the same nine code tables
+    5. every band: bit-packs its symbols with the shared codes at the bit phase its slice starts at in the
+       stitched string
+    6. gather of the band strings; the root ORs them together at their byte offsets and adds the
+       pad-count byte (iohelper.py:35-48)
+
+The result is byte-identical to encoding the whole image on one GPU (and to the reference).  The host
+logic below is written against a tiny communicator (`all_gather`, `gather`) so that it runs in one process
+over several bands (LocalComm, bands executed one after another) or one process per GPU under
+torch.distributed (DistComm; gloo or NCCL object collectives carry the metadata).
+"""
+import ctypes
+
+import numpy as np
+
+CHANNELS = 3
+KIND_DC, KIND_VALUE, KIND_LENGTH = 0, 1, 2
+CODE_MASK = np.uint64((1 << 58) - 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# planning
+# ------------------------------------------------------------------------------------------------
+def plan_bands(h, n_bands, align=16):
+    """Row boundaries [r_0 = 0, r_1, ..., r_K = h] with every interior boundary a multiple of `align`;
+    bands may be empty only if the image has fewer than K aligned rows groups."""
+    units = (h + align - 1) // align
+    n_bands = max(1, min(int(n_bands), units))
+    cuts = [min(h, align * ((units * b) // n_bands)) for b in range(n_bands)] + [h]
+    if len(cuts) > 2 and h - cuts[-2] < 2:          # a one-row band has no chroma row of its own
+        del cuts[-2]
+    return cuts
+
+
+def band_slice(h, r0, r1, halo=16):
+    """Rows of the source image band [r0, r1) needs: 16 rows of halo each side (one chroma block row),
+    so the band's blocks are whole block rows of the slice and K1 runs unchanged."""
+    return max(0, r0 - halo), min(h, r1 + halo)
+
+
+# ------------------------------------------------------------------------------------------------
+# seam state, histogram merge, bit offsets: pure functions (tests/test_bands_host.py)
+# ------------------------------------------------------------------------------------------------
+def seam_state(edges, b):
+    """edges: per band a dict(first_nz[3], last_nz[3], length[3], last_dc[3]).  Returns band b's
+    [(carry_zeros, prev_dc, more_after, closes_stream)] per channel (codec.run_length_coding and
+    differential_coding run over the WHOLE channel, codec.py:47-99)."""
+    out = []
+    for c in range(CHANNELS):
+        carry = 0
+        for e in edges[:b]:
+            if e["last_nz"][c] >= 0:
+                carry = e["length"][c] - 1 - e["last_nz"][c]
+            else:
+                carry += e["length"][c]
+        prev_dc = edges[b - 1]["last_dc"][c] if b > 0 else 0
+        more_after = any(e["last_nz"][c] >= 0 for e in edges[b + 1:])
+        out.append((int(carry), int(prev_dc), int(more_after), int(b == len(edges) - 1)))
+    return out
+
+
+def merge_histograms(band_hists, band_nsym):
+    """band_hists[b][s]: (symbols, counts, first_local) arrays of band b's symbol stream s (s = channel*3+kind);
+    band_nsym[b][s]: symbols of that stream in band b.  Returns per stream (symbols, counts) ordered by
+    first occurrence in the stitched stream (utils.group_by order, utils.py:83-96)."""
+    n_streams = len(band_hists[0])
+    merged = []
+    for s in range(n_streams):
+        syms, cnts, firsts, base = [], [], [], 0
+        for b, hists in enumerate(band_hists):
+            sym, cnt, first = hists[s]
+            syms.append(np.asarray(sym, np.int64))
+            cnts.append(np.asarray(cnt, np.int64))
+            firsts.append(np.asarray(first, np.int64) + base)
+            base += int(band_nsym[b][s])
+        sym, cnt, first = np.concatenate(syms), np.concatenate(cnts), np.concatenate(firsts)
+        if not sym.size:
+            merged.append((np.zeros(0, np.int32), np.zeros(0, np.uint32)))
+            continue
+        uniq, inv = np.unique(sym, return_inverse=True)
+        total = np.bincount(inv, weights=cnt.astype(np.float64), minlength=uniq.size).astype(np.int64)
+        gfirst = np.full(uniq.size, np.iinfo(np.int64).max, np.int64)
+        np.minimum.at(gfirst, inv, first)
+        order = np.argsort(gfirst, kind="stable")
+        merged.append((uniq[order].astype(np.int32), total[order].astype(np.uint32)))
+    return merged
+
+
+def build_tables(merged, huffman_build):
+    """Codes of every stream from the merged histograms.  huffman_build(freqs uint32[n]) -> (lens uint8[n],
+    codes uint64[n]) must replay the reference's heapq construction (hic_huffman_build_host).
+    Returns the packed table layout: index (n_streams, 2), symbols int32, packed uint64."""
+    index, syms, packed, pos = [], [], [], 0
+    for sym, cnt in merged:
+        if sym.size:
+            lens, codes = huffman_build(cnt)
+            syms.append(sym)
+            packed.append((lens.astype(np.uint64) << np.uint64(58)) | (codes & CODE_MASK))
+        index.append((pos, sym.size))
+        pos += sym.size
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return np.array(index, np.uint32).reshape(-1, 2), cat(syms, np.int32), cat(packed, np.uint64)
+
+
+def band_bits(tables, hists):
+    """Coded bits of one band's streams under the shared tables: sum of count * code length."""
+    index, syms, packed = tables
+    out = np.zeros(len(hists), np.uint64)
+    for s, (sym, cnt, _) in enumerate(hists):
+        if not len(sym):
+            continue
+        a, n = int(index[s, 0]), int(index[s, 1])
+        tab_sym = syms[a:a + n].astype(np.int64)
+        tab_len = (packed[a:a + n] >> np.uint64(58)).astype(np.int64)
+        order = np.argsort(tab_sym, kind="stable")
+        pos = np.searchsorted(tab_sym[order], np.asarray(sym, np.int64))
+        assert np.array_equal(tab_sym[order][pos], np.asarray(sym, np.int64)), "band symbol missing from the merged table"
+        out[s] = int((np.asarray(cnt, np.int64) * tab_len[order][pos]).sum())
+    return out
+
+
+def bit_layout(all_bits, b):
+    """all_bits[b'][s]: coded bits of stream s in band b'.  Band b's slice of stream s starts at bit
+    8 + sum of the bands above (8 = the pad-count byte).  Returns (start_bit[s] in 0..7, first byte[s])."""
+    above = np.zeros(len(all_bits[0]), np.uint64)
+    for bb in all_bits[:b]:
+        above += bb
+    pos = above + np.uint64(8)
+    return (pos % np.uint64(8)).astype(np.uint32), (pos // np.uint64(8)).astype(np.int64)
+
+
+def stitch(band_bytes, all_bits, n_streams):
+    """band_bytes[b][s]: the raw bytes band b packed for stream s (first byte at its `first byte`
+    position, bits pre-shifted to their phase).  Returns the framed payload of every stream
+    (iohelper.padded_bs_2_bytes layout)."""
+    out = []
+    for s in range(n_streams):
+        total = int(sum(int(bb[s]) for bb in all_bits))
+        pad = 8 - (total % 8)
+        buf = np.zeros(1 + (total + pad) // 8, np.uint8)
+        buf[0] = pad
+        for b, per_band in enumerate(band_bytes):
+            chunk = np.frombuffer(per_band[s], np.uint8)
+            if not chunk.size:
+                continue
+            _, first = bit_layout(all_bits, b)
+            a = int(first[s])
+            buf[a:a + chunk.size] |= chunk
+        out.append(buf.tobytes())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# communicators
+# ------------------------------------------------------------------------------------------------
+class DistComm:
+    """One process per band under torch.distributed (object collectives: metadata only)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_gather(self, obj):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def gather(self, obj, root=0):
+        out = [None] * self.size if self.rank == root else None
+        self.dist.gather_object(obj, out, dst=root, group=self.group)
+        return out
+
+
+def run_local(workers):
+    """Drive K band workers in one process (bands one after another on the current device, or on the
+    devices the workers were created for).  Each worker's steps() is a generator that yields
+    ("all_gather" | "gather", contribution) and receives the gathered list (None off the root of a
+    gather).  Returns the workers' return values."""
+    gens = [w.steps() for w in workers]
+    msgs = [next(g) for g in gens]
+    results = [None] * len(gens)
+    done = False
+    while not done:
+        kind = msgs[0][0]
+        gathered = [m[1] for m in msgs]
+        new = []
+        for i, g in enumerate(gens):
+            try:
+                new.append(g.send(gathered if (kind == "all_gather" or i == 0) else None))
+            except StopIteration as stop:
+                results[i] = stop.value
+                done = True
+        msgs = new
+    return results
+
+
+# ------------------------------------------------------------------------------------------------
+# the band worker (GPU)
+# ------------------------------------------------------------------------------------------------
+def _host_huffman(freqs):
+    from hiccup_b200 import _lib
+    freqs = np.ascontiguousarray(freqs, np.uint32)
+    lens, codes = np.empty(freqs.size, np.uint8), np.empty(freqs.size, np.uint64)
+    _lib.check(_lib.load().hic_huffman_build_host(freqs.ctypes.data, freqs.size, lens.ctypes.data, codes.ctypes.data))
+    return lens, codes
+
+
+class BandWorker:
+    """One band of an H x W image on one GPU.  `steps()` is the SPMD program: each `yield` is an
+    all-gather (the value yielded is this band's contribution, the value sent back is the list over
+    bands)."""
+
+    def __init__(self, band, n_bands, h, w, r0, r1, device=None, value_bins=8192, stream=None):
+        from hiccup_b200 import _lib, entropy
+        self._lib, self.device = _lib, device
+        self.band, self.n_bands, self.h, self.w, self.r0, self.r1 = band, n_bands, h, w, r0, r1
+        self.s0, self.s1 = band_slice(h, r0, r1)
+        self.stream = stream
+        if device is not None:
+            _lib.check(_lib.load().hic_set_device(int(device)))
+        hs = self.s1 - self.s0
+        self.g = _lib.geometry(hs, w)                      # geometry of the slice K1 runs on
+        g = self.g
+        skip_l, skip_c = (r0 - self.s0) // 8, (r0 - self.s0) // 16
+        rows_l = -(-(r1 - r0) // 8)
+        hc_band = min(r1, 2 * (h // 2)) // 2 - r0 // 2        # this band's rows of the (h // 2)-row chroma planes
+        rows_c = -(-hc_band // 8)
+        lay = _lib.StreamLayout()
+        lay.n_images, lay.skip_first, lay.blocks_per_image = 1, 1, g.blocks_per_image
+        nb = [rows_l * g.nbx_l, rows_c * g.nbx_c, rows_c * g.nbx_c]
+        off = [skip_l * g.nbx_l, g.nb_l + skip_c * g.nbx_c, g.nb_l + g.nb_c + skip_c * g.nbx_c]
+        for c in range(3):
+            lay.nb[c], lay.block_off[c], lay.len[c] = nb[c], off[c], 63 * nb[c]
+        self.layout, self.nb, self.block_off = lay, nb, off
+        self.d_rgb = _lib.DeviceBuffer(hs * w * 3)
+        self.d_coef = _lib.DeviceBuffer(g.blocks_per_image * 128)
+        self.d_ties = _lib.DeviceBuffer(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
+        self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+        self.encoder = entropy.EntropyEncoder(lay, value_bins)
+        self.rgb = None
+
+    def load(self, image):
+        """image: the whole H x W x 3 host array (only this band's slice is uploaded)."""
+        assert image.shape == (self.h, self.w, 3) and image.dtype == np.uint8
+        self.rgb = np.ascontiguousarray(image[self.s0:self.s1])
+
+    def _use_device(self):
+        if self.device is not None:
+            self._lib.check(self._lib.load().hic_set_device(int(self.device)))
+
+    def steps(self):
+        _lib, lib, st, enc, g = self._lib, self._lib.load(), self.stream, self.encoder, self.g
+        self._use_device()
+        self.d_rgb.upload(self.rgb, st)
+        _lib.check(lib.hic_dct_forward(self.d_rgb.ptr, 1, self.s1 - self.s0, self.w, self.d_coef.ptr, self.d_ties.ptr,
+                                       g.blocks_per_image, self.d_stats.ptr, st))
+        first_nz, last_nz = enc.scan(self.d_coef.ptr, st)
+        last_dc = [int(self.d_coef.download(np.int16, 1, st, offset=128 * (self.block_off[c] + self.nb[c] - 1))[0])
+                   for c in range(3)]
+        edges = yield ("all_gather", dict(first_nz=first_nz.tolist(), last_nz=last_nz.tolist(),
+                                          length=[63 * n for n in self.nb], last_dc=last_dc))
+        self._use_device()
+        enc.emit(self.d_coef.ptr, seam_state(edges, self.band), st)
+        index, entries, nsym_rl = enc.histograms(st)
+        hists, nsym = [], []
+        for s in range(9):
+            a, n = int(index[s, 0]), int(index[s, 1])
+            e = entries[a:a + n]
+            hists.append((e[:, 0].copy(), e[:, 1].astype(np.uint32), e[:, 2].astype(np.uint32)))
+            nsym.append(self.nb[s // 3] if s % 3 == KIND_DC else int(nsym_rl[s // 3]))
+        gathered = yield ("all_gather", dict(hists=hists, nsym=nsym))
+        self._use_device()
+        tables = build_tables(merge_histograms([m["hists"] for m in gathered], [m["nsym"] for m in gathered]), _host_huffman)
+        all_bits = [band_bits(tables, m["hists"]) for m in gathered]
+        start_bit, _ = bit_layout(all_bits, self.band)
+        enc.set_codes(tables[0], tables[1], tables[2], np.array(nsym, np.uint32), all_bits[self.band], start_bit, st)
+        out = enc.pack(st)
+        data = out.download(np.uint8, int(enc.total_bytes), st) if enc.total_bytes else np.zeros(0, np.uint8)
+        mine = [data[int(enc.byte_off[s]):int(enc.byte_off[s]) + int(enc.byte_len[s])].tobytes() for s in range(9)]
+        self.stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, st)
+        final = yield ("gather", dict(bytes=mine))               # the strings go to the root only
+        if final is None:
+            return None
+        return dict(tables=tables, all_bits=all_bits, band_bytes=[m["bytes"] for m in final])
+
+    def close(self):
+        self.encoder.close()
+        for b in (self.d_rgb, self.d_coef, self.d_ties, self.d_stats):
+            b.free()
+
+
+def assemble(result, h, w):
+    """The reference's HicImage (codec.jpeg_encode's return value) from the stitched bands."""
+    from hiccup_b200 import hicimage
+    index, syms, packed = result["tables"]
+    payloads = stitch(result["band_bytes"], result["all_bits"], 9)
+    tables, bits = [], []
+    for kind in range(3):
+        for c in range(3):
+            s = c * 3 + kind
+            a, n = int(index[s, 0]), int(index[s, 1])
+            conv = np.int32 if kind == KIND_DC else int
+            rows = [(conv(v), format(int(pk & CODE_MASK), "0%db" % int(pk >> np.uint64(58))))
+                    for v, pk in zip(syms[a:a + n].tolist(), packed[a:a + n])]
+            tables.append(hicimage.PayloadStringP.from_rows(rows))
+            bits.append(hicimage.BitStringP.from_framed(payloads[s]))
+    return hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(h, w), hicimage.TupP(h // 2, w // 2)])
+
+
+def encode_banded(image, n_bands, devices=None, value_bins=8192):
+    """Encode one image as `n_bands` row bands in this process (devices: optional list of CUDA device
+    indices, one per band, cycled; default: the current device for all).  Returns the HicImage."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w = image.shape[:2]
+    cuts = plan_bands(h, n_bands)
+    workers = []
+    for b in range(len(cuts) - 1):
+        dev = None if not devices else devices[b % len(devices)]
+        wk = BandWorker(b, len(cuts) - 1, h, w, cuts[b], cuts[b + 1], device=dev, value_bins=value_bins)
+        wk.load(image)
+        workers.append(wk)
+    try:
+        results = run_local(workers)
+    finally:
+        for wk in workers:
+            wk.close()
+    return assemble(results[0], h, w)
+
+
+def encode_banded_dist(image, comm, device=None, value_bins=8192, worker=None):
+    """SPMD form: rank r of `comm` encodes band r.  Every rank passes the same image array (only its slice
+    is touched).  Returns the HicImage on rank 0, None elsewhere."""
+    h, w = image.shape[:2]
+    cuts = plan_bands(h, comm.size)
+    if len(cuts) - 1 != comm.size:
+        raise ValueError("image of %d rows cannot be cut into %d bands of 16-row multiples" % (h, comm.size))
+    wk = worker or BandWorker(comm.rank, comm.size, h, w, cuts[comm.rank], cuts[comm.rank + 1], device=device,
+                              value_bins=value_bins)
+    wk.load(image)
+    gen = wk.steps()
+    kind, msg = next(gen)
+    result = None
+    try:
+        while True:
+            kind, msg = gen.send(comm.all_gather(msg) if kind == "all_gather" else comm.gather(msg, 0))
+    except StopIteration as stop:
+        result = stop.value
+    if worker is None:
+        wk.close()
+    return assemble(result, h, w) if comm.rank == 0 else None

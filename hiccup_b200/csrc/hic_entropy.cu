@@ -48,9 +48,19 @@ struct TileCarry {
     uint32_t sym_off;       // symbols emitted at positions before the tile
 };
 struct StreamTotals {
-    int last_nz;            // last non-zero position of the stream (-1: none)
+    int last_nz;            // filler limit: last non-zero position of the stream (-1: none), or INT_MAX
+                            // when a later row band of the same channel still holds a non-zero
     uint32_t nsym;          // run-length symbols including the trailing (0, 0)
+    int first_nz;           // first / last non-zero position inside this stream (-1: none)
+    int local_last_nz;
 };
+// Row-band sharding: a channel stream may be one band of a taller image.  The run-length
+// state that crosses the seam is handed in, so that every band emits exactly its slice of the whole
+// image's symbol list: `carry_zeros` zero positions since the last non-zero of the previous bands
+// (its fillers already belong to those bands), the previous band's last DC value, whether a later band
+// still holds a non-zero (then trailing zeros keep emitting fillers and there is no (0, 0) here), and
+// whether this band closes the stream (it appends the (0, 0) if the stream ends in zeros).
+typedef hic_band_carry BandCarry;
 struct CompactEntry {
     int32_t sym;
     uint32_t count, first;
@@ -205,26 +215,31 @@ rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __res
 
 // pass B: one thread per channel stream walks its tiles, producing the carries and stream totals,
 // and writes the trailing (0, 0) symbol (with its histogram contribution).
-__global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_seg, TileCarry* __restrict__ carry,
-                                       StreamTotals* __restrict__ totals, int16_t* __restrict__ values,
-                                       uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist,
-                                       uint32_t* __restrict__ first) {
+__global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_seg, const BandCarry* __restrict__ band,
+                                       TileCarry* __restrict__ carry, StreamTotals* __restrict__ totals,
+                                       int16_t* __restrict__ values, uint8_t* __restrict__ lengths,
+                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ first) {
     const int cs = blockIdx.x * blockDim.x + threadIdx.x;
     if (cs >= g.L.n_images * 3) return;
     const int img = cs / 3, c = cs % 3;
     int64_t t0 = (int64_t)img * g.tiles_per_image;
     for (int k = 0; k < c; ++k) t0 += g.tiles[k];
     const int per_tile = RLE_TB * (g.L.skip_first ? 63 : 64);
-    Segment run{-1, -1, 0};          // a virtual non-zero at position -1 carrying no symbol
+    const BandCarry bc = band ? band[cs] : BandCarry{0, 0, 0, 1};
+    const int prev0 = -1 - bc.carry_zeros;       // a virtual non-zero that far back, carrying no symbol
+    const int base = bc.carry_zeros / 15;        // fillers inside the carried run were emitted by earlier bands
+    Segment run{prev0, prev0, 0};
     bool any = false;
+    int first_nz = -1;
     for (int t = 0; t < g.tiles[c]; ++t) {
         const int start = t * per_tile;
         TileCarry tc;
         tc.prev_last = run.last;
-        tc.sym_off = (uint32_t)(run.count + (start - 1 - run.last) / 15);
+        tc.sym_off = (uint32_t)(run.count + (start - 1 - run.last) / 15 - base);
         carry[t0 + t] = tc;
         const Segment s = tile_seg[t0 + t];
         if (s.first >= 0) {
+            if (!any) first_nz = s.first;
             run.count += s.count + (s.first - run.last - 1) / 15;
             run.last = s.last;
             any = true;
@@ -232,9 +247,14 @@ __global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_
     }
     const int len = (int)g.L.len[c];
     StreamTotals st;
-    st.last_nz = any ? run.last : -1;
-    uint32_t nsym = any ? (uint32_t)run.count : 0u;
-    if (st.last_nz != len - 1 || len == 0) {          // trailing zeros -> one (0, 0)
+    st.first_nz = first_nz;
+    st.local_last_nz = any ? run.last : -1;
+    st.last_nz = bc.more_after ? 0x7FFFFFFF : st.local_last_nz;
+    // symbols up to the last local non-zero, then (if a later band continues the run) the fillers of the tail
+    uint32_t nsym = (uint32_t)(run.count + (bc.more_after ? (len - 1 - run.last) / 15 : 0) - (any || bc.more_after ? base : 0));
+    if (!any && !bc.more_after) nsym = 0;
+    const bool ends_in_zeros = (st.local_last_nz != len - 1) || len == 0 || bc.carry_zeros > 0 && !any;
+    if (bc.closes_stream && !bc.more_after && ends_in_zeros) {          // trailing zeros -> one (0, 0)
         const int64_t sym_base = cs_block_base(g, img, c) * 64;
         values[sym_base + nsym] = 0;
         lengths[sym_base + nsym] = 0;
@@ -247,6 +267,30 @@ __global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_
         ++nsym;
     }
     st.nsym = nsym;
+    totals[cs] = st;
+}
+
+// first / last non-zero position of every channel stream, from the tile summaries alone (what the host
+// needs to work out the seam state of row bands before the emit pass)
+__global__ void rle_edges_kernel(Geom g, const Segment* __restrict__ tile_seg, StreamTotals* __restrict__ totals) {
+    const int cs = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cs >= g.L.n_images * 3) return;
+    const int img = cs / 3, c = cs % 3;
+    int64_t t0 = (int64_t)img * g.tiles_per_image;
+    for (int k = 0; k < c; ++k) t0 += g.tiles[k];
+    int first_nz = -1, last_nz = -1;
+    for (int t = 0; t < g.tiles[c]; ++t) {
+        const Segment s = tile_seg[t0 + t];
+        if (s.first >= 0) {
+            if (first_nz < 0) first_nz = s.first;
+            last_nz = s.last;
+        }
+    }
+    StreamTotals st;
+    st.first_nz = first_nz;
+    st.local_last_nz = last_nz;
+    st.last_nz = last_nz;
+    st.nsym = 0;
     totals[cs] = st;
 }
 
@@ -274,7 +318,8 @@ struct EmitSmem {
 
 template <bool SKIP>
 __global__ void __launch_bounds__(RLE_TB)
-rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __restrict__ carry,
+rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __restrict__ band,
+                const TileCarry* __restrict__ carry,
                 const StreamTotals* __restrict__ totals, int16_t* __restrict__ dc_out, int16_t* __restrict__ values,
                 uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
                 uint32_t* __restrict__ err) {
@@ -312,7 +357,7 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
     // DC differences (codec.differential_coding): d[0] = DC[0], d[k] = DC[k] - DC[k-1]
     if (SKIP && active) {
         const int dc = HIC_ELEM(w, 0);
-        const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : 0;
+        const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : (band ? band[cs].prev_dc : 0);
         const int diff = dc - prev;
         dc_out[block_base + b] = (int16_t)diff;
         const int bin = diff + half;
@@ -321,7 +366,7 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const TileCarry* __res
     }
 
     // thread-local last non-zero
-    int my_last = -1;
+    int my_last = (int)0x80000000;          // none (below every carried virtual position)
     if (active) {
 #pragma unroll
         for (int e = SKIP ? 1 : 0; e < 64; ++e) {
@@ -812,7 +857,8 @@ pack_tile_bits_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* 
     if (threadIdx.x == 0) tile_bits[blockIdx.x] = total;
 }
 
-__global__ void pack_stream_scan_kernel(Geom g, const uint32_t* __restrict__ tile_bits, uint64_t* __restrict__ tile_off) {
+__global__ void pack_stream_scan_kernel(Geom g, const uint32_t* __restrict__ tile_bits, const uint32_t* __restrict__ start_bit,
+                                        uint64_t* __restrict__ tile_off) {
     const int ss = blockIdx.x * blockDim.x + threadIdx.x;
     if (ss >= g.L.n_images * 9) return;
     const int img = ss / 9, c = (ss % 9) / 3, k = ss % 3;
@@ -820,7 +866,8 @@ __global__ void pack_stream_scan_kernel(Geom g, const uint32_t* __restrict__ til
     for (int cc = 0; cc < 3; ++cc)
         for (int kk = 0; kk < 3; ++kk)
             if (cc < c || (cc == c && kk < k)) t0 += g.ptiles[cc][kk];
-    uint64_t run = 8;           // the pad-count byte comes first (iohelper.py:41-46)
+    uint64_t run = start_bit[ss];           // 8: the pad-count byte comes first (iohelper.py:41-46); 0..7: a row
+                                            // band's bits, pre-shifted to their phase in the stitched stream
     for (int t = 0; t < g.ptiles[c][k]; ++t) {
         tile_off[t0 + t] = run;
         run += tile_bits[t0 + t];
@@ -830,7 +877,8 @@ __global__ void pack_stream_scan_kernel(Geom g, const uint32_t* __restrict__ til
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __restrict__ ss_nsym,
                  const uint64_t* __restrict__ ss_nbits, const uint64_t* __restrict__ ss_byte_off,
-                 const uint64_t* __restrict__ tile_off, const int16_t* __restrict__ dc,
+                 const uint64_t* __restrict__ tile_off, const uint32_t* __restrict__ start_bit,
+                 const int16_t* __restrict__ dc,
                  const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths, uint8_t* __restrict__ out) {
     __shared__ uint32_t buf[PACK_WORDS];
     __shared__ uint32_t ssum[PACK_THREADS / 32];
@@ -868,7 +916,7 @@ pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __res
             o += l;
         }
     }
-    if (pr.tile == 0 && threadIdx.x == 0) {                 // pad count p = 8 - (nbits mod 8) in byte 0
+    if (pr.tile == 0 && threadIdx.x == 0 && start_bit[pr.ss] == 8) {    // pad count p = 8 - (nbits mod 8) in byte 0
         const uint32_t pad = 8u - (uint32_t)(ss_nbits[pr.ss] & 7);
         atomicOr(&buf[0], pad << 24);
     }
@@ -918,6 +966,10 @@ struct hic_entropy_plan {
     uint64_t* d_ptile_off = nullptr;
     uint64_t* d_ss_byte_len = nullptr;
     unsigned long long* d_pay_totals = nullptr; // [0] total payload bytes
+    uint32_t* d_start_bit = nullptr;            // per symbol stream: 8 = framed payload, 0..7 = raw band bits at that phase
+    BandCarry* d_band = nullptr;                // per channel stream: seam state of row-band sharding (else defaults)
+    bool band_mode = false;
+    bool start_is_default = true;               // d_start_bit holds 8 everywhere
     uint32_t* d_tier_count = nullptr;           // device Huffman builder: streams per size tier
     uint32_t* d_tier_list = nullptr;            // [tier][n_ss] stream ids
     bool device_built = false;                  // codes came from hic_entropy_build_codes_device
@@ -1007,7 +1059,7 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
                     p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
-                    p->d_pay_totals, p->d_tier_count, p->d_tier_list};
+                    p->d_pay_totals, p->d_tier_count, p->d_tier_list, p->d_start_bit, p->d_band};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
@@ -1056,6 +1108,8 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_ptile_off, p->total_ptiles));
     ok(dalloc(&p->d_ss_byte_len, p->n_ss));
     ok(dalloc(&p->d_pay_totals, 2));
+    ok(dalloc(&p->d_start_bit, p->n_ss));
+    ok(dalloc(&p->d_band, p->n_cs));
     ok(dalloc(&p->d_tier_count, N_TIERS));
     ok(dalloc(&p->d_tier_list, (size_t)N_TIERS * p->n_ss));
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
@@ -1063,6 +1117,10 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
         ok(cudaEventCreateWithFlags(&p->ev_join[a], cudaEventDisableTiming));
     }
     ok(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    if (e == cudaSuccess) {
+        std::vector<uint32_t> start(p->n_ss, 8u);
+        ok(cudaMemcpy(p->d_start_bit, start.data(), sizeof(uint32_t) * p->n_ss, cudaMemcpyHostToDevice));
+    }
     if (e != cudaSuccess) {
         hic_entropy_plan_destroy(p);
         return hic::fail(HIC_ERR_CUDA, "entropy plan allocation failed: %s", cudaGetErrorString(e));
@@ -1071,10 +1129,20 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     return HIC_OK;
 }
 
-int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stream) {
-    HIC_REQUIRE(p && d_coef, "NULL argument");
+static int ensure_row_capacity(hic_entropy_plan* p, uint64_t rows);
+
+// framed payloads again after a row-band pack (start bit 8 everywhere)
+static int restore_default_start(hic_entropy_plan* p, cudaStream_t st) {
+    if (p->start_is_default) return HIC_OK;
+    std::vector<uint32_t> start(p->n_ss, 8u);
+    HIC_CUDA(cudaMemcpyAsync(p->d_start_bit, start.data(), sizeof(uint32_t) * p->n_ss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    p->start_is_default = true;
+    return HIC_OK;
+}
+
+static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st) {
     const Geom& g = p->g;
-    cudaStream_t st = as_stream(stream);
     p->codes_ready = false;
     const size_t hist_n = (size_t)p->n_ss * g.nb_bins;
     HIC_CUDA(cudaMemsetAsync(p->d_hist, 0, hist_n * sizeof(uint32_t), st));
@@ -1085,8 +1153,14 @@ int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stre
         HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
     else
         HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
-    HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, p->d_carry, p->d_totals, p->d_values,
-                                                                 p->d_lengths, p->d_hist, p->d_first));
+    return HIC_OK;
+}
+
+static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry* d_band, cudaStream_t st) {
+    const Geom& g = p->g;
+    const unsigned tiles = (unsigned)p->total_tiles;
+    HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, d_band, p->d_carry, p->d_totals,
+                                                                 p->d_values, p->d_lengths, p->d_hist, p->d_first));
     {
         static bool emit_attr[64] = {false};
         int dev = 0;
@@ -1098,12 +1172,137 @@ int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stre
         }
     }
     if (g.L.skip_first)
-        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<true><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
-                                                        p->d_lengths, p->d_hist, p->d_first, p->d_err));
+        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<true><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
+                                                        p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err));
     else
-        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, p->d_carry, p->d_totals, p->d_dc, p->d_values,
-                                                         p->d_lengths, p->d_hist, p->d_first, p->d_err));
+        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
+                                                         p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err));
     HIC_LAUNCH("compact_kernel", st, compact_kernel<<<p->n_ss, 256, 0, st>>>(g, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
+    return HIC_OK;
+}
+
+int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stream) {
+    HIC_REQUIRE(p && d_coef, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    p->band_mode = false;
+    int rc = scan_pass(p, d_coef, st);
+    if (rc) return rc;
+    return emit_pass(p, d_coef, nullptr, st);
+}
+
+int hic_entropy_scan(hic_entropy_plan* p, const int16_t* d_coef, int32_t* h_first_nz, int32_t* h_last_nz, void* stream) {
+    HIC_REQUIRE(p && d_coef && h_first_nz && h_last_nz, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    int rc = scan_pass(p, d_coef, st);
+    if (rc) return rc;
+    HIC_LAUNCH("rle_edges_kernel", st, rle_edges_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->g, p->d_tile_seg, p->d_totals));
+    std::vector<StreamTotals> tot(p->n_cs);
+    HIC_CUDA(cudaMemcpyAsync(tot.data(), p->d_totals, sizeof(StreamTotals) * p->n_cs, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    for (int cs = 0; cs < p->n_cs; ++cs) {
+        h_first_nz[cs] = tot[cs].first_nz;
+        h_last_nz[cs] = tot[cs].local_last_nz;
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_emit(hic_entropy_plan* p, const int16_t* d_coef, const hic_band_carry* h_band, void* stream) {
+    HIC_REQUIRE(p && d_coef, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    p->band_mode = h_band != nullptr;
+    if (h_band) {
+        for (int cs = 0; cs < p->n_cs; ++cs)
+            HIC_REQUIRE(h_band[cs].carry_zeros >= 0 && h_band[cs].carry_zeros < (1 << 30), "stream %d: bad carry", cs);
+        HIC_CUDA(cudaMemcpyAsync(p->d_band, h_band, sizeof(BandCarry) * p->n_cs, cudaMemcpyHostToDevice, st));
+        HIC_CUDA(cudaStreamSynchronize(st));          // the caller's array may go
+    }
+    return emit_pass(p, d_coef, h_band ? p->d_band : nullptr, st);
+}
+
+int hic_entropy_histograms(hic_entropy_plan* p, uint32_t* h_index, int32_t* h_entries, uint64_t capacity, uint64_t* n_entries,
+                           uint32_t* h_nsym_rl, void* stream) {
+    HIC_REQUIRE(p && h_index && n_entries, "NULL argument");
+    cudaStream_t st = as_stream(stream);
+    uint32_t flags[4];
+    HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(h_index, p->d_index, sizeof(CompactIndex) * p->n_ss, cudaMemcpyDeviceToHost, st));
+    std::vector<StreamTotals> tot(p->n_cs);
+    HIC_CUDA(cudaMemcpyAsync(tot.data(), p->d_totals, sizeof(StreamTotals) * p->n_cs, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
+    if (flags[0]) return hic::fail(HIC_ERR_INVALID, "a symbol fell outside [-%d, %d): create the plan with more value_bins",
+                                   p->g.nb_bins / 2, p->g.nb_bins / 2);
+    *n_entries = flags[1];
+    if (h_nsym_rl)
+        for (int cs = 0; cs < p->n_cs; ++cs) h_nsym_rl[cs] = tot[cs].nsym;
+    if (h_entries) {
+        if (flags[1] > capacity) return hic::fail(HIC_ERR_CAPACITY, "%u histogram entries, room for %llu", flags[1], (unsigned long long)capacity);
+        static_assert(sizeof(CompactEntry) == 12, "entry layout");
+        if (flags[1]) {
+            HIC_CUDA(cudaMemcpyAsync(h_entries, p->d_entries, sizeof(CompactEntry) * flags[1], cudaMemcpyDeviceToHost, st));
+            HIC_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return HIC_OK;
+}
+
+int hic_entropy_set_codes(hic_entropy_plan* p, const uint32_t* h_index, const int32_t* h_row_sym, const uint64_t* h_row_packed,
+                          uint64_t total_rows, const uint32_t* h_nsym, const uint64_t* h_nbits, const uint32_t* h_start_bit,
+                          void* stream) {
+    HIC_REQUIRE(p && h_index && h_row_sym && h_row_packed && h_nsym && h_nbits, "NULL argument");
+    const Geom& g = p->g;
+    cudaStream_t st = as_stream(stream);
+    p->last_stream = st;
+    const int nss = p->n_ss;
+    std::vector<uint32_t> row_stream(total_rows), start(nss, 8u);
+    p->rows.assign(nss, 0); p->nsym.assign(nss, 0); p->nbits.assign(nss, 0);
+    p->byte_off.assign(nss, 0); p->byte_len.assign(nss, 0); p->row_off.assign(nss + 1, 0);
+    p->dev_row_start.assign(nss, 0);
+    uint64_t off = 0;
+    for (int s = 0; s < nss; ++s) {
+        const uint32_t r0 = h_index[2 * s], cnt = h_index[2 * s + 1];
+        HIC_REQUIRE((uint64_t)r0 + cnt <= total_rows, "stream %d: rows [%u, +%u) exceed %llu", s, r0, cnt, (unsigned long long)total_rows);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const int bin = h_row_sym[r0 + i] + ((s % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2);
+            HIC_REQUIRE(bin >= 0 && bin < g.nb_bins, "stream %d: symbol %d outside the plan's bins", s, h_row_sym[r0 + i]);
+            row_stream[r0 + i] = (uint32_t)s;
+        }
+        p->rows[s] = cnt;
+        p->dev_row_start[s] = r0;
+        p->row_off[s + 1] = p->row_off[s] + cnt;
+        p->nsym[s] = h_nsym[s];
+        p->nbits[s] = h_nbits[s];
+        if (h_start_bit) {
+            HIC_REQUIRE(h_start_bit[s] <= 8, "stream %d: start bit %u", s, h_start_bit[s]);
+            start[s] = h_start_bit[s];
+        }
+        if (h_nsym[s] == 0) continue;
+        const uint64_t len = start[s] == 8 ? 1 + (h_nbits[s] + (8 - (h_nbits[s] & 7))) / 8 : (start[s] + h_nbits[s] + 7) / 8;
+        p->byte_off[s] = off;
+        p->byte_len[s] = len;
+        off += (len + 3) & ~3ull;
+    }
+    p->total_bytes = off;
+    p->total_rows = total_rows;
+    int rc = ensure_row_capacity(p, total_rows + 1);
+    if (rc) return rc;
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_sym, h_row_sym, sizeof(int32_t) * total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_code, h_row_packed, sizeof(uint64_t) * total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_row_stream, row_stream.data(), sizeof(uint32_t) * total_rows, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_nsym, p->nsym.data(), sizeof(uint32_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_nbits, p->nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_off, p->byte_off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_len, p->byte_len.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_start_bit, start.data(), sizeof(uint32_t) * nss, cudaMemcpyHostToDevice, st));
+    HIC_CUDA(cudaMemcpyAsync(p->d_index, h_index, sizeof(CompactIndex) * nss, cudaMemcpyHostToDevice, st));
+    if (total_rows)
+        HIC_LAUNCH("lut_scatter_kernel", st, lut_scatter_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
+                                                                                   p->d_row_stream, total_rows, p->d_lut));
+    HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors go out of scope
+    p->start_is_default = h_start_bit == nullptr;
+    p->codes_ready = true;
+    p->device_built = false;
+    p->host_info_valid = true;
+    p->host_tables_valid = false;
     return HIC_OK;
 }
 
@@ -1112,6 +1311,10 @@ int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
     const Geom& g = p->g;
     cudaStream_t st = as_stream(stream);
     p->last_stream = st;
+    {
+        int rc0 = restore_default_start(p, st);
+        if (rc0) return rc0;
+    }
     uint32_t flags[4];
     HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
     std::vector<CompactIndex> index(p->n_ss);
@@ -1298,7 +1501,9 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     HIC_REQUIRE(g.nb_bins <= 8192, "the device Huffman builder handles up to 8192 value bins; use hic_entropy_build_codes");
     cudaStream_t st = as_stream(stream);
     p->last_stream = st;
-    int rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
+    int rc = restore_default_start(p, st);
+    if (rc) return rc;
+    rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
     if (rc) return rc;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1411,9 +1616,9 @@ int hic_entropy_pack(hic_entropy_plan* p, uint8_t* d_out, void* stream) {
     const unsigned tiles = (unsigned)p->total_ptiles;
     HIC_LAUNCH("pack_tile_bits_kernel", st, pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
                                                          p->d_ptile_bits));
-    HIC_LAUNCH("pack_stream_scan_kernel", st, pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_ptile_off));
+    HIC_LAUNCH("pack_stream_scan_kernel", st, pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_start_bit, p->d_ptile_off));
     HIC_LAUNCH("pack_emit_kernel", st, pack_emit_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off,
-                                                    p->d_ptile_off, p->d_dc, p->d_values, p->d_lengths, d_out));
+                                                    p->d_ptile_off, p->d_start_bit, p->d_dc, p->d_values, p->d_lengths, d_out));
     return HIC_OK;
 }
 

@@ -98,6 +98,53 @@ class EntropyEncoder:
     def symbolize(self, d_coef, stream=None):
         _lib.check(self.lib.hic_entropy_symbolize(self.plan, d_coef, stream))
 
+    # ---- row-band sharding: two-pass E1 with the seam state in between, external codes ----------
+    def scan(self, d_coef, stream=None):
+        """Pass 1.  Returns (first_nz, last_nz) int32 arrays over the channel streams (-1: none)."""
+        n_cs = self.layout.n_images * 3
+        first, last = np.empty(n_cs, np.int32), np.empty(n_cs, np.int32)
+        _lib.check(self.lib.hic_entropy_scan(self.plan, d_coef, first.ctypes.data, last.ctypes.data, stream))
+        return first, last
+
+    def emit(self, d_coef, band=None, stream=None):
+        """Pass 2.  band: list of (carry_zeros, prev_dc, more_after, closes_stream) per channel stream."""
+        arr = None
+        if band is not None:
+            arr = (_lib.BandCarry * len(band))(*[_lib.BandCarry(*[int(v) for v in b]) for b in band])
+        _lib.check(self.lib.hic_entropy_emit(self.plan, d_coef, arr, stream))
+
+    def histograms(self, stream=None):
+        """Compacted histograms of the last emit: (index (n_streams, 2), entries (n, 3) int32 rows of
+        (symbol, count, first occurrence), run-length symbol count per channel stream)."""
+        index = np.empty(2 * self.n_streams, np.uint32)
+        nsym_rl = np.empty(self.layout.n_images * 3, np.uint32)
+        n = ctypes.c_uint64(0)
+        _lib.check(self.lib.hic_entropy_histograms(self.plan, index.ctypes.data, None, 0, ctypes.byref(n), nsym_rl.ctypes.data, stream))
+        entries = np.empty((max(int(n.value), 1), 3), np.int32)
+        _lib.check(self.lib.hic_entropy_histograms(self.plan, index.ctypes.data, entries.ctypes.data, entries.shape[0],
+                                                   ctypes.byref(n), nsym_rl.ctypes.data, stream))
+        return index.reshape(-1, 2), entries[:int(n.value)], nsym_rl
+
+    def set_codes(self, index, symbols, packed, nsym, nbits, start_bit=None, stream=None):
+        """Install externally built codes (packed table layout) and this plan's symbol / bit counts."""
+        index = np.ascontiguousarray(index, np.uint32)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        packed = np.ascontiguousarray(packed, np.uint64)
+        nsym = np.ascontiguousarray(nsym, np.uint32)
+        nbits = np.ascontiguousarray(nbits, np.uint64)
+        sb = None if start_bit is None else np.ascontiguousarray(start_bit, np.uint32)
+        _lib.check(self.lib.hic_entropy_set_codes(self.plan, index.ctypes.data, symbols.ctypes.data, packed.ctypes.data,
+                                                  int(symbols.size), nsym.ctypes.data, nbits.ctypes.data,
+                                                  None if sb is None else sb.ctypes.data, stream))
+        n = self.n_streams
+        self.rows, self.nsym = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self.nbits, self.byte_off, self.byte_len = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        tr, tb = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(self.lib.hic_entropy_stream_info(self.plan, self.rows.ctypes.data, self.nsym.ctypes.data,
+                                                    self.nbits.ctypes.data, self.byte_off.ctypes.data,
+                                                    self.byte_len.ctypes.data, ctypes.byref(tr), ctypes.byref(tb)))
+        self.total_rows, self.total_bytes = tr.value, tb.value
+
     def build_codes(self, stream=None, on_device=False):
         """E2.  on_device=False: host heapq replay (reference-faithful default, any alphabet size);
         on_device=True: the same replay by one CTA per stream on the GPU (alphabets <= 8192)."""

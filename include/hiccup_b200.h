@@ -185,6 +185,37 @@ int hic_entropy_plan_destroy(hic_entropy_plan* plan);
  * (utils.group_by, utils.py:83-96, via huffman.py:17-19). */
 int hic_entropy_symbolize(hic_entropy_plan* plan, const int16_t* d_coef, void* stream);
 
+/* ---- row-band sharding of one tall image: E1 in two passes with the seam state in
+ * between, externally built codes, raw bit strings at a bit phase ------------------------------ */
+/* What crosses a band seam for one channel stream (index image * 3 + channel). */
+typedef struct hic_band_carry {
+    int32_t carry_zeros;      /* zero positions since the last non-zero of the bands above (0 for the top band) */
+    int32_t prev_dc;          /* DC value of the last block of the band above (0 for the top band) */
+    int32_t more_after;       /* a band below still holds a non-zero: trailing zeros here keep emitting fillers */
+    int32_t closes_stream;    /* bottom band: append the (0, 0) if the whole stream ends in zeros */
+} hic_band_carry;
+/* Pass 1: per-tile run summaries; h_first_nz / h_last_nz (3 n entries) receive the first and last
+ * non-zero run-length position of every channel stream (-1: none).  Synchronises `stream`. */
+int hic_entropy_scan(hic_entropy_plan* plan, const int16_t* d_coef, int32_t* h_first_nz, int32_t* h_last_nz, void* stream);
+/* Pass 2 (after hic_entropy_scan): symbols, DC differences and histograms with the seam state applied,
+ * so that the band's symbol lists are exactly its slice of the whole image's lists (codec.py:47-99
+ * runs over the whole channel).  h_band: 3 n entries, or NULL for stand-alone streams.
+ * hic_entropy_symbolize = scan + emit(NULL). */
+int hic_entropy_emit(hic_entropy_plan* plan, const int16_t* d_coef, const hic_band_carry* h_band, void* stream);
+/* The compacted histograms of the last emit: h_index[2 s], h_index[2 s + 1] = first entry and entry
+ * count of symbol stream s; h_entries: (symbol, count, first occurrence index) int32 triples;
+ * h_nsym_rl (3 n entries, may be NULL): run-length symbols per channel stream.  Synchronises. */
+int hic_entropy_histograms(hic_entropy_plan* plan, uint32_t* h_index, int32_t* h_entries, uint64_t capacity,
+                           uint64_t* n_entries, uint32_t* h_nsym_rl, void* stream);
+/* Install codes built elsewhere (the merged tables of all bands) in the packed layout of
+ * hic_entropy_tables_packed, with the symbol and bit counts of THIS plan's streams.  h_start_bit[s]:
+ * 8 (or NULL) = framed payload as usual; 0..7 = hic_entropy_pack writes the raw bits of stream s
+ * starting at that bit of its first byte, no pad-count byte (the host ORs the band strings together).
+ * Synchronises `stream`. */
+int hic_entropy_set_codes(hic_entropy_plan* plan, const uint32_t* h_index, const int32_t* h_row_sym,
+                          const uint64_t* h_row_packed, uint64_t total_rows, const uint32_t* h_nsym,
+                          const uint64_t* h_nbits, const uint32_t* h_start_bit, void* stream);
+
 /* E2 (host; synchronises `stream`) -- fetch the compacted histograms, build every Huffman code
  * exactly as HuffmanTree._construct does (huffman.py:60-79, heapq replay), upload code tables. */
 int hic_entropy_build_codes(hic_entropy_plan* plan, void* stream);

@@ -1,0 +1,50 @@
+"""Row-band sharded encode on the GPU (hiccup_b200/bands.py): K bands of one image, each through K1 and
+the two-pass entropy kernels with the seam state, stitched on the host -- must be byte-identical to the
+whole-image encode (itself pinned to the reference)."""
+import numpy as np
+import pytest
+
+from oracle import hiccup_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _image(kind, h, w, seed):
+    if kind == "synthetic":
+        return orc.synthetic_image(h, w, seed)
+    img = np.full((h, w, 3), 90, np.uint8)
+    if kind == "half":
+        img[:h // 2] = orc.synthetic_image(h // 2, w, seed)
+    elif kind == "bottom":
+        img[3 * h // 4:] = orc.synthetic_image(h - 3 * h // 4, w, seed)
+    elif kind == "middle":
+        img[h // 3:h // 3 + 24] = orc.synthetic_image(24, w, seed)
+    return img
+
+
+@pytest.mark.parametrize("kind,shape,k", [("synthetic", (96, 80), 2), ("synthetic", (130, 72), 3), ("synthetic", (426, 640), 4),
+                                          ("flat", (64, 48), 3), ("half", (128, 64), 4), ("bottom", (256, 64), 8),
+                                          ("middle", (192, 112), 6), ("synthetic", (50, 34), 2),
+                                          ("synthetic", (1080, 1920), 8), ("synthetic", (2048, 512), 5)])
+def test_banded_encode_equals_whole_image(kind, shape, k):
+    from hiccup_b200 import bands, codec, compression
+    rgb = _image(kind, shape[0], shape[1], 17)
+    want = codec.jpeg_encode(compression.jpeg_compression(rgb)).byte_stream()
+    got = bands.encode_banded(rgb, k).byte_stream()
+    assert len(got) == len(want) == 21
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, "payload %d differs (%d vs %d bytes)" % (i, len(a), len(b))
+
+
+def test_banded_encode_equals_oracle_and_decodes():
+    from hiccup_b200 import bands, codec, compression, hicimage
+    rgb = orc.synthetic_image(160, 96, 23)
+    planes = orc.jpeg_compression(rgb)
+    enc = orc.jpeg_encode(planes)
+    hi = bands.encode_banded(rgb, 3)
+    stream = hi.byte_stream()
+    for i in range(9):
+        assert [(int(a), b) for a, b in hi.payloads[i].rows] == [(int(a), b) for a, b in enc["tables"][i]]
+        assert stream[10 + i] == orc.padded_bits_to_bytes(enc["bits"][i])
+    out = compression.jpeg_decompression(codec.jpeg_decode(hicimage.HicImage.from_bytes(stream)))
+    assert np.array_equal(out, orc.jpeg_decompression(planes))
