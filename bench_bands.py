@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""bench_bands.py -- BASELINE config 5: one 16384x16384 RGB image, DCT mode, row-band sharded over the
+GPUs of one box (hiccup_b200/bands.py), then decoded.
+
+    python bench_bands.py [--steps K] [--warmup W] [--size 16384]                       # 1 GPU = 1 band
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench_bands.py --gpus N                                          # N bands
+
+A step = encode of the whole image as N bands (one per rank; the only cross-rank traffic is the
+metadata of bands.py over a gloo group -- no data-path collective) + decode of the stitched `.hic`
+stream on rank 0 (the format has no restart offsets, so the entropy decode of ONE image does not shard;
+DESIGN.md section 7).  Prints one JSON line on rank 0: encode MP/s (max over ranks), decode MP/s, and the
+combined encode+decode MP/s.  `strong` scaling: the image is fixed, the bands shrink with N.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (shared helpers: synthetic images, stdout protection)
+
+
+def big_synthetic(size, tile=2048):
+    """size x size x 3: a `tile`-sized synthetic image (SURVEY 8(d) recipe) repeated; generating 805 MB
+    of bicubic noise directly would take minutes of host time."""
+    base = bench.synthetic_image(min(tile, size), min(tile, size), 5000)
+    reps = -(-size // base.shape[0])
+    return np.ascontiguousarray(np.tile(base, (reps, reps, 1))[:size, :size])
+
+
+def main():
+    bench.claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--check", action="store_true", help="compare the stitched stream with a one-band encode on rank 0")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    torch.cuda.set_device(local_rank)
+    from hiccup_b200 import _lib, bands, codec, compression
+    _lib.check(_lib.load().hic_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        meta = dist.new_group(backend="gloo")            # host-side metadata exchange
+        comm = bands.DistComm(meta)
+    size = args.size
+    image = big_synthetic(size)
+    cuts = bands.plan_bands(size, world)
+    worker = bands.BandWorker(rank, world, size, size, cuts[rank], cuts[rank + 1], device=local_rank)
+    worker.load(image)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def encode_step():
+        if world == 1:
+            res = bands.run_local([worker])[0]
+        else:
+            gen = worker.steps()
+            kind, msg = next(gen)
+            res = None
+            try:
+                while True:
+                    kind, msg = gen.send(comm.all_gather(msg) if kind == "all_gather" else comm.gather(msg, 0))
+            except StopIteration as stop:
+                res = stop.value
+        return res
+
+    decoder, staging = None, None
+
+    def decode_step(res):
+        """Stitch the band strings (host), entropy decode + inverse transform, host buffers in and out."""
+        nonlocal decoder, staging
+        from hiccup_b200.batch import DctBatchCodec
+        if decoder is None:
+            decoder = DctBatchCodec(1, size, size)
+            staging = _lib.PinnedBuffer(bands.stitch_layout(res["all_bits"], 9)[3] + (1 << 20))
+        return decoder.decode(bands.to_encoded_streams(res, size, size, out=staging.array(np.uint8)))
+
+    res = None
+    for _ in range(args.warmup):
+        res = encode_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = encode_step()
+    barrier()
+    t_enc = (time.perf_counter() - t0) / args.steps
+    if dist is not None:
+        t = torch.tensor([t_enc], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_enc = float(t.item())
+    t_dec, same, out = None, None, None
+    hic = None
+    if rank == 0:
+        out = decode_step(res)
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            out = decode_step(res)
+        torch.cuda.synchronize()
+        t_dec = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        hic = bands.assemble(res, size, size)
+        if args.check:
+            whole = bands.encode_banded(image, 1)
+            same = whole.byte_stream() == hic.byte_stream()
+            same = bool(same and np.abs(out[0].astype(np.int16) - image.astype(np.int16)).mean() < 20)
+    barrier()
+    if rank == 0:
+        mp = size * size / 1e6
+        nbytes = sum(len(b) for b in hic.byte_stream())
+        line = {
+            "metric": bench.METRIC, "value": mp / (t_enc + t_dec), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": (t_enc + t_dec) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%dx%d RGB single image, DCT mode, row-band sharded across %d B200 (encode), decoded on rank 0"
+                                   % (size, size, world),
+                       "bands": [int(b - a) for a, b in zip(cuts, cuts[1:])], "parallelism": "row bands, host-side stitching, no collective",
+                       "timing": "host wall clock per step incl. host<->device copies, metadata exchange and stitching; max over ranks",
+                       "hic_bytes": nbytes},
+            "encode": {"value": mp / t_enc, "unit": bench.UNIT, "ms": t_enc * 1e3},
+            "decode": {"value": mp / t_dec, "unit": bench.UNIT, "ms": t_dec * 1e3, "where": "rank 0 only"},
+            "matches_one_band_encode": same,
+        }
+        bench.emit(line)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -143,25 +143,53 @@ def bit_layout(all_bits, b):
     return (pos % np.uint64(8)).astype(np.uint32), (pos // np.uint64(8)).astype(np.int64)
 
 
-def stitch(band_bytes, all_bits, n_streams):
-    """band_bytes[b][s]: the raw bytes band b packed for stream s (first byte at its `first byte`
-    position, bits pre-shifted to their phase).  Returns the framed payload of every stream
-    (iohelper.padded_bs_2_bytes layout)."""
-    out = []
+def stitch_layout(all_bits, n_streams):
+    """Byte layout of the stitched payloads in one buffer: per stream (offset (4-byte aligned), framed
+    length, payload bits), and the buffer size (with 16 readable bytes of slack for the decoder)."""
+    off, length, nbits, pos = [], [], [], 0
     for s in range(n_streams):
         total = int(sum(int(bb[s]) for bb in all_bits))
         pad = 8 - (total % 8)
-        buf = np.zeros(1 + (total + pad) // 8, np.uint8)
-        buf[0] = pad
+        n = 1 + (total + pad) // 8
+        off.append(pos)
+        length.append(n)
+        nbits.append(total)
+        pos += (n + 3) & ~3
+    return off, length, nbits, pos + 16
+
+
+def stitch_into(buf, band_bytes, all_bits, n_streams):
+    """Write the framed payload of every stream (iohelper.padded_bs_2_bytes layout) into `buf` (uint8, zeroed
+    by this call) at stitch_layout's offsets.  band_bytes[b][s]: the raw bytes band b packed for stream s,
+    its bits pre-shifted to their phase; neighbours share at most their first / last byte, which are ORed."""
+    off, length, nbits, size = stitch_layout(all_bits, n_streams)
+    assert buf.size >= size
+    firsts = [bit_layout(all_bits, b)[1] for b in range(len(band_bytes))]
+    for s in range(n_streams):
+        view = buf[off[s]:off[s] + length[s]]
+        view[:] = 0
+        view[0] = 8 - (nbits[s] % 8)
         for b, per_band in enumerate(band_bytes):
-            chunk = np.frombuffer(per_band[s], np.uint8)
-            if not chunk.size:
+            chunk = per_band[s] if isinstance(per_band[s], np.ndarray) else np.frombuffer(per_band[s], np.uint8)
+            n = chunk.size
+            if not n:
                 continue
-            _, first = bit_layout(all_bits, b)
-            a = int(first[s])
-            buf[a:a + chunk.size] |= chunk
-        out.append(buf.tobytes())
-    return out
+            a = int(firsts[b][s])
+            if n > 2:
+                view[a + 1:a + n - 1] = chunk[1:n - 1]           # the interior belongs to this band alone
+            view[a] |= chunk[0]
+            if n > 1:
+                view[a + n - 1] |= chunk[n - 1]
+    buf[size - 16:size] = 0
+    return off, length, nbits
+
+
+def stitch(band_bytes, all_bits, n_streams):
+    """The framed payloads as byte strings."""
+    size = stitch_layout(all_bits, n_streams)[3]
+    buf = np.zeros(size, np.uint8)
+    off, length, _ = stitch_into(buf, band_bytes, all_bits, n_streams)
+    return [buf[o:o + n].tobytes() for o, n in zip(off, length)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -181,6 +209,30 @@ class DistComm:
         return out
 
     def gather(self, obj, root=0):
+        """Gather to `root`.  Byte strings (the packed band payloads, the one bulky item) do not go through
+        pickled object collectives: ranks of one box hand them over as files in /dev/shm and only their
+        lengths travel as metadata."""
+        import os
+        if isinstance(obj, dict) and isinstance(obj.get("bytes"), list):
+            token = os.environ.get("MASTER_PORT", "0")
+            path = "/dev/shm/hic_band_%s_%d.bin" % (token, self.rank)
+            with open(path, "wb") as f:
+                for b in obj["bytes"]:
+                    f.write(b)
+            lens = self.all_gather([len(b) for b in obj["bytes"]])
+            out = None
+            if self.rank == root:
+                out = []
+                for r, ls in enumerate(lens):
+                    raw = np.fromfile("/dev/shm/hic_band_%s_%d.bin" % (token, r), dtype=np.uint8)
+                    parts, pos = [], 0
+                    for n in ls:
+                        parts.append(raw[pos:pos + n])
+                        pos += n
+                    out.append(dict(bytes=parts))
+            self.all_gather(0)                      # everyone waits until the root has read the files
+            os.remove(path)
+            return out
         out = [None] * self.size if self.rank == root else None
         self.dist.gather_object(obj, out, dst=root, group=self.group)
         return out
@@ -252,12 +304,16 @@ class BandWorker:
         self.d_ties = _lib.DeviceBuffer(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
         self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
         self.encoder = entropy.EntropyEncoder(lay, value_bins)
-        self.rgb = None
+        self.rgb, self._pinned, self._h_bytes = None, None, None
 
     def load(self, image):
         """image: the whole H x W x 3 host array (only this band's slice is uploaded)."""
         assert image.shape == (self.h, self.w, 3) and image.dtype == np.uint8
-        self.rgb = np.ascontiguousarray(image[self.s0:self.s1])
+        hs = self.s1 - self.s0
+        if self._pinned is None:
+            self._pinned = self._lib.PinnedBuffer(hs * self.w * 3)
+        self.rgb = self._pinned.array(np.uint8, hs * self.w * 3).reshape(hs, self.w, 3)
+        self.rgb[...] = image[self.s0:self.s1]
 
     def _use_device(self):
         if self.device is not None:
@@ -290,8 +346,14 @@ class BandWorker:
         start_bit, _ = bit_layout(all_bits, self.band)
         enc.set_codes(tables[0], tables[1], tables[2], np.array(nsym, np.uint32), all_bits[self.band], start_bit, st)
         out = enc.pack(st)
-        data = out.download(np.uint8, int(enc.total_bytes), st) if enc.total_bytes else np.zeros(0, np.uint8)
-        mine = [data[int(enc.byte_off[s]):int(enc.byte_off[s]) + int(enc.byte_len[s])].tobytes() for s in range(9)]
+        nbytes = int(enc.total_bytes)
+        if self._h_bytes is None or self._h_bytes.nbytes < nbytes:
+            if self._h_bytes is not None:
+                self._h_bytes.free()
+            self._h_bytes = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
+        data = out.download(np.uint8, nbytes, st, out=self._h_bytes.array(np.uint8, nbytes)) if nbytes else np.zeros(0, np.uint8)
+        # views of the pinned staging (valid until this worker's next pack)
+        mine = [data[int(enc.byte_off[s]):int(enc.byte_off[s]) + int(enc.byte_len[s])] for s in range(9)]
         self.stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, st)
         final = yield ("gather", dict(bytes=mine))               # the strings go to the root only
         if final is None:
@@ -300,8 +362,10 @@ class BandWorker:
 
     def close(self):
         self.encoder.close()
-        for b in (self.d_rgb, self.d_coef, self.d_ties, self.d_stats):
-            b.free()
+        for b in (self.d_rgb, self.d_coef, self.d_ties, self.d_stats, self._pinned, self._h_bytes):
+            if b is not None:
+                b.free()
+        self._pinned = self._h_bytes = None
 
 
 def assemble(result, h, w):
@@ -322,6 +386,18 @@ def assemble(result, h, w):
     return hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(h, w), hicimage.TupP(h // 2, w // 2)])
 
 
+def to_encoded_streams(result, h, w, out=None):
+    """The stitched bands as an entropy.EncodedStreams (what DctBatchCodec(1, h, w).decode takes).
+    out: optional uint8 staging array (ideally page-locked) of at least stitch_layout(...)[3] bytes."""
+    from hiccup_b200 import _lib, entropy
+    index, syms, packed = result["tables"]
+    size = stitch_layout(result["all_bits"], 9)[3]
+    buf = np.zeros(size, np.uint8) if out is None else out[:size]
+    off, length, nbits = stitch_into(buf, result["band_bytes"], result["all_bits"], 9)
+    return entropy.EncodedStreams(_lib.layout_dct(1, h, w), index, np.zeros(9, np.uint32), np.array(nbits, np.uint64),
+                                  np.array(off, np.uint64), np.array(length, np.uint64), syms, packed, buf[:size - 16])
+
+
 def encode_banded(image, n_bands, devices=None, value_bins=8192):
     """Encode one image as `n_bands` row bands in this process (devices: optional list of CUDA device
     indices, one per band, cycled; default: the current device for all).  Returns the HicImage."""
@@ -336,10 +412,10 @@ def encode_banded(image, n_bands, devices=None, value_bins=8192):
         workers.append(wk)
     try:
         results = run_local(workers)
+        return assemble(results[0], h, w)        # before close(): the band strings are views of pinned staging
     finally:
         for wk in workers:
             wk.close()
-    return assemble(results[0], h, w)
 
 
 def encode_banded_dist(image, comm, device=None, value_bins=8192, worker=None):
@@ -360,6 +436,8 @@ def encode_banded_dist(image, comm, device=None, value_bins=8192, worker=None):
             kind, msg = gen.send(comm.all_gather(msg) if kind == "all_gather" else comm.gather(msg, 0))
     except StopIteration as stop:
         result = stop.value
-    if worker is None:
-        wk.close()
-    return assemble(result, h, w) if comm.rank == 0 else None
+    try:
+        return assemble(result, h, w) if comm.rank == 0 else None
+    finally:
+        if worker is None:
+            wk.close()
