@@ -127,10 +127,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // 8x8 block (as 16 words of bytes, rows of 8) -> quantised zigzag int16 + near-tie mask.
 // Two rows (then two columns) ride in each f32x2 register pair.
 template <int KIND>
-__device__ __forceinline__ void transform_block(const uint32_t (&wv)[16], int umax, int vmax,
-                                                int16_t* __restrict__ dst, uint32_t block_index,
-                                                hic_tie_record* __restrict__ ties, uint32_t tie_capacity,
-                                                uint32_t* __restrict__ stats) {
+__device__ __forceinline__ bool transform_block(const uint32_t (&wv)[16], int umax, int vmax,
+                                                int16_t* __restrict__ dst) {
     // sum |x| over the block (exact, integer) for the error band
     uint32_t abs_sum = 0;
 #pragma unroll
@@ -201,18 +199,9 @@ __device__ __forceinline__ void transform_block(const uint32_t (&wv)[16], int um
         w.w = __byte_perm(bits[zz[8 * j + 6]], bits[zz[8 * j + 7]], 0x5410);
         out[j] = w;
     }
-    if (worst >= 0.5f) {        // some coefficient is within the float32 error band of a rounding tie:
-        const uint32_t slot = atomicAdd(&stats[0], 1u);     // the fix-up kernel redoes this block in float64
-        if (slot < tie_capacity) {
-            hic_tie_record rec;
-            rec.block = block_index;
-            rec.reserved = 0;
-            rec.mask = ~0ull;
-            ties[slot] = rec;
-        } else {
-            atomicAdd(&stats[3], 1u);
-        }
-    }
+    // some coefficient is within the float32 error band of a rounding tie: the fix-up kernel redoes
+    // this block in float64
+    return worst >= 0.5f;
 }
 
 // keep the first `cols` bytes of each row word pair and the first `rows` rows; the rest become 128
@@ -229,7 +218,7 @@ __device__ __forceinline__ void mask_block(uint32_t (&wv)[16], int rows, int col
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 3)
 forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
                hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
                uint32_t tie_capacity, uint32_t* __restrict__ stats) {
@@ -319,13 +308,11 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     }
 
     // ---- stage 1: colour conversion, four pixels (three words) at a time ----
-    // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes
-    static_assert(THREADS == 5 * RGROUPS + 22, "index stepping below assumes 192 = 5 * 34 + 22");
-    for (int ry = tid / RGROUPS, gx = tid % RGROUPS; ry < RH; ry += 5, gx += 22) {
-        if (gx >= RGROUPS) {
-            gx -= RGROUPS;
-            if (++ry >= RH) break;
-        }
+    // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes.  Groups 1..32
+    // of a row (the 128 tile columns) go one per lane, rows warp + 6 k; the two halo groups per row
+    // (columns x0-4..x0-1 and x0+128..x0+131) are a short extra pass.  All trip counts are compile-time.
+    static_assert(THREADS == 192 && RGROUPS == 34 && TW == 128, "stage 1 mapping");
+    auto convert_group = [&](int ry, int gx, bool store_y) {
         const uint32_t* rw = s.rgb + ry * RWORDS + 3 * (gx + SKIP / 4);
         const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
         const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
@@ -333,87 +320,131 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t lo = __dp4a(px[k], 0x004C9123u, 8192u);
-            const uint32_t hi = __dp4a(px[k], 0x00072513u, 0u);
-            const uint32_t yy = (lo + (hi << 8)) >> 14;
+            const uint32_t yy = __dp4a(px[k], 0x00072513u, lo >> 8) >> 6;       // (lo + 256 hi) >> 14
             yv[k] = yy;
             const uint32_t bias = 255u - yy;
             crv[k] = s.lut_cr[__dp4a(px[k], 0x00000001u, bias)];        // R - Y + 255
             cbv[k] = s.lut_cb[__dp4a(px[k], 0x00010000u, bias)];        // B - Y + 255
         }
-        const uint32_t crw = crv[0] | (crv[1] << 8) | (crv[2] << 16) | (crv[3] << 24);
-        const uint32_t cbw = cbv[0] | (cbv[1] << 8) | (cbv[2] << 16) | (cbv[3] << 24);
-        *reinterpret_cast<uint32_t*>(&s.cr[ry][4 * gx]) = crw;
-        *reinterpret_cast<uint32_t*>(&s.cb[ry][4 * gx]) = cbw;
-        if (ry >= 2 && ry < 2 + TH && gx >= 1 && gx <= TW / 4)
-            *reinterpret_cast<uint32_t*>(&s.y[ry - 2][4 * (gx - 1)]) = yv[0] | (yv[1] << 8) | (yv[2] << 16) | (yv[3] << 24);
+        *reinterpret_cast<uint32_t*>(&s.cr[ry][4 * gx]) =
+            __byte_perm(__byte_perm(crv[0], crv[1], 0x0040), __byte_perm(crv[2], crv[3], 0x0040), 0x5410);
+        *reinterpret_cast<uint32_t*>(&s.cb[ry][4 * gx]) =
+            __byte_perm(__byte_perm(cbv[0], cbv[1], 0x0040), __byte_perm(cbv[2], cbv[3], 0x0040), 0x5410);
+        if (store_y)
+            *reinterpret_cast<uint32_t*>(&s.y[ry - 2][4 * (gx - 1)]) =
+                __byte_perm(__byte_perm(yv[0], yv[1], 0x0040), __byte_perm(yv[2], yv[3], 0x0040), 0x5410);
+    };
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int k = 0; k < (RH + 5) / 6; ++k) {
+            const int ry = warp + 6 * k;
+            if (ry < RH) convert_group(ry, lane + 1, ry >= 2 && ry < 2 + TH);
+        }
+        if (tid < 2 * RH) convert_group(tid >> 1, (tid & 1) ? RGROUPS - 1 : 0, false);
     }
     __syncthreads();
 
     // ---- stage 2a: horizontal [1 4 6 4 1] at stride 2; chroma column cx reads region pixels 2 cx + 2 .. 2 cx + 6 ----
-    // 16 four-output groups per row: the 192 threads cover 6 (channel, row) pairs x 2 channels per step
-    for (int rr = tid >> 4; rr < 2 * RH; rr += THREADS / 16) {
-        const int j = tid & 15;
-        const int ch = rr >= RH ? 1 : 0, ry = rr - ch * RH;
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
-        const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
-        const uint32_t o0 = __dp4a(wb, 0x00010406u, __dp4a(wa, 0x04010000u, 0u));
-        const uint32_t o1 = __dp4a(wc, 0x00000001u, __dp4a(wb, 0x04060401u, 0u));
-        const uint32_t o2 = __dp4a(wc, 0x00010406u, __dp4a(wb, 0x04010000u, 0u));
-        const uint32_t o3 = __dp4a(wd, 0x00000001u, __dp4a(wc, 0x04060401u, 0u));
-        *reinterpret_cast<uint2*>(&s.hpass[ch][ry][4 * j]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    // 16 four-output groups per row: 12 rows per step, one channel after the other
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+        for (int k = 0; k < (RH + 11) / 12; ++k) {
+            const int ry = (tid >> 4) + 12 * k, j = tid & 15;
+            if (ry < RH) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
+                const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
+                const uint32_t o0 = __dp4a(wb, 0x00010406u, __dp4a(wa, 0x04010000u, 0u));
+                const uint32_t o1 = __dp4a(wc, 0x00000001u, __dp4a(wb, 0x04060401u, 0u));
+                const uint32_t o2 = __dp4a(wc, 0x00010406u, __dp4a(wb, 0x04010000u, 0u));
+                const uint32_t o3 = __dp4a(wd, 0x00000001u, __dp4a(wc, 0x04060401u, 0u));
+                *reinterpret_cast<uint2*>(&s.hpass[ch][ry][4 * j]) =
+                    make_uint2(__byte_perm(o0, o1, 0x5410), __byte_perm(o2, o3, 0x5410));
+            }
+        }
     }
     __syncthreads();
     // ---- stage 2b: vertical on two 16-bit lanes per word (sums stay below 2^16), (sum + 128) >> 8 ----
-    for (int rr = tid >> 4; rr < 2 * CH; rr += THREADS / 16) {
-        const int j = tid & 15;
-        const int ch = rr >= CH ? 1 : 0, cy = rr - ch * CH;
-        uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint2 t = *reinterpret_cast<const uint2*>(&s.hpass[ch][2 * cy + k][4 * j]);
-            const uint32_t wt = k == 2 ? 6u : ((k == 1 || k == 3) ? 4u : 1u);
-            v0 += wt * t.x;
-            v1 += wt * t.y;
+    for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+        for (int k = 0; k < (CH + 11) / 12; ++k) {
+            const int cy = (tid >> 4) + 12 * k, j = tid & 15;
+            if (cy < CH) {
+                uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const uint2 t = *reinterpret_cast<const uint2*>(&s.hpass[ch][2 * cy + q][4 * j]);
+                    const uint32_t wt = q == 2 ? 6u : ((q == 1 || q == 3) ? 4u : 1u);
+                    v0 += wt * t.x;
+                    v1 += wt * t.y;
+                }
+                const uint32_t packed = __byte_perm(v0, v1, 0x7531);       // the high byte of each 16-bit lane
+                *reinterpret_cast<uint32_t*>(ch == 0 ? &s.crd[cy][4 * j] : &s.cbd[cy][4 * j]) = packed;
+            }
         }
-        const uint32_t packed = __byte_perm(v0, v1, 0x7531);       // the high byte of each 16-bit lane
-        *reinterpret_cast<uint32_t*>(ch == 0 ? &s.crd[cy][4 * j] : &s.cbd[cy][4 * j]) = packed;
     }
     __syncthreads();
 
     // ---- stage 3: one 8x8 block per thread ----
     uint32_t wv[16];
+    bool flagged = false;
+    uint32_t block_index = 0;
     if (tid < NY_BLOCKS) {
         const int by = tid / (TW / 8), bx = tid % (TW / 8);
         const int BY = blockIdx.y * (TH / 8) + by, BX = blockIdx.x * (TW / 8) + bx;
-        if (BY >= g.nby_l || BX >= g.nbx_l) return;
-        const int rows = min(8, h - 8 * BY), cols = min(8, w - 8 * BX);      // valid pixels
+        if (BY < g.nby_l && BX < g.nbx_l) {
+            const int rows = min(8, h - 8 * BY), cols = min(8, w - 8 * BX);      // valid pixels
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint2 t = *reinterpret_cast<const uint2*>(&s.y[8 * by + r][8 * bx]);
-            wv[2 * r] = t.x;
-            wv[2 * r + 1] = t.y;
+            for (int r = 0; r < 8; ++r) {
+                const uint2 t = *reinterpret_cast<const uint2*>(&s.y[8 * by + r][8 * bx]);
+                wv[2 * r] = t.x;
+                wv[2 * r + 1] = t.y;
+            }
+            if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
+            block_index = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
+            flagged = transform_block<0>(wv, rows, cols, coef + (size_t)block_index * 64);
         }
-        if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
-        const uint32_t block_index = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
-        transform_block<0>(wv, rows, cols, coef + (size_t)block_index * 64, block_index, ties, tie_capacity, stats);
     } else {
         const int plane = (tid - NY_BLOCKS) / NC_BLOCKS;          // 0 = Cr, 1 = Cb
         const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
         const int by = local / (CW / 8), bx = local % (CW / 8);
         const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
-        if (BY >= g.nby_c || BX >= g.nbx_c) return;
-        const int rows = min(8, g.hc - 8 * BY), cols = min(8, g.wc - 8 * BX);
-        const uint8_t (*pl)[CW] = plane == 0 ? s.crd : s.cbd;
+        if (BY < g.nby_c && BX < g.nbx_c) {
+            const int rows = min(8, g.hc - 8 * BY), cols = min(8, g.wc - 8 * BX);
+            const uint8_t (*pl)[CW] = plane == 0 ? s.crd : s.cbd;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint2 t = *reinterpret_cast<const uint2*>(&pl[8 * by + r][8 * bx]);
-            wv[2 * r] = t.x;
-            wv[2 * r + 1] = t.y;
+            for (int r = 0; r < 8; ++r) {
+                const uint2 t = *reinterpret_cast<const uint2*>(&pl[8 * by + r][8 * bx]);
+                wv[2 * r] = t.x;
+                wv[2 * r + 1] = t.y;
+            }
+            if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
+            block_index = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c +
+                                     (int64_t)BY * g.nbx_c + BX);
+            flagged = transform_block<1>(wv, rows, cols, coef + (size_t)block_index * 64);
         }
-        if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
-        const uint32_t block_index = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c +
-                                                (int64_t)BY * g.nbx_c + BX);
-        transform_block<1>(wv, rows, cols, coef + (size_t)block_index * 64, block_index, ties, tie_capacity, stats);
+    }
+    // one slot request per warp (the warps are whole: luminance and chroma threads never share one)
+    const unsigned m = __ballot_sync(0xffffffffu, flagged);
+    if (m) {
+        const unsigned lane = tid & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&stats[0], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flagged) {
+            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < tie_capacity) {
+                hic_tie_record rec;
+                rec.block = block_index;
+                rec.reserved = 0;
+                rec.mask = ~0ull;
+                ties[slot] = rec;
+            } else {
+                atomicAdd(&stats[3], 1u);
+            }
+        }
     }
 }
 
