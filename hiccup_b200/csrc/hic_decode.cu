@@ -402,12 +402,20 @@ __global__ void sync_tile_scan_kernel(int n_ss, const uint32_t* __restrict__ ss_
     nsym_out[s] = run;
 }
 
+// The CTA's symbols are one contiguous run of the output, so they are staged in shared memory and
+// written out coalesced (a thread's own run is only a few symbols long: writing it straight to global
+// memory costs a 32-byte sector per 1- or 2-byte store).
+constexpr int WRITE_STAGE = 12288;           // staged symbols per CTA; the (rare) overflow is written directly
+
 __global__ void __launch_bounds__(SUB_PER_CTA)
 huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, int16_t* __restrict__ dc,
                      int16_t* __restrict__ values, uint8_t* __restrict__ lengths, uint32_t* __restrict__ err) {
-    __shared__ uint32_t s_words[CHUNK_WORDS + CHUNK_SLACK];
-    __shared__ int32_t s_l1[L1_SIZE];
+    extern __shared__ __align__(16) uint8_t write_raw[];
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(write_raw);
+    int32_t* s_l1 = reinterpret_cast<int32_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK));
+    int16_t* s_stage = reinterpret_cast<int16_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE);
     __shared__ uint32_t s_sum[SUB_PER_CTA / 32];
+    __shared__ uint32_t s_staged;               // symbols [0, s_staged) of the CTA went through the staging area
     const SyncTile t = a.tiles[blockIdx.x];
     const uint32_t end = (uint32_t)(8 + a.nbits[t.ss]);
     const uint32_t n_sub = (end + SUB_BITS - 1) / SUB_BITS;
@@ -415,6 +423,7 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     const bool active = sub < n_sub;
     const uint64_t gi = t.sub_base + threadIdx.x;
     const uint32_t chunk0 = t.sub0 * SUB_BITS;
+    if (threadIdx.x == 0) s_staged = 0xFFFFFFFFu;
     stage_chunk(a, t, s_words, s_l1);
     const BitReader br{s_words};
     const int32_t* l2 = a.lut2 + (size_t)t.ss * a.l2_cap;
@@ -432,24 +441,40 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     }
     if (lane == 31) s_sum[warp] = inc;
     __syncthreads();            // also orders stage_chunk before the decode below
-    uint32_t rank = inc - cnt;
-    for (int w = 0; w < warp; ++w) rank += s_sum[w];
-    if (!active) return;
+    uint32_t rank = inc - cnt, total = 0;
+    for (int w = 0; w < SUB_PER_CTA / 32; ++w) {
+        if (w < warp) rank += s_sum[w];
+        total += s_sum[w];
+    }
     const int img = t.ss / 9, c = (t.ss % 9) / 3, kind = t.ss % 3;
     const int64_t bb = cs_block_base(g, img, c);
     const uint32_t cap = (uint32_t)(kind == HIC_KIND_DC ? g.L.nb[c] : g.L.nb[c] * 64);
-    const uint32_t out_idx = tile_off[blockIdx.x] + rank;
-    if (out_idx + cnt > cap) {
-        atomicOr(err, 1u);
-        return;
+    const uint32_t tile_base = tile_off[blockIdx.x];
+    const bool fits = tile_base + total <= cap;
+    if (!fits && threadIdx.x == 0) atomicOr(err, 1u);
+    int16_t* out16 = kind == HIC_KIND_DC ? dc + bb : values + bb * 64;
+    uint8_t* out8 = kind == HIC_KIND_LENGTH ? lengths + bb * 64 : nullptr;
+    if (active && fits) {
+        const uint32_t start = sub == 0 ? 8u : a.sub_end[gi - 1];
+        uint32_t got = 0;
+        bool bad = false;
+        uint32_t e;
+        if (rank + cnt <= (uint32_t)WRITE_STAGE) {        // the usual case: into the staging area
+            e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, s_stage, nullptr, rank, bad);
+        } else {                                          // ranks grow with the thread index: everything from here on is direct
+            atomicMin(&s_staged, rank);
+            e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, out16, out8, tile_base + rank, bad);
+        }
+        if (bad || got != cnt || e != a.sub_end[gi] || (sub == n_sub - 1 && e != end)) atomicOr(err, 1u);
     }
-    const uint32_t start = sub == 0 ? 8u : a.sub_end[gi - 1];
-    uint32_t got = 0;
-    bool bad = false;
-    const uint32_t e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got,
-                                         kind == HIC_KIND_DC ? dc + bb : values + bb * 64,
-                                         kind == HIC_KIND_LENGTH ? lengths + bb * 64 : nullptr, out_idx, bad);
-    if (bad || got != cnt || e != a.sub_end[gi] || (sub == n_sub - 1 && e != end)) atomicOr(err, 1u);
+    __syncthreads();
+    if (!fits) return;
+    const uint32_t staged = min(total, s_staged);
+    if (out8) {
+        for (uint32_t i = threadIdx.x; i < staged; i += SUB_PER_CTA) out8[tile_base + i] = (uint8_t)s_stage[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < staged; i += SUB_PER_CTA) out16[tile_base + i] = s_stage[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -900,7 +925,17 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
             if (!changed) break;
         }
         HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
-        HIC_LAUNCH("huffman_write_kernel", st, huffman_write_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a, g, p->d_tile_symoff, p->d_dc, p->d_values, p->d_lengths, p->d_err));
+        {
+            constexpr int WRITE_SMEM = 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE + 2 * WRITE_STAGE;
+            static bool attr_set[64] = {false};
+            int dev = 0;
+            HIC_CUDA(cudaGetDevice(&dev));
+            if (dev >= 64 || !attr_set[dev]) {
+                HIC_CUDA(cudaFuncSetAttribute(huffman_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WRITE_SMEM));
+                if (dev < 64) attr_set[dev] = true;
+            }
+            HIC_LAUNCH("huffman_write_kernel", st, huffman_write_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, WRITE_SMEM, st>>>(a, g, p->d_tile_symoff, p->d_dc, p->d_values, p->d_lengths, p->d_err));
+        }
     }
     HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum));
     HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],

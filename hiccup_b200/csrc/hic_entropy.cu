@@ -523,12 +523,14 @@ compact_kernel(Geom g, const uint32_t* __restrict__ hist, const uint32_t* __rest
 
 // scatter the code rows into the dense per-stream lookup table: lut[ss][bin] = len << 58 | code
 __global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, const uint64_t* __restrict__ row_code,
-                                   const uint32_t* __restrict__ row_stream, uint64_t n_rows, uint64_t* __restrict__ lut) {
+                                   const uint32_t* __restrict__ row_stream, uint64_t n_rows, uint64_t* __restrict__ lut,
+                                   uint8_t* __restrict__ lut_len) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
     const uint32_t ss = row_stream[i];
     const int bias = (ss % 3) == HIC_KIND_LENGTH ? 0 : g.nb_bins / 2;
     lut[(size_t)ss * g.nb_bins + row_sym[i] + bias] = row_code[i];
+    lut_len[(size_t)ss * g.nb_bins + row_sym[i] + bias] = (uint8_t)(row_code[i] >> 58);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,8 +707,8 @@ huffman_replay_kernel(int tier, int G, int stride_slots, int n_ss, const Compact
 __global__ void __launch_bounds__(128)
 huffman_codes_kernel(Geom g, const CompactIndex* __restrict__ index, const uint32_t* __restrict__ leaf_freq,
                      const uint16_t* __restrict__ parent, const int32_t* __restrict__ row_sym,
-                     uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut, uint32_t* __restrict__ ss_nsym,
-                     uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
+                     uint64_t* __restrict__ row_code, uint64_t* __restrict__ lut, uint8_t* __restrict__ lut_len,
+                     uint32_t* __restrict__ ss_nsym, uint64_t* __restrict__ ss_nbits, uint32_t* __restrict__ err) {
     __shared__ unsigned long long s_bits;
     __shared__ uint32_t s_nsym;
     const int ss = blockIdx.x;
@@ -753,6 +755,7 @@ huffman_codes_kernel(Geom g, const CompactIndex* __restrict__ index, const uint3
         const uint32_t f = leaf_freq[ix.offset + i];
         row_code[ix.offset + i] = packed;
         lut[(size_t)ss * g.nb_bins + row_sym[ix.offset + i] + bias] = packed;
+        lut_len[(size_t)ss * g.nb_bins + row_sym[ix.offset + i] + bias] = (uint8_t)len;
         bits_sum += (unsigned long long)f * len;
         sym_sum += f;
     }
@@ -839,7 +842,7 @@ __device__ __forceinline__ uint64_t lookup_code(const Geom& g, const uint64_t* _
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
-pack_tile_bits_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __restrict__ ss_nsym,
+pack_tile_bits_kernel(Geom g, const uint8_t* __restrict__ lut_len, const uint32_t* __restrict__ ss_nsym,
                       const int16_t* __restrict__ dc, const int16_t* __restrict__ values,
                       const uint8_t* __restrict__ lengths, uint32_t* __restrict__ tile_bits) {
     __shared__ uint32_t ssum[PACK_THREADS / 32];
@@ -848,10 +851,27 @@ pack_tile_bits_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* 
     const uint32_t start = (uint32_t)pr.tile * PACK_TILE + threadIdx.x * PACK_SPT;
     uint32_t bits = 0;
     const int kind = pr.ss % 3;
+    const uint8_t* my = lut_len + (size_t)pr.ss * g.nb_bins;
+    if (start < nsym) {                 // code lengths only: a byte per symbol from the length table
+        const int64_t pos = pr.sym_base + start;
+        if (kind == HIC_KIND_LENGTH) {
+            const uint2 v = *reinterpret_cast<const uint2*>(lengths + pos);       // PACK_SPT = 8 symbols, 8-byte aligned
 #pragma unroll
-    for (int j = 0; j < PACK_SPT; ++j)
-        if (start + j < nsym)
-            bits += (uint32_t)(lookup_code(g, lut, pr.ss, kind, dc, values, lengths, pr.sym_base + start + j) >> 58);
+            for (int j = 0; j < PACK_SPT; ++j)
+                if (start + j < nsym) bits += __ldg(my + (((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFF));
+        } else if (kind == HIC_KIND_DC) {          // DC symbols start at an arbitrary block: scalar loads
+#pragma unroll
+            for (int j = 0; j < PACK_SPT; ++j)
+                if (start + j < nsym) bits += __ldg(my + (int)dc[pos + j] + g.nb_bins / 2);
+        } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(values + pos);        // 8 symbols, 16-byte aligned
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < PACK_SPT; ++j)
+                if (start + j < nsym)
+                    bits += __ldg(my + (int)(short)((wv[j >> 1] >> (16 * (j & 1))) & 0xFFFF) + g.nb_bins / 2);
+        }
+    }
     uint32_t total;
     block_excl_sum<PACK_THREADS>(bits, ssum, &total);
     if (threadIdx.x == 0) tile_bits[blockIdx.x] = total;
@@ -955,6 +975,7 @@ struct hic_entropy_plan {
     CompactEntry* d_entries = nullptr;
     CompactIndex* d_index = nullptr;
     uint64_t* d_lut = nullptr;
+    uint8_t* d_lut_len = nullptr;               // code length per bin (what the bit-count pass needs)
     int32_t* d_row_sym = nullptr;
     uint64_t* d_row_code = nullptr;
     uint32_t* d_row_stream = nullptr;
@@ -1059,7 +1080,7 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
                     p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
-                    p->d_pay_totals, p->d_tier_count, p->d_tier_list, p->d_start_bit, p->d_band};
+                    p->d_pay_totals, p->d_tier_count, p->d_tier_list, p->d_start_bit, p->d_band, p->d_lut_len};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
@@ -1101,6 +1122,7 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_entries, hist_n));
     ok(dalloc(&p->d_index, p->n_ss));
     ok(dalloc(&p->d_lut, hist_n));
+    ok(dalloc(&p->d_lut_len, hist_n));
     ok(dalloc(&p->d_ss_nsym, p->n_ss));
     ok(dalloc(&p->d_ss_nbits, p->n_ss));
     ok(dalloc(&p->d_ss_byte_off, p->n_ss));
@@ -1296,7 +1318,7 @@ int hic_entropy_set_codes(hic_entropy_plan* p, const uint32_t* h_index, const in
     HIC_CUDA(cudaMemcpyAsync(p->d_index, h_index, sizeof(CompactIndex) * nss, cudaMemcpyHostToDevice, st));
     if (total_rows)
         HIC_LAUNCH("lut_scatter_kernel", st, lut_scatter_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
-                                                                                   p->d_row_stream, total_rows, p->d_lut));
+                                                                                   p->d_row_stream, total_rows, p->d_lut, p->d_lut_len));
     HIC_CUDA(cudaStreamSynchronize(st));      // the staging vectors go out of scope
     p->start_is_default = h_start_bit == nullptr;
     p->codes_ready = true;
@@ -1419,7 +1441,7 @@ int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
     HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_off, p->byte_off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     if (p->total_rows) {
         HIC_LAUNCH("lut_scatter_kernel", st, lut_scatter_kernel<<<(unsigned)((p->total_rows + 255) / 256), 256, 0, st>>>(g, p->d_row_sym, p->d_row_code,
-                                                                                   p->d_row_stream, p->total_rows, p->d_lut));
+                                                                                   p->d_row_stream, p->total_rows, p->d_lut, p->d_lut_len));
     }
     HIC_CUDA(cudaMemcpyAsync(p->d_ss_byte_len, p->byte_len.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     // rows were uploaded in stream order: make the device index describe that layout
@@ -1536,7 +1558,7 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
         HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
     }
     HIC_LAUNCH("huffman_codes_kernel", st, huffman_codes_kernel<<<p->n_ss, 128, 0, st>>>(
-        g, p->d_index, leaf_freq, parent, p->d_row_sym, p->d_row_code, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_err));
+        g, p->d_index, leaf_freq, parent, p->d_row_sym, p->d_row_code, p->d_lut, p->d_lut_len, p->d_ss_nsym, p->d_ss_nbits, p->d_err));
     HIC_LAUNCH("payload_layout_kernel", st, payload_layout_kernel<<<1, 1024, 0, st>>>(p->n_ss, p->d_ss_nsym, p->d_ss_nbits,
         p->d_ss_byte_off, p->d_ss_byte_len, p->d_pay_totals));
     unsigned long long totals[2] = {0, 0};
@@ -1614,7 +1636,7 @@ int hic_entropy_pack(hic_entropy_plan* p, uint8_t* d_out, void* stream) {
     cudaStream_t st = as_stream(stream);
     HIC_CUDA(cudaMemsetAsync(d_out, 0, p->total_bytes, st));
     const unsigned tiles = (unsigned)p->total_ptiles;
-    HIC_LAUNCH("pack_tile_bits_kernel", st, pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
+    HIC_LAUNCH("pack_tile_bits_kernel", st, pack_tile_bits_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut_len, p->d_ss_nsym, p->d_dc, p->d_values, p->d_lengths,
                                                          p->d_ptile_bits));
     HIC_LAUNCH("pack_stream_scan_kernel", st, pack_stream_scan_kernel<<<(p->n_ss + 127) / 128, 128, 0, st>>>(g, p->d_ptile_bits, p->d_start_bit, p->d_ptile_off));
     HIC_LAUNCH("pack_emit_kernel", st, pack_emit_kernel<<<tiles, PACK_THREADS, 0, st>>>(g, p->d_lut, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off,
