@@ -23,6 +23,7 @@ struct DctTables {
     float dq[2][64];     // q h_u h_v / 256 (inverse)
     float rcpq[2][64];   // 1 / q
     int qi[2][64];       // q
+    int izz[64];         // natural index -> scan position
 };
 __constant__ DctTables c_tab;
 __constant__ uint8_t c_zigzag[64] = HIC_ZIGZAG8;
@@ -49,6 +50,7 @@ static int ensure_tables() {
                 t.qi[kind][8 * u + v] = q;
                 t.rcpq[kind][8 * u + v] = (float)(1.0 / q);
             }
+    for (int k = 0; k < 64; ++k) t.izz[h_zigzag[k]] = k;
     HIC_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
     if (dev < 64) done[dev] = true;
     return HIC_OK;
@@ -448,87 +450,120 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     }
 }
 
-// Float64 re-evaluation of every flagged coefficient with scipy's exact operation order.
-__global__ void __launch_bounds__(128)
+// Float64 re-evaluation of every flagged block with scipy's exact operation order: one WARP per
+// block.  The lanes rebuild the block's samples from the RGB source (for a chroma block the 19x19
+// window of Cr or Cb values, then the separable [1 4 6 4 1] pyramid), eight lanes run the row
+// transforms, eight the column transforms + quantisation, and the float32 result is corrected in place.
+constexpr int FIX_WARPS = 8;
+struct FixSmem {
+    double a[64];                 // row-transformed block
+    int16_t px[64];               // x - 128, zero padded
+    uint16_t hp[19][8];           // horizontal pass of the chroma window
+    uint8_t win[19][20];          // Cr or Cb of the 19x19 source window
+};
+
+__global__ void __launch_bounds__(32 * FIX_WARPS)
 fixup_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, int16_t* __restrict__ coef,
              const hic_tie_record* __restrict__ ties, uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    __shared__ FixSmem sm_all[FIX_WARPS];
+    FixSmem& sm = sm_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const uint32_t n_rec = min(stats[0], tie_capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+    const uint32_t warps = gridDim.x * FIX_WARPS;
+    uint32_t changed_total = 0, done = 0;
+    for (uint32_t i = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5); i < n_rec; i += warps) {
         const hic_tie_record rec = ties[i];
         const int64_t img = rec.block / g.blocks_per_image;
         int64_t local = rec.block - img * g.blocks_per_image;
         const uint8_t* src = rgb + (size_t)img * h * w * 3;
-        int16_t px[64];
-        int kind;
+        int kind, ph, pw, BY, BX;
         if (local < g.nb_l) {
-            kind = 0;
-            const int BY = (int)(local / g.nbx_l), BX = (int)(local % g.nbx_l);
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) {
-                    const int y = 8 * BY + r, x = 8 * BX + c;
-                    int val = 0;
-                    if (y < h && x < w) {
-                        const uint8_t* p = src + ((size_t)y * w + x) * 3;
-                        int yy, cr, cb;
-                        rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
-                        val = yy - 128;
-                    }
-                    px[8 * r + c] = (int16_t)val;
+            kind = 0; ph = h; pw = w;
+            BY = (int)(local / g.nbx_l); BX = (int)(local % g.nbx_l);
+            for (int e = lane; e < 64; e += 32) {
+                const int y = 8 * BY + (e >> 3), x = 8 * BX + (e & 7);
+                int val = 0;
+                if (y < h && x < w) {
+                    const uint8_t* p = src + ((size_t)y * w + x) * 3;
+                    int yy, cr, cb;
+                    rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
+                    val = yy - 128;
                 }
+                sm.px[e] = (int16_t)val;
+            }
         } else {
-            kind = 1;
+            kind = 1; ph = g.hc; pw = g.wc;
             local -= g.nb_l;
             const int plane = (int)(local / g.nb_c);
             local -= (int64_t)plane * g.nb_c;
-            const int BY = (int)(local / g.nbx_c), BX = (int)(local % g.nbx_c);
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) {
-                    const int cy = 8 * BY + r, cx = 8 * BX + c;
-                    int val = 0;
-                    if (cy < g.hc && cx < g.wc) {
-                        int sum = 0;
-                        for (int dy = 0; dy < 5; ++dy) {
-                            const int wy = dy == 2 ? 6 : ((dy == 1 || dy == 3) ? 4 : 1);
-                            const int y = reflect101(2 * cy - 2 + dy, h);
-                            for (int dx = 0; dx < 5; ++dx) {
-                                const int wx = dx == 2 ? 6 : ((dx == 1 || dx == 3) ? 4 : 1);
-                                const int x = reflect101(2 * cx - 2 + dx, w);
-                                const uint8_t* p = src + ((size_t)y * w + x) * 3;
-                                int yy, cr, cb;
-                                rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
-                                sum += wy * wx * (plane == 0 ? cr : cb);
-                            }
-                        }
-                        val = ((sum + 128) >> 8) - 128;
-                    }
-                    px[8 * r + c] = (int16_t)val;
+            BY = (int)(local / g.nbx_c); BX = (int)(local % g.nbx_c);
+            const int y0 = 16 * BY - 2, x0 = 16 * BX - 2;        // window origin in the source image
+            for (int e = lane; e < 19 * 19; e += 32) {
+                const int r = e / 19, c = e - r * 19;
+                const int y = reflect101(y0 + r, h), x = reflect101(x0 + c, w);
+                const uint8_t* p = src + ((size_t)y * w + x) * 3;
+                int yy, cr, cb;
+                rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
+                sm.win[r][c] = (uint8_t)(plane == 0 ? cr : cb);
+            }
+            __syncwarp();
+            for (int e = lane; e < 19 * 8; e += 32) {            // horizontal [1 4 6 4 1] at stride 2
+                const int r = e >> 3, c = e & 7;
+                const uint8_t* q = &sm.win[r][2 * c];
+                sm.hp[r][c] = (uint16_t)(q[0] + 4 * q[1] + 6 * q[2] + 4 * q[3] + q[4]);
+            }
+            __syncwarp();
+            for (int e = lane; e < 64; e += 32) {                // vertical, (sum + 128) >> 8
+                const int r = e >> 3, c = e & 7;
+                int val = 0;
+                if (8 * BY + r < g.hc && 8 * BX + c < g.wc) {
+                    const int sum = sm.hp[2 * r][c] + 4 * sm.hp[2 * r + 1][c] + 6 * sm.hp[2 * r + 2][c] +
+                                    4 * sm.hp[2 * r + 3][c] + sm.hp[2 * r + 4][c];
+                    val = ((sum + 128) >> 8) - 128;
                 }
-        }
-        int16_t* blk = coef + (size_t)rec.block * 64;
-        int32_t exact[64];
-        exact_quantised_block(px, c_tab.qi[kind], exact);
-        // coefficients outside the unpadded plane stay zero (transform.py:63, codec.py:288)
-        int ph, pw, BY2, BX2;
-        if (kind == 0) {
-            ph = h; pw = w;
-            const int64_t l2 = rec.block - img * g.blocks_per_image;
-            BY2 = (int)(l2 / g.nbx_l); BX2 = (int)(l2 % g.nbx_l);
-        } else {
-            ph = g.hc; pw = g.wc;
-            BY2 = (int)(local / g.nbx_c); BX2 = (int)(local % g.nbx_c);
-        }
-        uint32_t changed = 0;
-        for (int k = 1; k < 64; ++k) {
-            const int nat = c_zigzag[k];
-            int32_t v = exact[nat];
-            if (8 * BY2 + (nat >> 3) >= ph || 8 * BX2 + (nat & 7) >= pw) v = 0;
-            if ((int32_t)blk[k] != v) {
-                blk[k] = (int16_t)v;
-                ++changed;
+                sm.px[e] = (int16_t)val;
             }
         }
-        atomicAdd(&stats[1], 63u);
-        if (changed) atomicAdd(&stats[2], changed);
+        __syncwarp();
+        if (lane < 8) {                                          // rows (transform.py:78-80)
+            double row[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) row[j] = (double)sm.px[8 * lane + j];
+            ducc_dct2_8(row);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm.a[8 * lane + j] = row[j];
+        }
+        __syncwarp();
+        uint32_t changed = 0;
+        if (lane < 8) {                                          // columns, division by the table, np.round
+            double col[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) col[r] = sm.a[8 * r + lane];
+            ducc_dct2_8(col);
+            int16_t* blk = coef + (size_t)rec.block * 64;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int nat = 8 * r + lane;
+                if (nat == 0) continue;                          // DC is an exact integer in float32 too
+                int32_t v = round_half_even(ddiv(col[r], (double)c_tab.qi[kind][nat]));
+                // coefficients outside the unpadded plane stay zero (transform.py:63, codec.py:288)
+                if (8 * BY + r >= ph || 8 * BX + lane >= pw) v = 0;
+                const int k = c_tab.izz[nat];
+                if ((int32_t)blk[k] != v) {
+                    blk[k] = (int16_t)v;
+                    ++changed;
+                }
+            }
+        }
+        changed_total += changed;
+        ++done;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int off = 4; off; off >>= 1) changed_total += __shfl_down_sync(0xffffffffu, changed_total, off);
+    if (lane == 0) {
+        if (done) atomicAdd(&stats[1], 63u * done);
+        if (changed_total) atomicAdd(&stats[2], changed_total);
     }
 }
 }  // namespace k1
@@ -848,7 +883,7 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     else
         HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
-    HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 4, 128, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     return HIC_OK;
 }
 
