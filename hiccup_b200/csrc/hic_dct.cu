@@ -761,6 +761,67 @@ upsample_colour_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict
             o[2] = (uint8_t)b;
         }
 }
+
+// The same, four chroma samples (8 x 2 output pixels) per thread with word loads and stores: used when
+// the rows are word aligned (wc % 4 == 0, which makes w % 8 == 0 and out_w * 3 % 4 == 0).
+__global__ void __launch_bounds__(256)
+upsample_colour_vec_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ crp,
+                           const uint8_t* __restrict__ cbp, hic_dct_geometry g, int n, uint8_t* __restrict__ rgb) {
+    const int groups = g.wc / 4;
+    const int64_t per = (int64_t)g.hc * groups;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per * n) return;
+    const int64_t img = gid / per;
+    const int64_t rem = gid - img * per;
+    const int cy = (int)(rem / groups), cx = 4 * (int)(rem % groups);
+    const int ym = cy > 0 ? cy - 1 : (g.hc > 1 ? 1 : 0), yn = cy + 1 < g.hc ? cy + 1 : g.hc - 1;
+    int up[2][2][8];          // [channel][output row parity][output column]
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const uint8_t* p = (ch == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
+        int hrow[3][8];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint8_t* q = p + (size_t)(r == 0 ? ym : (r == 1 ? cy : yn)) * g.wc;
+            const uint32_t mid = __ldg(reinterpret_cast<const uint32_t*>(q + cx));
+            int sv[6];
+            sv[1] = mid & 0xFF; sv[2] = (mid >> 8) & 0xFF; sv[3] = (mid >> 16) & 0xFF; sv[4] = mid >> 24;
+            sv[0] = cx > 0 ? (int)__ldg(q + cx - 1) : (g.wc > 1 ? sv[2] : sv[1]);          // s[-1] = s[1]
+            sv[5] = cx + 4 < g.wc ? (int)__ldg(q + cx + 4) : sv[4];                          // s[n] = s[n-1]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hrow[r][2 * i] = sv[i] + 6 * sv[i + 1] + sv[i + 2];
+                hrow[r][2 * i + 1] = 4 * (sv[i + 1] + sv[i + 2]);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            up[ch][0][x] = (hrow[0][x] + 6 * hrow[1][x] + hrow[2][x] + 32) >> 6;
+            up[ch][1][x] = (4 * (hrow[1][x] + hrow[2][x]) + 32) >> 6;
+        }
+    }
+    const uint8_t* ysrc = yp + (size_t)img * g.h * g.w;
+    uint8_t* dst = rgb + (size_t)img * g.out_h * g.out_w * 3;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int oy = 2 * cy + dy, ox = 2 * cx;
+        const uint2 yw = __ldg(reinterpret_cast<const uint2*>(ysrc + (size_t)oy * g.w + ox));
+        uint8_t px[24];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int yy = (int)(((x < 4 ? yw.x : yw.y) >> (8 * (x & 3))) & 0xFF);
+            int r, gg, b;
+            ycrcb_to_rgb(yy, up[0][dy][x], up[1][dy][x], r, gg, b);
+            px[3 * x] = (uint8_t)r;
+            px[3 * x + 1] = (uint8_t)gg;
+            px[3 * x + 2] = (uint8_t)b;
+        }
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst + ((size_t)oy * g.out_w + ox) * 3);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            o[k] = (uint32_t)px[4 * k] | ((uint32_t)px[4 * k + 1] << 8) | ((uint32_t)px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
+    }
+}
 }  // namespace k7
 
 // ------------------------------------------------------------------------------------------------
@@ -933,7 +994,13 @@ int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint
     HIC_LAUNCH("inverse_kernel", st, k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
     HIC_LAUNCH("inverse_fixup_kernel", st, k7::inverse_fixup_kernel<<<148 * 4, 128, 0, st>>>(d_coef, g, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
     const int64_t quads = (int64_t)n * g.hc * g.wc;
-    HIC_LAUNCH("upsample_colour_kernel", st, k7::upsample_colour_kernel<<<grid_for(quads, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out));
+    const bool word_rows = g.wc % 4 == 0 && g.w % 8 == 0 && ((g.h * (int64_t)g.w) % 8 == 0) && ((g.hc * (int64_t)g.wc) % 4 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(d_y) & 7) == 0) && ((reinterpret_cast<uintptr_t>(d_cr) & 3) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(d_cb) & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_rgb_out) & 3) == 0);
+    if (word_rows)
+        HIC_LAUNCH("upsample_colour_kernel", st, k7::upsample_colour_vec_kernel<<<grid_for(quads / 4, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out));
+    else
+        HIC_LAUNCH("upsample_colour_kernel", st, k7::upsample_colour_kernel<<<grid_for(quads, 256), 256, 0, st>>>(d_y, d_cr, d_cb, g, n, d_rgb_out));
     return HIC_OK;
 }
 

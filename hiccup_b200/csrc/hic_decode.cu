@@ -552,11 +552,18 @@ __global__ void stream_scan64_kernel(int n_cs, int tiles0, int tiles1, int tiles
     stream_total[cs] = run;
 }
 
+// Every tile of 2048 symbols owns the run of positions its symbols cover (at most 15 each), stages
+// it in shared memory -- zeros included -- and writes it out coalesced; the tiles of a stream also
+// share the zero tail behind the last symbol.  Every AC position is therefore written exactly once
+// and the coefficient buffer needs no memset.
+constexpr int XSTAGE = 8192;                 // staged positions per pass (a tile covers <= 15 * XT)
+
 __global__ void __launch_bounds__(XTHREADS)
 expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths,
                       const uint32_t* __restrict__ nsym_arr, const int64_t* __restrict__ tile_off,
-                      int16_t* __restrict__ coef, uint32_t* __restrict__ err) {
+                      const int64_t* __restrict__ stream_total, int16_t* __restrict__ coef, uint32_t* __restrict__ err) {
     __shared__ int64_t s[XTHREADS / 32];
+    __shared__ int16_t stage[XSTAGE];
     const XRef r = locate(g.xtiles, g.xtiles_per_image, blockIdx.x);
     const int cs = r.img * 3 + r.c;
     const uint32_t nsym = nsym_arr[cs * 3 + HIC_KIND_LENGTH];
@@ -573,25 +580,56 @@ expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t*
         v[j] = in ? val[start + j] : 0;
         if (in) sum += l[j] + 1;
     }
-    const int64_t rank = block_excl_sum64<XTHREADS>(sum, s, nullptr);
-    int64_t pos = tile_off[blockIdx.x] + rank;
+    int64_t tile_total;
+    const int64_t rank = block_excl_sum64<XTHREADS>(sum, s, &tile_total);
+    const int64_t p0 = tile_off[blockIdx.x];
     const int64_t stream_len = g.L.len[r.c];
     int16_t* dst = coef + bb * 64;
+    const bool skip = g.L.skip_first != 0;
+    // positions fit 31 bits (hic_decode_plan_create): 32-bit arithmetic, division by the constant 63
+    auto out_index = [&](int64_t p) {
+        const uint32_t q = (uint32_t)p;
+        const uint32_t blk = q / 63u;
+        return skip ? (int64_t)blk * 64 + (q - blk * 63u) + 1 : p;
+    };
+    if (p0 + tile_total > stream_len) {
+        if (threadIdx.x == 0) atomicOr(err, 2u);
+    } else {
+        for (int64_t base = 0; base < tile_total; base += XSTAGE) {
+            const int span = (int)min((int64_t)XSTAGE, tile_total - base);
+            for (int i = threadIdx.x; i < span; i += XTHREADS) stage[i] = 0;
+            __syncthreads();
+            int64_t pos = rank;
 #pragma unroll
-    for (int j = 0; j < XSPT; ++j) {
-        if (start + j >= nsym) break;
-        const int64_t p = pos + l[j];
-        if (v[j] != 0) {
-            if (p >= stream_len) {
-                atomicOr(err, 2u);
-            } else if (g.L.skip_first) {
-                dst[(p / 63) * 64 + (p % 63) + 1] = (int16_t)v[j];
-            } else {
-                dst[p] = (int16_t)v[j];
+            for (int j = 0; j < XSPT; ++j) {
+                if (start + j >= nsym) break;
+                const int64_t q = pos + l[j] - base;
+                if (v[j] != 0 && q >= 0 && q < span) stage[q] = (int16_t)v[j];
+                pos += l[j] + 1;
             }
+            __syncthreads();
+            {
+                // walk the output incrementally: one division per thread, then += XTHREADS positions per step
+                const uint32_t q0 = (uint32_t)(p0 + base) + threadIdx.x;
+                uint32_t blk = q0 / 63u, e = q0 - blk * 63u;
+                for (int i = threadIdx.x; i < span; i += XTHREADS) {
+                    dst[skip ? (int64_t)blk * 64 + e + 1 : (int64_t)(p0 + base + i)] = stage[i];
+                    e += XTHREADS % 63;                  // 256 = 4 * 63 + 4
+                    blk += XTHREADS / 63;
+                    if (e >= 63u) {
+                        e -= 63u;
+                        ++blk;
+                    }
+                }
+            }
+            __syncthreads();
         }
-        pos = p + 1;
     }
+    // the zero tail behind the stream's last symbol, split over the stream's tiles
+    const int64_t tail0 = min(stream_total[cs], stream_len);
+    const int64_t share = (stream_len - tail0 + g.xtiles[r.c] - 1) / g.xtiles[r.c];
+    const int64_t a = tail0 + share * r.tile, b = min(stream_len, a + share);
+    for (int64_t p = a + threadIdx.x; p < b; p += XTHREADS) dst[out_index(p)] = 0;
 }
 
 // validates each channel stream's expanded length (codec.py:109-111: only a trailing (0,0) may
@@ -873,7 +911,6 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     HIC_CUDA(cudaMemcpyAsync(p->d_byte_off, off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     HIC_CUDA(cudaMemcpyAsync(p->d_nbits, nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
-    HIC_CUDA(cudaMemsetAsync(d_coef, 0, (size_t)p->total_blocks * 128, st));
     // ---- D1: tiles of SUB_PER_CTA subsequences, streams in order ----
     std::vector<SyncTile> tiles;
     std::vector<uint32_t> ss_tile0(nss + 1, 0);
@@ -942,7 +979,7 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
                                                                g.xtiles_per_image, p->d_tile_sum, p->d_tile_off,
                                                                p->d_stream_total));
     HIC_LAUNCH("expand_scatter_kernel", st, expand_scatter_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym,
-                                                                         p->d_tile_off, d_coef, p->d_err));
+                                                                         p->d_tile_off, p->d_stream_total, d_coef, p->d_err));
     HIC_LAUNCH("validate_kernel", st, validate_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym, p->d_stream_total, p->d_err));
     if (g.L.skip_first) {
         HIC_LAUNCH("dc_tile_sum_kernel", st, dc_tile_sum_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_sum));

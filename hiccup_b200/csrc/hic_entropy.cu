@@ -1542,6 +1542,8 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
         g, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
     // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams:
     // fork after the sort, join before the code read-out.
+    // (profiled as ONE span on `st` from fork to join: the 21 tier launches overlap each other)
+    hic::prof_begin("huffman_replay_kernel", st);
     HIC_CUDA(cudaEventRecord(p->ev_fork, st));
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
     for (int t = N_TIERS - 1; t >= 0; --t) {                             // longest chains first
@@ -1550,13 +1552,15 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
         const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
         const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
         cudaStream_t sx = (t % (hic_entropy_plan::N_AUX + 1)) == 0 ? st : p->aux[(t % (hic_entropy_plan::N_AUX + 1)) - 1];
-        HIC_LAUNCH("huffman_replay_kernel", sx, huffman_replay_kernel<<<grid, 32, (size_t)G * stride, sx>>>(
-            t, G, stride_slots, p->n_ss, p->d_index, leaf_freq, p->d_tier_count, p->d_tier_list, parent));
+        huffman_replay_kernel<<<grid, 32, (size_t)G * stride, sx>>>(t, G, stride_slots, p->n_ss, p->d_index, leaf_freq,
+                                                                     p->d_tier_count, p->d_tier_list, parent);
+        HIC_CHECK_LAUNCH("huffman_replay_kernel");
     }
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
         HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
         HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
     }
+    hic::prof_end(st);
     HIC_LAUNCH("huffman_codes_kernel", st, huffman_codes_kernel<<<p->n_ss, 128, 0, st>>>(
         g, p->d_index, leaf_freq, parent, p->d_row_sym, p->d_row_code, p->d_lut, p->d_lut_len, p->d_ss_nsym, p->d_ss_nbits, p->d_err));
     HIC_LAUNCH("payload_layout_kernel", st, payload_layout_kernel<<<1, 1024, 0, st>>>(p->n_ss, p->d_ss_nsym, p->d_ss_nbits,
