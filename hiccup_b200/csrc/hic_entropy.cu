@@ -365,95 +365,103 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
         else hist_add(hist, first, hbase + (size_t)HIC_KIND_DC * g.nb_bins + bin, (uint32_t)b);
     }
 
-    // thread-local last non-zero
-    int my_last = (int)0x80000000;          // none (below every carried virtual position)
+    // non-zero mask of the block's run-length positions: bit e = element e holds a non-zero
+    const int e0 = SKIP ? 1 : 0;
+    const int n_valid = active ? (SKIP ? 64 : max(0, min(64, len - (int)(64 * b)))) : 0;       // elements e0 .. n_valid-1 count
+    unsigned long long mask = 0;
     if (active) {
 #pragma unroll
-        for (int e = SKIP ? 1 : 0; e < 64; ++e) {
-            const int p = base + e;
-            if (HIC_ELEM(w, e) != 0 && (SKIP || p < len)) my_last = p;
+        for (int j = 0; j < 32; ++j) {
+            const unsigned lo = (w[j] & 0xFFFF) != 0, hi = ((unsigned)w[j] >> 16) != 0;
+            mask |= (unsigned long long)(lo | (hi << 1)) << (2 * j);
         }
+        if (SKIP) mask &= ~1ull;
+        if (n_valid < 64) mask &= (1ull << n_valid) - 1ull;
     }
+    const int my_last = mask ? base + 63 - __clzll((long long)mask) : (int)0x80000000;   // none: below every carried position
     const int prev = block_excl_max<RLE_TB>(my_last, tc.prev_last, sm.smax);
 
-    // count pass
-    const int zeros_before = base + (SKIP ? 1 : 0) - 1 - prev;       // zeros between prev and my first position
-    const int zmod0 = active ? zeros_before % 15 : 0;
+    // count pass on the mask alone: a gap of `gap` zeros that follows z0 zeros of the same run holds
+    // (z0 + gap) / 15 - z0 / 15 fillers inside this block (a filler sits on every 15th zero of a run)
+    const int zeros_before = base + e0 - 1 - prev;       // zeros between prev and my first position
+    const bool tail_counts = n_valid > e0 && base + n_valid - 1 < last_nz;      // my trailing zeros are inside a run
     uint32_t cnt = 0;
-    if (active) {
-        int zmod = zmod0;
-#pragma unroll
-        for (int e = SKIP ? 1 : 0; e < 64; ++e) {
-            const int p = base + e;
-            const bool valid = SKIP || p < len;
-            const bool nz = HIC_ELEM(w, e) != 0 && valid;
-            if (nz) {
-                ++cnt;
-                zmod = 0;
-            } else if (valid) {
-                if (++zmod == 15) {
-                    zmod = 0;
-                    if (p < last_nz) ++cnt;
-                }
-            }
+    {
+        unsigned long long m = mask;
+        int z0 = zeros_before, prev_e = e0 - 1;
+        while (m) {
+            const int e = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int run = z0 + (e - prev_e - 1);
+            cnt += 1u + (uint32_t)(run / 15 - z0 / 15);
+            z0 = 0;
+            prev_e = e;
         }
+        if (tail_counts) cnt += (uint32_t)((z0 + (n_valid - 1 - prev_e)) / 15 - z0 / 15);
     }
     uint32_t tile_total;
     const uint32_t rank = block_excl_sum<RLE_TB>(cnt, sm.ssum, &tile_total);
 
-    // emit pass (every lane runs the loop so that the warp votes below are convergent)
-    uint32_t local = rank;
-    int zmod = zmod0;
-    const size_t hv = hbase + (size_t)HIC_KIND_VALUE * g.nb_bins;
-    const unsigned lane = threadIdx.x & 31;
+    // emit pass into the staging area: only the non-zeros do any work
+    {
+        uint32_t local = rank;
+        int z0 = zeros_before, prev_e = e0 - 1;
 #pragma unroll
-    for (int e = SKIP ? 1 : 0; e < 64; ++e) {
-        const int p = base + e;
-        const bool valid = active && (SKIP || p < len);
-        const int val = HIC_ELEM(w, e);
-        const bool nz = val != 0 && valid;
-        bool emit = false;
-        int sym_len = 14, sym_val = 0;
-        if (nz) {
-            emit = true;
-            sym_len = zmod;
-            sym_val = val;
-            zmod = 0;
-        } else if (valid) {
-            if (++zmod == 15) {
-                zmod = 0;
-                emit = p < last_nz;
+        for (int e = e0; e < 64; ++e) {
+            if ((mask >> e) & 1ull) {
+                const int run = z0 + (e - prev_e - 1);
+                for (int f = run / 15 - z0 / 15; f > 0; --f) {           // fillers (14, 0): rare
+                    sm.val[local] = 0;
+                    sm.len[local] = 14;
+                    ++local;
+                }
+                sm.val[local] = (int16_t)HIC_ELEM(w, e);
+                sm.len[local] = (uint8_t)(run % 15);
+                ++local;
+                z0 = 0;
+                prev_e = e;
             }
         }
-        const unsigned em = __ballot_sync(0xffffffffu, emit);
-        if (em == 0) continue;
-        if (emit) {
-            sm.val[local] = (int16_t)sym_val;
-            sm.len[local] = (uint8_t)sym_len;
-            const uint32_t idx = tc.sym_off + local;
-            // zero-count histogram: aggregate lanes with the same bin; the lowest lane has the lowest index
-            const unsigned gl = __match_any_sync(em, sym_len);
-            if (lane == (unsigned)(__ffs(gl) - 1)) {
-                atomicAdd(&sm.hist_l[sym_len], (uint32_t)__popc(gl));
-                atomicMin(&sm.first_l[sym_len], idx);
+        if (tail_counts) {
+            for (int f = (z0 + (n_valid - 1 - prev_e)) / 15 - z0 / 15; f > 0; --f) {
+                sm.val[local] = 0;
+                sm.len[local] = 14;
+                ++local;
             }
-            const unsigned gv = __match_any_sync(em, sym_val);
-            if (lane == (unsigned)(__ffs(gv) - 1)) {
-                const int central = sym_val + EMIT_CENTRAL / 2;
-                if (central >= 0 && central < EMIT_CENTRAL) {
-                    atomicAdd(&sm.hist_v[central], (uint32_t)__popc(gv));
-                    atomicMin(&sm.first_v[central], idx);
+        }
+    }
+    __syncthreads();
+    // histograms over the staged symbols (convergent: lanes with the same bin are aggregated with
+    // match.any; the lowest lane of a group holds the lowest symbol index)
+    const size_t hv = hbase + (size_t)HIC_KIND_VALUE * g.nb_bins;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t i0 = 0; i0 < tile_total; i0 += RLE_TB) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool have = i < tile_total;
+        const unsigned em = __ballot_sync(0xffffffffu, have);
+        if (!have) continue;
+        const int sym_val = sm.val[i], sym_len = sm.len[i];
+        const uint32_t idx = tc.sym_off + i;
+        const unsigned gl = __match_any_sync(em, sym_len);
+        if (lane == (unsigned)(__ffs(gl) - 1)) {
+            atomicAdd(&sm.hist_l[sym_len], (uint32_t)__popc(gl));
+            atomicMin(&sm.first_l[sym_len], idx);
+        }
+        const unsigned gv = __match_any_sync(em, sym_val);
+        if (lane == (unsigned)(__ffs(gv) - 1)) {
+            const int central = sym_val + EMIT_CENTRAL / 2;
+            if (central >= 0 && central < EMIT_CENTRAL) {
+                atomicAdd(&sm.hist_v[central], (uint32_t)__popc(gv));
+                atomicMin(&sm.first_v[central], idx);
+            } else {
+                const int bin = sym_val + half;
+                if (bin < 0 || bin >= g.nb_bins) {
+                    atomicOr(err, 1u);
                 } else {
-                    const int bin = sym_val + half;
-                    if (bin < 0 || bin >= g.nb_bins) {
-                        atomicOr(err, 1u);
-                    } else {
-                        atomicAdd(&hist[hv + bin], (uint32_t)__popc(gv));
-                        if (first[hv + bin] > idx) atomicMin(&first[hv + bin], idx);
-                    }
+                    atomicAdd(&hist[hv + bin], (uint32_t)__popc(gv));
+                    if (first[hv + bin] > idx) atomicMin(&first[hv + bin], idx);
                 }
             }
-            ++local;
         }
     }
     __syncthreads();
