@@ -376,12 +376,24 @@ def main():
                          "algorithmic_gbs": round(ab / per / 1e6, 1) if ab and per > 0 else None,
                          "frac_of_peak": round(ab / per / 1e6 / peak, 4) if ab and per > 0 else None}
     dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this exact workload
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2.json")
+    if args.config == "c2" and (n, h, w, mode) == (1024, 426, 640, "dct") and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in json.load(f).items()}
+        traffic["upsample_colour_kernel"] = traffic.get("upsample_colour_vec_kernel")
+    for name in kernels:
+        kernels[name]["dram_traffic_bytes"] = traffic.get(name)
     roofline = None
     if dominant:
         k = kernels[dominant]
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": k["frac_of_peak"], "traffic": None, "peak_source": peak_src,
-                    "share_of_step": k["share_of_step"]}
+                    "frac": k["frac_of_peak"], "traffic": traffic.get(dominant), "peak_source": peak_src,
+                    "share_of_step": k["share_of_step"],
+                    "algorithmic_bytes": kernel_bytes(dominant, float(pixels), B, s_ac, bits_bytes, rows, n_ss, bins, mode),
+                    "note": "latency-bound serial heapq replay (DESIGN.md section 5); the HBM-bound kernels are listed under `kernels`"
+                            if dominant == "huffman_replay_kernel" else None}
     # the replay span stands for 21 tier launches
     gpu_launches = int(sum(v[1] for v in prof.values()) + 20 * prof.get("huffman_replay_kernel", (0, 0))[1])
 
