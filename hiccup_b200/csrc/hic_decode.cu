@@ -59,7 +59,7 @@ constexpr int L2_LONG = 0xFF;                // second-level length field: the c
 constexpr int SUB_BITS = 128;
 constexpr int SUB_PER_CTA = 256;
 constexpr int CHUNK_WORDS = SUB_BITS * SUB_PER_CTA / 32;      // 1024 words of bit stream per CTA
-constexpr int CHUNK_SLACK = 4;                                // a code may run 58 bits past the last boundary
+constexpr int CHUNK_SLACK = 8;                                // a code may run 58 bits past the last boundary
 constexpr int L1_FALLBACK = 0xFF;
 
 struct SyncTile {
@@ -265,9 +265,43 @@ __device__ __forceinline__ uint32_t decode_span(const BitReader& br, uint32_t ch
                                                 uint8_t* __restrict__ out8, uint32_t out_idx, bool& bad) {
     count = 0;
     const uint32_t stop = limit < end ? limit : end;
+    if (pos >= stop) return pos;
+    // a 64-bit bit buffer, MSB first, refilled a word at a time: at least 32 valid bits at every lookup,
+    // enough for both table levels (<= 20 bits); only the rare long codes rebuild a full 64-bit window
+    uint32_t wi = (pos - chunk0) >> 5;
+    const uint32_t sh = (pos - chunk0) & 31;
+    uint64_t buf = (((uint64_t)br.words[wi] << 32) | br.words[wi + 1]) << sh;
+    int avail = 64 - (int)sh;
+    wi += 2;
     while (pos < stop) {
-        int32_t sym = 0;
-        const uint32_t len = decode_one(br.window(pos - chunk0), l1, l2, ls, sym);
+        if (avail < 32) {
+            buf |= (uint64_t)br.words[wi] << (32 - avail);
+            avail += 32;
+            ++wi;
+        }
+        int32_t e = l1[(uint32_t)(buf >> (64 - L1_BITS))];
+        uint32_t len;
+        int32_t sym;
+        if (!(e & 0x80)) {
+            sym = e >> 8;
+            len = (uint32_t)(e & 0x7F);
+        } else {
+            len = 0;
+            sym = 0;
+            const uint32_t nb2 = (uint32_t)(e & 0x7F);
+            if (nb2 != 0x7F) {
+                const uint32_t idx = ((uint32_t)e >> 8) + (uint32_t)((buf >> (64 - L1_BITS - nb2)) & ((1u << nb2) - 1));
+                e = __ldg(l2 + idx);
+                if ((e & 0xFF) != L2_LONG) {
+                    sym = e >> 8;
+                    len = (uint32_t)(e & 0xFF);
+                } else {
+                    len = decode_long(br.window(pos - chunk0), ls, sym);
+                }
+            } else {
+                len = decode_long(br.window(pos - chunk0), ls, sym);
+            }
+        }
         if (len == 0 || pos + len > end) {
             bad = true;
             return stop;          // not a codeword boundary (or a corrupt stream): give up on this span
@@ -277,6 +311,16 @@ __device__ __forceinline__ uint32_t decode_span(const BitReader& br, uint32_t ch
         }
         ++count;
         pos += len;
+        if (len >= 32) {          // a long code: rebuild the buffer at the new position
+            wi = (pos - chunk0) >> 5;
+            const uint32_t s2 = (pos - chunk0) & 31;
+            buf = (((uint64_t)br.words[wi] << 32) | br.words[wi + 1]) << s2;
+            avail = 64 - (int)s2;
+            wi += 2;
+        } else {
+            buf <<= len;
+            avail -= (int)len;
+        }
     }
     return pos;
 }
