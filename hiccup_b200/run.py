@@ -1,0 +1,107 @@
+"""File-level driver, drop-in for reference hiccup/run.py:13-43 (the caller of the hot path; SURVEY 8(f)
+rank 1) plus a directory mode that feeds the batched GPU path.
+
+    compress(path, output, style)      run.py:18-29   image file -> <output>/<name>.<STYLE>-hic
+    decompress(path)                   run.py:32-43   .hic file -> pixels (the reference shows them in a window;
+                                                       here they are returned, and written with `save=`)
+    compress_many(paths, output, ...)  additive: same-shaped images are encoded as one GPU batch
+
+Like the reference, `cv2.imread` delivers BGR and the codec treats channel 0 as R (run.py:19), so files
+are interchangeable with the reference's in both directions.  Command line: python -m hiccup_b200.run
+-c IMG | -d HIC [-s JPEG|HIC] [-o OUT], the subset of bin/belch.py:26-49 that does not need a display.
+"""
+import argparse
+import os
+
+from hiccup_b200 import codec, compression, hicimage, model
+
+
+def img_name(path, c):
+    return os.path.split(path)[-1] + ".%s-hic" % c.value
+
+
+def _read(path):
+    import cv2
+    rgb = cv2.imread(path)
+    if rgb is None:
+        raise RuntimeError("cannot read image %r" % (path,))
+    return rgb
+
+
+def compress(path, output, c=model.Compression.JPEG):
+    rgb = _read(path)
+    if c == model.Compression.JPEG:
+        hi = codec.jpeg_encode(compression.jpeg_compression(rgb))
+    elif c == model.Compression.HIC:
+        hi = codec.wavelet_encode(compression.wavelet_compression(rgb))
+    else:
+        raise RuntimeError("Unknown compression type")
+    out = os.path.join(output, img_name(path, c))
+    hi.write_file(out)
+    return out
+
+
+def decompress(path, save=None):
+    hi = hicimage.HicImage.from_file(path)
+    if hi.hic_type == model.Compression.JPEG:
+        rgb = compression.jpeg_decompression(codec.jpeg_decode(hi))
+    elif hi.hic_type == model.Compression.HIC:
+        rgb = compression.wavelet_decompression(codec.wavelet_decode(hi))
+    else:
+        raise RuntimeError("Unknown compression type")
+    if save is not None:
+        import cv2
+        cv2.imwrite(save, rgb)
+    return rgb
+
+
+def compress_many(paths, output, c=model.Compression.JPEG, max_batch=256):
+    """Encode many files; images of one shape go through the batched codec together (one launch of
+    every kernel per group) and every `.hic` file equals what compress() writes for it."""
+    import numpy as np
+    from hiccup_b200.batch import DctBatchCodec, WaveletBatchCodec
+    groups = {}
+    for p in paths:
+        rgb = _read(p)
+        groups.setdefault(rgb.shape, []).append((p, rgb))
+    written = []
+    for shape, items in groups.items():
+        h, w = shape[:2]
+        for a in range(0, len(items), max_batch):
+            part = items[a:a + max_batch]
+            cls = DctBatchCodec if c == model.Compression.JPEG else WaveletBatchCodec
+            bc = cls(len(part), h, w)
+            try:
+                enc = bc.encode(np.stack([rgb for _, rgb in part]))
+                for (p, _), hi in zip(part, bc.hic_images(enc)):
+                    out = os.path.join(output, img_name(p, c))
+                    hi.write_file(out)
+                    written.append(out)
+            finally:
+                bc.close()
+    return written
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="hiccup image compression on the GPU (no GUI)")
+    ap.add_argument("--compress", "-c", metavar="IMG_PATH", nargs="+")
+    ap.add_argument("--decompress", "-d", metavar="HIC")
+    ap.add_argument("--compression", "-s", metavar="STYLE", default=model.Compression.HIC.value,
+                    choices=[model.Compression.HIC.value, model.Compression.JPEG.value])
+    ap.add_argument("--output", "-o", metavar="OUT", default=".")
+    args = ap.parse_args(argv)
+    style = model.Compression(args.compression)
+    if args.compress:
+        for out in (compress_many(args.compress, args.output, style) if len(args.compress) > 1
+                    else [compress(args.compress[0], args.output, style)]):
+            print(out)
+    elif args.decompress:
+        name = os.path.join(args.output, os.path.split(args.decompress)[-1] + ".png")
+        decompress(args.decompress, save=name)
+        print(name)
+    else:
+        raise RuntimeError("Illegal state")
+
+
+if __name__ == "__main__":
+    main()

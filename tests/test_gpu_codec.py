@@ -188,3 +188,38 @@ def test_pipelined_codec_equals_unchunked(mode, shape):
     assert got_hic == want_hic
     pipe.close()
     whole.close()
+
+
+def test_file_driver_writes_reference_files(tmp_path):
+    """run.compress / run.decompress (reference run.py:18-43): the .hic file is byte-identical to the one
+    the reference pickles, single file and directory (batched) mode alike."""
+    import cv2
+    from hiccup_b200 import run, model
+    names = ["syn64", "syn48x80", "flat32"]
+    paths = []
+    for nm in names:
+        g = load_golden(nm)
+        p = str(tmp_path / (nm + ".png"))
+        cv2.imwrite(p, g["rgb"])                      # imread returns exactly these bytes (PNG is lossless)
+        paths.append(p)
+    for nm, p in zip(names, paths):
+        g = load_golden(nm)
+        out = run.compress(p, str(tmp_path), model.Compression.JPEG)
+        want = pickle.dumps(pickle.loads(g["hic"].tobytes()))
+        assert open(out, "rb").read() == want
+        if str(g["decode_error"]) == "":
+            assert np.array_equal(run.decompress(out), g["rgb_out"])
+    many = tmp_path / "many"
+    many.mkdir()
+    outs = run.compress_many(paths + [paths[0]], str(many), model.Compression.JPEG)
+    assert len(outs) == 4
+    for nm, p in zip(names, paths):
+        g = load_golden(nm)
+        got = open(str(many / (nm + ".png.JPEG-hic")), "rb").read()
+        assert got == pickle.dumps(pickle.loads(g["hic"].tobytes()))
+    w = load_golden("w_syn64")
+    pw = str(tmp_path / "w.png")
+    cv2.imwrite(pw, w["rgb"])
+    out = run.compress(pw, str(tmp_path), model.Compression.HIC)
+    assert open(out, "rb").read() == pickle.dumps(pickle.loads(w["hic"].tobytes()))
+    assert np.array_equal(run.decompress(out), w["rgb_out"])
