@@ -928,22 +928,29 @@ pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __res
     const uint32_t rank = block_excl_sum<PACK_THREADS>(bits, ssum, &total);      // also orders the zeroing of buf
     const uint64_t g0 = tile_off[blockIdx.x];              // bit offset of the tile inside the stream's bytes
     const uint32_t skew = (uint32_t)(g0 & 31);
+    // the thread's codes are gathered in a 64-bit accumulator and flushed 32 bits at a time: a handful of
+    // shared-memory atomics per thread instead of up to three per symbol
     uint32_t o = skew + rank;
+    uint64_t acc = 0;
+    uint32_t nacc = 0;               // valid bits, right aligned in acc (bits above them are stale)
+    auto flush = [&](uint32_t k) {   // move the top k (1..32) valid bits to bit offset o of the tile buffer
+        const uint32_t word = (uint32_t)((acc >> (nacc - k)) & ((1ull << k) - 1ull)) << (32 - k);
+        const uint32_t wi = o >> 5, sh = o & 31;
+        atomicOr(&buf[wi], word >> sh);
+        if (sh + k > 32) atomicOr(&buf[wi + 1], word << (32 - sh));
+        o += k;
+        nacc -= k;
+    };
 #pragma unroll
     for (int j = 0; j < PACK_SPT; ++j) {
         const uint32_t l = (uint32_t)(codes[j] >> 58);
         if (l) {
-            const uint64_t left = (codes[j] & ((1ull << 58) - 1)) << (64 - l);     // code left-aligned in 64 bits
-            const uint32_t wi = o >> 5, sh = o & 31;
-            const uint32_t p0 = (uint32_t)(left >> (32 + sh));
-            const uint32_t p1 = (uint32_t)(left >> sh);
-            const uint32_t p2 = sh ? (uint32_t)(left << (32 - sh)) : 0u;
-            if (p0) atomicOr(&buf[wi], p0);
-            if (p1) atomicOr(&buf[wi + 1], p1);
-            if (p2) atomicOr(&buf[wi + 2], p2);
-            o += l;
+            while (nacc + l > 64) flush(min(nacc, 32u));
+            acc = (acc << l) | (codes[j] & ((1ull << 58) - 1));
+            nacc += l;
         }
     }
+    while (nacc) flush(min(nacc, 32u));
     if (pr.tile == 0 && threadIdx.x == 0 && start_bit[pr.ss] == 8) {    // pad count p = 8 - (nbits mod 8) in byte 0
         const uint32_t pad = 8u - (uint32_t)(ss_nbits[pr.ss] & 7);
         atomicOr(&buf[0], pad << 24);
