@@ -570,13 +570,23 @@ expand_tile_sum_kernel(Geom g, const uint8_t* __restrict__ lengths, const uint32
     const uint32_t nsym = nsym_arr[ss];
     const uint8_t* len = lengths + cs_block_base(g, r.img, r.c) * 64;
     const uint32_t start = (uint32_t)r.tile * XT + threadIdx.x * XSPT;
-    int64_t sum = 0;
+    static_assert(XSPT == 8, "one 8-byte load per thread");
+    uint32_t sum = 0;
+    if (start < nsym) {
+        const uint2 v = *reinterpret_cast<const uint2*>(len + start);       // 8 zero counts (0..14 each)
 #pragma unroll
-    for (int j = 0; j < XSPT; ++j)
-        if (start + j < nsym) sum += (int64_t)len[start + j] + 1;
-    int64_t total;
-    block_excl_sum64<XTHREADS>(sum, s, &total);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+        for (int j = 0; j < XSPT; ++j)
+            if (start + j < nsym) sum += (((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFFu) + 1u;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t total = 0;
+        for (int w = 0; w < XTHREADS / 32; ++w) total += s[w];
+        tile_sum[blockIdx.x] = total;
+    }
 }
 
 __global__ void stream_scan64_kernel(int n_cs, int tiles0, int tiles1, int tiles2, int per_image,

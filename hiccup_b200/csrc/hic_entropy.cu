@@ -304,7 +304,7 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t* 
 // Symbols of the tile are staged in shared memory and written out coalesced (the tile's output is
 // one contiguous run).  Histogram updates are aggregated per warp with match.any and accumulated in
 // shared memory for the central value bins and all zero-count bins; one flush per tile.
-constexpr int EMIT_CENTRAL = 256;            // value bins [-128, 128) are privatised in shared memory
+constexpr int EMIT_CENTRAL = 1024;           // value bins [-512, 512) are privatised in shared memory
 constexpr int EMIT_CAP = RLE_TB * 64;        // a position emits at most one symbol
 
 struct EmitSmem {
@@ -388,16 +388,22 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
     uint32_t cnt = 0;
     {
         unsigned long long m = mask;
-        int z0 = zeros_before, prev_e = e0 - 1;
-        while (m) {
+        int prev_e = e0 - 1;
+        if (m) {                                   // the first non-zero continues a run from the blocks before
             const int e = __ffsll((long long)m) - 1;
             m &= m - 1;
-            const int run = z0 + (e - prev_e - 1);
-            cnt += 1u + (uint32_t)(run / 15 - z0 / 15);
-            z0 = 0;
+            cnt += 1u + (uint32_t)((zeros_before + (e - prev_e - 1)) / 15 - zeros_before / 15);
             prev_e = e;
+            while (m) {                            // gaps inside the block: a filler only for 15 zeros or more
+                const int e2 = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int gap = e2 - prev_e - 1;
+                cnt += 1u + (gap >= 15 ? (uint32_t)(gap / 15) : 0u);
+                prev_e = e2;
+            }
         }
-        if (tail_counts) cnt += (uint32_t)((z0 + (n_valid - 1 - prev_e)) / 15 - z0 / 15);
+        const int zt = mask ? 0 : zeros_before;
+        if (tail_counts) cnt += (uint32_t)((zt + (n_valid - 1 - prev_e)) / 15 - zt / 15);
     }
     uint32_t tile_total;
     const uint32_t rank = block_excl_sum<RLE_TB>(cnt, sm.ssum, &tile_total);
@@ -409,14 +415,17 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
 #pragma unroll
         for (int e = e0; e < 64; ++e) {
             if ((mask >> e) & 1ull) {
-                const int run = z0 + (e - prev_e - 1);
-                for (int f = run / 15 - z0 / 15; f > 0; --f) {           // fillers (14, 0): rare
-                    sm.val[local] = 0;
-                    sm.len[local] = 14;
-                    ++local;
+                int run = z0 + (e - prev_e - 1);
+                if (run >= 15) {                                          // fillers (14, 0): rare
+                    for (int f = run / 15 - z0 / 15; f > 0; --f) {
+                        sm.val[local] = 0;
+                        sm.len[local] = 14;
+                        ++local;
+                    }
+                    run %= 15;
                 }
                 sm.val[local] = (int16_t)HIC_ELEM(w, e);
-                sm.len[local] = (uint8_t)(run % 15);
+                sm.len[local] = (uint8_t)run;
                 ++local;
                 z0 = 0;
                 prev_e = e;
@@ -569,7 +578,8 @@ constexpr int SORT_THREADS = 256;
 constexpr int REPLAY_SMEM_BUDGET = 48 * 1024;
 
 __global__ void __launch_bounds__(SORT_THREADS)
-huffman_sort_kernel(Geom g, const CompactEntry* __restrict__ entries, const CompactIndex* __restrict__ index,
+huffman_sort_kernel(Geom g, int n_lo, int n_hi, const CompactEntry* __restrict__ entries,
+                    const CompactIndex* __restrict__ index,
                     uint32_t* __restrict__ leaf_freq, int32_t* __restrict__ row_sym, uint32_t* __restrict__ tier_count,
                     uint32_t* __restrict__ tier_list, int n_ss, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t sort_raw[];
@@ -578,9 +588,10 @@ huffman_sort_kernel(Geom g, const CompactEntry* __restrict__ entries, const Comp
     const int n = (int)ix.count;
     if (n == 0) return;
     if (n > 8192) {
-        if (threadIdx.x == 0) atomicOr(err, 2u);
+        if (threadIdx.x == 0 && n_hi == 8192) atomicOr(err, 2u);
         return;
     }
+    if (n <= n_lo || n > n_hi) return;            // another launch (with a fitting shared-memory size) takes it
     int P = 1;
     while (P < n) P <<= 1;
     uint32_t* key = reinterpret_cast<uint32_t*>(sort_raw);
@@ -1553,8 +1564,11 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     uint32_t* leaf_freq = p->d_first;                                    // dead after the compaction
     uint16_t* parent = reinterpret_cast<uint16_t*>(p->d_hist);           // likewise (2 links per entry = 4 bytes)
     HIC_CUDA(cudaMemsetAsync(p->d_tier_count, 0, N_TIERS * sizeof(uint32_t), st));
+    // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
+    HIC_LAUNCH("huffman_sort_kernel", st, huffman_sort_kernel<<<p->n_ss, SORT_THREADS, 6 * 1024, st>>>(
+        g, 0, 1024, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
     HIC_LAUNCH("huffman_sort_kernel", st, huffman_sort_kernel<<<p->n_ss, SORT_THREADS, 6 * 8192, st>>>(
-        g, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
+        g, 1024, 8192, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
     // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams:
     // fork after the sort, join before the code read-out.
     // (profiled as ONE span on `st` from fork to join: the 21 tier launches overlap each other)
