@@ -100,7 +100,7 @@ constexpr int RGROUPS = RPIX / 4;
 constexpr int LEAD = 16;              // staged pixel q <-> image column x0 - LEAD + q
 constexpr int SKIP = 12;              // converted pixel p = q - SKIP <-> image column x0 - 4 + p
 constexpr int SPIX = RWORDS * 4 / 3;  // whole pixels in a staged row
-constexpr int C_PITCH = 144;          // Cr/Cb staging pitch (bytes), indexed by region pixel
+constexpr int C_PITCH = 136;          // Cr/Cb staging pitch (bytes), indexed by region pixel (34 groups of 4)
 constexpr int CW = TW / 2;            // chroma tile
 constexpr int CH = TH / 2;
 constexpr int NY_BLOCKS = (TW / 8) * (TH / 8);       // 128
@@ -109,20 +109,28 @@ constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // 192
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
 constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
 
+// R - Y spans [-179, 179] and B - Y [-226, 226] (extremes of cv2's weights), so the chroma lookup
+// tables need 359 and 453 entries; trimming them keeps the CTA at 4 per SM
+constexpr int CR_BIAS = 179, CB_BIAS = 226;
 struct Smem {
     union alignas(128) {
         uint32_t rgb[RH * RWORDS];                   // stage 0/1 (TMA destination)
         uint16_t hpass[2][RH][CW];                   // stage 2 (rgb is dead by then)
     };
     alignas(16) uint8_t y[TH][TW];
-    alignas(16) uint8_t cr[RH][C_PITCH];
-    alignas(16) uint8_t cb[RH][C_PITCH];
-    alignas(16) uint8_t crd[CH][CW];
-    alignas(16) uint8_t cbd[CH][CW];
-    alignas(16) uint8_t lut_cr[512];                 // Cr as a function of R - Y + 255
-    alignas(16) uint8_t lut_cb[512];                 // Cb as a function of B - Y + 255
+    union alignas(16) {
+        uint8_t cr[RH][C_PITCH];                     // stage 1 -> 2a
+        uint8_t crd[CH][CW];                         // stage 2b -> 3 (cr is dead by then)
+    };
+    union alignas(16) {
+        uint8_t cb[RH][C_PITCH];
+        uint8_t cbd[CH][CW];
+    };
+    alignas(8) uint8_t lut_cr[2 * CR_BIAS + 2];      // Cr as a function of R - Y + CR_BIAS
+    alignas(8) uint8_t lut_cb[2 * CB_BIAS + 4];      // Cb as a function of B - Y + CB_BIAS
     alignas(8) unsigned long long bar;
 };
+static_assert(sizeof(Smem) <= 57344, "four CTAs per SM: (228 KB - 4 x 1 KB reserved) / 4");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -220,7 +228,7 @@ __device__ __forceinline__ void mask_block(uint32_t (&wv)[16], int rows, int col
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
                hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
                uint32_t tie_capacity, uint32_t* __restrict__ stats) {
@@ -242,10 +250,10 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                 ::"r"(smem_u32(s.rgb)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                 : "memory");
-            // pull the tile of a CTA two waves ahead (3 CTAs on each of 148 SMs per wave) into L2, so that
+            // pull the tile of a CTA two waves ahead (4 CTAs on each of 148 SMs per wave) into L2, so that
             // its own load finds the data there
             const unsigned per_img = gridDim.x * gridDim.y;
-            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 2u * 3u * 148u;
+            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 2u * 4u * 148u;
             if (ahead < per_img * gridDim.z) {
                 const unsigned pz = ahead / per_img, rem = ahead - pz * per_img;
                 const unsigned py = rem / gridDim.x, pxb = rem - py * gridDim.x;
@@ -256,10 +264,9 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
     // chroma lookup tables (cv2's fixed point, compression.py:21): index = difference + 255
-    for (int i = tid; i < 511; i += THREADS) {
-        const int d = i - 255;
-        s.lut_cr[i] = (uint8_t)clamp_u8((d * 11682 + (128 << 14) + 8192) >> 14);
-        s.lut_cb[i] = (uint8_t)clamp_u8((d * 9241 + (128 << 14) + 8192) >> 14);
+    for (int i = tid; i < 2 * CB_BIAS + 1; i += THREADS) {
+        if (i < 2 * CR_BIAS + 1) s.lut_cr[i] = (uint8_t)clamp_u8(((i - CR_BIAS) * 11682 + (128 << 14) + 8192) >> 14);
+        s.lut_cb[i] = (uint8_t)clamp_u8(((i - CB_BIAS) * 9241 + (128 << 14) + 8192) >> 14);
     }
     if (!USE_TMA) {
         // generic loader (row pitch not a multiple of 16 bytes): bytes with the border rule applied
@@ -335,9 +342,8 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
             const uint32_t lo = __dp4a(px[k], 0x004C9123u, 8192u);
             const uint32_t yy = __dp4a(px[k], 0x00072513u, lo >> 8) >> 6;       // (lo + 256 hi) >> 14
             yv[k] = yy;
-            const uint32_t bias = 255u - yy;
-            crv[k] = s.lut_cr[__dp4a(px[k], 0x00000001u, bias)];        // R - Y + 255
-            cbv[k] = s.lut_cb[__dp4a(px[k], 0x00010000u, bias)];        // B - Y + 255
+            crv[k] = s.lut_cr[__dp4a(px[k], 0x00000001u, (uint32_t)CR_BIAS - yy)];      // R - Y + CR_BIAS
+            cbv[k] = s.lut_cb[__dp4a(px[k], 0x00010000u, (uint32_t)CB_BIAS - yy)];      // B - Y + CB_BIAS
         }
         *reinterpret_cast<uint32_t*>(&s.cr[ry][4 * gx]) =
             __byte_perm(__byte_perm(crv[0], crv[1], 0x0040), __byte_perm(crv[2], crv[3], 0x0040), 0x5410);
