@@ -27,6 +27,8 @@ constexpr int PACK_SPT = 8;          // symbols per thread in the pack kernels
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_TILE = PACK_SPT * PACK_THREADS;      // 2048 symbols
 constexpr int PACK_WORDS = 4096;     // 2048 symbols * 58 bits max + slack, in 32-bit words
+constexpr int PACK_SEG_TILES = 8;    // tiles a pack CTA walks one after the other (amortises its fixed costs)
+constexpr int PACK_SEG = PACK_SEG_TILES * PACK_TILE;    // 16384 symbols per pack segment = per CTA
 constexpr int LEN_BINS = 16;
 constexpr uint32_t MAX_CODE_LEN = 58;
 
@@ -73,7 +75,7 @@ struct Geom {               // kernel-side copy of the layout plus derived tile 
     hic_stream_layout L;
     int tiles[3];
     int tiles_per_image;
-    int ptiles[3][3];       // pack tiles per (channel, kind)
+    int ptiles[3][3];       // pack segments per (channel, kind)
     int ptiles_per_image;
     int nb_bins;            // value bins
 };
@@ -832,10 +834,10 @@ struct PackRef {
     int ss, tile;
     int64_t sym_base;       // element offset of the stream's symbols in its source array
 };
-__device__ __forceinline__ PackRef locate_pack_tile(const Geom& g, int64_t t) {
+__device__ __forceinline__ PackRef locate_pack_tile(const Geom& g, uint32_t t) {
     PackRef r;
-    const int img = (int)(t / g.ptiles_per_image);
-    int rem = (int)(t - (int64_t)img * g.ptiles_per_image);
+    const int img = (int)(t / (uint32_t)g.ptiles_per_image);
+    int rem = (int)(t - (uint32_t)img * (uint32_t)g.ptiles_per_image);
     int c = 0, k = 0;
     while (rem >= g.ptiles[c][k]) {
         rem -= g.ptiles[c][k];
@@ -851,13 +853,26 @@ __device__ __forceinline__ PackRef locate_pack_tile(const Geom& g, int64_t t) {
     return r;
 }
 
-__device__ __forceinline__ uint64_t lookup_code(const Geom& g, const uint64_t* __restrict__ lut, int ss, int kind,
-                                                const int16_t* __restrict__ dc, const int16_t* __restrict__ values,
-                                                const uint8_t* __restrict__ lengths, int64_t pos) {
-    int bin;
-    if (kind == HIC_KIND_LENGTH) bin = lengths[pos];
-    else bin = (int)(kind == HIC_KIND_DC ? dc[pos] : values[pos]) + g.nb_bins / 2;
-    return __ldg(lut + (size_t)ss * g.nb_bins + bin);
+// the histogram bins of a thread's PACK_SPT = 8 consecutive symbols (positions pos .. pos + 7; the symbol
+// arrays carry 64 elements of slack, so whole vectors may be read past the stream's end -- entries at or
+// beyond n_valid are garbage and must not be used as indices)
+__device__ __forceinline__ void load_bins(int kind, int half, const int16_t* __restrict__ dc,
+                                          const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths,
+                                          int64_t pos, uint32_t n_valid, int (&bin)[PACK_SPT]) {
+    static_assert(PACK_SPT == 8, "vector widths below");
+    if (kind == HIC_KIND_LENGTH) {
+        const uint2 v = *reinterpret_cast<const uint2*>(lengths + pos);       // 8-byte aligned
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bin[j] = (int)(((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFF);
+    } else if (kind == HIC_KIND_DC) {          // DC symbols start at an arbitrary block: scalar loads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bin[j] = (uint32_t)j < n_valid ? (int)dc[pos + j] + half : 0;
+    } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(values + pos);        // 16-byte aligned
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bin[j] = (int)(short)((wv[j >> 1] >> (16 * (j & 1))) & 0xFFFF) + half;
+    }
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
@@ -867,28 +882,27 @@ pack_tile_bits_kernel(Geom g, const uint8_t* __restrict__ lut_len, const uint32_
     __shared__ uint32_t ssum[PACK_THREADS / 32];
     const PackRef pr = locate_pack_tile(g, blockIdx.x);
     const uint32_t nsym = ss_nsym[pr.ss];
-    const uint32_t start = (uint32_t)pr.tile * PACK_TILE + threadIdx.x * PACK_SPT;
+    const uint32_t seg_start = (uint32_t)pr.tile * PACK_SEG;
+    if (seg_start >= nsym) {            // nothing in this segment (the grid covers the capacity)
+        if (threadIdx.x == 0) tile_bits[blockIdx.x] = 0;
+        return;
+    }
+    const uint32_t seg_end = min(nsym, seg_start + (uint32_t)PACK_SEG);
     uint32_t bits = 0;
-    const int kind = pr.ss % 3;
     const uint8_t* my = lut_len + (size_t)pr.ss * g.nb_bins;
-    if (start < nsym) {                 // code lengths only: a byte per symbol from the length table
-        const int64_t pos = pr.sym_base + start;
-        if (kind == HIC_KIND_LENGTH) {
-            const uint2 v = *reinterpret_cast<const uint2*>(lengths + pos);       // PACK_SPT = 8 symbols, 8-byte aligned
+    const int kind = pr.ss % 3, half = g.nb_bins / 2;
+    // code lengths only: a byte per symbol from the length table
+    for (uint32_t start = seg_start + threadIdx.x * PACK_SPT; start < seg_end; start += PACK_TILE) {
+        const uint32_t n_valid = min((uint32_t)PACK_SPT, seg_end - start);
+        int bin[PACK_SPT];
+        load_bins(kind, half, dc, values, lengths, pr.sym_base + start, n_valid, bin);
+        if (n_valid == PACK_SPT) {
 #pragma unroll
-            for (int j = 0; j < PACK_SPT; ++j)
-                if (start + j < nsym) bits += __ldg(my + (((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFF));
-        } else if (kind == HIC_KIND_DC) {          // DC symbols start at an arbitrary block: scalar loads
-#pragma unroll
-            for (int j = 0; j < PACK_SPT; ++j)
-                if (start + j < nsym) bits += __ldg(my + (int)dc[pos + j] + g.nb_bins / 2);
+            for (int j = 0; j < PACK_SPT; ++j) bits += __ldg(my + bin[j]);
         } else {
-            const uint4 v = *reinterpret_cast<const uint4*>(values + pos);        // 8 symbols, 16-byte aligned
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < PACK_SPT; ++j)
-                if (start + j < nsym)
-                    bits += __ldg(my + (int)(short)((wv[j >> 1] >> (16 * (j & 1))) & 0xFFFF) + g.nb_bins / 2);
+                if ((uint32_t)j < n_valid) bits += __ldg(my + bin[j]);
         }
     }
     uint32_t total;
@@ -923,57 +937,85 @@ pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __res
     __shared__ uint32_t ssum[PACK_THREADS / 32];
     const PackRef pr = locate_pack_tile(g, blockIdx.x);
     const uint32_t nsym = ss_nsym[pr.ss];
-    const uint32_t tile_start = (uint32_t)pr.tile * PACK_TILE;
-    if (tile_start >= nsym) return;
-    const int kind = pr.ss % 3;
+    const uint32_t seg_start = (uint32_t)pr.tile * PACK_SEG;
+    if (seg_start >= nsym) return;
+    const uint32_t seg_end = min(nsym, seg_start + (uint32_t)PACK_SEG);
     for (int i = threadIdx.x; i < PACK_WORDS; i += PACK_THREADS) buf[i] = 0;
-    uint64_t codes[PACK_SPT];
-    uint32_t bits = 0;
-    const uint32_t start = tile_start + threadIdx.x * PACK_SPT;
-#pragma unroll
-    for (int j = 0; j < PACK_SPT; ++j) {
-        codes[j] = start + j < nsym ? lookup_code(g, lut, pr.ss, kind, dc, values, lengths, pr.sym_base + start + j) : 0ull;
-        bits += (uint32_t)(codes[j] >> 58);
-    }
-    uint32_t total;
-    const uint32_t rank = block_excl_sum<PACK_THREADS>(bits, ssum, &total);      // also orders the zeroing of buf
-    const uint64_t g0 = tile_off[blockIdx.x];              // bit offset of the tile inside the stream's bytes
-    const uint32_t skew = (uint32_t)(g0 & 31);
-    // the thread's codes are gathered in a 64-bit accumulator and flushed 32 bits at a time: a handful of
-    // shared-memory atomics per thread instead of up to three per symbol
-    uint32_t o = skew + rank;
-    uint64_t acc = 0;
-    uint32_t nacc = 0;               // valid bits, right aligned in acc (bits above them are stale)
-    auto flush = [&](uint32_t k) {   // move the top k (1..32) valid bits to bit offset o of the tile buffer
-        const uint32_t word = (uint32_t)((acc >> (nacc - k)) & ((1ull << k) - 1ull)) << (32 - k);
-        const uint32_t wi = o >> 5, sh = o & 31;
-        atomicOr(&buf[wi], word >> sh);
-        if (sh + k > 32) atomicOr(&buf[wi + 1], word << (32 - sh));
-        o += k;
-        nacc -= k;
-    };
-#pragma unroll
-    for (int j = 0; j < PACK_SPT; ++j) {
-        const uint32_t l = (uint32_t)(codes[j] >> 58);
-        if (l) {
-            while (nacc + l > 64) flush(min(nacc, 32u));
-            acc = (acc << l) | (codes[j] & ((1ull << 58) - 1));
-            nacc += l;
-        }
-    }
-    while (nacc) flush(min(nacc, 32u));
+    const uint64_t* my = lut + (size_t)pr.ss * g.nb_bins;
+    const int kind = pr.ss % 3, half = g.nb_bins / 2;
+    uint32_t* const dst_base = reinterpret_cast<uint32_t*>(out + ss_byte_off[pr.ss]);
+    uint64_t g0 = tile_off[blockIdx.x];                    // bit offset of the segment inside the stream's bytes
     if (pr.tile == 0 && threadIdx.x == 0 && start_bit[pr.ss] == 8) {    // pad count p = 8 - (nbits mod 8) in byte 0
         const uint32_t pad = 8u - (uint32_t)(ss_nbits[pr.ss] & 7);
-        atomicOr(&buf[0], pad << 24);
+        atomicOr(dst_base, pad);                           // byte 0 of the little-endian word
     }
-    __syncthreads();
-    const uint32_t n_words = (skew + total + 31) >> 5;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ss_byte_off[pr.ss]) + (g0 >> 5);
-    for (uint32_t i = threadIdx.x; i < n_words; i += PACK_THREADS) {
-        const uint32_t v = __byte_perm(buf[i], 0, 0x0123);          // MSB-first bits -> byte order in memory
-        if (v == 0) continue;
-        if (i == 0 || i == n_words - 1) atomicOr(dst + i, v);       // words shared with a neighbouring tile
-        else dst[i] = v;
+    // the segment's tiles one after the other, the bit offset running along
+    for (uint32_t tile_start = seg_start; tile_start < seg_end; tile_start += PACK_TILE) {
+        uint64_t codes[PACK_SPT];
+        uint32_t bits = 0;
+        const uint32_t start = tile_start + threadIdx.x * PACK_SPT;
+        const uint32_t n_valid = start < seg_end ? min((uint32_t)PACK_SPT, seg_end - start) : 0u;
+        {
+            int bin[PACK_SPT];
+            if (n_valid) load_bins(kind, half, dc, values, lengths, pr.sym_base + start, n_valid, bin);
+            if (n_valid == PACK_SPT) {
+#pragma unroll
+                for (int j = 0; j < PACK_SPT; ++j) codes[j] = __ldg(my + bin[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < PACK_SPT; ++j) codes[j] = (uint32_t)j < n_valid ? __ldg(my + bin[j]) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < PACK_SPT; ++j) bits += (uint32_t)(codes[j] >> 58);
+        }
+        uint32_t total;
+        const uint32_t rank = block_excl_sum<PACK_THREADS>(bits, ssum, &total);  // its barriers also order the (re)zeroing of buf
+        const uint32_t skew = (uint32_t)(g0 & 31);
+        // The thread's codes are laid into a 64-bit window (hi = the output word being filled, lo = the
+        // spill into the next one) aligned with the tile buffer's words: a completed word is owned by this
+        // thread alone and is stored plainly; only the first word (shared with the thread before) and the
+        // last partial one (shared with the thread after) need an atomic OR.
+        uint32_t wi = (skew + rank) >> 5, fill = (skew + rank) & 31;
+        uint32_t hi = 0, lo = 0;
+        bool shared_word = true;
+        auto put = [&](uint32_t code, uint32_t l) {        // 1 <= l <= 32, code < 2^l
+            const uint32_t c = code << (32 - l);
+            hi |= c >> fill;
+            lo |= __funnelshift_r(0u, c, fill);
+            fill += l;
+            if (fill >= 32) {
+                if (shared_word) atomicOr(&buf[wi], hi);
+                else buf[wi] = hi;
+                shared_word = false;
+                ++wi;
+                hi = lo;
+                lo = 0;
+                fill -= 32;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PACK_SPT; ++j) {
+            const uint32_t l = (uint32_t)(codes[j] >> 58);
+            if (l > 32) {                                  // long codes are rare: two pieces
+                put((uint32_t)(codes[j] >> 32) & ((1u << 26) - 1u), l - 32);
+                put((uint32_t)codes[j], 32);
+            } else if (l) {
+                put((uint32_t)codes[j], l);
+            }
+        }
+        if (fill && hi) atomicOr(&buf[wi], hi);
+        __syncthreads();
+        const uint32_t n_words = (skew + total + 31) >> 5;
+        uint32_t* dst = dst_base + (g0 >> 5);
+        for (uint32_t i = threadIdx.x; i < n_words; i += PACK_THREADS) {
+            const uint32_t v = __byte_perm(buf[i], 0, 0x0123);      // MSB-first bits -> byte order in memory
+            buf[i] = 0;                                            // ready for the next tile
+            if (v == 0) continue;
+            if (i == 0 || i == n_words - 1) atomicOr(dst + i, v);   // words shared with a neighbouring tile
+            else dst[i] = v;
+        }
+        g0 += total;
+        // the next tile's stores into buf come after the barriers of its scan
     }
 }
 
@@ -1054,7 +1096,7 @@ static int fill_geom(const hic_stream_layout* L, int value_bins, Geom* g) {
         g->tiles_per_image += g->tiles[c];
         for (int k = 0; k < 3; ++k) {
             int64_t cap = k == HIC_KIND_DC ? (L->skip_first ? L->nb[c] : 0) : L->nb[c] * 64;
-            g->ptiles[c][k] = (int)((cap + PACK_TILE - 1) / PACK_TILE);
+            g->ptiles[c][k] = (int)((cap + PACK_SEG - 1) / PACK_SEG);
             g->ptiles_per_image += g->ptiles[c][k];
         }
     }

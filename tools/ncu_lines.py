@@ -1,8 +1,14 @@
-"""Per-source-line executed warp instructions from an ncu report (cuda,sass source page)."""
+"""Per-source-line executed warp instructions from an ncu report (cuda,sass source page).
+
+    python tools/ncu_lines.py report.ncu-rep [top [kernel-regex]]
+"""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"]
+if len(sys.argv) > 3:
+    cmd += ["-k", "regex:" + sys.argv[3]]
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = None; hdr = None; lines = collections.OrderedDict()
 for r in rows:
