@@ -62,6 +62,7 @@ SIGNATURES = {
     "hic_stream_sync": (c_int, [c_void_p]),
     "hic_profile_enable": (c_int, [c_int]),
     "hic_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
+    "hic_profile_timeline": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_dct_geometry_of": (c_int, [c_int32, c_int32, ctypes.POINTER(Geometry)]),
     "hic_dct_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
     "hic_blocks_to_planes": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -252,6 +253,14 @@ def profile_report():
     buf = ctypes.create_string_buffer(1 << 16)
     check(load().hic_profile_report(buf, len(buf)))
     return {k: (v[0], v[1]) for k, v in json.loads(buf.value.decode()).items()}
+
+
+def profile_timeline():
+    """[(kernel, stream number, start ms, end ms)] of the spans recorded since the last report."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 24)
+    check(load().hic_profile_timeline(buf, len(buf)))
+    return [tuple(e) for e in json.loads(buf.value.decode())]
 
 
 def stream_create():

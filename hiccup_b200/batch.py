@@ -253,7 +253,7 @@ class PipelinedCodec:
         self.codecs = [cls(self.chunk, h, w, stream=st, **kw) for st in self.streams]
         self.out_shape = (self.n,) + self.codecs[0].out_shape[1:]
 
-    def round_trip(self, rgb, out, on_encoded=None, repeat=1):
+    def round_trip(self, rgb, out, on_encoded=None, repeat=1, trace=None, resident=False):
         """Encode then decode every chunk of `rgb` (n, h, w, 3) into `out` (out_shape); both should be
         page-locked for the copies to overlap.  `repeat` > 1 streams the same batch through that many
         times without draining the pipeline in between (a stream of batches).  Returns the compressed
@@ -261,8 +261,15 @@ class PipelinedCodec:
 
         Two gates keep the slots out of lockstep: one chunk at a time owns the bulk host->device copy
         and one the bulk device->host copy, so copies queue first-in first-out at full PCIe rate while
-        the other slots are in their kernel phases."""
+        the other slots are in their kernel phases.
+
+        `resident`: skip the bulk copies (each slot re-encodes the chunk its device buffer already holds
+        and leaves the pixels on the device) -- the device-resident rate of the same pipeline.
+
+        `trace`: optional list that receives (slot, visit, phase, t_begin, t_end) host timestamps of the
+        phases as they already synchronise (no extra synchronisation is added)."""
         import threading
+        import time
         assert rgb.shape == (self.n, self.h, self.w, 3) and out.shape == self.out_shape
         totals = [0] * self.slots
         errors = []
@@ -276,17 +283,30 @@ class PipelinedCodec:
                 for v in range(slot, repeat * self.n_chunks, self.slots):
                     c = v % self.n_chunks
                     a, b = c * self.chunk, (c + 1) * self.chunk
+                    t0 = time.perf_counter()
                     with gate_in:
-                        codec.upload(rgb[a:b])
-                        _lib.sync(codec.stream)
+                        t1 = time.perf_counter()
+                        if not resident:
+                            codec.upload(rgb[a:b])
+                            _lib.sync(codec.stream)
+                    t2 = time.perf_counter()
                     enc = codec.encode_resident()
+                    t3 = time.perf_counter()
                     if v < self.n_chunks:
                         totals[slot] += int(enc.data.nbytes)
                     if on_encoded is not None:
                         on_encoded(a, enc)
                     codec.decode_resident(enc)
+                    t4 = time.perf_counter()
                     with gate_out:
-                        codec.fetch(out[a:b])
+                        t5 = time.perf_counter()
+                        if not resident:
+                            codec.fetch(out[a:b])
+                        else:
+                            _lib.sync(codec.stream)
+                    t6 = time.perf_counter()
+                    if trace is not None:
+                        trace.append((slot, v, t0, t1, t2, t3, t4, t5, t6))
             except Exception as e:      # surfaced to the caller below
                 errors.append(e)
 

@@ -63,6 +63,9 @@ int hic_stream_sync(void* stream);                       /* blocks the host */
  * as JSON into buf and clears the record. */
 int hic_profile_enable(int on);
 int hic_profile_report(char* buf, size_t buflen);
+/* The spans recorded so far as a JSON array of [kernel, stream number, start ms, end ms] (relative to the
+ * first span); does not clear them.  A development aid for pipelined runs over several CUDA streams. */
+int hic_profile_timeline(char* buf, size_t buflen);
 
 /* ---- DCT-mode geometry ----------------------------------------------------------------------- */
 typedef struct hic_dct_geometry {
