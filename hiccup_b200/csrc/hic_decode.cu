@@ -606,84 +606,117 @@ __global__ void stream_scan64_kernel(int n_cs, int tiles0, int tiles1, int tiles
     stream_total[cs] = run;
 }
 
-// Every tile of 2048 symbols owns the run of positions its symbols cover (at most 15 each), stages
-// it in shared memory -- zeros included -- and writes it out coalesced; the tiles of a stream also
-// share the zero tail behind the last symbol.  Every AC position is therefore written exactly once
-// and the coefficient buffer needs no memset.
-constexpr int XSTAGE = 8192;                 // staged positions per pass (a tile covers <= 15 * XT)
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_sum32(uint32_t v, uint32_t* smem, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        if (w < warp) base += smem[w];
+        tot += smem[w];
+    }
+    *total = tot;
+    __syncthreads();
+    return base + inc - v;
+}
+
+// Every tile of 2048 symbols owns the run of positions its symbols cover (at most 15 each).  The run is
+// staged in shared memory in OUTPUT order -- zeros included, and in the block layout with the DC slot
+// of every block it crosses (written as zero here; dc_write_kernel fills the DC values afterwards) --
+// and leaves as 16-byte vectors; only the partial vectors at the two ends of the run go out element by
+// element.  The tiles of a stream also share the zero tail behind the last symbol.  Every AC position
+// is therefore written exactly once and the coefficient buffer needs no memset.
+constexpr int XSTAGE = 8192;                 // staged output elements per pass (a tile covers <= 15 * XT positions)
 
 __global__ void __launch_bounds__(XTHREADS)
 expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths,
                       const uint32_t* __restrict__ nsym_arr, const int64_t* __restrict__ tile_off,
                       const int64_t* __restrict__ stream_total, int16_t* __restrict__ coef, uint32_t* __restrict__ err) {
-    __shared__ int64_t s[XTHREADS / 32];
-    __shared__ int16_t stage[XSTAGE];
+    __shared__ uint32_t s[XTHREADS / 32];
+    __shared__ __align__(16) int16_t stage[XSTAGE];
     const XRef r = locate(g.xtiles, g.xtiles_per_image, blockIdx.x);
     const int cs = r.img * 3 + r.c;
     const uint32_t nsym = nsym_arr[cs * 3 + HIC_KIND_LENGTH];
     const int64_t bb = cs_block_base(g, r.img, r.c);
-    const uint8_t* len = lengths + bb * 64;
-    const int16_t* val = values + bb * 64;
-    const uint32_t start = (uint32_t)r.tile * XT + threadIdx.x * XSPT;
-    int l[XSPT], v[XSPT];
-    int64_t sum = 0;
-#pragma unroll
-    for (int j = 0; j < XSPT; ++j) {
-        const bool in = start + j < nsym;
-        l[j] = in ? len[start + j] : 0;
-        v[j] = in ? val[start + j] : 0;
-        if (in) sum += l[j] + 1;
-    }
-    int64_t tile_total;
-    const int64_t rank = block_excl_sum64<XTHREADS>(sum, s, &tile_total);
-    const int64_t p0 = tile_off[blockIdx.x];
     const int64_t stream_len = g.L.len[r.c];
     int16_t* dst = coef + bb * 64;
     const bool skip = g.L.skip_first != 0;
     // positions fit 31 bits (hic_decode_plan_create): 32-bit arithmetic, division by the constant 63
-    auto out_index = [&](int64_t p) {
-        const uint32_t q = (uint32_t)p;
-        const uint32_t blk = q / 63u;
-        return skip ? (int64_t)blk * 64 + (q - blk * 63u) + 1 : p;
-    };
-    if (p0 + tile_total > stream_len) {
-        if (threadIdx.x == 0) atomicOr(err, 2u);
-    } else {
-        for (int64_t base = 0; base < tile_total; base += XSTAGE) {
-            const int span = (int)min((int64_t)XSTAGE, tile_total - base);
-            for (int i = threadIdx.x; i < span; i += XTHREADS) stage[i] = 0;
-            __syncthreads();
-            int64_t pos = rank;
+    auto out_index = [&](uint32_t q) { return skip ? q + q / 63u + 1u : q; };
+    const uint32_t tile_first = (uint32_t)r.tile * XT;
+    if (tile_first < nsym) {
+        const uint32_t start = tile_first + threadIdx.x * XSPT;
+        static_assert(XSPT == 8, "one 8-byte and one 16-byte load per thread");
+        uint32_t l[XSPT];
+        int v[XSPT];
+        uint32_t sum = 0;
+        const uint32_t n_valid = start < nsym ? min((uint32_t)XSPT, nsym - start) : 0u;
+        if (n_valid) {          // the symbol arrays carry slack: whole vectors may be read past the end
+            const uint2 lv = *reinterpret_cast<const uint2*>(lengths + bb * 64 + start);
+            const uint4 vv = *reinterpret_cast<const uint4*>(values + bb * 64 + start);
+            const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int j = 0; j < XSPT; ++j) {
-                if (start + j >= nsym) break;
-                const int64_t q = pos + l[j] - base;
-                if (v[j] != 0 && q >= 0 && q < span) stage[q] = (int16_t)v[j];
-                pos += l[j] + 1;
+                const bool in = (uint32_t)j < n_valid;
+                l[j] = in ? ((j < 4 ? lv.x : lv.y) >> (8 * (j & 3))) & 0xFFu : 0u;
+                v[j] = in ? (int)(short)((vw[j >> 1] >> (16 * (j & 1))) & 0xFFFF) : 0;
+                sum += in ? l[j] + 1u : 0u;
             }
-            __syncthreads();
-            {
-                // walk the output incrementally: one division per thread, then += XTHREADS positions per step
-                const uint32_t q0 = (uint32_t)(p0 + base) + threadIdx.x;
-                uint32_t blk = q0 / 63u, e = q0 - blk * 63u;
-                for (int i = threadIdx.x; i < span; i += XTHREADS) {
-                    dst[skip ? (int64_t)blk * 64 + e + 1 : (int64_t)(p0 + base + i)] = stage[i];
-                    e += XTHREADS % 63;                  // 256 = 4 * 63 + 4
-                    blk += XTHREADS / 63;
-                    if (e >= 63u) {
-                        e -= 63u;
-                        ++blk;
+        } else {
+#pragma unroll
+            for (int j = 0; j < XSPT; ++j) {
+                l[j] = 0;
+                v[j] = 0;
+            }
+        }
+        uint32_t tile_total;
+        const uint32_t rank = block_excl_sum32<XTHREADS>(sum, s, &tile_total);
+        const int64_t p0_64 = tile_off[blockIdx.x];
+        if (p0_64 + tile_total > stream_len || tile_total == 0) {
+            if (threadIdx.x == 0) atomicOr(err, 2u);
+        } else {
+            const uint32_t p0 = (uint32_t)p0_64;
+            const uint32_t o_begin = out_index(p0), o_end = out_index(p0 + tile_total - 1u) + 1u;
+            for (uint32_t base = o_begin & ~7u; base < o_end; base += XSTAGE) {
+                const uint32_t span = min((uint32_t)XSTAGE, o_end - base);
+                const uint32_t nvec = (span + 7u) >> 3;
+                for (uint32_t i = threadIdx.x; i < nvec; i += XTHREADS) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+                uint32_t pos = p0 + rank;
+#pragma unroll
+                for (int j = 0; j < XSPT; ++j) {
+                    const uint32_t q = out_index(pos + l[j]) - base;       // wraps below `base`: fails the bound check
+                    if (v[j] != 0 && q < span) stage[q] = (int16_t)v[j];
+                    pos += (uint32_t)j < n_valid ? l[j] + 1u : 0u;
+                }
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < nvec; i += XTHREADS) {
+                    const uint32_t o = base + 8u * i;
+                    if (o >= o_begin && o + 8u <= o_end) {
+                        *reinterpret_cast<uint4*>(dst + o) = reinterpret_cast<const uint4*>(stage)[i];
+                    } else {
+#pragma unroll
+                        for (uint32_t k = 0; k < 8u; ++k)
+                            if (o + k >= o_begin && o + k < o_end) dst[o + k] = stage[8u * i + k];
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
     // the zero tail behind the stream's last symbol, split over the stream's tiles
     const int64_t tail0 = min(stream_total[cs], stream_len);
     const int64_t share = (stream_len - tail0 + g.xtiles[r.c] - 1) / g.xtiles[r.c];
     const int64_t a = tail0 + share * r.tile, b = min(stream_len, a + share);
-    for (int64_t p = a + threadIdx.x; p < b; p += XTHREADS) dst[out_index(p)] = 0;
+    for (int64_t p = a + threadIdx.x; p < b; p += XTHREADS) dst[out_index((uint32_t)p)] = 0;
 }
 
 // validates each channel stream's expanded length (codec.py:109-111: only a trailing (0,0) may
