@@ -302,7 +302,29 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t* 
     if (first[bin] > index) atomicMin(&first[bin], index);
 }
 
-// pass C: emit symbols, DC differences and histograms.
+// DC differences (codec.differential_coding): d[0] = DC[0], d[k] = DC[k] - DC[k-1], with their histogram
+// and first-occurrence indices.  A kernel of its own, ahead of the run-length passes: the DC alphabets
+// are the largest of an image (luminance ~1700 symbols on C2), so their Huffman construction is the
+// longest dependent chain of the encoder -- hic_entropy_build_codes_device starts it as soon as this
+// kernel and its compaction are done, side by side with rle_emit.
+__global__ void __launch_bounds__(RLE_TB)
+dc_diff_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __restrict__ band, int16_t* __restrict__ dc_out,
+               uint32_t* __restrict__ hist, uint32_t* __restrict__ first, uint32_t* __restrict__ err) {
+    const TileRef tr = locate_tile(g, blockIdx.x);
+    const int cs = tr.img * 3 + tr.c;
+    const int64_t b = (int64_t)tr.tile * RLE_TB + threadIdx.x;
+    if (b >= g.L.nb[tr.c]) return;
+    const int64_t block_base = cs_block_base(g, tr.img, tr.c);
+    const int dc = (int)__ldg(coef + (block_base + b) * 64);
+    const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : (band ? band[cs].prev_dc : 0);
+    const int diff = dc - prev;
+    dc_out[block_base + b] = (int16_t)diff;
+    const int bin = diff + g.nb_bins / 2;
+    if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
+    else hist_add(hist, first, ((size_t)cs * 3 + HIC_KIND_DC) * g.nb_bins + bin, (uint32_t)b);
+}
+
+// pass C: emit run-length symbols and their histograms.
 // Symbols of the tile are staged in shared memory and written out coalesced (the tile's output is
 // one contiguous run).  Histogram updates are aggregated per warp with match.any and accumulated in
 // shared memory for the central value bins and all zero-count bins; one flush per tile.
@@ -356,16 +378,8 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
     }
     const int base = SKIP ? (int)(63 * b) - 1 : (int)(64 * b);
 
-    // DC differences (codec.differential_coding): d[0] = DC[0], d[k] = DC[k] - DC[k-1]
-    if (SKIP && active) {
-        const int dc = HIC_ELEM(w, 0);
-        const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : (band ? band[cs].prev_dc : 0);
-        const int diff = dc - prev;
-        dc_out[block_base + b] = (int16_t)diff;
-        const int bin = diff + half;
-        if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
-        else hist_add(hist, first, hbase + (size_t)HIC_KIND_DC * g.nb_bins + bin, (uint32_t)b);
-    }
+    // (the DC differences and their histograms are dc_diff_kernel's: they feed the longest Huffman
+    // constructions, which start while this kernel is still running)
 
     // non-zero mask of the block's run-length positions: bit e = element e holds a non-zero
     const int e0 = SKIP ? 1 : 0;
@@ -508,11 +522,20 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
 // ------------------------------------------------------------------------------------------------
 // histogram compaction: one CTA per symbol stream
 // ------------------------------------------------------------------------------------------------
+// stream selection of the per-stream kernels: everything, the DC streams only, the run-length streams only
+enum { SEL_ALL = 0, SEL_DC = 1, SEL_AC = 2 };
+__device__ __forceinline__ int selected_stream(int sel, int i) {
+    return sel == SEL_ALL ? i : (sel == SEL_DC ? 3 * i : 3 * (i >> 1) + 1 + (i & 1));
+}
+static inline int selected_count(int sel, int n_cs) { return sel == SEL_ALL ? 3 * n_cs : (sel == SEL_DC ? n_cs : 2 * n_cs); }
+
+// The bins it reads are reset on the way (count 0, first occurrence 0xFFFFFFFF), so the histogram
+// arrays are clean again for the next batch without a memset over all of them.
 __global__ void __launch_bounds__(256)
-compact_kernel(Geom g, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ first,
+compact_kernel(Geom g, int sel, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
                CompactEntry* __restrict__ entries, CompactIndex* __restrict__ index, uint32_t* __restrict__ cursor) {
     __shared__ uint32_t s_count, s_base, s_pos;
-    const int ss = blockIdx.x;
+    const int ss = selected_stream(sel, blockIdx.x);
     const int kind = ss % 3;
     const int bins = kind == HIC_KIND_LENGTH ? LEN_BINS : g.nb_bins;
     const size_t off = (size_t)ss * g.nb_bins;
@@ -536,6 +559,8 @@ compact_kernel(Geom g, const uint32_t* __restrict__ hist, const uint32_t* __rest
         if (cnt) {
             const uint32_t pos = s_base + atomicAdd(&s_pos, 1u);
             entries[pos] = CompactEntry{i - bias, cnt, first[off + i]};
+            hist[off + i] = 0;
+            first[off + i] = 0xFFFFFFFFu;
         }
     }
 }
@@ -580,12 +605,12 @@ constexpr int SORT_THREADS = 256;
 constexpr int REPLAY_SMEM_BUDGET = 48 * 1024;
 
 __global__ void __launch_bounds__(SORT_THREADS)
-huffman_sort_kernel(Geom g, int n_lo, int n_hi, const CompactEntry* __restrict__ entries,
+huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, const CompactEntry* __restrict__ entries,
                     const CompactIndex* __restrict__ index,
                     uint32_t* __restrict__ leaf_freq, int32_t* __restrict__ row_sym, uint32_t* __restrict__ tier_count,
                     uint32_t* __restrict__ tier_list, int n_ss, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t sort_raw[];
-    const int ss = blockIdx.x;
+    const int ss = selected_stream(sel, blockIdx.x);
     const CompactIndex ix = index[ss];
     const int n = (int)ix.count;
     if (n == 0) return;
@@ -1061,6 +1086,13 @@ struct hic_entropy_plan {
     bool start_is_default = true;               // d_start_bit holds 8 everywhere
     uint32_t* d_tier_count = nullptr;           // device Huffman builder: streams per size tier
     uint32_t* d_tier_list = nullptr;            // [tier][n_ss] stream ids
+    uint32_t* d_tier_count_dc = nullptr;        // the same for the DC streams, whose construction starts early
+    uint32_t* d_tier_list_dc = nullptr;
+    uint32_t* d_leaf_freq = nullptr;            // builder scratch: leaf frequencies at the compaction offsets
+    uint32_t* d_parent = nullptr;               // builder scratch: two uint16 parent links per entry
+    bool hist_clean = false;                    // d_hist / d_first hold their reset values
+    cudaEvent_t ev_dc = nullptr;                // DC histograms compacted (recorded by the emit pass)
+    bool dc_early = false;                      // the last emit pass recorded ev_dc
     bool device_built = false;                  // codes came from hic_entropy_build_codes_device
     bool host_info_valid = false;               // rows/nsym/nbits/byte_off/byte_len mirror the device
     bool host_tables_valid = false;
@@ -1148,7 +1180,8 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
                     p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
-                    p->d_pay_totals, p->d_tier_count, p->d_tier_list, p->d_start_bit, p->d_band, p->d_lut_len};
+                    p->d_pay_totals, p->d_tier_count, p->d_tier_list, p->d_start_bit, p->d_band, p->d_lut_len,
+                    p->d_tier_count_dc, p->d_tier_list_dc, p->d_leaf_freq, p->d_parent};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
@@ -1156,6 +1189,7 @@ int hic_entropy_plan_destroy(hic_entropy_plan* p) {
         if (p->ev_join[a]) cudaEventDestroy(p->ev_join[a]);
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_dc) cudaEventDestroy(p->ev_dc);
     delete p;
     return HIC_OK;
 }
@@ -1202,11 +1236,23 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_band, p->n_cs));
     ok(dalloc(&p->d_tier_count, N_TIERS));
     ok(dalloc(&p->d_tier_list, (size_t)N_TIERS * p->n_ss));
+    ok(dalloc(&p->d_tier_count_dc, N_TIERS));
+    ok(dalloc(&p->d_tier_list_dc, (size_t)N_TIERS * p->n_ss));
+    ok(dalloc(&p->d_leaf_freq, hist_n));
+    ok(dalloc(&p->d_parent, hist_n));
+    // (default priority: with the highest priority the replay's small shared-memory-heavy CTAs displace the
+    // wide kernels of other chunks and the pipelined batch path slows down, 27.6 -> 30.0 ms per C2 batch)
     for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
         ok(cudaStreamCreateWithFlags(&p->aux[a], cudaStreamNonBlocking));
         ok(cudaEventCreateWithFlags(&p->ev_join[a], cudaEventDisableTiming));
     }
     ok(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&p->ev_dc, cudaEventDisableTiming));
+    if (e == cudaSuccess) {
+        ok(cudaMemset(p->d_hist, 0, hist_n * sizeof(uint32_t)));
+        ok(cudaMemset(p->d_first, 0xFF, hist_n * sizeof(uint32_t)));
+        p->hist_clean = e == cudaSuccess;
+    }
     if (e == cudaSuccess) {
         std::vector<uint32_t> start(p->n_ss, 8u);
         ok(cudaMemcpy(p->d_start_bit, start.data(), sizeof(uint32_t) * p->n_ss, cudaMemcpyHostToDevice));
@@ -1235,8 +1281,11 @@ static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st
     const Geom& g = p->g;
     p->codes_ready = false;
     const size_t hist_n = (size_t)p->n_ss * g.nb_bins;
-    HIC_CUDA(cudaMemsetAsync(p->d_hist, 0, hist_n * sizeof(uint32_t), st));
-    HIC_CUDA(cudaMemsetAsync(p->d_first, 0xFF, hist_n * sizeof(uint32_t), st));
+    if (!p->hist_clean) {          // normally the compaction of the previous batch has reset every bin it found in use
+        HIC_CUDA(cudaMemsetAsync(p->d_hist, 0, hist_n * sizeof(uint32_t), st));
+        HIC_CUDA(cudaMemsetAsync(p->d_first, 0xFF, hist_n * sizeof(uint32_t), st));
+    }
+    p->hist_clean = false;
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
     const unsigned tiles = (unsigned)p->total_tiles;
     if (g.L.skip_first)
@@ -1249,6 +1298,13 @@ static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st
 static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry* d_band, cudaStream_t st) {
     const Geom& g = p->g;
     const unsigned tiles = (unsigned)p->total_tiles;
+    p->dc_early = false;
+    if (g.L.skip_first) {
+        HIC_LAUNCH("dc_diff_kernel", st, dc_diff_kernel<<<tiles, RLE_TB, 0, st>>>(d_coef, g, d_band, p->d_dc, p->d_hist, p->d_first, p->d_err));
+        HIC_LAUNCH("compact_kernel", st, compact_kernel<<<selected_count(SEL_DC, p->n_cs), 256, 0, st>>>(g, SEL_DC, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
+        HIC_CUDA(cudaEventRecord(p->ev_dc, st));
+        p->dc_early = true;
+    }
     HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, d_band, p->d_carry, p->d_totals,
                                                                  p->d_values, p->d_lengths, p->d_hist, p->d_first));
     {
@@ -1267,7 +1323,11 @@ static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry
     else
         HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
                                                          p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err));
-    HIC_LAUNCH("compact_kernel", st, compact_kernel<<<p->n_ss, 256, 0, st>>>(g, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
+    {
+        const int sel = g.L.skip_first ? SEL_AC : SEL_ALL;
+        HIC_LAUNCH("compact_kernel", st, compact_kernel<<<selected_count(sel, p->n_cs), 256, 0, st>>>(g, sel, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
+    }
+    p->hist_clean = true;
     return HIC_OK;
 }
 
@@ -1603,31 +1663,64 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
         HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
         if (dev < 64) attr_set[dev] = true;
     }
-    uint32_t* leaf_freq = p->d_first;                                    // dead after the compaction
-    uint16_t* parent = reinterpret_cast<uint16_t*>(p->d_hist);           // likewise (2 links per entry = 4 bytes)
-    HIC_CUDA(cudaMemsetAsync(p->d_tier_count, 0, N_TIERS * sizeof(uint32_t), st));
-    // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
-    HIC_LAUNCH("huffman_sort_kernel", st, huffman_sort_kernel<<<p->n_ss, SORT_THREADS, 6 * 1024, st>>>(
-        g, 0, 1024, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
-    HIC_LAUNCH("huffman_sort_kernel", st, huffman_sort_kernel<<<p->n_ss, SORT_THREADS, 6 * 8192, st>>>(
-        g, 1024, 8192, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, p->d_tier_count, p->d_tier_list, p->n_ss, p->d_err));
-    // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams:
-    // fork after the sort, join before the code read-out.
-    // (profiled as ONE span on `st` from fork to join: the 21 tier launches overlap each other)
-    hic::prof_begin("huffman_replay_kernel", st);
-    HIC_CUDA(cudaEventRecord(p->ev_fork, st));
-    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
-    for (int t = N_TIERS - 1; t >= 0; --t) {                             // longest chains first
-        const int stride_slots = h_tier_bound[t] + 2;
-        const int stride = 8 * stride_slots;
-        const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
-        const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
-        cudaStream_t sx = (t % (hic_entropy_plan::N_AUX + 1)) == 0 ? st : p->aux[(t % (hic_entropy_plan::N_AUX + 1)) - 1];
-        huffman_replay_kernel<<<grid, 32, (size_t)G * stride, sx>>>(t, G, stride_slots, p->n_ss, p->d_index, leaf_freq,
-                                                                     p->d_tier_count, p->d_tier_list, parent);
-        HIC_CHECK_LAUNCH("huffman_replay_kernel");
+    uint32_t* leaf_freq = p->d_leaf_freq;
+    uint16_t* parent = reinterpret_cast<uint16_t*>(p->d_parent);         // 2 links per entry = 4 bytes
+    constexpr int N_AUX = hic_entropy_plan::N_AUX;
+    // one sort + replay pass over a selection of the streams; `lanes` are the CUDA streams its tiers are dealt to
+    auto sort_pass = [&](int sel, uint32_t* tier_count, uint32_t* tier_list, cudaStream_t s0) -> int {
+        const unsigned grid = (unsigned)selected_count(sel, p->n_cs);
+        HIC_CUDA(cudaMemsetAsync(tier_count, 0, N_TIERS * sizeof(uint32_t), s0));
+        // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
+        HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 1024, s0>>>(
+            g, sel, 0, 1024, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+        HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 8192, s0>>>(
+            g, sel, 1024, 8192, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+        return HIC_OK;
+    };
+    auto replay_pass = [&](const uint32_t* tier_count, const uint32_t* tier_list, cudaStream_t* lanes, int n_lanes) -> int {
+        for (int t = N_TIERS - 1; t >= 0; --t) {                         // longest chains first
+            const int stride_slots = h_tier_bound[t] + 2;
+            const int stride = 8 * stride_slots;
+            const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
+            const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
+            huffman_replay_kernel<<<grid, 32, (size_t)G * stride, lanes[t % n_lanes]>>>(t, G, stride_slots, p->n_ss, p->d_index, leaf_freq,
+                                                                                          tier_count, tier_list, parent);
+            HIC_CHECK_LAUNCH("huffman_replay_kernel");
+        }
+        return HIC_OK;
+    };
+    // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams.  The DC
+    // streams (the longest chains) do not wait for the run-length symbols at all: their pass hangs on the
+    // event the emit pass recorded after the DC compaction and overlaps rle_emit on `st`.
+    const bool dc_early = p->dc_early && g.L.skip_first;
+    const int n_dc_lanes = dc_early ? 4 : 0;
+    if (dc_early) {
+        cudaStream_t* dl = p->aux;                                       // aux[0..3]
+        HIC_CUDA(cudaStreamWaitEvent(dl[0], p->ev_dc, 0));
+        rc = sort_pass(SEL_DC, p->d_tier_count_dc, p->d_tier_list_dc, dl[0]);
+        if (rc) return rc;
+        HIC_CUDA(cudaEventRecord(p->ev_join[0], dl[0]));
+        for (int a = 1; a < n_dc_lanes; ++a) HIC_CUDA(cudaStreamWaitEvent(dl[a], p->ev_join[0], 0));
+        rc = replay_pass(p->d_tier_count_dc, p->d_tier_list_dc, dl, n_dc_lanes);
+        if (rc) return rc;
     }
-    for (int a = 0; a < hic_entropy_plan::N_AUX; ++a) {
+    rc = sort_pass(dc_early ? SEL_AC : SEL_ALL, p->d_tier_count, p->d_tier_list, st);
+    if (rc) return rc;
+    // (profiled as ONE span on `st` from fork to join: the tier launches overlap each other)
+    hic::prof_begin("huffman_replay_kernel", st);
+    {
+        cudaStream_t lanes[N_AUX + 1];
+        int n_lanes = 0;
+        lanes[n_lanes++] = st;
+        HIC_CUDA(cudaEventRecord(p->ev_fork, st));
+        for (int a = n_dc_lanes; a < N_AUX; ++a) {
+            HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
+            lanes[n_lanes++] = p->aux[a];
+        }
+        rc = replay_pass(p->d_tier_count, p->d_tier_list, lanes, n_lanes);
+        if (rc) return rc;
+    }
+    for (int a = 0; a < N_AUX; ++a) {
         HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
         HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
     }

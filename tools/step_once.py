@@ -22,6 +22,9 @@ def main():
         codec.encode_device()
         codec.decode_device()
     _lib.sync()
+    rows = np.asarray(codec.encoder.rows).reshape(n, 3, 3)       # [image, channel, kind]
+    print("alphabet sizes (mean / max over images), channels lum cr cb x kinds dc value length:")
+    print(np.round(rows.mean(axis=0)).astype(int).tolist(), rows.max(axis=0).tolist())
     for k, (ms, launches) in sorted(_lib.profile_report().items(), key=lambda kv: -kv[1][0]):
         print("%-28s %8.4f ms x %d" % (k, ms / max(launches, 1), launches))
 
