@@ -109,9 +109,18 @@ constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // 192
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
 constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
 
-// R - Y spans [-179, 179] and B - Y [-226, 226] (extremes of cv2's weights), so the chroma lookup
-// tables need 359 and 453 entries; trimming them keeps the CTA at 4 per SM
-constexpr int CR_BIAS = 179, CB_BIAS = 226;
+// Colour conversion constants (cv2's 14-bit fixed point, compression.py:21), scaled by 4 so that every
+// result lands in byte 2 of its accumulator and the packing PRMTs pick it up without a shift:
+//   Y  = (4899 R + 9617 G + 1868 B + 8192) >> 14                 = byte 2 of two 16x8-bit dot products
+//   Cr = ((R - Y) 11682 + (128 << 14) + 8192) >> 14, clamped     = byte 2 of min(46728 R - 46728 Y + C4, 2^24 - 1)
+//   Cb = ((B - Y)  9241 + (128 << 14) + 8192) >> 14              = byte 2 of      36964 B - 36964 Y + C4
+// R - Y spans [-179, 179] and B - Y [-226, 226] (extremes of cv2's weights): Cr reaches 256 only at the
+// top (hence the min) and never goes below 0; Cb stays inside 1..255.  All arithmetic instead of the
+// shared-memory lookup tables of the first version: the kernel's stalls were on the shared-memory pipe.
+constexpr uint32_t W_RG = (4u * 9617u << 16) | (4u * 4899u);     // dp2a.lo: R (byte 0) and G (byte 1)
+constexpr uint32_t W_B = 4u * 1868u;                             // dp2a.hi: B (byte 2); byte 3 weighs 0
+constexpr uint32_t K_CR = 4u * 11682u, K_CB = 4u * 9241u;
+constexpr uint32_t C4 = 4u * ((128u << 14) + 8192u);
 struct Smem {
     union alignas(128) {
         uint32_t rgb[RH * RWORDS];                   // stage 0/1 (TMA destination)
@@ -126,8 +135,6 @@ struct Smem {
         uint8_t cb[RH][C_PITCH];
         uint8_t cbd[CH][CW];
     };
-    alignas(8) uint8_t lut_cr[2 * CR_BIAS + 2];      // Cr as a function of R - Y + CR_BIAS
-    alignas(8) uint8_t lut_cb[2 * CB_BIAS + 4];      // Cb as a function of B - Y + CB_BIAS
     alignas(8) unsigned long long bar;
 };
 static_assert(sizeof(Smem) <= 57344, "four CTAs per SM: (228 KB - 4 x 1 KB reserved) / 4");
@@ -263,11 +270,6 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
             }
         }
     }
-    // chroma lookup tables (cv2's fixed point, compression.py:21): index = difference + 255
-    for (int i = tid; i < 2 * CB_BIAS + 1; i += THREADS) {
-        if (i < 2 * CR_BIAS + 1) s.lut_cr[i] = (uint8_t)clamp_u8(((i - CR_BIAS) * 11682 + (128 << 14) + 8192) >> 14);
-        s.lut_cb[i] = (uint8_t)clamp_u8(((i - CB_BIAS) * 9241 + (128 << 14) + 8192) >> 14);
-    }
     if (!USE_TMA) {
         // generic loader (row pitch not a multiple of 16 bytes): bytes with the border rule applied
         const uint8_t* src = rgb + (size_t)img * h * w * 3;
@@ -336,22 +338,22 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         const uint32_t* rw = s.rgb + ry * RWORDS + 3 * (gx + SKIP / 4);
         const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
         const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
-        uint32_t yv[4], crv[4], cbv[4];
+        uint32_t yv[4], crv[4], cbv[4];          // results in byte 2
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t lo = __dp4a(px[k], 0x004C9123u, 8192u);
-            const uint32_t yy = __dp4a(px[k], 0x00072513u, lo >> 8) >> 6;       // (lo + 256 hi) >> 14
-            yv[k] = yy;
-            crv[k] = s.lut_cr[__dp4a(px[k], 0x00000001u, (uint32_t)CR_BIAS - yy)];      // R - Y + CR_BIAS
-            cbv[k] = s.lut_cb[__dp4a(px[k], 0x00010000u, (uint32_t)CB_BIAS - yy)];      // B - Y + CB_BIAS
+            const uint32_t acc = __dp2a_hi(W_B, px[k], __dp2a_lo(W_RG, px[k], 4u * 8192u));
+            const uint32_t yy = acc >> 16;
+            yv[k] = acc;
+            crv[k] = min(__dp2a_lo(K_CR, px[k], C4 - K_CR * yy), 0x00FFFFFFu);
+            cbv[k] = __dp2a_hi(K_CB, px[k], C4 - K_CB * yy);
         }
         *reinterpret_cast<uint32_t*>(&s.cr[ry][4 * gx]) =
-            __byte_perm(__byte_perm(crv[0], crv[1], 0x0040), __byte_perm(crv[2], crv[3], 0x0040), 0x5410);
+            __byte_perm(__byte_perm(crv[0], crv[1], 0x0062), __byte_perm(crv[2], crv[3], 0x0062), 0x5410);
         *reinterpret_cast<uint32_t*>(&s.cb[ry][4 * gx]) =
-            __byte_perm(__byte_perm(cbv[0], cbv[1], 0x0040), __byte_perm(cbv[2], cbv[3], 0x0040), 0x5410);
+            __byte_perm(__byte_perm(cbv[0], cbv[1], 0x0062), __byte_perm(cbv[2], cbv[3], 0x0062), 0x5410);
         if (store_y)
             *reinterpret_cast<uint32_t*>(&s.y[ry - 2][4 * (gx - 1)]) =
-                __byte_perm(__byte_perm(yv[0], yv[1], 0x0040), __byte_perm(yv[2], yv[3], 0x0040), 0x5410);
+                __byte_perm(__byte_perm(yv[0], yv[1], 0x0062), __byte_perm(yv[2], yv[3], 0x0062), 0x5410);
     };
     {
         const int warp = tid >> 5, lane = tid & 31;

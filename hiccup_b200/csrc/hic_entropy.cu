@@ -410,12 +410,23 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
             m &= m - 1;
             cnt += 1u + (uint32_t)((zeros_before + (e - prev_e - 1)) / 15 - zeros_before / 15);
             prev_e = e;
-            while (m) {                            // gaps inside the block: a filler only for 15 zeros or more
-                const int e2 = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int gap = e2 - prev_e - 1;
-                cnt += 1u + (gap >= 15 ? (uint32_t)(gap / 15) : 0u);
-                prev_e = e2;
+            // the other non-zeros: one symbol each, plus fillers only where 15 or more zeros lie between two
+            // of them -- looked for with shifts (a run of 15 zero bits strictly between the first and the
+            // last non-zero); only such a block walks its gaps one by one
+            const int top = 63 - __clzll((long long)mask);
+            const unsigned long long z = ~mask & ((1ull << top) - 1ull) & ~((2ull << e) - 1ull);
+            const unsigned long long z2 = z & (z >> 1), z4 = z2 & (z2 >> 2), z8 = z4 & (z4 >> 4);
+            if ((z8 & (z4 >> 8) & (z2 >> 12) & (z >> 14)) == 0ull) {
+                cnt += (uint32_t)__popcll(m);
+                prev_e = top;
+            } else {
+                while (m) {
+                    const int e2 = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const int gap = e2 - prev_e - 1;
+                    cnt += 1u + (gap >= 15 ? (uint32_t)(gap / 15) : 0u);
+                    prev_e = e2;
+                }
             }
         }
         const int zt = mask ? 0 : zeros_before;
