@@ -561,32 +561,42 @@ __device__ __forceinline__ int64_t block_excl_sum64(int64_t v, int64_t* smem, in
     return base + inc - v;
 }
 
+// positions covered by each tile of 2048 symbols: sum of (zero count + 1).  One WARP per tile (a lane
+// reads four 16-byte vectors and adds their bytes with the SIMD absolute-difference instruction), eight
+// tiles per CTA, no shared memory and no barrier: the grid covers the capacity, most of it empty tiles.
 __global__ void __launch_bounds__(XTHREADS)
 expand_tile_sum_kernel(Geom g, const uint8_t* __restrict__ lengths, const uint32_t* __restrict__ nsym_arr,
-                       int64_t* __restrict__ tile_sum) {
-    __shared__ int64_t s[XTHREADS / 32];
-    const XRef r = locate(g.xtiles, g.xtiles_per_image, blockIdx.x);
+                       int64_t* __restrict__ tile_sum, int64_t total_tiles) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (XTHREADS / 32) + (threadIdx.x >> 5);
+    if (t >= total_tiles) return;
+    const XRef r = locate(g.xtiles, g.xtiles_per_image, t);
     const int ss = (r.img * 3 + r.c) * 3 + HIC_KIND_LENGTH;
     const uint32_t nsym = nsym_arr[ss];
-    const uint8_t* len = lengths + cs_block_base(g, r.img, r.c) * 64;
-    const uint32_t start = (uint32_t)r.tile * XT + threadIdx.x * XSPT;
-    static_assert(XSPT == 8, "one 8-byte load per thread");
+    const uint32_t tile_first = (uint32_t)r.tile * XT;
     uint32_t sum = 0;
-    if (start < nsym) {
-        const uint2 v = *reinterpret_cast<const uint2*>(len + start);       // 8 zero counts (0..14 each)
+    if (tile_first < nsym) {
+        const uint32_t in_tile = min((uint32_t)XT, nsym - tile_first);
+        const uint8_t* len = lengths + cs_block_base(g, r.img, r.c) * 64 + tile_first;      // 16-byte aligned
+        static_assert(XT == 4 * 32 * 16, "four 16-byte vectors per lane");
 #pragma unroll
-        for (int j = 0; j < XSPT; ++j)
-            if (start + j < nsym) sum += (((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFFu) + 1u;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)(j * 32 + lane) * 16u;
+            if (off >= in_tile) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(len + off);       // the symbol arrays carry slack past the end
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t valid = min(16u, in_tile - off);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t nb = valid > 4u * k ? min(4u, valid - 4u * k) : 0u;
+                const uint32_t keep = nb == 4u ? 0xFFFFFFFFu : ((1u << (8u * nb)) - 1u);
+                sum += __vsadu4(wv[k] & keep, 0u) + nb;
+            }
+        }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int64_t total = 0;
-        for (int w = 0; w < XTHREADS / 32; ++w) total += s[w];
-        tile_sum[blockIdx.x] = total;
-    }
+    if (lane == 0) tile_sum[t] = (int64_t)sum;
 }
 
 __global__ void stream_scan64_kernel(int n_cs, int tiles0, int tiles1, int tiles2, int per_image,
@@ -1061,7 +1071,7 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
             HIC_LAUNCH("huffman_write_kernel", st, huffman_write_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, WRITE_SMEM, st>>>(a, g, p->d_tile_symoff, p->d_dc, p->d_values, p->d_lengths, p->d_err));
         }
     }
-    HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum));
+    HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)((p->total_xtiles + XTHREADS / 32 - 1) / (XTHREADS / 32)), XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum, p->total_xtiles));
     HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
                                                                g.xtiles_per_image, p->d_tile_sum, p->d_tile_off,
                                                                p->d_stream_total));

@@ -12,6 +12,7 @@
 // run of l zeros; trailing zeros collapse to (0, 0) and their count is dropped).  Every position
 // emits at most one symbol, so a tile of positions has a bounded output and the output index is an
 // exclusive prefix sum -- no serial dependency besides two small carries per tile.
+#include <stdlib.h>
 #include <algorithm>
 #include <mutex>
 #include <thread>
@@ -341,22 +342,19 @@ struct EmitSmem {
 };
 
 template <bool SKIP>
-__global__ void __launch_bounds__(RLE_TB)
-rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __restrict__ band,
+__device__ __forceinline__ void rle_emit_tile(EmitSmem& sm, const uint32_t tile_id, const int16_t* __restrict__ coef, const Geom& g,
                 const TileCarry* __restrict__ carry,
-                const StreamTotals* __restrict__ totals, int16_t* __restrict__ dc_out, int16_t* __restrict__ values,
+                const StreamTotals* __restrict__ totals, int16_t* __restrict__ values,
                 uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
                 uint32_t* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t emit_raw[];
-    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_raw);
-    const TileRef tr = locate_tile(g, blockIdx.x);
+    const TileRef tr = locate_tile(g, tile_id);
     const int cs = tr.img * 3 + tr.c;
     const int64_t nb = g.L.nb[tr.c];
     const int64_t b = (int64_t)tr.tile * RLE_TB + threadIdx.x;
     const int64_t block_base = cs_block_base(g, tr.img, tr.c);
     const int len = (int)g.L.len[tr.c];
     const int last_nz = totals[cs].last_nz;
-    const TileCarry tc = carry[blockIdx.x];
+    const TileCarry tc = carry[tile_id];
     const int half = g.nb_bins / 2;
     const size_t hbase = (size_t)cs * 3 * g.nb_bins;
 
@@ -527,6 +525,26 @@ rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __res
             atomicAdd(&hist[hl], c);
             if (first[hl] > sm.first_l[threadIdx.x]) atomicMin(&first[hl], sm.first_l[threadIdx.x]);
         }
+    }
+}
+
+// Persistent launch: EMIT_CTAS_PER_SM CTAs per SM walk the tiles.  One CTA slot per SM (shared memory and
+// threads) is deliberately left free: the DC Huffman constructions -- a few long-running one-warp CTAs
+// with their heaps in shared memory -- run beside this kernel and must find room while it is busy.
+constexpr int EMIT_CTAS_PER_SM = 3;
+
+template <bool SKIP>
+__global__ void __launch_bounds__(RLE_TB)
+rle_emit_kernel(const int16_t* __restrict__ coef, Geom g, const BandCarry* __restrict__ band,
+                const TileCarry* __restrict__ carry,
+                const StreamTotals* __restrict__ totals, int16_t* __restrict__ dc_out, int16_t* __restrict__ values,
+                uint8_t* __restrict__ lengths, uint32_t* __restrict__ hist, uint32_t* __restrict__ first,
+                uint32_t* __restrict__ err, uint32_t n_tiles) {
+    extern __shared__ __align__(16) uint8_t emit_raw[];
+    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_raw);
+    for (uint32_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        rle_emit_tile<SKIP>(sm, tile_id, coef, g, carry, totals, values, lengths, hist, first, err);
+        __syncthreads();            // the staging area and the privatised histograms are reused
     }
 }
 
@@ -1104,6 +1122,8 @@ struct hic_entropy_plan {
     bool hist_clean = false;                    // d_hist / d_first hold their reset values
     cudaEvent_t ev_dc = nullptr;                // DC histograms compacted (recorded by the emit pass)
     bool dc_early = false;                      // the last emit pass recorded ev_dc
+    bool prefer_device = false;                 // the last code build ran on the device: start the next DC pass eagerly
+    bool dc_launched = false;                   // a DC pass is in flight on aux[0..DC_LANES) and not yet joined
     bool device_built = false;                  // codes came from hic_entropy_build_codes_device
     bool host_info_valid = false;               // rows/nsym/nbits/byte_off/byte_len mirror the device
     bool host_tables_valid = false;
@@ -1288,9 +1308,88 @@ static int restore_default_start(hic_entropy_plan* p, cudaStream_t st) {
     return HIC_OK;
 }
 
+// ---- device Huffman builder plumbing (kernels above; orchestration in hic_entropy_build_codes_device) ----
+constexpr int DC_LANES = 4;                     // auxiliary streams that carry the early DC pass
+
+static int builder_prepare(hic_entropy_plan* p) {
+    const Geom& g = p->g;
+    int rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    HIC_CUDA(cudaGetDevice(&dev));
+    const int max_stride = 8 * (h_tier_bound[N_TIERS - 1] + 2);
+    if (dev >= 64 || !attr_set[dev]) {
+        HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    return HIC_OK;
+}
+
+// sort + tier filing of a selection of the streams on stream s0
+static int builder_sort_pass(hic_entropy_plan* p, int sel, uint32_t* tier_count, uint32_t* tier_list, cudaStream_t s0) {
+    const Geom& g = p->g;
+    const unsigned grid = (unsigned)selected_count(sel, p->n_cs);
+    HIC_CUDA(cudaMemsetAsync(tier_count, 0, N_TIERS * sizeof(uint32_t), s0));
+    // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
+    HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 1024, s0>>>(
+        g, sel, 0, 1024, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+    HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 8192, s0>>>(
+        g, sel, 1024, 8192, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+    return HIC_OK;
+}
+
+// the replay of every size tier, dealt to the given CUDA streams (longest chains first)
+static int builder_replay_pass(hic_entropy_plan* p, const uint32_t* tier_count, const uint32_t* tier_list, cudaStream_t* lanes,
+                               int n_lanes) {
+    for (int t = N_TIERS - 1; t >= 0; --t) {
+        const int stride_slots = h_tier_bound[t] + 2;
+        const int stride = 8 * stride_slots;
+        const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
+        const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
+        huffman_replay_kernel<<<grid, 32, (size_t)G * stride, lanes[t % n_lanes]>>>(t, G, stride_slots, p->n_ss, p->d_index, p->d_leaf_freq,
+                                                                                      tier_count, tier_list,
+                                                                                      reinterpret_cast<uint16_t*>(p->d_parent));
+        HIC_CHECK_LAUNCH("huffman_replay_kernel");
+    }
+    return HIC_OK;
+}
+
+// The DC streams' pass on aux[0..DC_LANES): it hangs on the event the emit pass records after the DC
+// compaction, not on the run-length symbols, so it runs beside rle_emit.
+static int launch_dc_pass(hic_entropy_plan* p) {
+    cudaStream_t* dl = p->aux;
+    HIC_CUDA(cudaStreamWaitEvent(dl[0], p->ev_dc, 0));
+    int rc = builder_sort_pass(p, SEL_DC, p->d_tier_count_dc, p->d_tier_list_dc, dl[0]);
+    if (rc) return rc;
+    HIC_CUDA(cudaEventRecord(p->ev_join[0], dl[0]));
+    for (int a = 1; a < DC_LANES; ++a) HIC_CUDA(cudaStreamWaitEvent(dl[a], p->ev_join[0], 0));
+    rc = builder_replay_pass(p, p->d_tier_count_dc, p->d_tier_list_dc, dl, DC_LANES);
+    if (rc) return rc;
+    p->dc_launched = true;
+    return HIC_OK;
+}
+
+// make `st` wait for a DC pass that is still in flight (paths that do not consume it)
+static int join_dc_pass(hic_entropy_plan* p, cudaStream_t st) {
+    if (!p->dc_launched) return HIC_OK;
+    for (int a = 0; a < DC_LANES; ++a) {
+        HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
+        HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
+    }
+    p->dc_launched = false;
+    return HIC_OK;
+}
+
+static bool serial_build() { return getenv("HIC_ENTROPY_SERIAL") != nullptr; }
+
 static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st) {
     const Geom& g = p->g;
     p->codes_ready = false;
+    {
+        int rc = join_dc_pass(p, st);           // an unconsumed DC pass of the previous batch still reads the entries
+        if (rc) return rc;
+    }
     const size_t hist_n = (size_t)p->n_ss * g.nb_bins;
     if (!p->hist_clean) {          // normally the compaction of the previous batch has reset every bin it found in use
         HIC_CUDA(cudaMemsetAsync(p->d_hist, 0, hist_n * sizeof(uint32_t), st));
@@ -1315,6 +1414,14 @@ static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry
         HIC_LAUNCH("compact_kernel", st, compact_kernel<<<selected_count(SEL_DC, p->n_cs), 256, 0, st>>>(g, SEL_DC, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
         HIC_CUDA(cudaEventRecord(p->ev_dc, st));
         p->dc_early = true;
+        // launched ahead of rle_emit when the codes are going to be built on the device (as they were last
+        // time): kernels that are launched first are placed first
+        if (p->prefer_device && g.nb_bins <= 8192 && !serial_build()) {
+            int rc = builder_prepare(p);
+            if (rc) return rc;
+            rc = launch_dc_pass(p);
+            if (rc) return rc;
+        }
     }
     HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, d_band, p->d_carry, p->d_totals,
                                                                  p->d_values, p->d_lengths, p->d_hist, p->d_first));
@@ -1328,12 +1435,18 @@ static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry
             if (dev < 64) emit_attr[dev] = true;
         }
     }
-    if (g.L.skip_first)
-        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<true><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
-                                                        p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err));
-    else
-        HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<tiles, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
-                                                         p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err));
+    {
+        int dev = 0, sms = 148;
+        HIC_CUDA(cudaGetDevice(&dev));
+        HIC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const unsigned grid = std::min(tiles, (unsigned)(sms * EMIT_CTAS_PER_SM));
+        if (g.L.skip_first)
+            HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<true><<<grid, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
+                                                            p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err, tiles));
+        else
+            HIC_LAUNCH("rle_emit_kernel", st, rle_emit_kernel<false><<<grid, RLE_TB, sizeof(EmitSmem), st>>>(d_coef, g, d_band, p->d_carry, p->d_totals, p->d_dc,
+                                                             p->d_values, p->d_lengths, p->d_hist, p->d_first, p->d_err, tiles));
+    }
     {
         const int sel = g.L.skip_first ? SEL_AC : SEL_ALL;
         HIC_LAUNCH("compact_kernel", st, compact_kernel<<<selected_count(sel, p->n_cs), 256, 0, st>>>(g, sel, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
@@ -1413,6 +1526,11 @@ int hic_entropy_set_codes(hic_entropy_plan* p, const uint32_t* h_index, const in
     const Geom& g = p->g;
     cudaStream_t st = as_stream(stream);
     p->last_stream = st;
+    p->prefer_device = false;
+    {
+        int rc = join_dc_pass(p, st);
+        if (rc) return rc;
+    }
     const int nss = p->n_ss;
     std::vector<uint32_t> row_stream(total_rows), start(nss, 8u);
     p->rows.assign(nss, 0); p->nsym.assign(nss, 0); p->nbits.assign(nss, 0);
@@ -1472,8 +1590,11 @@ int hic_entropy_build_codes(hic_entropy_plan* p, void* stream) {
     const Geom& g = p->g;
     cudaStream_t st = as_stream(stream);
     p->last_stream = st;
+    p->prefer_device = false;
     {
-        int rc0 = restore_default_start(p, st);
+        int rc0 = join_dc_pass(p, st);
+        if (rc0) return rc0;
+        rc0 = restore_default_start(p, st);
         if (rc0) return rc0;
     }
     uint32_t flags[4];
@@ -1662,60 +1783,47 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
     HIC_REQUIRE(g.nb_bins <= 8192, "the device Huffman builder handles up to 8192 value bins; use hic_entropy_build_codes");
     cudaStream_t st = as_stream(stream);
     p->last_stream = st;
+    p->prefer_device = true;
     int rc = restore_default_start(p, st);
     if (rc) return rc;
-    rc = ensure_row_capacity(p, (uint64_t)p->n_ss * g.nb_bins);
+    rc = builder_prepare(p);
     if (rc) return rc;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    HIC_CUDA(cudaGetDevice(&dev));
-    const int max_stride = 8 * (h_tier_bound[N_TIERS - 1] + 2);
-    if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
-        if (dev < 64) attr_set[dev] = true;
-    }
     uint32_t* leaf_freq = p->d_leaf_freq;
     uint16_t* parent = reinterpret_cast<uint16_t*>(p->d_parent);         // 2 links per entry = 4 bytes
     constexpr int N_AUX = hic_entropy_plan::N_AUX;
-    // one sort + replay pass over a selection of the streams; `lanes` are the CUDA streams its tiers are dealt to
-    auto sort_pass = [&](int sel, uint32_t* tier_count, uint32_t* tier_list, cudaStream_t s0) -> int {
-        const unsigned grid = (unsigned)selected_count(sel, p->n_cs);
-        HIC_CUDA(cudaMemsetAsync(tier_count, 0, N_TIERS * sizeof(uint32_t), s0));
-        // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
-        HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 1024, s0>>>(
-            g, sel, 0, 1024, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
-        HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 8192, s0>>>(
-            g, sel, 1024, 8192, p->d_entries, p->d_index, leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
-        return HIC_OK;
-    };
-    auto replay_pass = [&](const uint32_t* tier_count, const uint32_t* tier_list, cudaStream_t* lanes, int n_lanes) -> int {
-        for (int t = N_TIERS - 1; t >= 0; --t) {                         // longest chains first
-            const int stride_slots = h_tier_bound[t] + 2;
-            const int stride = 8 * stride_slots;
-            const int G = std::max(1, std::min(32, REPLAY_SMEM_BUDGET / stride));
-            const unsigned grid = (unsigned)((p->n_ss + G - 1) / G);
-            huffman_replay_kernel<<<grid, 32, (size_t)G * stride, lanes[t % n_lanes]>>>(t, G, stride_slots, p->n_ss, p->d_index, leaf_freq,
-                                                                                          tier_count, tier_list, parent);
-            HIC_CHECK_LAUNCH("huffman_replay_kernel");
-        }
-        return HIC_OK;
-    };
+    static_assert(DC_LANES < N_AUX, "the run-length pass needs lanes of its own");
     // The replay is latency-bound, so the tiers run side by side on the plan's auxiliary streams.  The DC
     // streams (the longest chains) do not wait for the run-length symbols at all: their pass hangs on the
-    // event the emit pass recorded after the DC compaction and overlaps rle_emit on `st`.
-    const bool dc_early = p->dc_early && g.L.skip_first;
-    const int n_dc_lanes = dc_early ? 4 : 0;
-    if (dc_early) {
-        cudaStream_t* dl = p->aux;                                       // aux[0..3]
-        HIC_CUDA(cudaStreamWaitEvent(dl[0], p->ev_dc, 0));
-        rc = sort_pass(SEL_DC, p->d_tier_count_dc, p->d_tier_list_dc, dl[0]);
+    // event the emit pass recorded after the DC compaction and overlaps rle_emit on `st` -- the emit pass
+    // has already launched it when the previous batch was built on the device too.
+    // HIC_ENTROPY_SERIAL (environment): keep the DC pass on `st`, ahead of the run-length pass, so that
+    // per-kernel timings are not blurred by the overlap (bench.py's kernel table); results are identical.
+    const bool has_dc = p->dc_early && g.L.skip_first;
+    const bool serial = serial_build() && !p->dc_launched;
+    if (has_dc && serial) {
+        rc = builder_sort_pass(p, SEL_DC, p->d_tier_count_dc, p->d_tier_list_dc, st);
         if (rc) return rc;
-        HIC_CUDA(cudaEventRecord(p->ev_join[0], dl[0]));
-        for (int a = 1; a < n_dc_lanes; ++a) HIC_CUDA(cudaStreamWaitEvent(dl[a], p->ev_join[0], 0));
-        rc = replay_pass(p->d_tier_count_dc, p->d_tier_list_dc, dl, n_dc_lanes);
+        hic::prof_begin("huffman_replay_kernel", st);
+        cudaStream_t lanes[N_AUX + 1];
+        lanes[0] = st;
+        HIC_CUDA(cudaEventRecord(p->ev_fork, st));
+        for (int a = 0; a < N_AUX; ++a) {
+            HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
+            lanes[a + 1] = p->aux[a];
+        }
+        rc = builder_replay_pass(p, p->d_tier_count_dc, p->d_tier_list_dc, lanes, N_AUX + 1);
+        if (rc) return rc;
+        for (int a = 0; a < N_AUX; ++a) {
+            HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
+            HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
+        }
+        hic::prof_end(st);
+    } else if (has_dc && !p->dc_launched) {
+        rc = launch_dc_pass(p);
         if (rc) return rc;
     }
-    rc = sort_pass(dc_early ? SEL_AC : SEL_ALL, p->d_tier_count, p->d_tier_list, st);
+    const int n_dc_lanes = p->dc_launched ? DC_LANES : 0;
+    rc = builder_sort_pass(p, has_dc ? SEL_AC : SEL_ALL, p->d_tier_count, p->d_tier_list, st);
     if (rc) return rc;
     // (profiled as ONE span on `st` from fork to join: the tier launches overlap each other)
     hic::prof_begin("huffman_replay_kernel", st);
@@ -1728,13 +1836,14 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
             HIC_CUDA(cudaStreamWaitEvent(p->aux[a], p->ev_fork, 0));
             lanes[n_lanes++] = p->aux[a];
         }
-        rc = replay_pass(p->d_tier_count, p->d_tier_list, lanes, n_lanes);
+        rc = builder_replay_pass(p, p->d_tier_count, p->d_tier_list, lanes, n_lanes);
         if (rc) return rc;
     }
     for (int a = 0; a < N_AUX; ++a) {
         HIC_CUDA(cudaEventRecord(p->ev_join[a], p->aux[a]));
         HIC_CUDA(cudaStreamWaitEvent(st, p->ev_join[a], 0));
     }
+    p->dc_launched = false;
     hic::prof_end(st);
     HIC_LAUNCH("huffman_codes_kernel", st, huffman_codes_kernel<<<p->n_ss, 128, 0, st>>>(
         g, p->d_index, leaf_freq, parent, p->d_row_sym, p->d_row_code, p->d_lut, p->d_lut_len, p->d_ss_nsym, p->d_ss_nbits, p->d_err));
