@@ -936,6 +936,7 @@ struct hic_decode_plan {
     int64_t* d_tile_off = nullptr;
     int64_t* d_stream_total = nullptr;
     bool tables_ready = false;
+    hic::SmallXfer xfer;                        // page-locked staging of the small transfers (reset after every synchronisation)
 };
 
 template <typename T>
@@ -947,6 +948,7 @@ extern "C" {
 
 int hic_decode_plan_destroy(hic_decode_plan* p) {
     if (!p) return HIC_OK;
+    p->xfer.destroy();
     void* ptrs[] = {p->d_mlut, p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
                     p->d_sub_cnt, p->d_tile_start, p->d_tile_cnt, p->d_tile_symoff, p->d_index_own, p->d_row_sym_own,
                     p->d_row_packed_own, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
@@ -1048,10 +1050,14 @@ int hic_decode_set_tables_packed(hic_decode_plan* p, const uint32_t* h_index, co
         HIC_CUDA(dalloc2(&p->d_row_packed_own, p->row_capacity));
     }
     static_assert(sizeof(RowIndex) == 2 * sizeof(uint32_t), "index layout");
-    HIC_CUDA(cudaMemcpyAsync(p->d_index_own, h_index, sizeof(RowIndex) * p->n_ss, cudaMemcpyHostToDevice, st));
+    // (through the SMs when the caller's arrays are page-locked: see SmallXfer)
+    int rc = hic::small_h2d(p->xfer, p->d_index_own, h_index, sizeof(RowIndex) * p->n_ss, st);
+    if (rc) return rc;
     if (total) {
-        HIC_CUDA(cudaMemcpyAsync(p->d_row_sym_own, h_row_sym, sizeof(int32_t) * total, cudaMemcpyHostToDevice, st));
-        HIC_CUDA(cudaMemcpyAsync(p->d_row_packed_own, h_row_packed, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
+        rc = hic::small_h2d(p->xfer, p->d_row_sym_own, h_row_sym, sizeof(int32_t) * total, st);
+        if (rc) return rc;
+        rc = hic::small_h2d(p->xfer, p->d_row_packed_own, h_row_packed, sizeof(uint64_t) * total, st);
+        if (rc) return rc;
     }
     return hic_decode_set_tables_device(p, p->d_index_own, p->d_row_sym_own ? p->d_row_sym_own : (const int32_t*)p->d_index_own,
                                         p->d_row_packed_own ? p->d_row_packed_own : (const uint64_t*)p->d_index_own, total, stream);
@@ -1106,8 +1112,12 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     std::vector<uint64_t> nbits(h_nbits, h_nbits + nss), off(h_byte_off, h_byte_off + nss);
     for (int s = 0; s < nss; ++s)
         HIC_REQUIRE((off[s] & 3) == 0, "stream %d is not 4-byte aligned", s);
-    HIC_CUDA(cudaMemcpyAsync(p->d_byte_off, off.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
-    HIC_CUDA(cudaMemcpyAsync(p->d_nbits, nbits.data(), sizeof(uint64_t) * nss, cudaMemcpyHostToDevice, st));
+    {
+        int rc = hic::small_h2d(p->xfer, p->d_byte_off, off.data(), sizeof(uint64_t) * nss, st);
+        if (rc) return rc;
+        rc = hic::small_h2d(p->xfer, p->d_nbits, nbits.data(), sizeof(uint64_t) * nss, st);
+        if (rc) return rc;
+    }
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
     // ---- D1: tiles of SUB_PER_CTA subsequences, streams in order ----
     std::vector<SyncTile> tiles;
@@ -1142,10 +1152,16 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
         HIC_CUDA(dalloc2(&p->d_sub_end, p->sub_capacity));
         HIC_CUDA(dalloc2(&p->d_sub_cnt, p->sub_capacity));
     }
-    HIC_CUDA(cudaMemcpyAsync(p->d_ss_tile0, ss_tile0.data(), sizeof(uint32_t) * (nss + 1), cudaMemcpyHostToDevice, st));
+    {
+        int rc = hic::small_h2d(p->xfer, p->d_ss_tile0, ss_tile0.data(), sizeof(uint32_t) * (nss + 1), st);
+        if (rc) return rc;
+    }
     HIC_CUDA(cudaMemsetAsync(p->d_nsym, 0, sizeof(uint32_t) * nss, st));
     if (n_tiles) {
-        HIC_CUDA(cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(SyncTile) * n_tiles, cudaMemcpyHostToDevice, st));
+        {
+            int rc = hic::small_h2d(p->xfer, p->d_tiles, tiles.data(), sizeof(SyncTile) * n_tiles, st);
+            if (rc) return rc;
+        }
         SyncArgs a;
         a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2; a.mlut = p->d_mlut; a.l2_cap = p->l2_cap; a.sorted_left = p->d_sorted_left; a.sorted_row = p->d_sorted_row;
         a.index = p->d_index; a.row_sym = p->d_row_sym; a.row_packed = p->d_row_packed; a.tiles = p->d_tiles; a.sub_end = p->d_sub_end;
@@ -1154,10 +1170,13 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
         for (int round = 0; round < 1024; ++round) {
             HIC_CUDA(cudaMemsetAsync(p->d_err + 1, 0, sizeof(uint32_t), st));
             HIC_LAUNCH("huffman_resync_kernel", st, huffman_sync_kernel<true><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
-            uint32_t changed = 0;
-            HIC_CUDA(cudaMemcpyAsync(&changed, p->d_err + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            const void* h_changed = nullptr;
+            {
+                int rc = hic::small_d2h(p->xfer, p->d_err + 1, sizeof(uint32_t), st, &h_changed);
+                if (rc) return rc;
+            }
             HIC_CUDA(cudaStreamSynchronize(st));
-            if (!changed) break;
+            if (!*static_cast<const volatile uint32_t*>(h_changed)) break;
         }
         HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
         {
@@ -1186,10 +1205,15 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
                                                                    p->d_stream_total));
         HIC_LAUNCH("dc_write_kernel", st, dc_write_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_off, d_coef));
     }
-    uint32_t flags[4];
-    HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    const void* h_flags = nullptr;
+    {
+        int rc = hic::small_d2h(p->xfer, p->d_err, 4 * sizeof(uint32_t), st, &h_flags);
+        if (rc) return rc;
+    }
     HIC_CUDA(cudaStreamSynchronize(st));
-    if (flags[0]) return hic::fail(HIC_ERR_CORRUPT, "bit streams did not decode cleanly (flags 0x%x)", flags[0]);
+    const uint32_t flags0 = static_cast<const volatile uint32_t*>(h_flags)[0];
+    p->xfer.reset();                 // everything staged has been consumed
+    if (flags0) return hic::fail(HIC_ERR_CORRUPT, "bit streams did not decode cleanly (flags 0x%x)", flags0);
     return HIC_OK;
 }
 

@@ -1124,6 +1124,7 @@ struct hic_entropy_plan {
     bool dc_early = false;                      // the last emit pass recorded ev_dc
     bool prefer_device = false;                 // the last code build ran on the device: start the next DC pass eagerly
     bool dc_launched = false;                   // a DC pass is in flight on aux[0..DC_LANES) and not yet joined
+    hic::SmallXfer xfer;                        // page-locked staging of the small transfers (reset after every synchronisation)
     bool device_built = false;                  // codes came from hic_entropy_build_codes_device
     bool host_info_valid = false;               // rows/nsym/nbits/byte_off/byte_len mirror the device
     bool host_tables_valid = false;
@@ -1208,6 +1209,7 @@ int hic_layout_flat(int32_t n, int64_t len, hic_stream_layout* out) {
 
 int hic_entropy_plan_destroy(hic_entropy_plan* p) {
     if (!p) return HIC_OK;
+    p->xfer.destroy();
     void* ptrs[] = {p->d_tile_seg, p->d_carry, p->d_totals, p->d_dc, p->d_values, p->d_lengths, p->d_hist, p->d_first,
                     p->d_err, p->d_entries, p->d_index, p->d_lut, p->d_row_sym, p->d_row_code, p->d_row_stream,
                     p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ptile_bits, p->d_ptile_off, p->d_ss_byte_len,
@@ -1736,12 +1738,21 @@ static int fetch_host_info(hic_entropy_plan* p, cudaStream_t st) {
     std::vector<CompactIndex> index(nss);
     p->rows.assign(nss, 0); p->nsym.assign(nss, 0); p->nbits.assign(nss, 0);
     p->byte_off.assign(nss, 0); p->byte_len.assign(nss, 0); p->row_off.assign(nss + 1, 0);
-    HIC_CUDA(cudaMemcpyAsync(index.data(), p->d_index, sizeof(CompactIndex) * nss, cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaMemcpyAsync(p->nsym.data(), p->d_ss_nsym, sizeof(uint32_t) * nss, cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaMemcpyAsync(p->nbits.data(), p->d_ss_nbits, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaMemcpyAsync(p->byte_off.data(), p->d_ss_byte_off, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaMemcpyAsync(p->byte_len.data(), p->d_ss_byte_len, sizeof(uint64_t) * nss, cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaStreamSynchronize(st));
+    {
+        const void* h[5] = {};
+        const void* src[5] = {p->d_index, p->d_ss_nsym, p->d_ss_nbits, p->d_ss_byte_off, p->d_ss_byte_len};
+        void* dst[5] = {index.data(), p->nsym.data(), p->nbits.data(), p->byte_off.data(), p->byte_len.data()};
+        const size_t bytes[5] = {sizeof(CompactIndex) * nss, sizeof(uint32_t) * nss, sizeof(uint64_t) * nss, sizeof(uint64_t) * nss,
+                                 sizeof(uint64_t) * nss};
+        p->xfer.reset();
+        for (int i = 0; i < 5; ++i) {
+            int rc = hic::small_d2h(p->xfer, src[i], bytes[i], st, &h[i]);
+            if (rc) return rc;
+        }
+        HIC_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 5; ++i) memcpy(dst[i], h[i], bytes[i]);
+        p->xfer.reset();
+    }
     // rows of a device build sit at the compaction offsets, which are not in stream order
     p->dev_row_start.assign(nss, 0);
     for (int s = 0; s < nss; ++s) {
@@ -1851,9 +1862,20 @@ extern "C" int hic_entropy_build_codes_device(hic_entropy_plan* p, void* stream)
         p->d_ss_byte_off, p->d_ss_byte_len, p->d_pay_totals));
     unsigned long long totals[2] = {0, 0};
     uint32_t flags[4];
-    HIC_CUDA(cudaMemcpyAsync(totals, p->d_pay_totals, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaMemcpyAsync(flags, p->d_err, sizeof(flags), cudaMemcpyDeviceToHost, st));
-    HIC_CUDA(cudaStreamSynchronize(st));
+    {
+        // (through the SMs into page-locked staging: a copy-engine transfer would wait behind the bulk
+        // downloads other streams have queued)
+        const void *h_tot = nullptr, *h_flg = nullptr;
+        p->xfer.reset();
+        rc = hic::small_d2h(p->xfer, p->d_pay_totals, sizeof(unsigned long long), st, &h_tot);
+        if (rc) return rc;
+        rc = hic::small_d2h(p->xfer, p->d_err, sizeof(flags), st, &h_flg);
+        if (rc) return rc;
+        HIC_CUDA(cudaStreamSynchronize(st));
+        memcpy(totals, h_tot, sizeof(unsigned long long));
+        memcpy(flags, h_flg, sizeof(flags));
+        p->xfer.reset();
+    }
     if (flags[0] & 1u) return hic::fail(HIC_ERR_INVALID, "a symbol fell outside [-%d, %d): create the plan with more value_bins",
                                         g.nb_bins / 2, g.nb_bins / 2);
     if (flags[0] & 2u) return hic::fail(HIC_ERR_INVALID, "an alphabet exceeds 8192 symbols; use hic_entropy_build_codes");
@@ -1908,10 +1930,13 @@ int hic_entropy_tables_packed(hic_entropy_plan* p, uint32_t* h_index, int32_t* h
     HIC_REQUIRE(p->codes_ready, "hic_entropy_build_codes has not run");
     cudaStream_t st = as_stream(stream);
     static_assert(sizeof(CompactIndex) == 2 * sizeof(uint32_t), "index layout");
-    HIC_CUDA(cudaMemcpyAsync(h_index, p->d_index, sizeof(CompactIndex) * p->n_ss, cudaMemcpyDeviceToHost, st));
+    int rc = hic::small_d2h_to(h_index, p->d_index, sizeof(CompactIndex) * p->n_ss, st);
+    if (rc) return rc;
     if (p->total_rows) {
-        HIC_CUDA(cudaMemcpyAsync(h_row_sym, p->d_row_sym, sizeof(int32_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
-        HIC_CUDA(cudaMemcpyAsync(h_row_packed, p->d_row_code, sizeof(uint64_t) * p->total_rows, cudaMemcpyDeviceToHost, st));
+        rc = hic::small_d2h_to(h_row_sym, p->d_row_sym, sizeof(int32_t) * p->total_rows, st);
+        if (rc) return rc;
+        rc = hic::small_d2h_to(h_row_packed, p->d_row_code, sizeof(uint64_t) * p->total_rows, st);
+        if (rc) return rc;
     }
     return HIC_OK;
 }

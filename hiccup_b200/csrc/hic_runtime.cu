@@ -1,6 +1,7 @@
 // hic_runtime.cu -- device/stream/memory plumbing of the C ABI (include/hiccup_b200.h).
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -62,6 +63,99 @@ void prof_end(cudaStream_t st) {
     if (!t_open_end) return;
     cudaEventRecord(t_open_end, st);
     t_open_end = nullptr;
+}
+
+// ---- small transfers through the SMs ----------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+sm_copy_kernel(char* __restrict__ dst, const char* __restrict__ src, size_t bytes, int vec16) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (vec16) {
+        const size_t n16 = bytes / 16;
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        for (size_t i = tid; i < n16; i += step) d[i] = s[i];
+        done = n16 * 16;
+    }
+    for (size_t i = done + tid; i < bytes; i += step) dst[i] = src[i];
+}
+
+}  // namespace
+
+bool device_can_read_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+}
+
+int launch_sm_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return HIC_OK;
+    const int vec16 = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+    const size_t items = vec16 ? bytes / 16 + 16 : bytes;
+    const unsigned grid = (unsigned)std::min<size_t>(64, (items + 255) / 256);
+    sm_copy_kernel<<<grid, 256, 0, st>>>(static_cast<char*>(dst), static_cast<const char*>(src), bytes, vec16);
+    HIC_CHECK_LAUNCH("sm_copy_kernel");
+    return HIC_OK;
+}
+
+namespace {
+int stage_reserve(SmallXfer& x, size_t bytes, char** out) {
+    const size_t need = (x.used + 15) / 16 * 16 + bytes;
+    if (need > x.cap) {
+        if (x.used != 0) return hic::fail(HIC_ERR_CAPACITY, "small-transfer staging of %zu bytes is in use; %zu more needed", x.cap, bytes);
+        if (x.h_stage) cudaFreeHost(x.h_stage);
+        x.h_stage = nullptr;
+        x.cap = std::max<size_t>(need + need / 2, 1u << 20);
+        HIC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&x.h_stage), x.cap));
+    }
+    x.used = (x.used + 15) / 16 * 16;
+    *out = x.h_stage + x.used;
+    x.used += bytes;
+    return HIC_OK;
+}
+}  // namespace
+
+void SmallXfer::destroy() {
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr;
+    cap = used = 0;
+}
+
+int small_h2d(SmallXfer& x, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return HIC_OK;
+    if (bytes > SMALL_XFER_MAX) {
+        HIC_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return HIC_OK;
+    }
+    if (device_can_read_host(h_src)) return launch_sm_copy(d_dst, h_src, bytes, st);
+    char* stage = nullptr;
+    if (x.cap - std::min(x.cap, (x.used + 15) / 16 * 16) < bytes && x.used != 0) {      // no room left this call: the plain way
+        HIC_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return HIC_OK;
+    }
+    int rc = stage_reserve(x, bytes, &stage);
+    if (rc) return rc;
+    memcpy(stage, h_src, bytes);
+    return launch_sm_copy(d_dst, stage, bytes, st);
+}
+
+int small_d2h(SmallXfer& x, const void* d_src, size_t bytes, cudaStream_t st, const void** h_where) {
+    char* stage = nullptr;
+    int rc = stage_reserve(x, bytes, &stage);
+    if (rc) return rc;
+    *h_where = stage;
+    return launch_sm_copy(stage, d_src, bytes, st);
+}
+
+int small_d2h_to(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return HIC_OK;
+    if (bytes <= SMALL_XFER_MAX && device_can_read_host(h_dst)) return launch_sm_copy(h_dst, d_src, bytes, st);
+    HIC_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    return HIC_OK;
 }
 
 }  // namespace hic
@@ -178,11 +272,13 @@ int hic_host_free(void* h_ptr) {
     return HIC_OK;
 }
 
-// Bulk copies stay single asynchronous transfers.  A copy engine serves its queue strictly in order
-// (tools/ce_fifo.py: a 64 KB copy on another stream waits the full ~2 ms behind a queued 105 MB copy, also
-// when that copy is enqueued as 4 MB pieces), but pacing the pieces from the host so that small copies
-// of other streams can slip in between made the pipelined batch path slower overall (27.9 -> 30.7 ms per
-// 1024-image batch, tools/pipe_one.py), so it is not done.
+// Bulk copies (image batches, compressed payloads) are single asynchronous copy-engine transfers.  A copy
+// engine serves its queue strictly in order (tools/ce_fifo.py: a 64 KB copy on another stream waits the
+// full ~2 ms behind a queued 105 MB copy, also when that copy is enqueued as 4 MB pieces).  What helped the
+// pipelined batch path was taking the SMALL transfers off the engines (SmallXfer above: 27.9 -> 25.3 ms
+// per 1024-image batch, tools/pipe_one.py).  Two other remedies were measured and dropped: pacing the
+// bulk pieces from the host so that other copies can slip in between (30.7 ms), and sending the 20 MB
+// compressed payloads of a chunk through the SMs as well (28.4 ms).
 int hic_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
     HIC_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, hic::as_stream(stream)));
     return HIC_OK;
