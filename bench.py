@@ -465,7 +465,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ch_, cw_, what = cpu_sample_shape(h, w)
-        n_cpu = max(1, min(16, int(4.5e6 // (ch_ * cw_))))
+        n_cpu = max(2, min(64, int(17.5e6 // (ch_ * cw_))))      # ~10 s of single-core work
         v, dt = cpu_baseline_sample(ch_, cw_, n_cpu, 2000, mode)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%d x %s of this workload, full encode+decode through the oracle port "

@@ -223,10 +223,14 @@ int hic_entropy_set_codes(hic_entropy_plan* plan, const uint32_t* h_index, const
  * exactly as HuffmanTree._construct does (huffman.py:60-79, heapq replay), upload code tables. */
 int hic_entropy_build_codes(hic_entropy_plan* plan, void* stream);
 
-/* E2 on the device -- the same heapq replay run by one CTA per symbol stream in shared memory
- * (alphabets up to 8192 symbols); nothing but 32 bytes of totals crosses PCIe.  Produces exactly
- * the codes of hic_entropy_build_codes (tests/test_gpu_codec.py compares them).  The per-stream
- * results and tables are downloaded lazily by the two query functions below. */
+/* E2 on the device -- the same heapq replay, one lane per symbol stream with its heap in shared
+ * memory (alphabets up to 8192 symbols); nothing but 32 bytes of totals crosses PCIe.  Produces
+ * exactly the codes of hic_entropy_build_codes (tests/test_gpu_codec.py compares them).  The
+ * per-stream results and tables are downloaded lazily by the two query functions below.
+ * Once a plan has built its codes here, its next hic_entropy_symbolize / hic_entropy_emit launches
+ * the DC streams' pass itself, on the plan's own CUDA streams beside the run-length kernels (the
+ * other builders wait for it); results do not depend on that.  With HIC_ENTROPY_SERIAL set in the
+ * environment everything stays on `stream`, one kernel after the other (per-kernel timing). */
 int hic_entropy_build_codes_device(hic_entropy_plan* plan, void* stream);
 
 /* Results of E2, all host arrays indexed by symbol stream s (9 n entries; kind 0 entries are

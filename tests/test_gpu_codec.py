@@ -163,6 +163,48 @@ def test_batch_codec_matches_single_image_path():
     bc.close()
 
 
+def test_decode_from_pageable_and_page_locked_tables():
+    """The small transfers of the decoder go through an SM copy kernel: directly from page-locked host
+    arrays (the batch codec's staging), through the plan's staging area from pageable ones.  Both decode
+    to the same pixels, repeatedly (the staging area is reset after every synchronisation)."""
+    from hiccup_b200 import entropy
+    from hiccup_b200.batch import DctBatchCodec
+    n, h, w = 3, 88, 120
+    rgb = np.stack([orc.synthetic_image(h, w, 90 + i) for i in range(n)])
+    bc = DctBatchCodec(n, h, w)
+    enc = bc.encode(rgb)                               # tables and payloads are views of page-locked staging
+    want = bc.decode(enc).copy()
+    pageable = entropy.EncodedStreams(enc.layout, enc.index.copy(), enc.nsym.copy(), enc.nbits.copy(), enc.byte_off.copy(),
+                                      enc.byte_len.copy(), enc.symbols.copy(), enc.packed.copy(), enc.data.copy())
+    for _ in range(3):
+        assert np.array_equal(bc.decode(pageable), want)
+        assert np.array_equal(bc.decode(enc), want)
+    for i in range(n):
+        assert np.array_equal(want[i], orc.jpeg_decompression(orc.jpeg_compression(rgb[i])))
+    bc.close()
+
+
+def test_encoder_twice_on_one_plan_resets_its_histograms():
+    """The compaction resets the histogram bins it reads, so a plan encodes batch after batch without a
+    memset over the histogram arrays; a second, different batch must not see counts of the first."""
+    from hiccup_b200.batch import DctBatchCodec
+    n, h, w = 2, 72, 104
+    a = np.stack([orc.synthetic_image(h, w, 400 + i) for i in range(n)])
+    b = np.stack([orc.synthetic_image(h, w, 500 + i) for i in range(n)])
+    bc = DctBatchCodec(n, h, w)
+    fresh = DctBatchCodec(n, h, w)
+    bc.encode(a)
+    got = [im.byte_stream() for im in bc.hic_images(bc.encode(b))]
+    want = [im.byte_stream() for im in fresh.hic_images(fresh.encode(b))]
+    assert got == want
+    for host_codes in (True, False, True):             # the host builder and the device builder interleaved
+        bc.device_codes = not host_codes
+        assert [im.byte_stream() for im in bc.hic_images(bc.encode(a if host_codes else b))] == \
+               [im.byte_stream() for im in fresh.hic_images(fresh.encode(a if host_codes else b))]
+    bc.close()
+    fresh.close()
+
+
 @pytest.mark.parametrize("mode,shape", [("dct", (72, 104)), ("wavelet", (64, 96))])
 def test_pipelined_codec_equals_unchunked(mode, shape):
     """Chunks over concurrent streams/threads produce the same bytes and pixels as one launch per batch."""
