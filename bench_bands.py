@@ -139,6 +139,7 @@ def main():
         bench.emit(line)
     if dist is not None:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
     return 0
 

@@ -210,32 +210,67 @@ class DistComm:
 
     def gather(self, obj, root=0):
         """Gather to `root`.  Byte strings (the packed band payloads, the one bulky item) do not go through
-        pickled object collectives: ranks of one box hand them over as files in /dev/shm and only their
-        lengths travel as metadata."""
-        import os
+        pickled object collectives: every rank of the box copies its strings once into a shared-memory file
+        it keeps mapped (/dev/shm), the root maps the other ranks' files and gets VIEWS of them -- no second
+        copy, no file reads -- and only the lengths travel as metadata.  Two files per rank alternate, so the
+        views the root received stay valid until the gather after the next one."""
         if isinstance(obj, dict) and isinstance(obj.get("bytes"), list):
-            token = os.environ.get("MASTER_PORT", "0")
-            path = "/dev/shm/hic_band_%s_%d.bin" % (token, self.rank)
-            with open(path, "wb") as f:
-                for b in obj["bytes"]:
-                    f.write(b)
-            lens = self.all_gather([len(b) for b in obj["bytes"]])
-            out = None
-            if self.rank == root:
-                out = []
-                for r, ls in enumerate(lens):
-                    raw = np.fromfile("/dev/shm/hic_band_%s_%d.bin" % (token, r), dtype=np.uint8)
-                    parts, pos = [], 0
-                    for n in ls:
-                        parts.append(raw[pos:pos + n])
-                        pos += n
-                    out.append(dict(bytes=parts))
-            self.all_gather(0)                      # everyone waits until the root has read the files
-            os.remove(path)
+            lens_mine = [int(len(b)) for b in obj["bytes"]]
+            self._turn = getattr(self, "_turn", 0) ^ 1
+            mm = self._shared_file(self.rank, self._turn, sum(lens_mine), create=True)
+            pos = 0
+            for b, n in zip(obj["bytes"], lens_mine):
+                mm[pos:pos + n] = np.frombuffer(b, np.uint8) if isinstance(b, (bytes, bytearray)) else b
+                pos += n
+            lens = self.all_gather(lens_mine)           # also orders every rank's copy before the root's reads
+            if self.rank != root:
+                return None
+            out = []
+            for r, ls in enumerate(lens):
+                raw = self._shared_file(r, self._turn, sum(ls), create=False)
+                parts, pos = [], 0
+                for n in ls:
+                    parts.append(raw[pos:pos + n])
+                    pos += n
+                out.append(dict(bytes=parts))
             return out
         out = [None] * self.size if self.rank == root else None
         self.dist.gather_object(obj, out, dst=root, group=self.group)
         return out
+
+    def _shared_file(self, rank, turn, nbytes, create):
+        """uint8 view of rank `rank`'s shared-memory file number `turn`, at least `nbytes` long.  The owner
+        creates and grows it (powers of two, so a growing band rarely remaps); readers remap when the file
+        on disk is longer than their mapping."""
+        import os
+        if not hasattr(self, "_maps"):
+            self._maps = {}
+            self._token = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "0"))
+        path = "/dev/shm/hic_band_%s_%d_%d.bin" % (self._token, rank, turn)
+        cur = self._maps.get((rank, turn))
+        if create:
+            if cur is None or cur.size < nbytes:
+                size = 1 << max(20, int(nbytes - 1).bit_length())
+                with open(path, "ab") as f:
+                    f.truncate(size)
+                cur = np.memmap(path, dtype=np.uint8, mode="r+", shape=(size,))
+                self._maps[(rank, turn)] = cur
+        elif cur is None or cur.size < nbytes:
+            cur = np.memmap(path, dtype=np.uint8, mode="r", shape=(os.path.getsize(path),))
+            self._maps[(rank, turn)] = cur
+        return cur
+
+    def close(self):
+        """Unmap and remove this rank's shared-memory files."""
+        import os
+        for (rank, turn), mm in list(getattr(self, "_maps", {}).items()):
+            del mm
+            if rank == self.rank:
+                try:
+                    os.remove("/dev/shm/hic_band_%s_%d_%d.bin" % (self._token, rank, turn))
+                except OSError:
+                    pass
+        self._maps = {}
 
 
 def run_local(workers):

@@ -94,6 +94,8 @@ def _gloo_worker(rank, world, port, shape, seed, out_path):
                 f.write("ok")
         else:
             assert hic is None
+        dist.barrier()
+        comm.close()
     finally:
         dist.destroy_process_group()
 
