@@ -61,6 +61,9 @@ constexpr int SUB_PER_CTA = 256;
 constexpr int CHUNK_WORDS = SUB_BITS * SUB_PER_CTA / 32;      // 1024 words of bit stream per CTA
 constexpr int CHUNK_SLACK = 8;                                // a code may run 58 bits past the last boundary
 constexpr int L1_FALLBACK = 0xFF;
+constexpr int PK_BITS = 10;                  // window of the packed multi-symbol table of the zero-count streams
+constexpr int PK_SIZE = 1 << PK_BITS;
+constexpr int PK_MAX_SYMS = 5;
 
 struct SyncTile {
     uint32_t ss;            // symbol stream
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256)
 build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restrict__ row_sym,
                     const uint64_t* __restrict__ row_packed, int32_t* __restrict__ lut1, int32_t* __restrict__ lut2,
                     int l2_cap, uint64_t* __restrict__ sorted_left, uint32_t* __restrict__ sorted_row,
-                    uint16_t* __restrict__ mlut) {
+                    uint16_t* __restrict__ mlut, uint32_t* __restrict__ pklut) {
     __shared__ uint32_t extra[L1_SIZE];          // max (len - 12) under each 12-bit prefix
     __shared__ uint32_t offs[L1_SIZE];
     __shared__ uint32_t wsum[8];
@@ -179,6 +182,31 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
                 ++cnt;
             }
             mym[pfx] = (uint16_t)((cnt << 8) | pos);
+        }
+    }
+    // Zero-count streams (symbols 0..14, short codes): the final decode also takes several symbols per
+    // lookup.  For every PK_BITS-bit window: bits 0-2 = whole codes inside it (at most PK_MAX_SYMS),
+    // bits 3-6 = their bits, bits 8.. = the symbols, 4 bits each.  A stream that owns a symbol outside
+    // 0..15 (a foreign file) gets an all-zero table and is decoded one symbol at a time.
+    if (ss % 3 == HIC_KIND_LENGTH) {
+        __shared__ int s_wide;
+        if (threadIdx.x == 0) s_wide = 0;
+        __syncthreads();
+        for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+            if ((uint32_t)row_sym[r] > 15u) s_wide = 1;
+        __syncthreads();
+        uint32_t* myp = pklut + (size_t)(ss / 3) * PK_SIZE;
+        for (uint32_t w = threadIdx.x; w < (uint32_t)PK_SIZE; w += blockDim.x) {
+            uint32_t pos = 0, cnt = 0, syms = 0;
+            while (!s_wide && cnt < (uint32_t)PK_MAX_SYMS) {
+                const int32_t e = (int32_t)extra[(w << (L1_BITS - PK_BITS + pos)) & (L1_SIZE - 1)];
+                const uint32_t len = (uint32_t)(e & 0x7F);
+                if ((e & 0x80) || len == 0 || pos + len > (uint32_t)PK_BITS) break;
+                syms |= (uint32_t)((e >> 8) & 15) << (4 * cnt);
+                pos += len;
+                ++cnt;
+            }
+            myp[w] = cnt ? (cnt | (pos << 3) | (syms << 8)) : 0u;
         }
     }
     if (!s_need_sort) return;
@@ -418,6 +446,92 @@ __device__ __forceinline__ uint32_t decode_span_count(const BitReader& br, uint3
     return pos;
 }
 
+// The final decode of a zero-count stream into the staging area: while a PK_BITS-bit window cannot cross
+// the span's upper boundary, one lookup in the packed table yields up to PK_MAX_SYMS symbols; the last bits
+// before the boundary (and anything the table does not hold) go one symbol at a time as in decode_span.
+__device__ __forceinline__ uint32_t decode_span_packed(const BitReader& br, uint32_t chunk0, uint32_t pos, uint32_t limit,
+                                                       uint32_t end, const int32_t* __restrict__ l1,
+                                                       const uint32_t* __restrict__ pk, const int32_t* __restrict__ l2,
+                                                       const LongSearch& ls, uint32_t& count, uint8_t* __restrict__ stage,
+                                                       uint32_t out_idx, bool& bad) {
+    count = 0;
+    const uint32_t stop = limit < end ? limit : end;
+    if (pos >= stop) return pos;
+    uint32_t wi = (pos - chunk0) >> 5;
+    const uint32_t sh = (pos - chunk0) & 31;
+    uint64_t buf = (((uint64_t)br.words[wi] << 32) | br.words[wi + 1]) << sh;
+    int avail = 64 - (int)sh;
+    wi += 2;
+    uint8_t* out = stage + out_idx;
+    while (pos < stop) {
+        if (avail < 32) {
+            buf |= (uint64_t)br.words[wi] << (32 - avail);
+            avail += 32;
+            ++wi;
+        }
+        if (pos + PK_BITS <= stop) {
+            const uint32_t m = pk[(uint32_t)(buf >> (64 - PK_BITS))];
+            const uint32_t n = m & 7u;
+            if (n) {
+                const uint32_t adv = (m >> 3) & 15u;
+                uint8_t* o = out + count;
+                o[0] = (uint8_t)((m >> 8) & 15u);
+                if (n > 1) o[1] = (uint8_t)((m >> 12) & 15u);
+                if (n > 2) o[2] = (uint8_t)((m >> 16) & 15u);
+                if (n > 3) o[3] = (uint8_t)((m >> 20) & 15u);
+                if (n > 4) o[4] = (uint8_t)((m >> 24) & 15u);
+                static_assert(PK_MAX_SYMS == 5, "five symbol fields");
+                count += n;
+                pos += adv;
+                buf <<= adv;
+                avail -= (int)adv;
+                continue;
+            }
+        }
+        int32_t e = l1[(uint32_t)(buf >> (64 - L1_BITS))];
+        uint32_t len;
+        int32_t sym;
+        if (!(e & 0x80)) {
+            sym = e >> 8;
+            len = (uint32_t)(e & 0x7F);
+        } else {
+            len = 0;
+            sym = 0;
+            const uint32_t nb2 = (uint32_t)(e & 0x7F);
+            if (nb2 != 0x7F) {
+                const uint32_t idx = ((uint32_t)e >> 8) + (uint32_t)((buf >> (64 - L1_BITS - nb2)) & ((1u << nb2) - 1));
+                e = __ldg(l2 + idx);
+                if ((e & 0xFF) != L2_LONG) {
+                    sym = e >> 8;
+                    len = (uint32_t)(e & 0xFF);
+                } else {
+                    len = decode_long(br.window(pos - chunk0), ls, sym);
+                }
+            } else {
+                len = decode_long(br.window(pos - chunk0), ls, sym);
+            }
+        }
+        if (len == 0 || pos + len > end) {
+            bad = true;
+            return stop;
+        }
+        out[count] = (uint8_t)sym;
+        ++count;
+        pos += len;
+        if (len >= 32) {
+            wi = (pos - chunk0) >> 5;
+            const uint32_t s2 = (pos - chunk0) & 31;
+            buf = (((uint64_t)br.words[wi] << 32) | br.words[wi + 1]) << s2;
+            avail = 64 - (int)s2;
+            wi += 2;
+        } else {
+            buf <<= len;
+            avail -= (int)len;
+        }
+    }
+    return pos;
+}
+
 struct SyncArgs {
     const uint8_t* bytes;
     const uint64_t* byte_off;
@@ -425,6 +539,7 @@ struct SyncArgs {
     const int32_t* lut1;
     const int32_t* lut2;
     const uint16_t* mlut;
+    const uint32_t* pklut;
     int l2_cap;
     const uint64_t* sorted_left;
     const uint32_t* sorted_row;
@@ -548,7 +663,8 @@ __global__ void sync_tile_scan_kernel(int n_ss, const uint32_t* __restrict__ ss_
 // The CTA's symbols are one contiguous run of the output, so they are staged in shared memory and
 // written out coalesced (a thread's own run is only a few symbols long: writing it straight to global
 // memory costs a 32-byte sector per 1- or 2-byte store).
-constexpr int WRITE_STAGE = 12288;           // staged symbols per CTA; the (rare) overflow is written directly
+constexpr int WRITE_STAGE = 10240;           // staged 16-bit symbols per CTA (twice as many of the byte-wide zero counts,
+                                             // whose short codes put ~15 000 symbols into a tile); the rare overflow is written directly
 
 __global__ void __launch_bounds__(SUB_PER_CTA)
 huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, int16_t* __restrict__ dc,
@@ -556,7 +672,8 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     extern __shared__ __align__(16) uint8_t write_raw[];
     uint32_t* s_words = reinterpret_cast<uint32_t*>(write_raw);
     int32_t* s_l1 = reinterpret_cast<int32_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK));
-    int16_t* s_stage = reinterpret_cast<int16_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE);
+    uint32_t* s_pk = reinterpret_cast<uint32_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE);
+    int16_t* s_stage = reinterpret_cast<int16_t*>(write_raw + 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE + 4 * PK_SIZE);
     __shared__ uint32_t s_sum[SUB_PER_CTA / 32];
     __shared__ uint32_t s_staged;               // symbols [0, s_staged) of the CTA went through the staging area
     const SyncTile t = a.tiles[blockIdx.x];
@@ -568,6 +685,11 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     const uint32_t chunk0 = t.sub0 * SUB_BITS;
     if (threadIdx.x == 0) s_staged = 0xFFFFFFFFu;
     stage_chunk(a, t, s_words, s_l1);
+    const bool packed = t.ss % 3 == HIC_KIND_LENGTH;
+    if (packed) {
+        const uint32_t* pk = a.pklut + (size_t)(t.ss / 3) * PK_SIZE;
+        for (int i = threadIdx.x; i < PK_SIZE; i += blockDim.x) s_pk[i] = __ldg(pk + i);
+    }
     const BitReader br{s_words};
     const int32_t* l2 = a.lut2 + (size_t)t.ss * a.l2_cap;
     const RowIndex ridx = a.index[t.ss];
@@ -602,8 +724,10 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
         uint32_t got = 0;
         bool bad = false;
         uint32_t e;
-        if (rank + cnt <= (uint32_t)WRITE_STAGE) {        // the usual case: into the staging area
-            e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, s_stage, nullptr, rank, bad);
+        if (rank + cnt <= (uint32_t)(packed ? 2 * WRITE_STAGE : WRITE_STAGE)) {        // the usual case: into the staging area
+            if (packed) e = decode_span_packed(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, s_pk, l2, ls, got,
+                                               reinterpret_cast<uint8_t*>(s_stage), rank, bad);
+            else e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, s_stage, nullptr, rank, bad);
         } else {                                          // ranks grow with the thread index: everything from here on is direct
             atomicMin(&s_staged, rank);
             e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, out16, out8, tile_base + rank, bad);
@@ -614,7 +738,8 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     if (!fits) return;
     const uint32_t staged = min(total, s_staged);
     if (out8) {
-        for (uint32_t i = threadIdx.x; i < staged; i += SUB_PER_CTA) out8[tile_base + i] = (uint8_t)s_stage[i];
+        const uint8_t* stage8 = reinterpret_cast<const uint8_t*>(s_stage);
+        for (uint32_t i = threadIdx.x; i < staged; i += SUB_PER_CTA) out8[tile_base + i] = stage8[i];
     } else {
         for (uint32_t i = threadIdx.x; i < staged; i += SUB_PER_CTA) out16[tile_base + i] = s_stage[i];
     }
@@ -908,6 +1033,7 @@ struct hic_decode_plan {
     int32_t* d_lut1 = nullptr;
     int32_t* d_lut2 = nullptr;
     uint16_t* d_mlut = nullptr;                 // multi-symbol table of the sync passes
+    uint32_t* d_pklut = nullptr;                // packed multi-symbol table of the zero-count streams (per channel stream)
     int l2_cap = L2_CAP_MIN;
     uint64_t* d_sorted_left = nullptr;          // 2 x row capacity (bitonic padding)
     uint32_t* d_sorted_row = nullptr;
@@ -949,7 +1075,7 @@ extern "C" {
 int hic_decode_plan_destroy(hic_decode_plan* p) {
     if (!p) return HIC_OK;
     p->xfer.destroy();
-    void* ptrs[] = {p->d_mlut, p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
+    void* ptrs[] = {p->d_pklut, p->d_mlut, p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
                     p->d_sub_cnt, p->d_tile_start, p->d_tile_cnt, p->d_tile_symoff, p->d_index_own, p->d_row_sym_own,
                     p->d_row_packed_own, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
                     p->d_tile_off, p->d_stream_total};
@@ -988,6 +1114,7 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
     ok(dalloc2(&p->d_lengths, p->total_blocks * 64 + 64));
     ok(dalloc2(&p->d_lut1, (size_t)p->n_ss * L1_SIZE));
     ok(dalloc2(&p->d_mlut, (size_t)p->n_ss * L1_SIZE));
+    ok(dalloc2(&p->d_pklut, (size_t)p->n_cs * PK_SIZE));
     {
         int cap = L2_CAP_MAX;
         while (cap > L2_CAP_MIN && (size_t)cap * p->n_ss > ((size_t)1 << 28)) cap >>= 1;
@@ -1028,7 +1155,7 @@ int hic_decode_set_tables_device(hic_decode_plan* p, const void* d_index, const 
         HIC_CUDA(dalloc2(&p->d_sorted_row, 2 * p->sorted_capacity));
     }
     HIC_LAUNCH("build_tables_kernel", st, build_tables_kernel<<<p->n_ss, 256, 0, st>>>(p->d_index, p->d_row_sym, p->d_row_packed, p->d_lut1, p->d_lut2,
-                                                                                         p->l2_cap, p->d_sorted_left, p->d_sorted_row, p->d_mlut));
+                                                                                         p->l2_cap, p->d_sorted_left, p->d_sorted_row, p->d_mlut, p->d_pklut));
     p->tables_ready = true;
     return HIC_OK;
 }
@@ -1163,7 +1290,7 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
             if (rc) return rc;
         }
         SyncArgs a;
-        a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2; a.mlut = p->d_mlut; a.l2_cap = p->l2_cap; a.sorted_left = p->d_sorted_left; a.sorted_row = p->d_sorted_row;
+        a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2; a.mlut = p->d_mlut; a.pklut = p->d_pklut; a.l2_cap = p->l2_cap; a.sorted_left = p->d_sorted_left; a.sorted_row = p->d_sorted_row;
         a.index = p->d_index; a.row_sym = p->d_row_sym; a.row_packed = p->d_row_packed; a.tiles = p->d_tiles; a.sub_end = p->d_sub_end;
         a.sub_cnt = p->d_sub_cnt; a.tile_start = p->d_tile_start; a.tile_cnt = p->d_tile_cnt; a.changed = p->d_err + 1;
         HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
@@ -1180,7 +1307,7 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
         }
         HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
         {
-            constexpr int WRITE_SMEM = 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE + 2 * WRITE_STAGE;
+            constexpr int WRITE_SMEM = 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE + 4 * PK_SIZE + 2 * WRITE_STAGE;
             static bool attr_set[64] = {false};
             int dev = 0;
             HIC_CUDA(cudaGetDevice(&dev));
