@@ -195,7 +195,7 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
         for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x)
             if ((uint32_t)row_sym[r] > 15u) s_wide = 1;
         __syncthreads();
-        uint32_t* myp = pklut + (size_t)(ss / 3) * PK_SIZE;
+        uint32_t* myp = pklut + ((size_t)(ss / 3) * 2 + 1) * PK_SIZE;
         for (uint32_t w = threadIdx.x; w < (uint32_t)PK_SIZE; w += blockDim.x) {
             uint32_t pos = 0, cnt = 0, syms = 0;
             while (!s_wide && cnt < (uint32_t)PK_MAX_SYMS) {
@@ -207,6 +207,24 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
                 ++cnt;
             }
             myp[w] = cnt ? (cnt | (pos << 3) | (syms << 8)) : 0u;
+        }
+    }
+    // Run-length value streams: pairs.  bits 0-1 = whole codes inside the window (at most 2) whose symbols
+    // fit 12 signed bits, bits 2-5 = their bits, bits 8-19 and 20-31 = the symbols.
+    if (ss % 3 == HIC_KIND_VALUE) {
+        uint32_t* myp = pklut + (size_t)(ss / 3) * 2 * PK_SIZE;
+        for (uint32_t w = threadIdx.x; w < (uint32_t)PK_SIZE; w += blockDim.x) {
+            uint32_t pos = 0, cnt = 0, syms = 0;
+            while (cnt < 2u) {
+                const int32_t e = (int32_t)extra[(w << (L1_BITS - PK_BITS + pos)) & (L1_SIZE - 1)];
+                const uint32_t len = (uint32_t)(e & 0x7F);
+                const int32_t sym = e >> 8;
+                if ((e & 0x80) || len == 0 || pos + len > (uint32_t)PK_BITS || sym < -2048 || sym > 2047) break;
+                syms |= ((uint32_t)sym & 0xFFFu) << (12 * cnt);
+                pos += len;
+                ++cnt;
+            }
+            myp[w] = cnt ? (cnt | (pos << 2) | (syms << 8)) : 0u;
         }
     }
     if (!s_need_sort) return;
@@ -449,11 +467,14 @@ __device__ __forceinline__ uint32_t decode_span_count(const BitReader& br, uint3
 // The final decode of a zero-count stream into the staging area: while a PK_BITS-bit window cannot cross
 // the span's upper boundary, one lookup in the packed table yields up to PK_MAX_SYMS symbols; the last bits
 // before the boundary (and anything the table does not hold) go one symbol at a time as in decode_span.
+// (T = uint8_t: zero counts, five 4-bit symbols per entry; T = int16_t: run-length values, two 12-bit ones)
+template <typename T>
 __device__ __forceinline__ uint32_t decode_span_packed(const BitReader& br, uint32_t chunk0, uint32_t pos, uint32_t limit,
                                                        uint32_t end, const int32_t* __restrict__ l1,
                                                        const uint32_t* __restrict__ pk, const int32_t* __restrict__ l2,
-                                                       const LongSearch& ls, uint32_t& count, uint8_t* __restrict__ stage,
+                                                       const LongSearch& ls, uint32_t& count, T* __restrict__ stage,
                                                        uint32_t out_idx, bool& bad) {
+    constexpr bool BYTES = sizeof(T) == 1;
     count = 0;
     const uint32_t stop = limit < end ? limit : end;
     if (pos >= stop) return pos;
@@ -462,7 +483,7 @@ __device__ __forceinline__ uint32_t decode_span_packed(const BitReader& br, uint
     uint64_t buf = (((uint64_t)br.words[wi] << 32) | br.words[wi + 1]) << sh;
     int avail = 64 - (int)sh;
     wi += 2;
-    uint8_t* out = stage + out_idx;
+    T* out = stage + out_idx;
     while (pos < stop) {
         if (avail < 32) {
             buf |= (uint64_t)br.words[wi] << (32 - avail);
@@ -471,16 +492,21 @@ __device__ __forceinline__ uint32_t decode_span_packed(const BitReader& br, uint
         }
         if (pos + PK_BITS <= stop) {
             const uint32_t m = pk[(uint32_t)(buf >> (64 - PK_BITS))];
-            const uint32_t n = m & 7u;
+            const uint32_t n = BYTES ? (m & 7u) : (m & 3u);
             if (n) {
-                const uint32_t adv = (m >> 3) & 15u;
-                uint8_t* o = out + count;
-                o[0] = (uint8_t)((m >> 8) & 15u);
-                if (n > 1) o[1] = (uint8_t)((m >> 12) & 15u);
-                if (n > 2) o[2] = (uint8_t)((m >> 16) & 15u);
-                if (n > 3) o[3] = (uint8_t)((m >> 20) & 15u);
-                if (n > 4) o[4] = (uint8_t)((m >> 24) & 15u);
-                static_assert(PK_MAX_SYMS == 5, "five symbol fields");
+                const uint32_t adv = BYTES ? ((m >> 3) & 15u) : ((m >> 2) & 15u);
+                T* o = out + count;
+                if (BYTES) {
+                    o[0] = (T)((m >> 8) & 15u);
+                    if (n > 1) o[1] = (T)((m >> 12) & 15u);
+                    if (n > 2) o[2] = (T)((m >> 16) & 15u);
+                    if (n > 3) o[3] = (T)((m >> 20) & 15u);
+                    if (n > 4) o[4] = (T)((m >> 24) & 15u);
+                    static_assert(PK_MAX_SYMS == 5, "five symbol fields");
+                } else {
+                    o[0] = (T)((int32_t)(m << 12) >> 20);
+                    if (n > 1) o[1] = (T)((int32_t)m >> 20);
+                }
                 count += n;
                 pos += adv;
                 buf <<= adv;
@@ -515,7 +541,7 @@ __device__ __forceinline__ uint32_t decode_span_packed(const BitReader& br, uint
             bad = true;
             return stop;
         }
-        out[count] = (uint8_t)sym;
+        out[count] = (T)sym;
         ++count;
         pos += len;
         if (len >= 32) {
@@ -685,9 +711,10 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
     const uint32_t chunk0 = t.sub0 * SUB_BITS;
     if (threadIdx.x == 0) s_staged = 0xFFFFFFFFu;
     stage_chunk(a, t, s_words, s_l1);
-    const bool packed = t.ss % 3 == HIC_KIND_LENGTH;
-    if (packed) {
-        const uint32_t* pk = a.pklut + (size_t)(t.ss / 3) * PK_SIZE;
+    const bool packed = t.ss % 3 == HIC_KIND_LENGTH;     // byte-wide symbols, five per lookup
+    const bool paired = t.ss % 3 == HIC_KIND_VALUE;      // two per lookup
+    if (packed || paired) {
+        const uint32_t* pk = a.pklut + ((size_t)(t.ss / 3) * 2 + (packed ? 1 : 0)) * PK_SIZE;
         for (int i = threadIdx.x; i < PK_SIZE; i += blockDim.x) s_pk[i] = __ldg(pk + i);
     }
     const BitReader br{s_words};
@@ -725,8 +752,10 @@ huffman_write_kernel(SyncArgs a, Geom g, const uint32_t* __restrict__ tile_off, 
         bool bad = false;
         uint32_t e;
         if (rank + cnt <= (uint32_t)(packed ? 2 * WRITE_STAGE : WRITE_STAGE)) {        // the usual case: into the staging area
-            if (packed) e = decode_span_packed(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, s_pk, l2, ls, got,
-                                               reinterpret_cast<uint8_t*>(s_stage), rank, bad);
+            if (packed) e = decode_span_packed<uint8_t>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, s_pk, l2, ls, got,
+                                                        reinterpret_cast<uint8_t*>(s_stage), rank, bad);
+            else if (paired) e = decode_span_packed<int16_t>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, s_pk, l2, ls, got,
+                                                             s_stage, rank, bad);
             else e = decode_span<true>(br, chunk0, start, (sub + 1) * SUB_BITS, end, s_l1, l2, ls, got, s_stage, nullptr, rank, bad);
         } else {                                          // ranks grow with the thread index: everything from here on is direct
             atomicMin(&s_staged, rank);
@@ -1033,7 +1062,7 @@ struct hic_decode_plan {
     int32_t* d_lut1 = nullptr;
     int32_t* d_lut2 = nullptr;
     uint16_t* d_mlut = nullptr;                 // multi-symbol table of the sync passes
-    uint32_t* d_pklut = nullptr;                // packed multi-symbol table of the zero-count streams (per channel stream)
+    uint32_t* d_pklut = nullptr;                // packed multi-symbol tables per channel stream: [0] value pairs, [1] zero counts
     int l2_cap = L2_CAP_MIN;
     uint64_t* d_sorted_left = nullptr;          // 2 x row capacity (bitonic padding)
     uint32_t* d_sorted_row = nullptr;
@@ -1114,7 +1143,7 @@ int hic_decode_plan_create(const hic_stream_layout* L, hic_decode_plan** out) {
     ok(dalloc2(&p->d_lengths, p->total_blocks * 64 + 64));
     ok(dalloc2(&p->d_lut1, (size_t)p->n_ss * L1_SIZE));
     ok(dalloc2(&p->d_mlut, (size_t)p->n_ss * L1_SIZE));
-    ok(dalloc2(&p->d_pklut, (size_t)p->n_cs * PK_SIZE));
+    ok(dalloc2(&p->d_pklut, (size_t)p->n_cs * 2 * PK_SIZE));
     {
         int cap = L2_CAP_MAX;
         while (cap > L2_CAP_MIN && (size_t)cap * p->n_ss > ((size_t)1 << 28)) cap >>= 1;
