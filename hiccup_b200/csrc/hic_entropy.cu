@@ -1025,39 +1025,67 @@ pack_emit_kernel(Geom g, const uint64_t* __restrict__ lut, const uint32_t* __res
         uint32_t total;
         const uint32_t rank = block_excl_sum<PACK_THREADS>(bits, ssum, &total);  // its barriers also order the (re)zeroing of buf
         const uint32_t skew = (uint32_t)(g0 & 31);
-        // The thread's codes are laid into a 64-bit window (hi = the output word being filled, lo = the
-        // spill into the next one) aligned with the tile buffer's words: a completed word is owned by this
-        // thread alone and is stored plainly; only the first word (shared with the thread before) and the
-        // last partial one (shared with the thread after) need an atomic OR.
         uint32_t wi = (skew + rank) >> 5, fill = (skew + rank) & 31;
-        uint32_t hi = 0, lo = 0;
-        bool shared_word = true;
-        auto put = [&](uint32_t code, uint32_t l) {        // 1 <= l <= 32, code < 2^l
-            const uint32_t c = code << (32 - l);
-            hi |= c >> fill;
-            lo |= __funnelshift_r(0u, c, fill);
-            fill += l;
-            if (fill >= 32) {
-                if (shared_word) atomicOr(&buf[wi], hi);
-                else buf[wi] = hi;
-                shared_word = false;
-                ++wi;
-                hi = lo;
-                lo = 0;
-                fill -= 32;
-            }
-        };
+        uint32_t l_or = 0;
 #pragma unroll
-        for (int j = 0; j < PACK_SPT; ++j) {
-            const uint32_t l = (uint32_t)(codes[j] >> 58);
-            if (l > 32) {                                  // long codes are rare: two pieces
-                put((uint32_t)(codes[j] >> 32) & ((1u << 26) - 1u), l - 32);
-                put((uint32_t)codes[j], 32);
-            } else if (l) {
-                put((uint32_t)codes[j], l);
+        for (int j = 0; j < PACK_SPT; ++j) l_or |= (uint32_t)(codes[j] >> 58);
+        if (bits <= 64u && !(l_or & 32u)) {                                 // every code shorter than 32 bits
+            // The usual case, without a branch per symbol (lanes would take it at different symbols, so the
+            // warp would pay for it at every one): the thread's codes are concatenated in a 64-bit register,
+            // left-aligned, and land in the three words they can touch with one atomic OR each.
+            uint32_t ahi = 0, alo = 0;
+#pragma unroll
+            for (int j = 0; j < PACK_SPT; ++j) {
+                const uint32_t l = (uint32_t)(codes[j] >> 58);              // 0 .. 31
+                ahi = __funnelshift_l(alo, ahi, l);                         // (ahi:alo) <<= l
+                alo = (alo << l) | (uint32_t)codes[j];
             }
+            if (bits) {
+                // left-align the `bits` valid bits in (ahi:alo)
+                const uint32_t up = 64u - bits;                             // 0 .. 63
+                if (up >= 32u) {
+                    ahi = alo << (up - 32u);
+                    alo = 0u;
+                } else {
+                    ahi = __funnelshift_l(alo, ahi, up);
+                    alo = up ? alo << up : alo;
+                }
+                const uint32_t w0 = ahi >> fill;
+                const uint32_t w1 = __funnelshift_r(alo, ahi, fill);        // low word of (ahi:alo) >> fill
+                const uint32_t w2 = fill ? alo << (32u - fill) : 0u;
+                if (w0) atomicOr(&buf[wi], w0);
+                if (w1) atomicOr(&buf[wi + 1], w1);
+                if (w2) atomicOr(&buf[wi + 2], w2);
+            }
+        } else {
+            // Long codes: laid into a 64-bit window (hi = the output word being filled, lo = the spill into
+            // the next one) aligned with the tile buffer's words, flushed a word at a time.
+            uint32_t hi = 0, lo = 0;
+            auto put = [&](uint32_t code, uint32_t l) {        // 1 <= l <= 32, code < 2^l
+                const uint32_t c = code << (32 - l);
+                hi |= c >> fill;
+                lo |= __funnelshift_r(0u, c, fill);
+                fill += l;
+                if (fill >= 32) {
+                    atomicOr(&buf[wi], hi);
+                    ++wi;
+                    hi = lo;
+                    lo = 0;
+                    fill -= 32;
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < PACK_SPT; ++j) {
+                const uint32_t l = (uint32_t)(codes[j] >> 58);
+                if (l > 32) {                                  // two pieces
+                    put((uint32_t)(codes[j] >> 32) & ((1u << 26) - 1u), l - 32);
+                    put((uint32_t)codes[j], 32);
+                } else if (l) {
+                    put((uint32_t)codes[j], l);
+                }
+            }
+            if (fill && hi) atomicOr(&buf[wi], hi);
         }
-        if (fill && hi) atomicOr(&buf[wi], hi);
         __syncthreads();
         const uint32_t n_words = (skew + total + 31) >> 5;
         uint32_t* dst = dst_base + (g0 >> 5);
