@@ -469,122 +469,148 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     }
 }
 
-// Float64 re-evaluation of every flagged block with scipy's exact operation order: one WARP per
-// block.  The lanes rebuild the block's samples from the RGB source (for a chroma block the 19x19
-// window of Cr or Cb values, then the separable [1 4 6 4 1] pyramid), eight lanes run the row
-// transforms, eight the column transforms + quantisation, and the float32 result is corrected in place.
+// Float64 re-evaluation of every flagged block with scipy's exact operation order.  A warp takes FOUR
+// flagged blocks at a time: all 32 lanes rebuild each block's samples from the RGB source in turn (for a
+// chroma block the 19x19 window of Cr or Cb values, then the separable [1 4 6 4 1] pyramid); then every
+// group of eight lanes runs its own block's eight row transforms, then its eight column transforms +
+// quantisation, and corrects the float32 result in place -- the float64 passes are the long part, and
+// with one block per warp 24 of the 32 lanes sat idle in them.
 constexpr int FIX_WARPS = 8;
+constexpr int FIX_GROUP = 4;      // blocks per warp
 struct FixSmem {
     double a[64];                 // row-transformed block
     int16_t px[64];               // x - 128, zero padded
     uint16_t hp[19][8];           // horizontal pass of the chroma window
     uint8_t win[19][20];          // Cr or Cb of the 19x19 source window
 };
+struct FixBlock {                 // where a flagged block sits
+    int kind, ph, pw, BY, BX, plane;
+    int64_t img;
+};
+__device__ __forceinline__ FixBlock fix_locate(uint32_t block, const hic_dct_geometry& g, int h, int w) {
+    FixBlock f;
+    f.img = block / g.blocks_per_image;
+    int64_t local = block - f.img * g.blocks_per_image;
+    if (local < g.nb_l) {
+        f.kind = 0; f.ph = h; f.pw = w; f.plane = 0;
+        f.BY = (int)(local / g.nbx_l); f.BX = (int)(local % g.nbx_l);
+    } else {
+        f.kind = 1; f.ph = g.hc; f.pw = g.wc;
+        local -= g.nb_l;
+        f.plane = (int)(local / g.nb_c);
+        local -= (int64_t)f.plane * g.nb_c;
+        f.BY = (int)(local / g.nbx_c); f.BX = (int)(local % g.nbx_c);
+    }
+    return f;
+}
 
 __global__ void __launch_bounds__(32 * FIX_WARPS)
 fixup_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, int16_t* __restrict__ coef,
              const hic_tie_record* __restrict__ ties, uint32_t tie_capacity, uint32_t* __restrict__ stats) {
-    __shared__ FixSmem sm_all[FIX_WARPS];
-    FixSmem& sm = sm_all[threadIdx.x >> 5];
+    __shared__ FixSmem sm_all[FIX_WARPS][FIX_GROUP];
     const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3, l8 = lane & 7;
     const uint32_t n_rec = min(stats[0], tie_capacity);
     const uint32_t warps = gridDim.x * FIX_WARPS;
     uint32_t changed_total = 0, done = 0;
-    for (uint32_t i = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5); i < n_rec; i += warps) {
-        const hic_tie_record rec = ties[i];
-        const int64_t img = rec.block / g.blocks_per_image;
-        int64_t local = rec.block - img * g.blocks_per_image;
-        const uint8_t* src = rgb + (size_t)img * h * w * 3;
-        int kind, ph, pw, BY, BX;
-        if (local < g.nb_l) {
-            kind = 0; ph = h; pw = w;
-            BY = (int)(local / g.nbx_l); BX = (int)(local % g.nbx_l);
-            for (int e = lane; e < 64; e += 32) {
-                const int y = 8 * BY + (e >> 3), x = 8 * BX + (e & 7);
-                int val = 0;
-                if (y < h && x < w) {
+    for (uint32_t base = (blockIdx.x * FIX_WARPS + (threadIdx.x >> 5)) * FIX_GROUP; base < n_rec; base += warps * FIX_GROUP) {
+        // ---- all lanes: the samples of each of the (up to) four blocks ----
+        for (int k = 0; k < FIX_GROUP && base + k < n_rec; ++k) {
+            FixSmem& sm = sm_all[threadIdx.x >> 5][k];
+            const FixBlock f = fix_locate(ties[base + k].block, g, h, w);
+            const uint8_t* src = rgb + (size_t)f.img * h * w * 3;
+            if (f.kind == 0) {
+                for (int e = lane; e < 64; e += 32) {
+                    const int y = 8 * f.BY + (e >> 3), x = 8 * f.BX + (e & 7);
+                    int val = 0;
+                    if (y < h && x < w) {
+                        const uint8_t* p = src + ((size_t)y * w + x) * 3;
+                        int yy, cr, cb;
+                        rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
+                        val = yy - 128;
+                    }
+                    sm.px[e] = (int16_t)val;
+                }
+            } else {
+                const int y0 = 16 * f.BY - 2, x0 = 16 * f.BX - 2;        // window origin in the source image
+                for (int e = lane; e < 19 * 19; e += 32) {
+                    const int r = e / 19, c = e - r * 19;
+                    const int y = reflect101(y0 + r, h), x = reflect101(x0 + c, w);
                     const uint8_t* p = src + ((size_t)y * w + x) * 3;
                     int yy, cr, cb;
                     rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
-                    val = yy - 128;
+                    sm.win[r][c] = (uint8_t)(f.plane == 0 ? cr : cb);
                 }
-                sm.px[e] = (int16_t)val;
-            }
-        } else {
-            kind = 1; ph = g.hc; pw = g.wc;
-            local -= g.nb_l;
-            const int plane = (int)(local / g.nb_c);
-            local -= (int64_t)plane * g.nb_c;
-            BY = (int)(local / g.nbx_c); BX = (int)(local % g.nbx_c);
-            const int y0 = 16 * BY - 2, x0 = 16 * BX - 2;        // window origin in the source image
-            for (int e = lane; e < 19 * 19; e += 32) {
-                const int r = e / 19, c = e - r * 19;
-                const int y = reflect101(y0 + r, h), x = reflect101(x0 + c, w);
-                const uint8_t* p = src + ((size_t)y * w + x) * 3;
-                int yy, cr, cb;
-                rgb_to_ycrcb(p[0], p[1], p[2], yy, cr, cb);
-                sm.win[r][c] = (uint8_t)(plane == 0 ? cr : cb);
-            }
-            __syncwarp();
-            for (int e = lane; e < 19 * 8; e += 32) {            // horizontal [1 4 6 4 1] at stride 2
-                const int r = e >> 3, c = e & 7;
-                const uint8_t* q = &sm.win[r][2 * c];
-                sm.hp[r][c] = (uint16_t)(q[0] + 4 * q[1] + 6 * q[2] + 4 * q[3] + q[4]);
-            }
-            __syncwarp();
-            for (int e = lane; e < 64; e += 32) {                // vertical, (sum + 128) >> 8
-                const int r = e >> 3, c = e & 7;
-                int val = 0;
-                if (8 * BY + r < g.hc && 8 * BX + c < g.wc) {
-                    const int sum = sm.hp[2 * r][c] + 4 * sm.hp[2 * r + 1][c] + 6 * sm.hp[2 * r + 2][c] +
-                                    4 * sm.hp[2 * r + 3][c] + sm.hp[2 * r + 4][c];
-                    val = ((sum + 128) >> 8) - 128;
+                __syncwarp();
+                for (int e = lane; e < 19 * 8; e += 32) {            // horizontal [1 4 6 4 1] at stride 2
+                    const int r = e >> 3, c = e & 7;
+                    const uint8_t* q = &sm.win[r][2 * c];
+                    sm.hp[r][c] = (uint16_t)(q[0] + 4 * q[1] + 6 * q[2] + 4 * q[3] + q[4]);
                 }
-                sm.px[e] = (int16_t)val;
+                __syncwarp();
+                for (int e = lane; e < 64; e += 32) {                // vertical, (sum + 128) >> 8
+                    const int r = e >> 3, c = e & 7;
+                    int val = 0;
+                    if (8 * f.BY + r < g.hc && 8 * f.BX + c < g.wc) {
+                        const int sum = sm.hp[2 * r][c] + 4 * sm.hp[2 * r + 1][c] + 6 * sm.hp[2 * r + 2][c] +
+                                        4 * sm.hp[2 * r + 3][c] + sm.hp[2 * r + 4][c];
+                        val = ((sum + 128) >> 8) - 128;
+                    }
+                    sm.px[e] = (int16_t)val;
+                }
             }
         }
         __syncwarp();
-        if (lane < 8) {                                          // rows (transform.py:78-80)
+        // ---- eight lanes per block: rows, then columns ----
+        const bool mine = base + grp < n_rec;
+        FixSmem& sm = sm_all[threadIdx.x >> 5][grp];
+        if (mine) {                                              // rows (transform.py:78-80)
             double row[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) row[j] = (double)sm.px[8 * lane + j];
+            for (int j = 0; j < 8; ++j) row[j] = (double)sm.px[8 * l8 + j];
             ducc_dct2_8(row);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sm.a[8 * lane + j] = row[j];
+            for (int j = 0; j < 8; ++j) sm.a[8 * l8 + j] = row[j];
         }
         __syncwarp();
         uint32_t changed = 0;
-        if (lane < 8) {                                          // columns, division by the table, np.round
+        if (mine) {                                              // columns, division by the table, np.round
+            const uint32_t block = ties[base + grp].block;
+            const FixBlock f = fix_locate(block, g, h, w);
             double col[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) col[r] = sm.a[8 * r + lane];
+            for (int r = 0; r < 8; ++r) col[r] = sm.a[8 * r + l8];
             ducc_dct2_8(col);
-            int16_t* blk = coef + (size_t)rec.block * 64;
+            int16_t* blk = coef + (size_t)block * 64;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int nat = 8 * r + lane;
+                const int nat = 8 * r + l8;
                 if (nat == 0) continue;                          // DC is an exact integer in float32 too
-                int32_t v = round_half_even(ddiv(col[r], (double)c_tab.qi[kind][nat]));
+                int32_t v = round_half_even(ddiv(col[r], (double)c_tab.qi[f.kind][nat]));
                 // coefficients outside the unpadded plane stay zero (transform.py:63, codec.py:288)
-                if (8 * BY + r >= ph || 8 * BX + lane >= pw) v = 0;
+                if (8 * f.BY + r >= f.ph || 8 * f.BX + l8 >= f.pw) v = 0;
                 const int k = c_tab.izz[nat];
                 if ((int32_t)blk[k] != v) {
                     blk[k] = (int16_t)v;
                     ++changed;
                 }
             }
+            if (l8 == 0) ++done;
         }
         changed_total += changed;
-        ++done;
         __syncwarp();
     }
 #pragma unroll
-    for (int off = 4; off; off >>= 1) changed_total += __shfl_down_sync(0xffffffffu, changed_total, off);
+    for (int off = 16; off; off >>= 1) {
+        changed_total += __shfl_down_sync(0xffffffffu, changed_total, off);
+        done += __shfl_down_sync(0xffffffffu, done, off);
+    }
     if (lane == 0) {
         if (done) atomicAdd(&stats[1], 63u * done);
         if (changed_total) atomicAdd(&stats[2], changed_total);
     }
 }
+
 }  // namespace k1
 
 // ------------------------------------------------------------------------------------------------
