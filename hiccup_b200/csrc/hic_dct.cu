@@ -721,43 +721,77 @@ __global__ void __launch_bounds__(128)
 inverse_fixup_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, uint8_t* __restrict__ yp,
                      uint8_t* __restrict__ crp, uint8_t* __restrict__ cbp, const hic_tie_record* __restrict__ ties,
                      uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    // eight lanes per flagged block (four blocks per warp): lane r runs the block's row r, then its column
+    // r, in exact_decoded_block's order (rows first, then columns, /256, +128); the row results cross the
+    // lanes through shared memory
+    __shared__ double s_a[4][4][64];                 // [warp][block of the warp][row-transformed block]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, l8 = lane & 7;
     const uint32_t n_rec = min(stats[0], tie_capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
-        const hic_tie_record rec = ties[i];
-        const int64_t img = rec.block / g.blocks_per_image;
-        int64_t local = rec.block - img * g.blocks_per_image;
+    const uint32_t groups = gridDim.x * (blockDim.x / 8);
+    uint32_t changed_total = 0, done = 0;
+    for (uint32_t base = (blockIdx.x * (blockDim.x / 32) + warp) * 4; base < n_rec; base += groups) {
+        const uint32_t i = base + grp;
+        const bool mine = i < n_rec;
+        double* a = s_a[warp][grp];
         int kind = 0, ph = g.h, pw = g.w, nbx = g.nbx_l;
-        uint8_t* plane = yp + (size_t)img * g.h * g.w;
-        if (local >= g.nb_l) {
-            kind = 1;
-            local -= g.nb_l;
-            const int p = (int)(local / g.nb_c);
-            local -= (int64_t)p * g.nb_c;
-            ph = g.hc; pw = g.wc; nbx = g.nbx_c;
-            plane = (p == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
+        uint8_t* plane = nullptr;
+        int BY = 0, BX = 0;
+        if (mine) {
+            const hic_tie_record rec = ties[i];
+            const int64_t img = rec.block / g.blocks_per_image;
+            int64_t local = rec.block - img * g.blocks_per_image;
+            plane = yp + (size_t)img * g.h * g.w;
+            if (local >= g.nb_l) {
+                kind = 1;
+                local -= g.nb_l;
+                const int p = (int)(local / g.nb_c);
+                local -= (int64_t)p * g.nb_c;
+                ph = g.hc; pw = g.wc; nbx = g.nbx_c;
+                plane = (p == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
+            }
+            BY = (int)(local / nbx);
+            BX = (int)(local % nbx);
+            const int16_t* blk = coef + (size_t)rec.block * 64;
+            double row[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int nat = 8 * l8 + j;
+                row[j] = (double)((int32_t)blk[c_tab.izz[nat]] * c_tab.qi[kind][nat]);
+            }
+            ducc_dct3_8(row);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[8 * l8 + j] = row[j];
         }
-        const int BY = (int)(local / nbx), BX = (int)(local % nbx);
-        const int16_t* blk = coef + (size_t)rec.block * 64;
-        int32_t cq[64];
-        for (int k = 0; k < 64; ++k) {
-            const int nat = c_zigzag[k];
-            cq[nat] = (int32_t)blk[k] * c_tab.qi[kind][nat];
-        }
-        double exact[64];
-        exact_decoded_block(cq, exact);
-        uint32_t changed = 0;
-        for (int y = 0; y < 8; ++y)
-            for (int x = 0; x < 8; ++x) {
-                if (8 * BY + y >= ph || 8 * BX + x >= pw) continue;
-                const uint8_t v = wrap_u8(exact[8 * y + x]);
-                uint8_t* dst = plane + (size_t)(8 * BY + y) * pw + 8 * BX + x;
+        __syncwarp();
+        if (mine) {
+            double col[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) col[r] = a[8 * r + l8];
+            ducc_dct3_8(col);
+            uint32_t changed = 0;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) {
+                if (8 * BY + y >= ph || 8 * BX + l8 >= pw) continue;
+                const uint8_t v = wrap_u8(dadd(ddiv(col[y], 256.0), 128.0));
+                uint8_t* dst = plane + (size_t)(8 * BY + y) * pw + 8 * BX + l8;
                 if (*dst != v) {
                     *dst = v;
                     ++changed;
                 }
             }
-        atomicAdd(&stats[1], 64u);
-        if (changed) atomicAdd(&stats[2], changed);
+            changed_total += changed;
+            if (l8 == 0) ++done;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        changed_total += __shfl_down_sync(0xffffffffu, changed_total, off);
+        done += __shfl_down_sync(0xffffffffu, done, off);
+    }
+    if (lane == 0) {
+        if (done) atomicAdd(&stats[1], 64u * done);
+        if (changed_total) atomicAdd(&stats[2], changed_total);
     }
 }
 
