@@ -94,17 +94,32 @@ build_tables_kernel(const RowIndex* __restrict__ index, const int32_t* __restric
     __syncthreads();
     const uint64_t r0 = index[ss].offset, r1 = r0 + index[ss].count;
     constexpr uint64_t CODE_MASK = (1ull << 58) - 1;
-    for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-        const uint32_t len = (uint32_t)(row_packed[r] >> 58);
-        const uint64_t code = row_packed[r] & CODE_MASK;
-        if (len == 0) continue;
-        if (len <= L1_BITS) {
-            const uint32_t base = (uint32_t)(code << (L1_BITS - len));
-            const int32_t entry = (row_sym[r] << 8) | (int32_t)len;
-            for (uint32_t j = 0; j < (1u << (L1_BITS - len)); ++j) my1[base + j] = entry;
-        } else {
-            atomicMax(&extra[(uint32_t)(code >> (len - L1_BITS))], min(len - L1_BITS, (uint32_t)L2_MAX_EXTRA));
-            if (len > L1_BITS + L2_MAX_EXTRA) s_need_sort = 1;
+    // A code of `len` <= 12 bits owns 2^(12 - len) consecutive first-level entries: a warp takes 32 rows at a
+    // time and all its lanes fill each row's span together (one thread alone would write 2048 entries for a
+    // 1-bit code while the rest of the CTA waits).
+    for (uint64_t rb = r0 + (threadIdx.x & ~31u); rb < r1; rb += blockDim.x) {
+        const uint64_t r = rb + (threadIdx.x & 31);
+        uint32_t span = 0, base = 0;
+        int32_t entry = 0;
+        if (r < r1) {
+            const uint32_t len = (uint32_t)(row_packed[r] >> 58);
+            const uint64_t code = row_packed[r] & CODE_MASK;
+            if (len != 0 && len <= L1_BITS) {
+                base = (uint32_t)(code << (L1_BITS - len));
+                entry = (row_sym[r] << 8) | (int32_t)len;
+                span = 1u << (L1_BITS - len);
+            } else if (len != 0) {
+                atomicMax(&extra[(uint32_t)(code >> (len - L1_BITS))], min(len - L1_BITS, (uint32_t)L2_MAX_EXTRA));
+                if (len > L1_BITS + L2_MAX_EXTRA) s_need_sort = 1;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, span != 0);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t n = __shfl_sync(0xffffffffu, span, k), b = __shfl_sync(0xffffffffu, base, k);
+            const int32_t e = __shfl_sync(0xffffffffu, entry, k);
+            for (uint32_t j = threadIdx.x & 31; j < n; j += 32) my1[b + j] = e;
         }
     }
     __syncthreads();
