@@ -60,6 +60,7 @@ SIGNATURES = {
     "hic_stream_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "hic_stream_destroy": (c_int, [c_void_p]),
     "hic_stream_sync": (c_int, [c_void_p]),
+    "hic_set_blocking_sync": (c_int, [c_int]),
     "hic_profile_enable": (c_int, [c_int]),
     "hic_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_profile_timeline": (c_int, [ctypes.c_char_p, c_size_t]),

@@ -11,6 +11,8 @@ kernels as the single-image drop-in functions (compression.py / codec.py / wavel
 images.  Host-side results are views of page-locked staging owned by the codec (valid until the next
 call of the same method).
 """
+import os
+
 import numpy as np
 
 from hiccup_b200 import _lib, entropy, hicimage
@@ -237,11 +239,17 @@ class PipelinedCodec:
         pipe.round_trip(rgb, out, on_encoded=lambda first_image, enc: ...)  # enc: EncodedStreams of a chunk
     """
 
-    def __init__(self, n, h, w, chunk=128, slots=3, mode="dct", device=None, **kw):
+    def __init__(self, n, h, w, chunk=128, slots=3, mode="dct", device=None, blocking_sync=False, **kw):
         _lib.require_device()
         if device is not None:
             _lib.check(_lib.load().hic_set_device(int(device)))
         self.device = device
+        # Host threads spin while they wait (the driver's default).  Blocking waits (hic_set_blocking_sync) were
+        # measured and are opt-in: they cost 4 % on one GPU (27.0 -> 28.0 ms per C2 batch) and do not help when
+        # four pipelines share a box (71.6 -> 83.7 ms per batch and rank: the host side of PCIe is the limit
+        # there, not the cores).
+        if blocking_sync or os.environ.get("HIC_BLOCKING_SYNC"):
+            _lib.check(_lib.load().hic_set_blocking_sync(1))
         self.n, self.h, self.w = int(n), int(h), int(w)
         self.chunk = max(1, min(int(chunk), self.n))
         if self.n % self.chunk:

@@ -240,6 +240,13 @@ int hic_set_device(int device) {
     return HIC_OK;
 }
 
+int hic_set_blocking_sync(int on) {
+    // how host threads wait for the device: yielding the core (blocking) instead of spinning (opt-in: the
+    // pipelined batch path keeps one host thread per slot waiting most of the time)
+    HIC_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    return HIC_OK;
+}
+
 int hic_device_name(char* buf, size_t buflen) {
     HIC_REQUIRE(buf != nullptr && buflen > 0, "buf is NULL");
     int dev = 0;

@@ -46,6 +46,10 @@ int hic_version(void);
 const char* hic_last_error(void);
 int hic_device_count(int* count);
 int hic_set_device(int device);
+/* How host threads wait for the current device from now on: 1 = block (yield the core), 0 = the driver's
+ * default (spin when cores are plentiful).  Optional: PipelinedCodec(blocking_sync=True) uses it for its
+ * per-slot host threads; on the boxes measured spinning was faster (batch.py). */
+int hic_set_blocking_sync(int on);
 int hic_device_name(char* buf, size_t buflen);
 int hic_malloc(void** d_ptr, size_t bytes);
 int hic_free(void* d_ptr);
