@@ -1,4 +1,4 @@
-"""One configuration of PipelinedCodec.round_trip, streamed (development aid; env selects copy pacing)."""
+"""One configuration of PipelinedCodec.round_trip, streamed: ms per 1024-image batch (development aid)."""
 import sys, os, time
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,4 +22,4 @@ reps = 6
 t = time.perf_counter()
 pipe.round_trip(host, out, repeat=reps)
 dt = (time.perf_counter() - t) / reps * 1e3
-print("piece %s KB depth %s chunk %d slots %d: %.1f ms per batch" % (os.environ.get("HIC_COPY_PIECE_KB", "-"), os.environ.get("HIC_COPY_DEPTH", "-"), chunk, slots, dt), flush=True)
+print("chunk %d slots %d: %.1f ms per batch" % (chunk, slots, dt), flush=True)
