@@ -107,3 +107,28 @@ def test_two_rank_gloo_band_encode(tmp_path):
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_gloo_worker, args=(2, port, (96, 64), 3, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_shared_memory_band_files_grow_and_remap(monkeypatch):
+    """The band strings travel through mapped /dev/shm files: the owner grows its file, a reader that mapped
+    the shorter file remaps, and views taken on one turn survive the other turn's write."""
+    monkeypatch.setenv("MASTER_PORT", "test%d" % os.getpid())
+    owner, reader = object.__new__(bands.DistComm), object.__new__(bands.DistComm)
+    owner.rank, reader.rank = 1, 0
+    try:
+        a = owner._shared_file(1, 0, 1000, create=True)
+        a[:1000] = np.arange(1000, dtype=np.uint8)
+        view = reader._shared_file(1, 0, 1000, create=False)[:1000]
+        assert np.array_equal(view, np.arange(1000, dtype=np.uint8))
+        big = (3 << 20) + 17                                   # beyond the first power-of-two size
+        b = owner._shared_file(1, 0, big, create=True)
+        assert b.size >= big and np.array_equal(b[:1000], np.arange(1000, dtype=np.uint8))     # growing keeps the content
+        b[big - 1] = 99
+        assert reader._shared_file(1, 0, big, create=False)[big - 1] == 99
+        other = owner._shared_file(1, 1, 500, create=True)      # the alternate file of the same rank
+        other[:500] = 7
+        assert np.array_equal(view, np.arange(1000, dtype=np.uint8))
+    finally:
+        owner.close()
+        reader.close()
+    assert not [f for f in os.listdir("/dev/shm") if ("test%d" % os.getpid()) in f]
