@@ -459,7 +459,9 @@ def main():
         ms_e2e, ms_drained = float(t[0].item()), float(t[1].item())
     e2e_value = world * pixels / 1e6 / (ms_e2e / args.steps / 1e3)
     tb = table_bytes[0] // max(args.steps, 1)
-    h2d = int(host_rgb.nbytes + payload + tb)
+    # round_trip decodes every chunk from the payload and tables the encoder left on the device: they are
+    # downloaded (results of the call) but not uploaded again
+    h2d = int(host_rgb.nbytes)
     d2h = int(payload + tb + host_out.nbytes)
     # the unchunked codec's last results, for the parity counters
     enc_res = codec.encode(host_rgb)
@@ -497,7 +499,8 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "api": "PipelinedCodec.round_trip(repeat=steps): chunks of %d images over 8 slots, steps streamed "
-                           "back to back" % chunk,
+                           "back to back; each chunk is decoded from the compressed payload the encoder left on the device "
+                           "(downloaded to the host as a result, not uploaded again)" % chunk,
                     "drained_value": world * pixels / 1e6 / (ms_drained / args.steps / 1e3), "drained_ms_per_step": ms_drained / args.steps,
                     "matches_unchunked": e2e_same},
             "gpu_launches": gpu_launches, "parity": parity,

@@ -261,7 +261,7 @@ class PipelinedCodec:
         self.codecs = [cls(self.chunk, h, w, stream=st, **kw) for st in self.streams]
         self.out_shape = (self.n,) + self.codecs[0].out_shape[1:]
 
-    def round_trip(self, rgb, out, on_encoded=None, repeat=1, trace=None, resident=False):
+    def round_trip(self, rgb, out, on_encoded=None, repeat=1, trace=None, resident=False, from_device=True):
         """Encode then decode every chunk of `rgb` (n, h, w, 3) into `out` (out_shape); both should be
         page-locked for the copies to overlap.  `repeat` > 1 streams the same batch through that many
         times without draining the pipeline in between (a stream of batches).  Returns the compressed
@@ -270,6 +270,10 @@ class PipelinedCodec:
         Two gates keep the slots out of lockstep: one chunk at a time owns the bulk host->device copy
         and one the bulk device->host copy, so copies queue first-in first-out at full PCIe rate while
         the other slots are in their kernel phases.
+
+        `from_device`: decode each chunk from the compressed payload and code tables the encoder left on the
+        device (they are downloaded to the host all the same -- they are a result of the call -- but not
+        uploaded again); False sends the host copy back up, as decoding a file would.
 
         `resident`: skip the bulk copies (each slot re-encodes the chunk its device buffer already holds
         and leaves the pixels on the device) -- the device-resident rate of the same pipeline.
@@ -304,7 +308,10 @@ class PipelinedCodec:
                         totals[slot] += int(enc.data.nbytes)
                     if on_encoded is not None:
                         on_encoded(a, enc)
-                    codec.decode_resident(enc)
+                    if from_device:
+                        codec.decode_device()
+                    else:
+                        codec.decode_resident(enc)
                     t4 = time.perf_counter()
                     with gate_out:
                         t5 = time.perf_counter()

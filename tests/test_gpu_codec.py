@@ -224,10 +224,11 @@ def test_pipelined_codec_equals_unchunked(mode, shape):
             got_hic[first + k] = im.byte_stream()
 
     out = np.empty(pipe.out_shape, np.uint8)
-    for _ in range(2):          # twice: staging buffers are reused
-        pipe.round_trip(rgb, out, on_encoded=on_encoded)
-    assert np.array_equal(out, want)
-    assert got_hic == want_hic
+    for from_device in (True, False, True):          # staging buffers are reused; both decode inputs
+        out[...] = 0
+        pipe.round_trip(rgb, out, on_encoded=on_encoded, from_device=from_device)
+        assert np.array_equal(out, want)
+        assert got_hic == want_hic
     pipe.close()
     whole.close()
 
