@@ -165,6 +165,23 @@ CONFIGS = {
 }
 
 
+def load_traffic(config):
+    """{kernel: DRAM bytes per launch} from the newest profiles/rNN_traffic_<config>.json, and that file's name
+    (None, None-ish when there is no capture for this workload: the numbers are then null, not stale)."""
+    import glob
+    if config is None:
+        return {}, None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_traffic_%s.json" % config)))
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        raw = json.load(f)
+    traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in raw.items() if isinstance(v, dict) and "dram_read_bytes" in v}
+    if "upsample_colour_vec_kernel" in traffic:
+        traffic["upsample_colour_kernel"] = traffic["upsample_colour_vec_kernel"]
+    return traffic, "profiles/" + os.path.basename(files[-1]) + " (ncu --set full, one launch each; captured at the commit that added the file)"
+
+
 def _oracle_round_trip(rgb, mode):
     from oracle import hiccup_oracle as orc
     if mode == "dct":
@@ -239,6 +256,186 @@ def run_reference(args):
     }
     emit(line)
     return 0
+
+
+def run_e2e(args, cfg, codec, host_rgb, rank, local_rank, world, dist, barrier):
+    """The host-to-host arm.  The public batched call is PipelinedCodec: chunks of the batch flow through
+    concurrent slots so H2D, kernels and D2H overlap; inputs and outputs are page-locked host arrays and every
+    step copies the whole batch in and the compressed streams, code tables and decoded pixels out.
+
+    One GPU: PipelinedCodec.round_trip(host_rgb, host_out).  Several GPUs: the ranks' batches form ONE job
+    in shared page-locked host memory (hiccup_b200/jobs.py) and every rank's pipeline takes chunks from one
+    ticket counter (PipelinedCodec.run_job) -- by-image partition with the share of each GPU decided by how
+    fast its path to host memory turns out to be, because on a multi-GPU box those paths are not alike.
+
+    Beside the real thing the same call runs with copy_only=True (identical copies, threads and gates, no
+    kernels): `copy_floor_ms` is what PCIe and host memory allow this very pattern on this box at this N."""
+    import torch
+    from hiccup_b200 import _lib
+    from hiccup_b200.batch import PipelinedCodec
+    from hiccup_b200.jobs import SharedJob
+    mode = cfg["mode"]
+    n, h, w = cfg["images"], cfg["height"], cfg["width"]
+    pixels = n * h * w
+    steps = args.steps
+    chunk = n if n < 8 else n // 8
+    pipe = PipelinedCodec(n, h, w, chunk=chunk, slots=8, mode=mode, device=local_rank)
+    table_bytes = [0]
+
+    def on_encoded(first, e):
+        table_bytes[0] += int(e.symbols.nbytes + e.packed.nbytes + e.index.nbytes)
+
+    def max_over_ranks(*vals):
+        if dist is None:
+            return vals
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t.tolist())
+
+    def sum_over_ranks(*vals):
+        if dist is None:
+            return vals
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return tuple(float(v) for v in t.tolist())
+
+    def timed(fn):
+        barrier()
+        t = time.perf_counter()
+        out = fn()
+        _lib.sync()
+        ms = (time.perf_counter() - t) * 1e3          # this rank's wall clock from the common start to its own end
+        barrier()
+        return ms, out
+
+    job = None
+    extra = {}
+    if world > 1:
+        job = SharedJob("bench%s" % os.environ.get("MASTER_PORT", "0"), rank, world, n, h, w, pipe.out_shape[1], pipe.out_shape[2],
+                        barrier=dist.barrier)
+        job.inputs[rank][...] = host_rgb
+        host_in, host_out = job.inputs[rank], job.outputs[rank]
+        for _ in range(2):
+            job.reset()
+            pipe.run_job(job)
+        job.reset()
+        ms, (payload, chunks_mine) = timed(lambda: pipe.run_job(job, on_encoded=on_encoded, repeat=steps))
+        job.reset()
+        ms_floor, _ = timed(lambda: pipe.run_job(job, repeat=steps, copy_only=True))
+        # the fixed partition of round 1 (every rank its own 1/N of the images), and its floor
+        for _ in range(2):
+            pipe.round_trip(host_in, host_out)
+        ms_static, _ = timed(lambda: pipe.round_trip(host_in, host_out, repeat=steps))
+        ms_static_floor, _ = timed(lambda: pipe.round_trip(host_in, host_out, repeat=steps, copy_only=True))
+        ms, ms_floor, ms_static, ms_static_floor = max_over_ranks(ms, ms_floor, ms_static, ms_static_floor)
+        payload_job, tables_job = sum_over_ranks(float(payload), float(table_bytes[0]))
+        shares = [0.0] * world
+        shares[rank] = float(chunks_mine)
+        shares = [int(v) for v in sum_over_ranks(*shares)]
+        per_step_chunks = world * (n // chunk)
+        h2d = int(world * host_rgb.nbytes)
+        d2h = int(payload_job + tables_job / steps + world * host_out.nbytes)
+        api = ("PipelinedCodec.run_job(SharedJob, repeat=steps): the %d ranks' batches are one job in shared page-locked host "
+               "memory; chunks of %d images are taken from one ticket counter by whichever rank has a free slot (8 slots per "
+               "rank), steps streamed back to back; each chunk is decoded from the payload its encoder left on the device "
+               "(downloaded as a result, not uploaded again)" % (world, chunk))
+        extra = {"chunks_taken_per_rank": shares, "chunks_per_step": per_step_chunks,
+                 "static_partition": {"ms_per_step": ms_static / steps, "value": world * pixels / 1e6 / (ms_static / steps / 1e3),
+                                      "copy_floor_ms": ms_static_floor / steps,
+                                      "what": "round 1's fixed share per rank (PipelinedCodec.round_trip on its own batch)"}}
+        ms_drained = None
+    else:
+        host_out, _keep_out = pinned_array(_lib, pipe.out_shape)
+        host_in = host_rgb
+        for _ in range(2):
+            pipe.round_trip(host_in, host_out)
+        # (a) one batch per call, pipeline drained between steps
+        ms_drained, _ = timed(lambda: [pipe.round_trip(host_in, host_out) for _ in range(steps)])
+        # (b) the K steps as a stream of batches through the same pipeline (no drain in between); every step
+        # still copies its whole batch in and its streams, tables and pixels out
+        ms, payload = timed(lambda: pipe.round_trip(host_in, host_out, on_encoded=on_encoded, repeat=steps))
+        ms_floor, _ = timed(lambda: pipe.round_trip(host_in, host_out, repeat=steps, copy_only=True))
+        h2d = int(host_rgb.nbytes)
+        d2h = int(payload + table_bytes[0] // max(steps, 1) + host_out.nbytes)
+        api = ("PipelinedCodec.round_trip(repeat=steps): chunks of %d images over 8 slots, steps streamed back to back; each "
+               "chunk is decoded from the compressed payload the encoder left on the device (downloaded to the host as a "
+               "result, not uploaded again)" % chunk)
+    e2e_value = world * pixels / 1e6 / (ms / steps / 1e3)
+
+    # ---- parity of what the timed path produced (outside the timed region) ----
+    # (1) the pipelined / job path against the unchunked codec on this rank's whole batch
+    enc_res = codec.encode(host_rgb)
+    codec.decode(enc_res)
+    mine = codec._h_out.array(np.uint8)[:host_out.size]
+    e2e_same = bool(np.array_equal(host_out.reshape(-1), mine))
+    # (2) k images of THIS batch against the oracle (the CPU restatement of the reference): code tables, framed
+    # bit strings and decoded pixels, bit for bit
+    parity = oracle_parity(codec, enc_res, mine.reshape(pipe.out_shape), host_rgb, mode, k=8 if pixels / n <= (1 << 20) else 0,
+                           seed=rank)
+    if mode == "dct":
+        parity.update({"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),
+                                        "changed": int(codec.forward_stats[2])},
+                       "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
+                                        "changed": int(codec.inverse_stats[2])}})
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": ms / steps, "api": api,
+           "copy_floor_ms": ms_floor / steps, "frac_of_copy_floor": (ms_floor / ms) if ms else None,
+           "copy_floor_how": "the same call with copy_only=True: identical bulk copies, slot threads and gates, no kernels, all ranks at once",
+           "matches_unchunked": e2e_same}
+    if ms_drained is not None:
+        e2e["drained_value"] = world * pixels / 1e6 / (ms_drained / steps / 1e3)
+        e2e["drained_ms_per_step"] = ms_drained / steps
+    e2e.update(extra)
+    if job is not None:
+        job.close()
+    pipe.close()
+    return e2e, e2e_same, parity
+
+
+def oracle_parity(codec, enc, decoded, host_rgb, mode, k, seed):
+    """k random images of the benchmark's own batch through the oracle: every code table, every framed bit
+    string and every decoded pixel must be equal.  Returns {"checked_images", "mismatches", ...}."""
+    out = {"checked_images": 0, "mismatches": 0, "against": "oracle port (numpy restatement of the reference), bit-exact"}
+    if k <= 0:
+        out["note"] = "images above 1 MP: the oracle comparison of whole images lives in tests/test_gpu_full_size.py"
+        return out
+    from oracle import hiccup_oracle as orc
+    rng = np.random.default_rng(77 + seed)
+    n = host_rgb.shape[0]
+    picks = sorted(set(int(i) for i in rng.choice(n, size=min(k, n), replace=False)))
+    bad = []
+    for i in picks:
+        rgb = np.array(host_rgb[i])
+        if mode == "dct":
+            planes = orc.jpeg_compression(rgb)
+            want = orc.jpeg_encode(planes)
+            pixels = orc.jpeg_decompression(orc.jpeg_decode(want))
+            kinds = 3
+        else:
+            planes = orc.wavelet_compression(rgb)
+            want = orc.wavelet_encode(planes)
+            pixels = orc.wavelet_decompression(orc.wavelet_decode(want))
+            kinds = 2
+        ok = True
+        for kind in range(kinds):
+            for c in range(3):
+                s = (i * 3 + c) * 3 + (kind if mode == "dct" else kind + 1)
+                j = kind * 3 + c
+                if enc.framed(s) != orc.padded_bits_to_bytes(want["bits"][j]):
+                    ok = False
+                if [(int(a), b) for a, b in enc.table(s)] != [(int(a), b) for a, b in want["tables"][j]]:
+                    ok = False
+        if not np.array_equal(decoded[i], pixels):
+            ok = False
+        if not ok:
+            bad.append(i)
+    out["checked_images"] = len(picks)
+    out["mismatches"] = len(bad)
+    out["images"] = picks
+    if bad:
+        out["mismatched_images"] = bad
+    return out
+
 
 
 _REAL_STDOUT = None
@@ -388,13 +585,9 @@ def main():
                          "algorithmic_gbs": round(ab / per / 1e6, 1) if ab and per > 0 else None,
                          "frac_of_peak": round(ab / per / 1e6 / peak, 4) if ab and per > 0 else None}
     dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
-    # DRAM traffic per launch from the committed `ncu --set full` capture of this exact workload
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2.json")
-    if args.config == "c2" and (n, h, w, mode) == (1024, 426, 640, "dct") and os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in json.load(f).items()}
-        traffic["upsample_colour_kernel"] = traffic.get("upsample_colour_vec_kernel")
+    # DRAM traffic per launch: not measurable inside this run (it needs ncu), so it is quoted from the newest
+    # committed `ncu --set full` capture of this exact workload, and the line says which file that was
+    traffic, traffic_source = load_traffic(args.config if (n, h, w, mode) == tuple(CONFIGS[args.config][k] for k in ("images", "height", "width", "mode")) else None)
     for name in kernels:
         kernels[name]["dram_traffic_bytes"] = traffic.get(name)
     roofline = None
@@ -416,63 +609,32 @@ def main():
         roofline_hbm = {"kernel": name, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": k["frac_of_peak"], "traffic": traffic.get(name), "share_of_step": k["share_of_step"],
                         "algorithmic_bytes": kernel_bytes(name, float(pixels), B, s_ac, bits_bytes, rows, n_ss, bins, mode)}
+    # K1, the kernel north_star sets the 60 % target for, rides inside `roofline` whatever the dominant kernel is
+    if roofline is not None:
+        roofline["traffic_source"] = traffic_source
+        k1_name = "forward_kernel" if mode == "dct" else "wavelet_forward_kernel"
+        if k1_name in kernels:
+            k = kernels[k1_name]
+            roofline["north_star_kernel"] = {
+                "kernel": k1_name, "what": "fused colour + pyrDown + DCT + quantise + zigzag (K1)" if mode == "dct" else "fused colour + 3-level db1 + quantise + zigzag (K9)",
+                "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac_of_peak"],
+                "ms_per_launch": k["ms_per_launch"], "traffic": traffic.get(k1_name),
+                "algorithmic_bytes": kernel_bytes(k1_name, float(pixels), B, s_ac, bits_bytes, rows, n_ss, bins, mode),
+                "target_frac": 0.60}
     # the replay span stands for 21 tier launches
     gpu_launches = int(sum(v[1] for v in prof.values()) + 20 * prof.get("huffman_replay_kernel", (0, 0))[1])
 
     # ---- end-to-end arm (host buffers, copies inside the timed region) ---------------------
-    # The public batched call: PipelinedCodec.round_trip(host_rgb, host_out) -- chunks of the batch
-    # flow through concurrent slots so H2D, kernels and D2H overlap.  Inputs and outputs are
-    # page-locked host arrays; every step copies the whole batch in and the compressed streams, code
-    # tables and decoded pixels out.
-    from hiccup_b200.batch import PipelinedCodec
-    chunk = n if n < 8 else n // 8
-    pipe = PipelinedCodec(n, h, w, chunk=chunk, slots=8, mode=mode, device=local_rank)
-    host_out, _keep_out = pinned_array(_lib, pipe.out_shape)
-    table_bytes = [0]
+    e2e, e2e_same, parity = run_e2e(args, cfg, codec, host_rgb, rank, local_rank, world, dist, barrier)
 
-    def on_encoded(first, e):
-        table_bytes[0] += int(e.symbols.nbytes + e.packed.nbytes + e.index.nbytes)
-
-    for _ in range(2):
-        pipe.round_trip(host_rgb, host_out)
-    barrier()
-    # (a) one batch per call, pipeline drained between steps
-    t_d = time.perf_counter()
-    for _ in range(args.steps):
-        pipe.round_trip(host_rgb, host_out)
-    torch.cuda.synchronize()
-    ms_drained = (time.perf_counter() - t_d) * 1e3
-    barrier()
-    # (b) the K steps as a stream of batches through the same pipeline (no drain in between); every
-    # step still copies its whole batch in and its streams, tables and pixels out
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    t_e2e = time.perf_counter()
-    payload = pipe.round_trip(host_rgb, host_out, on_encoded=on_encoded, repeat=args.steps)
-    e3.record()
-    barrier()
-    wall_e2e = time.perf_counter() - t_e2e
-    ms_e2e = max(e2.elapsed_time(e3), wall_e2e * 1e3)      # slots run on their own streams: wall clock rules
+    # a parity failure on any rank fails the run (after the line is printed, so that it can be read)
+    bad = (0 if e2e_same else 1) + int(parity.get("mismatches", 0))
     if dist is not None:
-        t = torch.tensor([ms_e2e, ms_drained], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e, ms_drained = float(t[0].item()), float(t[1].item())
-    e2e_value = world * pixels / 1e6 / (ms_e2e / args.steps / 1e3)
-    tb = table_bytes[0] // max(args.steps, 1)
-    # round_trip decodes every chunk from the payload and tables the encoder left on the device: they are
-    # downloaded (results of the call) but not uploaded again
-    h2d = int(host_rgb.nbytes)
-    d2h = int(payload + tb + host_out.nbytes)
-    # the unchunked codec's last results, for the parity counters
-    enc_res = codec.encode(host_rgb)
-    codec.decode(enc_res)
-    e2e_same = bool(np.array_equal(host_out.reshape(-1)[:1 << 24], codec._h_out.array(np.uint8)[:1 << 24]))
-    parity = None
-    if mode == "dct":
-        parity = {"forward_ties": {"flagged_blocks": int(codec.forward_stats[0]), "reevaluated": int(codec.forward_stats[1]),
-                                   "changed": int(codec.forward_stats[2])},
-                  "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
-                                   "changed": int(codec.inverse_stats[2])}}
+        t = torch.tensor([float(bad), float(parity.get("checked_images", 0))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        bad = int(t[0].item())
+        parity["checked_images_all_ranks"] = int(t[1].item())
+        parity["failures_all_ranks"] = bad
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -497,18 +659,16 @@ def main():
                                      "(HIC_ENTROPY_SERIAL); shares are of that pass" % args.steps,
                               "serialised_ms_per_step": ms_serial / args.steps},
             "cpu_baseline": cpu, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "api": "PipelinedCodec.round_trip(repeat=steps): chunks of %d images over 8 slots, steps streamed "
-                           "back to back; each chunk is decoded from the compressed payload the encoder left on the device "
-                           "(downloaded to the host as a result, not uploaded again)" % chunk,
-                    "drained_value": world * pixels / 1e6 / (ms_drained / args.steps / 1e3), "drained_ms_per_step": ms_drained / args.steps,
-                    "matches_unchunked": e2e_same},
+            "e2e": e2e,
             "gpu_launches": gpu_launches, "parity": parity,
         }
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        sys.stderr.write("bench.py: PARITY FAILURE -- %s\n" % json.dumps(parity))
+        return 3
     return 0
 
 

@@ -54,6 +54,9 @@ SIGNATURES = {
     "hic_free": (c_int, [c_void_p]),
     "hic_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
     "hic_host_free": (c_int, [c_void_p]),
+    "hic_host_register": (c_int, [c_void_p, c_size_t]),
+    "hic_host_unregister": (c_int, [c_void_p]),
+    "hic_ticket_take": (c_int, [c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "hic_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "hic_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "hic_memset": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),

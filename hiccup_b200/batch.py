@@ -109,6 +109,16 @@ class _BatchCodec:
         return entropy.EncodedStreams(self.layout, index, enc.nsym.copy(), enc.nbits.copy(),
                                       enc.byte_off.copy(), enc.byte_len.copy(), sym, packed, data)
 
+    def download_payload_sized(self):
+        """The device->host copies of encode_resident() without its kernels: as many payload and table bytes
+        as the last real encode of this codec produced (PipelinedCodec's copy-only floor)."""
+        enc = self.encoder
+        nbytes = int(getattr(enc, "total_bytes", 0) or 0)
+        if not nbytes or self._h_data is None or enc._out is None:
+            raise RuntimeError("copy-only pass before any real encode of this codec")
+        enc._out.download(np.uint8, nbytes, self.stream, out=self._h_data.array(np.uint8, nbytes))
+        enc.tables_packed(self.stream, out=self._h_tab)
+
     def decode(self, enc, out=None):
         """out: optional preallocated uint8 array of out_shape (ideally page-locked) to receive the pixels."""
         self.decode_resident(enc)
@@ -261,7 +271,8 @@ class PipelinedCodec:
         self.codecs = [cls(self.chunk, h, w, stream=st, **kw) for st in self.streams]
         self.out_shape = (self.n,) + self.codecs[0].out_shape[1:]
 
-    def round_trip(self, rgb, out, on_encoded=None, repeat=1, trace=None, resident=False, from_device=True):
+    def round_trip(self, rgb, out, on_encoded=None, repeat=1, trace=None, resident=False, from_device=True,
+                   copy_only=False):
         """Encode then decode every chunk of `rgb` (n, h, w, 3) into `out` (out_shape); both should be
         page-locked for the copies to overlap.  `repeat` > 1 streams the same batch through that many
         times without draining the pipeline in between (a stream of batches).  Returns the compressed
@@ -278,11 +289,53 @@ class PipelinedCodec:
         `resident`: skip the bulk copies (each slot re-encodes the chunk its device buffer already holds
         and leaves the pixels on the device) -- the device-resident rate of the same pipeline.
 
+        `copy_only`: the same bulk copies, slot threads and gates with NO kernels (the payload-sized download
+        uses the size of the slot's last real encode): what PCIe alone allows this call -- its floor.
+
         `trace`: optional list that receives (slot, visit, phase, t_begin, t_end) host timestamps of the
         phases as they already synchronise (no extra synchronisation is added)."""
+        assert rgb.shape == (self.n, self.h, self.w, 3) and out.shape == self.out_shape
+        total = repeat * self.n_chunks
+
+        def tickets(slot):
+            for v in range(slot, total, self.slots):
+                c = v % self.n_chunks
+                yield v, c * self.chunk, rgb[c * self.chunk:(c + 1) * self.chunk], out[c * self.chunk:(c + 1) * self.chunk], v < self.n_chunks
+
+        payload, _ = self._run(tickets, on_encoded, trace, resident, from_device, copy_only)
+        return payload
+
+    def run_job(self, job, repeat=1, on_encoded=None, from_device=True, copy_only=False, trace=None):
+        """This rank's share of a box-wide job (hiccup_b200/jobs.py): chunks of EVERY rank's batch are handed
+        out from one shared ticket counter, so a GPU whose path to host memory is faster -- PCIe root ports
+        and sockets are not symmetric on a multi-GPU box -- takes more of them, and the job ends when the
+        counter runs out instead of when the slowest link has moved a fixed share.  Images are independent
+        (by-image partition, no collective); every rank reads and writes the shared, page-locked host
+        buffers of the job directly.  Returns (payload bytes this rank produced in the first pass, chunks
+        this rank processed).  `on_encoded(first_image, enc)` gets the job-wide index of the chunk's first
+        image."""
+        assert job.in_shape[1:] == (self.h, self.w, 3) and job.n % self.chunk == 0
+        per_rank = job.n // self.chunk
+        total = repeat * job.world * per_rank
+        done = [0] * self.slots
+
+        def tickets(slot):
+            while True:
+                v = job.take()
+                if v >= total:
+                    return
+                done[slot] += 1
+                u = v % (job.world * per_rank)
+                owner, c = u // per_rank, u % per_rank
+                a, b = c * self.chunk, (c + 1) * self.chunk
+                yield v, owner * job.n + a, job.inputs[owner][a:b], job.outputs[owner][a:b], v < job.world * per_rank
+
+        payload, _ = self._run(tickets, on_encoded, trace, False, from_device, copy_only)
+        return payload, sum(done)
+
+    def _run(self, tickets, on_encoded, trace, resident, from_device, copy_only):
         import threading
         import time
-        assert rgb.shape == (self.n, self.h, self.w, 3) and out.shape == self.out_shape
         totals = [0] * self.slots
         errors = []
         gate_in, gate_out = threading.Lock(), threading.Lock()
@@ -292,31 +345,33 @@ class PipelinedCodec:
                 if self.device is not None:
                     _lib.check(_lib.load().hic_set_device(int(self.device)))
                 codec = self.codecs[slot]
-                for v in range(slot, repeat * self.n_chunks, self.slots):
-                    c = v % self.n_chunks
-                    a, b = c * self.chunk, (c + 1) * self.chunk
+                for v, first_image, src, dst, count_payload in tickets(slot):
                     t0 = time.perf_counter()
                     with gate_in:
                         t1 = time.perf_counter()
                         if not resident:
-                            codec.upload(rgb[a:b])
+                            codec.upload(src)
                             _lib.sync(codec.stream)
                     t2 = time.perf_counter()
-                    enc = codec.encode_resident()
-                    t3 = time.perf_counter()
-                    if v < self.n_chunks:
-                        totals[slot] += int(enc.data.nbytes)
-                    if on_encoded is not None:
-                        on_encoded(a, enc)
-                    if from_device:
-                        codec.decode_device()
+                    if copy_only:
+                        codec.download_payload_sized()
+                        t3 = t4 = time.perf_counter()
                     else:
-                        codec.decode_resident(enc)
-                    t4 = time.perf_counter()
+                        enc = codec.encode_resident()
+                        t3 = time.perf_counter()
+                        if count_payload:
+                            totals[slot] += int(enc.data.nbytes)
+                        if on_encoded is not None:
+                            on_encoded(first_image, enc)
+                        if from_device:
+                            codec.decode_device()
+                        else:
+                            codec.decode_resident(enc)
+                        t4 = time.perf_counter()
                     with gate_out:
                         t5 = time.perf_counter()
                         if not resident:
-                            codec.fetch(out[a:b])
+                            codec.fetch(dst)
                         else:
                             _lib.sync(codec.stream)
                     t6 = time.perf_counter()
@@ -332,7 +387,7 @@ class PipelinedCodec:
             t.join()
         if errors:
             raise errors[0]
-        return sum(totals)
+        return sum(totals), None
 
     def close(self):
         for c in self.codecs:

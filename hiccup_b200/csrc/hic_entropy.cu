@@ -19,6 +19,7 @@
 #include <vector>
 #include "hic_core.cuh"
 #include "hic_huffman.cuh"
+#include "hic_replay.cuh"
 #include "hic_runtime.cuh"
 
 namespace hic {
@@ -620,13 +621,15 @@ static const int h_tier_bound[N_TIERS] = {16, 32, 64, 128, 192, 256, 384, 512, 6
                                           1024, 1280, 1536, 1792, 2048, 2560, 3072, 4096, 6144, 8192};
 constexpr int SORT_THREADS = 256;
 constexpr int REPLAY_SMEM_BUDGET = 48 * 1024;
+constexpr int REPLAY_NARROW_BUDGET = 44 * 1024;
 
 __global__ void __launch_bounds__(SORT_THREADS)
-huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, const CompactEntry* __restrict__ entries,
+huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, int allow_narrow, const CompactEntry* __restrict__ entries,
                     const CompactIndex* __restrict__ index,
                     uint32_t* __restrict__ leaf_freq, int32_t* __restrict__ row_sym, uint32_t* __restrict__ tier_count,
                     uint32_t* __restrict__ tier_list, int n_ss, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t sort_raw[];
+    __shared__ unsigned long long s_total;
     const int ss = selected_stream(sel, blockIdx.x);
     const CompactIndex ix = index[ss];
     const int n = (int)ix.count;
@@ -641,10 +644,15 @@ huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, const CompactEntry* __r
     uint32_t* key = reinterpret_cast<uint32_t*>(sort_raw);
     uint16_t* order = reinterpret_cast<uint16_t*>(sort_raw + 4 * P);
     const CompactEntry* my = entries + ix.offset;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    unsigned long long my_total = 0;
     for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
         key[i] = i < n ? my[i].first : 0xFFFFFFFFu;
         order[i] = (uint16_t)(i < n ? i : 0);
+        if (i < n) my_total += my[i].count;
     }
+    if (my_total) atomicAdd(&s_total, my_total);
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -672,6 +680,9 @@ huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, const CompactEntry* __r
     if (threadIdx.x == 0 && n >= 2) {
         int t = 0;
         while (c_tier_bound[t] < n) ++t;
+        // a stream whose symbols number fewer than 2^18 replays on packed one-word heap entries (hic_replay.cuh):
+        // tiers N_TIERS .. 2 N_TIERS - 1
+        if (allow_narrow && s_total < (unsigned long long)REPLAY_NARROW_TOTAL) t += N_TIERS;
         const uint32_t pos = atomicAdd(&tier_count[t], 1u);
         tier_list[(size_t)t * n_ss + pos] = (uint32_t)ss;
     }
@@ -765,6 +776,38 @@ huffman_replay_kernel(int tier, int G, int stride_slots, int n_ss, const Compact
         siftdown(0, size - 1, make_uint2((uint32_t)next, l.y + r.y));      // heapq.heappush
         ++next;
     }
+}
+
+// The same replay on packed one-word heap entries (hic_replay.cuh) for the streams filed in the narrow
+// tiers: half the shared memory per stream, and (MODE 2) two heap levels per shared-memory round trip.
+template <int MODE>
+__global__ void __launch_bounds__(32)
+huffman_replay_narrow_kernel(int tier, int G, int stride_slots, int n_ss, const CompactIndex* __restrict__ index,
+                             const uint32_t* __restrict__ leaf_freq, const uint32_t* __restrict__ tier_count,
+                             const uint32_t* __restrict__ tier_list, uint16_t* __restrict__ parent) {
+    extern __shared__ __align__(16) uint8_t replay_raw[];
+    const uint32_t count = tier_count[N_TIERS + tier];
+    const uint32_t first = blockIdx.x * (uint32_t)G;
+    if (first >= count) return;
+    const int lane = threadIdx.x;
+    const int mine = (int)min((uint32_t)G, count - first);
+    uint32_t my_off = 0;
+    int my_n = 0;
+    if (lane < mine) {
+        const CompactIndex ix = index[tier_list[(size_t)(N_TIERS + tier) * n_ss + first + lane]];
+        my_off = ix.offset;
+        my_n = (int)ix.count;
+    }
+    uint32_t* base = reinterpret_cast<uint32_t*>(replay_raw);
+    for (int k = 0; k < mine; ++k) {          // all lanes fill the heaps: leaves in first-occurrence order
+        const uint32_t off = __shfl_sync(0xffffffffu, my_off, k);
+        const int n = __shfl_sync(0xffffffffu, my_n, k);
+        uint32_t* slot = base + (size_t)k * stride_slots;
+        for (int i = lane; i < n; i += 32) slot[i + 1] = (leaf_freq[off + i] << REPLAY_ID_BITS) | (uint32_t)i;
+    }
+    __syncwarp();
+    if (lane >= mine) return;
+    replay_narrow<MODE>(base + (size_t)lane * stride_slots, my_n, stride_slots, parent + 2 * (size_t)my_off);
 }
 
 __global__ void __launch_bounds__(128)
@@ -1283,10 +1326,10 @@ int hic_entropy_plan_create(const hic_stream_layout* layout, int32_t value_bins,
     ok(dalloc(&p->d_pay_totals, 2));
     ok(dalloc(&p->d_start_bit, p->n_ss));
     ok(dalloc(&p->d_band, p->n_cs));
-    ok(dalloc(&p->d_tier_count, N_TIERS));
-    ok(dalloc(&p->d_tier_list, (size_t)N_TIERS * p->n_ss));
-    ok(dalloc(&p->d_tier_count_dc, N_TIERS));
-    ok(dalloc(&p->d_tier_list_dc, (size_t)N_TIERS * p->n_ss));
+    ok(dalloc(&p->d_tier_count, 2 * N_TIERS));                       // wide tiers, then narrow tiers
+    ok(dalloc(&p->d_tier_list, (size_t)2 * N_TIERS * p->n_ss));
+    ok(dalloc(&p->d_tier_count_dc, 2 * N_TIERS));
+    ok(dalloc(&p->d_tier_list_dc, (size_t)2 * N_TIERS * p->n_ss));
     ok(dalloc(&p->d_leaf_freq, hist_n));
     ok(dalloc(&p->d_parent, hist_n));
     // (default priority: with the highest priority the replay's small shared-memory-heavy CTAs displace the
@@ -1339,21 +1382,37 @@ static int builder_prepare(hic_entropy_plan* p) {
     const int max_stride = 8 * (h_tier_bound[N_TIERS - 1] + 2);
     if (dev >= 64 || !attr_set[dev]) {
         HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
+        // (the sort kernel's 48 KB of dynamic shared memory plus its static word need the opt-in too)
+        HIC_CUDA(cudaFuncSetAttribute(huffman_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_replay_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, REPLAY_SMEM_BUDGET));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_replay_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, REPLAY_SMEM_BUDGET));
         if (dev < 64) attr_set[dev] = true;
     }
     return HIC_OK;
+}
+
+// HIC_REPLAY_WIDE (environment): every stream on the two-word entries (the round-1 path, for A/B timing);
+// HIC_REPLAY_MODE = 1 | 2: one or two heap levels per step in the packed replay (hic_replay.cuh)
+static bool replay_allow_narrow() {
+    static const bool on = getenv("HIC_REPLAY_WIDE") == nullptr;
+    return on;
+}
+static int replay_mode() {
+    static const int mode = getenv("HIC_REPLAY_MODE") ? atoi(getenv("HIC_REPLAY_MODE")) : 2;
+    return mode == 1 ? 1 : 2;
 }
 
 // sort + tier filing of a selection of the streams on stream s0
 static int builder_sort_pass(hic_entropy_plan* p, int sel, uint32_t* tier_count, uint32_t* tier_list, cudaStream_t s0) {
     const Geom& g = p->g;
     const unsigned grid = (unsigned)selected_count(sel, p->n_cs);
-    HIC_CUDA(cudaMemsetAsync(tier_count, 0, N_TIERS * sizeof(uint32_t), s0));
+    HIC_CUDA(cudaMemsetAsync(tier_count, 0, 2 * N_TIERS * sizeof(uint32_t), s0));
+    const int narrow = replay_allow_narrow() ? 1 : 0;
     // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
     HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 1024, s0>>>(
-        g, sel, 0, 1024, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+        g, sel, 0, 1024, narrow, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
     HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 8192, s0>>>(
-        g, sel, 1024, 8192, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+        g, sel, 1024, 8192, narrow, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
     return HIC_OK;
 }
 
@@ -1369,6 +1428,21 @@ static int builder_replay_pass(hic_entropy_plan* p, const uint32_t* tier_count, 
                                                                                       tier_count, tier_list,
                                                                                       reinterpret_cast<uint16_t*>(p->d_parent));
         HIC_CHECK_LAUNCH("huffman_replay_kernel");
+        if (!replay_allow_narrow()) continue;
+        // the narrow tier of the same size: one word per heap entry, and a smaller budget per warp so that
+        // five CTAs fit an SM (5 x (44 + 1) KB)
+        const int nslots = h_tier_bound[t] + 4;
+        const int nstride = 4 * nslots;
+        const int NG = std::max(1, std::min(32, REPLAY_NARROW_BUDGET / nstride));
+        const unsigned ngrid = (unsigned)((p->n_ss + NG - 1) / NG);
+        cudaStream_t lane_st = lanes[(t + n_lanes / 2) % n_lanes];
+        if (replay_mode() == 1)
+            huffman_replay_narrow_kernel<1><<<ngrid, 32, (size_t)NG * nstride, lane_st>>>(t, NG, nslots, p->n_ss, p->d_index, p->d_leaf_freq, tier_count,
+                                                                                          tier_list, reinterpret_cast<uint16_t*>(p->d_parent));
+        else
+            huffman_replay_narrow_kernel<2><<<ngrid, 32, (size_t)NG * nstride, lane_st>>>(t, NG, nslots, p->n_ss, p->d_index, p->d_leaf_freq, tier_count,
+                                                                                          tier_list, reinterpret_cast<uint16_t*>(p->d_parent));
+        HIC_CHECK_LAUNCH("huffman_replay_narrow_kernel");
     }
     return HIC_OK;
 }

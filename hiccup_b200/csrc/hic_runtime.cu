@@ -279,6 +279,24 @@ int hic_host_free(void* h_ptr) {
     return HIC_OK;
 }
 
+int hic_host_register(void* h_ptr, size_t bytes) {
+    HIC_REQUIRE(h_ptr != nullptr && bytes > 0, "nothing to register");
+    HIC_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+    return HIC_OK;
+}
+
+int hic_host_unregister(void* h_ptr) {
+    HIC_CUDA(cudaHostUnregister(h_ptr));
+    return HIC_OK;
+}
+
+int hic_ticket_take(void* h_counter, int64_t count, int64_t* first) {
+    HIC_REQUIRE(h_counter != nullptr && first != nullptr, "NULL argument");
+    HIC_REQUIRE((reinterpret_cast<uintptr_t>(h_counter) & 7) == 0, "the counter must be 8-byte aligned");
+    *first = __atomic_fetch_add(static_cast<int64_t*>(h_counter), count, __ATOMIC_ACQ_REL);
+    return HIC_OK;
+}
+
 // Bulk copies (image batches, compressed payloads) are single asynchronous copy-engine transfers.  A copy
 // engine serves its queue strictly in order (tools/ce_fifo.py: a 64 KB copy on another stream waits the
 // full ~2 ms behind a queued 105 MB copy, also when that copy is enqueued as 4 MB pieces).  What helped the

@@ -55,6 +55,15 @@ int hic_malloc(void** d_ptr, size_t bytes);
 int hic_free(void* d_ptr);
 int hic_host_alloc(void** h_ptr, size_t bytes);          /* pinned */
 int hic_host_free(void* h_ptr);
+/* Page-lock host memory the caller already owns (e.g. a /dev/shm mapping several ranks of one box share)
+ * so that bulk copies to and from it run asynchronously at full PCIe rate; portable across contexts.
+ * The reference is one process on one image (run.py:18-43); these two and hic_ticket_take exist for the
+ * box-wide job queue of hiccup_b200/jobs.py (by-image partition with link-aware load balancing). */
+int hic_host_register(void* h_ptr, size_t bytes);
+int hic_host_unregister(void* h_ptr);
+/* Atomically take `count` tickets from a 64-bit counter in (possibly shared, process-crossing) host
+ * memory: *first = the old value, counter += count.  h_counter must be 8-byte aligned. */
+int hic_ticket_take(void* h_counter, int64_t count, int64_t* first);
 int hic_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int hic_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int hic_memset(void* d_ptr, int value, size_t bytes, void* stream);

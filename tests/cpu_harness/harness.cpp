@@ -3,7 +3,9 @@
 // linked into libhiccup_b200.so and nothing under hiccup_b200/ loads it.
 // Build: g++ -O2 -ffp-contract=off -std=c++17 -shared -fPIC harness.cpp -o libhic_cpu_harness.so
 #include <string.h>
+#include <stdlib.h>
 #include "../../hiccup_b200/csrc/hic_core.cuh"
+#include "../../hiccup_b200/csrc/hic_replay.cuh"
 
 using namespace hic;
 
@@ -139,6 +141,25 @@ void hx_colour_inv(const uint8_t* ycrcb, int n, uint8_t* rgb) {
         ycrcb_to_rgb(ycrcb[3 * i], ycrcb[3 * i + 1], ycrcb[3 * i + 2], r, g, b);
         rgb[3 * i] = (uint8_t)r; rgb[3 * i + 1] = (uint8_t)g; rgb[3 * i + 2] = (uint8_t)b;
     }
+}
+
+// The device Huffman builder's packed heapq replay (csrc/hic_replay.cuh) on the host.  freqs: leaf
+// frequencies in first-occurrence order (their sum below 2^18, 2 <= n <= 8192); par: 2 n parent links out
+// (bit 15 = left child).  mode = 1 | 2: one or two heap levels per step (both are compiled into the library).
+int hx_replay_narrow(const uint32_t* freqs, int n, int mode, uint16_t* par) {
+    if (n < 2 || n > REPLAY_NARROW_MAX_LEAVES) return 1;
+    unsigned long long total = 0;
+    for (int i = 0; i < n; ++i) total += freqs[i];
+    if (total >= REPLAY_NARROW_TOTAL) return 2;
+    const int slots = (n + 4 + 15) / 16 * 16;
+    uint32_t* slot = static_cast<uint32_t*>(aligned_alloc(64, sizeof(uint32_t) * slots));
+    for (int i = 0; i < slots; ++i) slot[i] = 0xDEADBEEFu;        // stale words the prefetches may read
+    for (int i = 0; i < n; ++i) slot[i + 1] = (freqs[i] << REPLAY_ID_BITS) | (uint32_t)i;
+    for (int i = 0; i < 2 * n; ++i) par[i] = 0;
+    if (mode == 2) replay_narrow<2>(slot, n, slots, par);
+    else replay_narrow<1>(slot, n, slots, par);
+    free(slot);
+    return 0;
 }
 
 }  // extern "C"

@@ -34,3 +34,59 @@ def test_matches_real_heapq_with_many_ties():
 def test_geometric_frequencies_deep_tree():
     freqs = [2 ** i for i in range(31)]
     assert _build(freqs) == orc.huffman_codes(freqs)
+
+
+# ---- the device builder's packed 32-bit replay (csrc/hic_replay.cuh), run on the host ---------------
+def _harness():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_harness", "libhic_cpu_harness.so")
+    import __graft_entry__
+    __graft_entry__.build()
+    return ctypes.CDLL(path)
+
+
+def _codes_from_parents(par, n):
+    """What huffman_codes_kernel reads off the parent links: leaf -> root, first popped (left) = '1'."""
+    root = 2 * n - 2
+    out = []
+    for i in range(n):
+        node, bits = i, ""
+        while node != root:
+            p = int(par[node])
+            bits = ("1" if p & 0x8000 else "0") + bits
+            node = p & 0x7FFF
+        out.append(bits)
+    return out
+
+
+def _replay_narrow(freqs, mode):
+    lib = _harness()
+    f = np.ascontiguousarray(freqs, np.uint32)
+    par = np.zeros(2 * len(f), np.uint16)
+    rc = lib.hx_replay_narrow(f.ctypes.data_as(ctypes.c_void_p), len(f), mode, par.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, rc
+    return _codes_from_parents(par, len(f))
+
+
+def test_packed_replay_matches_real_heapq():
+    rng = np.random.default_rng(1)
+    for mode in (1, 2):
+        for n in list(range(2, 70)) + [100, 255, 256, 257, 1000, 1431, 2047, 2048, 4099, 8192]:
+            for hi in (2, 3, 5, 31):
+                freqs = rng.integers(1, hi, n)
+                assert _replay_narrow(freqs, mode) == orc.huffman_codes(freqs), (mode, n, hi)
+        # skewed: a few heavy symbols and a long tail of ones (what DC-difference histograms mode like)
+        for n in (300, 1737, 3000):
+            freqs = np.ones(n, np.int64)
+            freqs[:40] = rng.integers(1, 4000, 40)
+            rng.shuffle(freqs)
+            assert _replay_narrow(freqs, mode) == orc.huffman_codes(freqs), (mode, n)
+        freqs = [2 ** i for i in range(17)]                       # sum 2^17 - 1: deepest tree that still packs
+        assert _replay_narrow(freqs, mode) == orc.huffman_codes(freqs)
+
+
+def test_packed_replay_refuses_what_does_not_pack():
+    lib = _harness()
+    f = np.array([1 << 17, 1 << 17], np.uint32)                   # sum = 2^18
+    par = np.zeros(4, np.uint16)
+    assert lib.hx_replay_narrow(f.ctypes.data_as(ctypes.c_void_p), 2, 1, par.ctypes.data_as(ctypes.c_void_p)) == 2
