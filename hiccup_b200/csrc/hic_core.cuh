@@ -320,68 +320,111 @@ HIC_HD int reflect101(int i, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast float32 8-point transforms (Arai-Agui-Nakajima factorisation: 5 multiplies, 29 adds).
-// Forward: out[k] = S_k / g_k with S_k = sum_n x_n cos((2n+1) k pi / 16), g_0 = 1,
-// g_k = 1 / (2 cos(k pi / 16)).  Inverse: with in[k] = X_k * h_k, h_0 = 1, h_k = 2 cos(k pi / 16),
-// out[n] = X_0 + 2 sum_k X_k cos(pi k (2n+1) / 16)  (scipy's unnormalised DCT-III).
-// The scale factors are folded into the quantisation tables by the callers.
+// fast float32 8-point transforms: even / odd split with a DENSE odd part.
+//
+// Forward (DCT-II): s_i = x_i + x_{7-i}, d_i = x_i - x_{7-i}; the even outputs are a 4-point DCT of s
+// (two butterflies + one rotation written as two FMAs), the odd outputs are the 4x4 matrix
+// cos((2i+1) k pi / 16) applied to d with every row divided by its first entry, i.e. three FMAs per
+// output.  8 + 8 + 12 = 28 operations (Arai-Agui-Nakajima needs 29 adds + 5 multiplies: it saves
+// multiplications, which cost nothing on FMA hardware), and -- what matters here -- no cancellation between
+// large intermediates: a rigorous first-order bound of the float32 rounding error of the two-pass 8x8
+// transform is 12.6 units of 4 u E (u = 2^-24, E = sum |x|) for the worst coefficient against 224 for AAN,
+// and 9.8 units of 4 u S / 256 against 337 for the inverse (csrc/hic_dct_bound.h derives the bounds from
+// THIS code by running it on a value type that carries error bounds; tools/dct_error_bound.py is the
+// independent Python derivation; tests/test_oracle_dct.py compares the two and searches for bad blocks).
+// Output k is S_k * eo_forward_scale(k), S_k = sum_n x_n cos((2n+1) k pi / 16); the scale factors are
+// folded into the quantisation tables by the callers.
+//
+// Inverse (scipy's unnormalised DCT-III, out[n] = X_0 + 2 sum_k X_k cos(pi k (2n+1) / 16)): the mirror.
+// Input k must be X_k * eo_inverse_prescale(k) (folded into the dequantisation table).
+//
+// T is float, double, the packed two-lane f2 (hic_f32x2.cuh) or the bound-carrying value of hic_dct_bound.h;
+// eo_fma(a, b, c) = a * b + c in one rounding where the type has a fused operation.
 // ------------------------------------------------------------------------------------------------
+HIC_HD float eo_fma(float a, float b, float c) { return fmaf(a, b, c); }
+HIC_HD double eo_fma(double a, double b, double c) { return fma(a, b, c); }
+
+#define HIC_EO_T 0.41421356237309503445          /* tan(pi/8) */
+/* ratios of c_m = cos(m pi/16): the odd rows of the forward matrix divided by their first entry */
+#define HIC_EO_F13 0.84775906502257347697        /* c3/c1 */
+#define HIC_EO_F15 0.56645449735052155749        /* c5/c1 */
+#define HIC_EO_F17 0.19891236737965806158        /* c7/c1 */
+#define HIC_EO_F37 0.23463313526982051971        /* c7/c3 */
+#define HIC_EO_F31 1.17958042710327459801        /* c1/c3 */
+#define HIC_EO_F35 0.66817863791929898998        /* c5/c3 */
+#define HIC_EO_F51 1.76536686473017923049        /* c1/c5 */
+#define HIC_EO_F57 0.35115330235708458462        /* c7/c5 */
+#define HIC_EO_F53 1.49660576266548894786        /* c3/c5 */
+#define HIC_EO_F75 2.84775906502257303288        /* c5/c7 */
+#define HIC_EO_F73 4.26197262739566706813        /* c3/c7 */
+#define HIC_EO_F71 5.02733949212584629862        /* c1/c7 */
+
+// the part after the first butterflies: s_i = x_i + x_{7-i}, d_i = x_i - x_{7-i}
 template <typename T>
-HIC_HD void aan_forward8(T& d0, T& d1, T& d2, T& d3, T& d4, T& d5, T& d6, T& d7) {
-    const T t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6;
-    const T t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
-    const T e10 = t0 + t3, e13 = t0 - t3, e11 = t1 + t2, e12 = t1 - t2;
-    d0 = e10 + e11;
-    d4 = e10 - e11;
-    const T z1 = (e12 + e13) * T(0.70710678118654752440);
-    d2 = e13 + z1;
-    d6 = e13 - z1;
-    const T o10 = t4 + t5, o11 = t5 + t6, o12 = t6 + t7;
-    const T z5 = (o10 - o12) * T(0.38268343236508977173);
-    const T z2 = T(0.54119610014619698440) * o10 + z5;
-    const T z4 = T(1.30656296487637652786) * o12 + z5;
-    const T z3 = o11 * T(0.70710678118654752440);
-    const T z11 = t7 + z3, z13 = t7 - z3;
-    d5 = z13 + z2;
-    d3 = z13 - z2;
-    d1 = z11 + z4;
-    d7 = z11 - z4;
+HIC_HD void eo_forward8_tail(const T& s0, const T& s1, const T& s2, const T& s3, const T& d0, const T& d1, const T& d2,
+                             const T& d3, T& x0, T& x1, T& x2, T& x3, T& x4, T& x5, T& x6, T& x7) {
+    const T a = s0 + s3, p = s0 - s3, b = s1 + s2, q = s2 - s1;          // q = -(s1 - s2)
+    x0 = a + b;
+    x4 = a - b;                                                         // S_4 / cos(pi/4)
+    x2 = eo_fma(T(-HIC_EO_T), q, p);                                    // S_2 / cos(pi/8)
+    x6 = eo_fma(T(HIC_EO_T), p, q);                                     // S_6 / cos(pi/8)
+    // odd part: S_k / cos(k pi/16)
+    x1 = eo_fma(T(HIC_EO_F17), d3, eo_fma(T(HIC_EO_F15), d2, eo_fma(T(HIC_EO_F13), d1, d0)));
+    x3 = eo_fma(T(-HIC_EO_F35), d3, eo_fma(T(-HIC_EO_F31), d2, eo_fma(T(-HIC_EO_F37), d1, d0)));
+    x5 = eo_fma(T(HIC_EO_F53), d3, eo_fma(T(HIC_EO_F57), d2, eo_fma(T(-HIC_EO_F51), d1, d0)));
+    x7 = eo_fma(T(-HIC_EO_F71), d3, eo_fma(T(HIC_EO_F73), d2, eo_fma(T(-HIC_EO_F75), d1, d0)));
 }
 
 template <typename T>
-HIC_HD void aan_inverse8(T& d0, T& d1, T& d2, T& d3, T& d4, T& d5, T& d6, T& d7) {
-    const T e10 = d0 + d4, e11 = d0 - d4, e13 = d2 + d6;
-    const T e12 = (d2 - d6) * T(1.41421356237309504880) - e13;
-    const T t0 = e10 + e13, t3 = e10 - e13, t1 = e11 + e12, t2 = e11 - e12;
-    const T z13 = d5 + d3, z10 = d5 - d3, z11 = d1 + d7, z12 = d1 - d7;
-    const T t7 = z11 + z13;
-    const T o11 = (z11 - z13) * T(1.41421356237309504880);
-    const T z5 = (z10 + z12) * T(1.84775906502257351225);
-    const T o10 = z5 - z12 * T(1.08239220029239396880);
-    const T o12 = z5 - z10 * T(2.61312592975275305571);
-    const T t6 = o12 - t7, t5 = o11 - t6, t4 = o10 - t5;
-    d0 = t0 + t7;
-    d7 = t0 - t7;
-    d1 = t1 + t6;
-    d6 = t1 - t6;
-    d2 = t2 + t5;
-    d5 = t2 - t5;
-    d3 = t3 + t4;
-    d4 = t3 - t4;
+HIC_HD void eo_forward8(T& x0, T& x1, T& x2, T& x3, T& x4, T& x5, T& x6, T& x7) {
+    const T s0 = x0 + x7, d0 = x0 - x7, s1 = x1 + x6, d1 = x1 - x6;
+    const T s2 = x2 + x5, d2 = x2 - x5, s3 = x3 + x4, d3 = x3 - x4;
+    eo_forward8_tail(s0, s1, s2, s3, d0, d1, d2, d3, x0, x1, x2, x3, x4, x5, x6, x7);
 }
 
-// forward scale g_k and inverse prescale h_k (see above)
-HIC_HD double aan_g(int k) { return k == 0 ? 1.0 : 1.0 / (2.0 * cos(k * 3.14159265358979323846 / 16.0)); }
-HIC_HD double aan_h(int k) { return k == 0 ? 1.0 : 2.0 * cos(k * 3.14159265358979323846 / 16.0); }
+// in: X_k * eo_inverse_prescale(k).  Pivots (coefficient 1): X_1 in o0, X_5 in o1, X_3 in o2, X_7 in o3.
+template <typename T>
+HIC_HD void eo_inverse8(T& x0, T& x1, T& x2, T& x3, T& x4, T& x5, T& x6, T& x7) {
+    const T A = x0 + x4, B = x0 - x4;
+    const T C = eo_fma(T(HIC_EO_T), x6, x2);                            // in2 + t in6
+    const T D = eo_fma(T(-HIC_EO_T), x2, x6);                           // in6 - t in2
+    const T e0 = A + C, e3 = A - C, e1 = B - D, e2 = B + D;
+    // odd part: every pivot entry is +-c1, so three ratios serve all twelve products
+    const T o0 = eo_fma(T(-HIC_EO_F17), x7, eo_fma(T(-HIC_EO_F15), x5, eo_fma(T(-HIC_EO_F13), x3, x1)));
+    const T o1 = eo_fma(T(HIC_EO_F15), x7, eo_fma(T(HIC_EO_F17), x3, eo_fma(T(HIC_EO_F13), x1, x5)));
+    const T o2 = eo_fma(T(-HIC_EO_F13), x7, eo_fma(T(-HIC_EO_F17), x5, eo_fma(T(HIC_EO_F15), x1, x3)));
+    const T o3 = eo_fma(T(-HIC_EO_F13), x5, eo_fma(T(HIC_EO_F15), x3, eo_fma(T(HIC_EO_F17), x1, x7)));
+    x0 = e0 + o0;
+    x7 = e0 - o0;
+    x1 = e1 + o1;
+    x6 = e1 - o1;
+    x2 = e2 + o2;
+    x5 = e2 - o2;
+    x3 = e3 + o3;
+    x4 = e3 - o3;
+}
 
-// Safety factor of the near-tie band: a float32 quantised value v = C/q is trusted when its
-// distance to the nearest half-integer exceeds HIC_TIE_KAPPA * 2^-24 * 4 * E / q, E = sum |x| over
-// the block.  (A first-order bound for the two AAN passes is ~14; tests/cpu_harness measures the
-// observed maximum, see DESIGN.md.)
-#define HIC_TIE_KAPPA 16.0
-// Same idea for the decode transform: a float32 sample p is trusted when its distance to the nearest
-// integer (where the reference's uint8 truncation steps) exceeds HIC_INV_KAPPA * 2^-24 * 4 * S / 256,
-// S = sum |coef * q| over the block.
-#define HIC_INV_KAPPA 16.0
+// Scale factors, derived by running the transforms above in double on unit vectors (so they cannot drift
+// from the code): forward output k = S_k * eo_forward_scale(k); inverse input k = X_k * eo_inverse_prescale(k).
+inline double eo_forward_scale(int k) {
+    double x[8] = {1, 0, 0, 0, 0, 0, 0, 0};                     // S_k of the unit impulse at n = 0 is cos(k pi/16)
+    eo_forward8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+    return x[k] / cos(k * 3.14159265358979323846 / 16.0);
+}
+inline double eo_inverse_prescale(int k) {
+    double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    x[k] = 1.0;
+    eo_inverse8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+    const double want = k == 0 ? 1.0 : 2.0 * cos(k * 3.14159265358979323846 / 16.0);      // coefficient of X_k in out[0]
+    return want / x[0];
+}
+
+// The near-tie bands.  A float32 quantised value C/q is trusted when its distance to the nearest
+// half-integer exceeds kappa(u, v) * 4 u E / q (u = 2^-24, E = sum |x - 128| over the block); a float32
+// decoded sample when its distance to the nearest integer (where the reference's uint8 truncation steps)
+// exceeds 4 u / 256 * sum_k w_k |coef_k q_k| + 2^-15.  kappa(u, v) and w_k are RIGOROUS first-order bounds
+// of the rounding error of the code above (hic_dct_bound.h), times HIC_BAND_MARGIN for everything of
+// second order; blocks inside a band are redone in float64 by the fix-up kernels.
+#define HIC_BAND_MARGIN 1.125
 
 }  // namespace hic

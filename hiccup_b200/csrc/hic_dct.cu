@@ -9,6 +9,7 @@
 #include <string.h>
 #include <mutex>
 #include "hic_core.cuh"
+#include "hic_dct_bound.h"
 #include "hic_f32x2.cuh"
 #include "hic_runtime.cuh"
 
@@ -18,10 +19,11 @@ namespace hic {
 // constant tables (per device)
 // ------------------------------------------------------------------------------------------------
 struct DctTables {
-    float rq[2][64];     // [0 = luminance, 1 = chroma][natural index]: 4 g_u g_v / q  (forward)
-    float qf[2][64];     // q as float
-    float dq[2][64];     // q h_u h_v / 256 (inverse)
-    float rcpq[2][64];   // 1 / q
+    float2 rq2[2][64];   // [0 = luminance, 1 = chroma][natural index]: 4 / (scale_u scale_v q), twice (both f32x2 lanes)
+    float rq[2][64];     // the same once (the one-block-per-thread variant pairs neighbouring columns)
+    float kq[2][64];     // near-tie band per unit E: kappa(u, v) * margin * 4 u / q   (0 for DC: it is exact)
+    float dq[2][64];     // q prescale_u prescale_v / 256 (inverse)
+    float qw[2][64];     // inverse band weight: q * w(u, v) * margin
     int qi[2][64];       // q
     int izz[64];         // natural index -> scan position
 };
@@ -39,18 +41,27 @@ static int ensure_tables() {
     HIC_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
     if (dev < 64 && done[dev]) return HIC_OK;
-    DctTables t;
-    for (int kind = 0; kind < 2; ++kind)
-        for (int u = 0; u < 8; ++u)
-            for (int v = 0; v < 8; ++v) {
-                const int q = (kind == 0 ? h_lum : h_chroma)[8 * u + v];
-                t.rq[kind][8 * u + v] = (float)(4.0 * aan_g(u) * aan_g(v) / q);
-                t.qf[kind][8 * u + v] = (float)q;
-                t.dq[kind][8 * u + v] = (float)(q * aan_h(u) * aan_h(v) / 256.0);
-                t.qi[kind][8 * u + v] = q;
-                t.rcpq[kind][8 * u + v] = (float)(1.0 / q);
-            }
-    for (int k = 0; k < 64; ++k) t.izz[h_zigzag[k]] = k;
+    static DctTables t;
+    static bool built = false;
+    if (!built) {
+        const DctBounds bounds = dct_bounds();          // rigorous float32 error bounds of the transforms (hic_dct_bound.h)
+        const double u24 = 1.0 / 16777216.0;
+        for (int kind = 0; kind < 2; ++kind)
+            for (int u = 0; u < 8; ++u)
+                for (int v = 0; v < 8; ++v) {
+                    const int nat = 8 * u + v;
+                    const int q = (kind == 0 ? h_lum : h_chroma)[nat];
+                    const float rq = (float)(4.0 / (eo_forward_scale(u) * eo_forward_scale(v) * q));
+                    t.rq2[kind][nat] = make_float2(rq, rq);
+                    t.rq[kind][nat] = rq;
+                    t.kq[kind][nat] = nat == 0 ? 0.f : (float)(bounds.kappa_fwd[nat] * HIC_BAND_MARGIN * 4.0 * u24 / q);
+                    t.dq[kind][nat] = (float)(q * eo_inverse_prescale(u) * eo_inverse_prescale(v) / 256.0);
+                    t.qw[kind][nat] = (float)(q * bounds.w_inv[nat] * HIC_BAND_MARGIN);
+                    t.qi[kind][nat] = q;
+                }
+        for (int k = 0; k < 64; ++k) t.izz[h_zigzag[k]] = k;
+        built = true;
+    }
     HIC_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
     if (dev < 64) done[dev] = true;
     return HIC_OK;
@@ -85,12 +96,16 @@ static int geometry_of(int h, int w, hic_dct_geometry* g) {
 // K1: fused encode transform
 // ------------------------------------------------------------------------------------------------
 namespace k1 {
-// Tile: 128 x 64 luminance pixels = 16 x 8 Y blocks + 8 x 4 Cr blocks + 8 x 4 Cb blocks = 192
-// blocks, one thread each in the transform stage.  The staged RGB region covers image columns
-// x0-16 .. x0+132 and rows y0-2 .. y0+64 (pyrDown needs columns x0-2 .. x0+128 and rows
-// y0-2 .. y0+64).  The 16-pixel lead is what TMA demands: the innermost start offset of a box must
-// be a multiple of 16 bytes (a 12-byte-aligned start faults with "illegal instruction"; probed in
-// tools/scratch/tma_test.cu), and 3 * (x0 - lead) is a multiple of 16 only for lead = 0 mod 16.
+// Tile: 128 x 64 luminance pixels = 16 x 8 Y blocks + 8 x 4 Cr blocks + 8 x 4 Cb blocks = 192 blocks.
+// In the transform stage a thread carries TWO blocks, one in each lane of the packed f32x2 registers
+// (two luminance blocks four block rows apart, or the Cr and the Cb block of one position): every
+// butterfly, FMA and quantiser step is one instruction for both, nothing is ever transposed between the
+// row and the column pass, and the constants are loaded once per pair -- 96 threads per tile.
+// The staged RGB region covers image columns x0-16 .. x0+132 and rows y0-2 .. y0+64 (pyrDown needs
+// columns x0-2 .. x0+128 and rows y0-2 .. y0+64).  The 16-pixel lead is what TMA demands: the innermost
+// start offset of a box must be a multiple of 16 bytes (a 12-byte-aligned start faults with "illegal
+// instruction"; probed in tools/scratch/tma_test.cu), and 3 * (x0 - lead) is a multiple of 16 only for
+// lead = 0 mod 16.
 constexpr int TW = 128;
 constexpr int TH = 64;
 constexpr int RH = TH + 3;            // staged rows
@@ -103,9 +118,11 @@ constexpr int SPIX = RWORDS * 4 / 3;  // whole pixels in a staged row
 constexpr int C_PITCH = 136;          // Cr/Cb staging pitch (bytes), indexed by region pixel (34 groups of 4)
 constexpr int CW = TW / 2;            // chroma tile
 constexpr int CH = TH / 2;
+constexpr int CD_PITCH = CW + 8;      // pitch of the downsampled chroma tiles: block rows land in different banks
 constexpr int NY_BLOCKS = (TW / 8) * (TH / 8);       // 128
-constexpr int NC_BLOCKS = (CW / 8) * (CH / 8);       // 32
-constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // 192
+constexpr int NC_BLOCKS = (CW / 8) * (CH / 8);       // 32 per chroma plane
+constexpr int NY_PAIRS = NY_BLOCKS / 2;              // two blocks per thread: 64 threads carry blocks (by, bx) and (by + 4, bx)
+constexpr int threads_of(int bpt) { return bpt == 2 ? NY_PAIRS + NC_BLOCKS : NY_BLOCKS + 2 * NC_BLOCKS; }      // 96 | 192
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
 constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
 
@@ -129,11 +146,11 @@ struct Smem {
     alignas(16) uint8_t y[TH][TW];
     union alignas(16) {
         uint8_t cr[RH][C_PITCH];                     // stage 1 -> 2a
-        uint8_t crd[CH][CW];                         // stage 2b -> 3 (cr is dead by then)
+        uint8_t crd[CH][CD_PITCH];                   // stage 2b -> 3 (cr is dead by then)
     };
     union alignas(16) {
         uint8_t cb[RH][C_PITCH];
-        uint8_t cbd[CH][CW];
+        uint8_t cbd[CH][CD_PITCH];
     };
     alignas(8) unsigned long long bar;
 };
@@ -141,36 +158,119 @@ static_assert(sizeof(Smem) <= 57344, "four CTAs per SM: (228 KB - 4 x 1 KB reser
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 8x8 block (as 16 words of bytes, rows of 8) -> quantised zigzag int16 + near-tie mask.
-// Two rows (then two columns) ride in each f32x2 register pair.
-template <int KIND>
-__device__ __forceinline__ bool transform_block(const uint32_t (&wv)[16], int umax, int vmax,
-                                                int16_t* __restrict__ dst) {
-    // sum |x| over the block (exact, integer) for the error band
+// Two 8x8 blocks (each as 16 words of bytes, rows of 8; block A rides in the low lane, B in the high lane)
+// -> quantised zigzag int16 of both + their near-tie flags (bit 0: A, bit 1: B).  `kind` (0 = luminance,
+// 1 = chroma tables) is a run-time value so that there is ONE instance of this long straight-line code for
+// all warps of the CTA: the kernel's top stall is instruction fetch.
+__device__ __forceinline__ unsigned transform_pair(int kind, const uint32_t (&wa)[16], const uint32_t (&wb)[16],
+                                                   int16_t* __restrict__ dst_a, int16_t* __restrict__ dst_b) {
+    // E = sum |x - 128| over each block (exact, integer) for the error band
+    uint32_t ea = 0, eb = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        ea = __vsadu4(wa[i], 0x80808080u) + ea;
+        eb = __vsadu4(wb[i], 0x80808080u) + eb;
+    }
+    const float fea = (float)ea, feb = (float)eb;
+
+    // row pass.  Bytes become floats by splicing them into 2^23 (value 2^23 + byte); the level shift
+    // folds into the first butterflies: d_i = x_i - x_{7-i} is exact as it stands, and with
+    // y_i = x_{7-i} - (2^23 + 128),  s_i = (x_i - 128) + (x_{7-i} - 128) = 2 y_i + d_i, exact as well.
+    const f2 shift(-(8388608.0f + 128.0f)), two(2.0f);
+    f2 a[64];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        f2 x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float fa = __uint_as_float(__byte_perm(wa[2 * r + (c >> 2)], 0x4B000000u, 0x7540 + (c & 3)));
+            const float fb = __uint_as_float(__byte_perm(wb[2 * r + (c >> 2)], 0x4B000000u, 0x7540 + (c & 3)));
+            x[c] = f2(fa, fb);
+        }
+        f2 s[4], d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            d[i] = x[i] - x[7 - i];
+            s[i] = fma2(two, x[7 - i] + shift, d[i]);
+        }
+        eo_forward8_tail(s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3], a[8 * r + 0], a[8 * r + 1], a[8 * r + 2],
+                         a[8 * r + 3], a[8 * r + 4], a[8 * r + 5], a[8 * r + 6], a[8 * r + 7]);
+    }
+    // column pass, in place: a[8 u + v] = coefficient (u, v) of both blocks
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        eo_forward8(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c]);
+    // quantise: t = RN(v * rq + MAGIC) holds round-half-even(v * rq) in its low mantissa bits;
+    // d = v * rq - round(v * rq); near a tie when |d| + E * kq >= 1/2 (kq = the rigorous error bound of this
+    // coefficient per unit E, hic_dct_bound.h; 0 for DC, which is an exact integer)
+    float worst_a = 0.f, worst_b = 0.f;
+    const f2 magic2(MAGIC);
+    const float2* __restrict__ rq2 = c_tab.rq2[kind];
+    const float* __restrict__ kqt = c_tab.kq[kind];
+#pragma unroll
+    for (int nat = 0; nat < 64; ++nat) {
+        f2 rq;
+        rq.v = *reinterpret_cast<const unsigned long long*>(&rq2[nat]);
+        const f2 t = fma2(a[nat], rq, magic2);
+        const f2 d = fma2(a[nat], rq, magic2 - t);
+        a[nat] = t;
+        if (nat != 0) {
+            const float kq = kqt[nat];
+            worst_a = fmaxf(worst_a, fmaf(fea, kq, fabsf(d.lo())));
+            worst_b = fmaxf(worst_b, fmaf(feb, kq, fabsf(d.hi())));
+        }
+    }
+    constexpr uint8_t zz[64] = HIC_ZIGZAG8;
+    int4* out_a = reinterpret_cast<int4*>(dst_a);
+    int4* out_b = reinterpret_cast<int4*>(dst_b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int4 wa4, wb4;
+        int* pa = reinterpret_cast<int*>(&wa4);
+        int* pb = reinterpret_cast<int*>(&wb4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const f2 t0 = a[zz[8 * j + 2 * e]], t1 = a[zz[8 * j + 2 * e + 1]];
+            pa[e] = __byte_perm(__float_as_int(t0.lo()), __float_as_int(t1.lo()), 0x5410);
+            pb[e] = __byte_perm(__float_as_int(t0.hi()), __float_as_int(t1.hi()), 0x5410);
+        }
+        out_a[j] = wa4;
+        if (dst_b) out_b[j] = wb4;
+    }
+    // some coefficient is within the float32 error band of a rounding tie: the fix-up kernel redoes the
+    // block in float64 (the slack covers the roundings of this very comparison)
+    return (worst_a >= 0.499999f ? 1u : 0u) | (worst_b >= 0.499999f ? 2u : 0u);
+}
+
+// One 8x8 block per thread: two rows (then two columns) ride in each f32x2 register pair.  Half the
+// registers of transform_pair (twice the warps per SM) at the price of re-pairing the 64 values between the
+// passes.
+__device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&wv)[16], int16_t* __restrict__ dst) {
     uint32_t abs_sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) abs_sum = __vsadu4(wv[i], 0x80808080u) + abs_sum;
-    const float band = (float)(HIC_TIE_KAPPA * 4.0 / 16777216.0) * (float)abs_sum;
-
-    // row pass: rows (2 rp, 2 rp + 1) together; bytes become floats by splicing them into 2^23
-    const f2 shift(-(8388608.0f + 128.0f));
-    f2 a[32];
+    const float fe = (float)abs_sum;
+    const f2 shift(-(8388608.0f + 128.0f)), two(2.0f);
+    f2 a[32];        // a[rp * 8 + v] = row-transformed (rows 2 rp, 2 rp + 1), horizontal frequency v
 #pragma unroll
     for (int rp = 0; rp < 4; ++rp) {
-        f2 d[8];
+        f2 x[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const uint32_t top = wv[4 * rp + (c >> 2)], bot = wv[4 * rp + 2 + (c >> 2)];
-            const float ft = __uint_as_float(__byte_perm(top, 0x4B000000u, 0x7540 + (c & 3)));
-            const float fb = __uint_as_float(__byte_perm(bot, 0x4B000000u, 0x7540 + (c & 3)));
-            d[c] = f2(ft, fb) + shift;
+            x[c] = f2(__uint_as_float(__byte_perm(top, 0x4B000000u, 0x7540 + (c & 3))),
+                      __uint_as_float(__byte_perm(bot, 0x4B000000u, 0x7540 + (c & 3))));
         }
-        aan_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+        f2 s[4], d[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[rp * 8 + c] = d[c];
+        for (int i = 0; i < 4; ++i) {
+            d[i] = x[i] - x[7 - i];
+            s[i] = fma2(two, x[7 - i] + shift, d[i]);
+        }
+        eo_forward8_tail(s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3], a[8 * rp + 0], a[8 * rp + 1], a[8 * rp + 2],
+                         a[8 * rp + 3], a[8 * rp + 4], a[8 * rp + 5], a[8 * rp + 6], a[8 * rp + 7]);
     }
-    // column pass: columns (2 cp, 2 cp + 1) together
-    f2 b[32];        // b[r * 4 + cp] = natural (8 r + 2 cp, 8 r + 2 cp + 1)
+    f2 b[32];        // b[u * 4 + cp] = coefficients (u, 2 cp) and (u, 2 cp + 1)
 #pragma unroll
     for (int cp = 0; cp < 4; ++cp) {
         f2 d[8];
@@ -179,66 +279,88 @@ __device__ __forceinline__ bool transform_block(const uint32_t (&wv)[16], int um
             const f2 left = a[(r >> 1) * 8 + 2 * cp], right = a[(r >> 1) * 8 + 2 * cp + 1];
             d[r] = (r & 1) ? f2(left.hi(), right.hi()) : f2(left.lo(), right.lo());
         }
-        aan_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+        eo_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
 #pragma unroll
         for (int r = 0; r < 8; ++r) b[r * 4 + cp] = d[r];
     }
-    // quantise: t = RN(v * rq + MAGIC) holds round-half-even(v * rq) in its low mantissa bits;
-    // d = v * rq - round(v * rq); near a tie when |d| + band / q >= 1/2
-    int bits[64];
     float worst = 0.f;
     const f2 magic2(MAGIC);
+    const float* __restrict__ rqt = c_tab.rq[kind];
+    const float* __restrict__ kqt = c_tab.kq[kind];
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
         const int n0 = (p >> 2) * 8 + 2 * (p & 3);
-        const f2 rq(c_tab.rq[KIND][n0], c_tab.rq[KIND][n0 + 1]);
+        f2 rq;
+        rq.v = *reinterpret_cast<const unsigned long long*>(&rqt[n0]);
         const f2 t = fma2(b[p], rq, magic2);
         const f2 d = fma2(b[p], rq, magic2 - t);
-        bits[n0] = __float_as_int(t.lo());
-        bits[n0 + 1] = __float_as_int(t.hi());
-        if (p != 0) worst = fmaxf(worst, fmaf(band, c_tab.rcpq[KIND][n0], fabsf(d.lo())));   // DC is exact
-        worst = fmaxf(worst, fmaf(band, c_tab.rcpq[KIND][n0 + 1], fabsf(d.hi())));
-    }
-    const bool cropped = (umax < 8) | (vmax < 8);
-    if (cropped) {
-#pragma unroll
-        for (int nat = 0; nat < 64; ++nat)
-            if ((nat >> 3) >= umax || (nat & 7) >= vmax) bits[nat] = __float_as_int(MAGIC);
+        b[p] = t;
+        if (p != 0) worst = fmaxf(worst, fmaf(fe, kqt[n0], fabsf(d.lo())));      // DC is exact
+        worst = fmaxf(worst, fmaf(fe, kqt[n0 + 1], fabsf(d.hi())));
     }
     constexpr uint8_t zz[64] = HIC_ZIGZAG8;
     int4* out = reinterpret_cast<int4*>(dst);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        int4 w;
-        w.x = __byte_perm(bits[zz[8 * j + 0]], bits[zz[8 * j + 1]], 0x5410);
-        w.y = __byte_perm(bits[zz[8 * j + 2]], bits[zz[8 * j + 3]], 0x5410);
-        w.z = __byte_perm(bits[zz[8 * j + 4]], bits[zz[8 * j + 5]], 0x5410);
-        w.w = __byte_perm(bits[zz[8 * j + 6]], bits[zz[8 * j + 7]], 0x5410);
-        out[j] = w;
-    }
-    // some coefficient is within the float32 error band of a rounding tie: the fix-up kernel redoes
-    // this block in float64
-    return worst >= 0.5f;
-}
-
-// keep the first `cols` bytes of each row word pair and the first `rows` rows; the rest become 128
-// (x - 128 = 0: the reference zero-pads after the level shift, transform.py:186-188)
-__device__ __forceinline__ void mask_block(uint32_t (&wv)[16], int rows, int cols) {
-    const uint32_t keep_lo = cols >= 4 ? 0xFFFFFFFFu : ((1u << (8 * cols)) - 1u);
-    const uint32_t keep_hi = cols >= 8 ? 0xFFFFFFFFu : (cols > 4 ? ((1u << (8 * (cols - 4))) - 1u) : 0u);
+        int4 w4;
+        int* pw = reinterpret_cast<int*>(&w4);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const bool row_ok = r < rows;
-        wv[2 * r] = row_ok ? ((wv[2 * r] & keep_lo) | (0x80808080u & ~keep_lo)) : 0x80808080u;
-        wv[2 * r + 1] = row_ok ? ((wv[2 * r + 1] & keep_hi) | (0x80808080u & ~keep_hi)) : 0x80808080u;
+        for (int e = 0; e < 4; ++e) {
+            const int n_lo = zz[8 * j + 2 * e], n_hi = zz[8 * j + 2 * e + 1];
+            const f2 t0 = b[(n_lo >> 3) * 4 + ((n_lo & 7) >> 1)], t1 = b[(n_hi >> 3) * 4 + ((n_hi & 7) >> 1)];
+            const int v0 = __float_as_int((n_lo & 1) ? t0.hi() : t0.lo()), v1 = __float_as_int((n_hi & 1) ? t1.hi() : t1.lo());
+            pw[e] = __byte_perm(v0, v1, 0x5410);
+        }
+        out[j] = w4;
+    }
+    return worst >= 0.499999f ? 1u : 0u;
+}
+
+// Blocks that hang over the bottom / right edge of their plane: the reference crops the coefficient plane
+// back to the channel shape (transform.py:63) and re-pads it with zeros (codec.py:288,294), so
+// coefficients at rows >= rows or columns >= cols of such a block are zero.  Rare (edge blocks of shapes
+// that are not multiples of 8): a separate pass over the 128 bytes the thread has just stored.
+__device__ __noinline__ void crop_block(int16_t* __restrict__ blk, int rows, int cols) {
+    for (int k = 0; k < 64; ++k) {
+        const int nat = c_zigzag[k];
+        if ((nat >> 3) >= rows || (nat & 7) >= cols) blk[k] = 0;
     }
 }
 
-template <bool USE_TMA>
-__global__ void __launch_bounds__(THREADS, 4)
+__device__ __forceinline__ void push_ties(unsigned flagged, uint32_t block_index, hic_tie_record* __restrict__ ties,
+                                          uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    // one slot request per warp
+    const unsigned m = __ballot_sync(0xffffffffu, flagged != 0);
+    if (m) {
+        const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&stats[0], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flagged) {
+            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < tie_capacity) {
+                hic_tie_record rec;
+                rec.block = block_index;
+                rec.reserved = 0;
+                rec.mask = ~0ull;
+                ties[slot] = rec;
+            } else {
+                atomicAdd(&stats[3], 1u);
+            }
+        }
+    }
+}
+
+// BPT = blocks per thread in the transform stage: 2 -> 96 threads, everything packed, no re-pairing between the
+// passes, 168 registers (12 warps per SM); 1 -> 192 threads, 80-odd registers (24 warps per SM).
+template <bool USE_TMA, int BPT>
+__global__ void __launch_bounds__(threads_of(BPT), 4)
 forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
                hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
                uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    constexpr int THREADS = threads_of(BPT);
+    constexpr int WARPS = THREADS / 32;
+    constexpr int R16 = THREADS / 16;          // rows per step of the 16-lanes-per-row stages
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -284,7 +406,7 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
             o[2] = q[2];
         }
     }
-    __syncthreads();           // barrier initialised / generic load + tables visible
+    __syncthreads();           // barrier initialised / generic load visible
     if (USE_TMA) {
         const uint32_t bar = smem_u32(&s.bar);
         asm volatile(
@@ -331,9 +453,9 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
 
     // ---- stage 1: colour conversion, four pixels (three words) at a time ----
     // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes.  Groups 1..32
-    // of a row (the 128 tile columns) go one per lane, rows warp + 6 k; the two halo groups per row
+    // of a row (the 128 tile columns) go one per lane, rows warp + WARPS k; the two halo groups per row
     // (columns x0-4..x0-1 and x0+128..x0+131) are a short extra pass.  All trip counts are compile-time.
-    static_assert(THREADS == 192 && RGROUPS == 34 && TW == 128, "stage 1 mapping");
+    static_assert(RGROUPS == 34 && TW == 128, "stage 1 mapping");
     auto convert_group = [&](int ry, int gx, bool store_y) {
         const uint32_t* rw = s.rgb + ry * RWORDS + 3 * (gx + SKIP / 4);
         const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
@@ -358,21 +480,25 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     {
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-        for (int k = 0; k < (RH + 5) / 6; ++k) {
-            const int ry = warp + 6 * k;
+        for (int k = 0; k < (RH + WARPS - 1) / WARPS; ++k) {
+            const int ry = warp + WARPS * k;
             if (ry < RH) convert_group(ry, lane + 1, ry >= 2 && ry < 2 + TH);
         }
-        if (tid < 2 * RH) convert_group(tid >> 1, (tid & 1) ? RGROUPS - 1 : 0, false);
+#pragma unroll
+        for (int k = 0; k < (2 * RH + THREADS - 1) / THREADS; ++k) {
+            const int i = tid + THREADS * k;
+            if (i < 2 * RH) convert_group(i >> 1, (i & 1) ? RGROUPS - 1 : 0, false);
+        }
     }
     __syncthreads();
 
     // ---- stage 2a: horizontal [1 4 6 4 1] at stride 2; chroma column cx reads region pixels 2 cx + 2 .. 2 cx + 6 ----
-    // 16 four-output groups per row: 12 rows per step, one channel after the other
+    // 16 four-output groups per row: R16 rows per step, one channel after the other
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
-        for (int k = 0; k < (RH + 11) / 12; ++k) {
-            const int ry = (tid >> 4) + 12 * k, j = tid & 15;
+        for (int k = 0; k < (RH + R16 - 1) / R16; ++k) {
+            const int ry = (tid >> 4) + R16 * k, j = tid & 15;
             if (ry < RH) {
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
                 const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
@@ -390,8 +516,8 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
-        for (int k = 0; k < (CH + 11) / 12; ++k) {
-            const int cy = (tid >> 4) + 12 * k, j = tid & 15;
+        for (int k = 0; k < (CH + R16 - 1) / R16; ++k) {
+            const int cy = (tid >> 4) + R16 * k, j = tid & 15;
             if (cy < CH) {
                 uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
 #pragma unroll
@@ -407,66 +533,126 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
     __syncthreads();
+    // ---- stage 2c (edge tiles only): samples outside the planes become 128, i.e. zero after the level
+    // shift -- the reference zero-pads after x - 128 (transform.py:186-188).  Only the part of the tile past
+    // the plane is visited. ----
+    {
+        const int vy = min(TH, h - y0), vx = min(TW, w - x0);                          // valid rows / columns of the tiles
+        const int vcy = min(CH, g.hc - y0 / 2), vcx = min(CW, g.wc - x0 / 2);
+        if (vy < TH || vx < TW || vcy < CH || vcx < CW) {
+            const int ry0 = max(vy, 0), rc0 = max(vcy, 0);
+            for (int i = tid; i < (TH - ry0) * (TW / 4); i += THREADS)                 // whole rows below the plane
+                *reinterpret_cast<uint32_t*>(&s.y[ry0 + i / (TW / 4)][4 * (i % (TW / 4))]) = 0x80808080u;
+            for (int i = tid; i < (CH - rc0) * (CW / 4); i += THREADS) {
+                *reinterpret_cast<uint32_t*>(&s.crd[rc0 + i / (CW / 4)][4 * (i % (CW / 4))]) = 0x80808080u;
+                *reinterpret_cast<uint32_t*>(&s.cbd[rc0 + i / (CW / 4)][4 * (i % (CW / 4))]) = 0x80808080u;
+            }
+            if (vx < TW) {                                                              // columns right of the plane
+                const int c0 = max(vx, 0), nc = TW - c0;
+                for (int i = tid; i < ry0 * nc; i += THREADS) s.y[i / nc][c0 + i % nc] = 128;
+            }
+            if (vcx < CW) {
+                const int c0 = max(vcx, 0), nc = CW - c0;
+                for (int i = tid; i < rc0 * nc; i += THREADS) {
+                    s.crd[i / nc][c0 + i % nc] = 128;
+                    s.cbd[i / nc][c0 + i % nc] = 128;
+                }
+            }
+            __syncthreads();
+        }
+    }
 
-    // ---- stage 3: one 8x8 block per thread ----
-    uint32_t wv[16];
-    bool flagged = false;
-    uint32_t block_index = 0;
-    if (tid < NY_BLOCKS) {
-        const int by = tid / (TW / 8), bx = tid % (TW / 8);
-        const int BY = blockIdx.y * (TH / 8) + by, BX = blockIdx.x * (TW / 8) + bx;
-        if (BY < g.nby_l && BX < g.nbx_l) {
-            const int rows = min(8, h - 8 * BY), cols = min(8, w - 8 * BX);      // valid pixels
+    // ---- stage 3: the 8x8 blocks ----
+    unsigned fl = 0;
+    uint32_t ia = 0, ib = 0;
+    if (BPT == 2) {
+        uint32_t wa[16], wb[16];
+        const uint8_t *pa = nullptr, *pb = nullptr;
+        int pitch = 0, kind = 0, rows_a = 8, rows_b = 8, cols = 8;
+        bool have_a = false, have_b = false;
+        if (tid < NY_PAIRS) {
+            const int by = tid / (TW / 8), bx = tid % (TW / 8);          // blocks (by, bx) and (by + 4, bx)
+            const int BYa = blockIdx.y * (TH / 8) + by, BYb = BYa + 4, BX = blockIdx.x * (TW / 8) + bx;
+            have_a = BYa < g.nby_l && BX < g.nbx_l;
+            have_b = BYb < g.nby_l && BX < g.nbx_l;
+            pa = &s.y[8 * by][8 * bx];
+            pb = &s.y[8 * by + 32][8 * bx];
+            pitch = TW;
+            ia = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BYa * g.nbx_l + BX);
+            ib = ia + 4u * (uint32_t)g.nbx_l;
+            rows_a = h - 8 * BYa;
+            rows_b = h - 8 * BYb;
+            cols = w - 8 * BX;
+        } else {
+            const int local = tid - NY_PAIRS;                               // Cr block in the low lane, Cb in the high lane
+            const int by = local / (CW / 8), bx = local % (CW / 8);
+            const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
+            have_a = have_b = BY < g.nby_c && BX < g.nbx_c;
+            pa = &s.crd[8 * by][8 * bx];
+            pb = &s.cbd[8 * by][8 * bx];
+            pitch = CD_PITCH;
+            kind = 1;
+            ia = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)BY * g.nbx_c + BX);
+            ib = ia + (uint32_t)g.nb_c;
+            rows_a = rows_b = g.hc - 8 * BY;
+            cols = g.wc - 8 * BX;
+        }
+        if (have_a) {            // (false only for block rows / columns past the plane, at the bottom / right edge)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const uint2 t = *reinterpret_cast<const uint2*>(&s.y[8 * by + r][8 * bx]);
-                wv[2 * r] = t.x;
-                wv[2 * r + 1] = t.y;
+                const uint2 ta = *reinterpret_cast<const uint2*>(pa + r * pitch);
+                const uint2 tb = *reinterpret_cast<const uint2*>(pb + r * pitch);
+                wa[2 * r] = ta.x;
+                wa[2 * r + 1] = ta.y;
+                wb[2 * r] = tb.x;
+                wb[2 * r + 1] = tb.y;
             }
-            if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
-            block_index = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
-            flagged = transform_block<0>(wv, rows, cols, coef + (size_t)block_index * 64);
+            fl = transform_pair(kind, wa, wb, coef + (size_t)ia * 64, have_b ? coef + (size_t)ib * 64 : nullptr);
+            if (!have_b) fl &= 1u;
+            if (cols < 8 || rows_a < 8) crop_block(coef + (size_t)ia * 64, min(8, rows_a), min(8, cols));
+            if (have_b && (cols < 8 || rows_b < 8)) crop_block(coef + (size_t)ib * 64, min(8, rows_b), min(8, cols));
         }
     } else {
-        const int plane = (tid - NY_BLOCKS) / NC_BLOCKS;          // 0 = Cr, 1 = Cb
-        const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
-        const int by = local / (CW / 8), bx = local % (CW / 8);
-        const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
-        if (BY < g.nby_c && BX < g.nbx_c) {
-            const int rows = min(8, g.hc - 8 * BY), cols = min(8, g.wc - 8 * BX);
-            const uint8_t (*pl)[CW] = plane == 0 ? s.crd : s.cbd;
+        uint32_t wv[16];
+        const uint8_t* pa = nullptr;
+        int pitch = 0, kind = 0, rows = 8, cols = 8;
+        bool have = false;
+        if (tid < NY_BLOCKS) {
+            const int by = tid / (TW / 8), bx = tid % (TW / 8);
+            const int BY = blockIdx.y * (TH / 8) + by, BX = blockIdx.x * (TW / 8) + bx;
+            have = BY < g.nby_l && BX < g.nbx_l;
+            pa = &s.y[8 * by][8 * bx];
+            pitch = TW;
+            ia = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
+            rows = h - 8 * BY;
+            cols = w - 8 * BX;
+        } else {
+            const int plane = (tid - NY_BLOCKS) / NC_BLOCKS;          // 0 = Cr, 1 = Cb
+            const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
+            const int by = local / (CW / 8), bx = local % (CW / 8);
+            const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
+            have = BY < g.nby_c && BX < g.nbx_c;
+            pa = plane == 0 ? &s.crd[8 * by][8 * bx] : &s.cbd[8 * by][8 * bx];
+            pitch = CD_PITCH;
+            kind = 1;
+            ia = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c + (int64_t)BY * g.nbx_c + BX);
+            rows = g.hc - 8 * BY;
+            cols = g.wc - 8 * BX;
+        }
+        if (have) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const uint2 t = *reinterpret_cast<const uint2*>(&pl[8 * by + r][8 * bx]);
+                const uint2 t = *reinterpret_cast<const uint2*>(pa + r * pitch);
                 wv[2 * r] = t.x;
                 wv[2 * r + 1] = t.y;
             }
-            if (rows < 8 || cols < 8) mask_block(wv, rows, cols);
-            block_index = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c +
-                                     (int64_t)BY * g.nbx_c + BX);
-            flagged = transform_block<1>(wv, rows, cols, coef + (size_t)block_index * 64);
+            fl = transform_single(kind, wv, coef + (size_t)ia * 64);
+            if (cols < 8 || rows < 8) crop_block(coef + (size_t)ia * 64, min(8, rows), min(8, cols));
         }
     }
-    // one slot request per warp (the warps are whole: luminance and chroma threads never share one)
-    const unsigned m = __ballot_sync(0xffffffffu, flagged);
-    if (m) {
-        const unsigned lane = tid & 31, leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&stats[0], (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (flagged) {
-            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
-            if (slot < tie_capacity) {
-                hic_tie_record rec;
-                rec.block = block_index;
-                rec.reserved = 0;
-                rec.mask = ~0ull;
-                ties[slot] = rec;
-            } else {
-                atomicAdd(&stats[3], 1u);
-            }
-        }
-    }
+    // the warps are whole (luminance and chroma threads never share one) and converged again here
+    push_ties(fl & 1u, ia, ties, tie_capacity, stats);
+    if (BPT == 2) push_ties(fl & 2u, ib, ties, tie_capacity, stats);
 }
 
 // Float64 re-evaluation of every flagged block with scipy's exact operation order.  A warp takes FOUR
@@ -626,7 +812,7 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
                                               uint32_t* __restrict__ stats) {
     constexpr uint8_t zz[64] = HIC_ZIGZAG8;
     float v[64];
-    float energy = 0.f;          // S = sum |coef * q|
+    float energy = 0.f;          // sum |coef * q| * w: the error band of the samples
     int ac_bits = 0;
     const int4* in = reinterpret_cast<const int4*>(src);
 #pragma unroll
@@ -640,18 +826,18 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
             const float flo = (float)lo, fhi = (float)hi;
             v[zz[k0]] = flo * c_tab.dq[KIND][zz[k0]];
             v[zz[k0 + 1]] = fhi * c_tab.dq[KIND][zz[k0 + 1]];
-            energy = fmaf(fabsf(flo), c_tab.qf[KIND][zz[k0]], energy);
-            energy = fmaf(fabsf(fhi), c_tab.qf[KIND][zz[k0 + 1]], energy);
+            energy = fmaf(fabsf(flo), c_tab.qw[KIND][zz[k0]], energy);
+            energy = fmaf(fabsf(fhi), c_tab.qw[KIND][zz[k0 + 1]], energy);
             ac_bits |= k0 == 0 ? (words[e] & 0xFFFF0000) : words[e];
         }
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r)
-        aan_inverse8(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5],
-                     v[8 * r + 6], v[8 * r + 7]);
+        eo_inverse8(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5],
+                    v[8 * r + 6], v[8 * r + 7]);
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        aan_inverse8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+        eo_inverse8(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
     const int rows = min(8, ph - 8 * BY), cols = min(8, pw - 8 * BX);
     // distance of every sample to the nearest integer, where the reference's uint8 truncation steps
     float margin = 1e30f;
@@ -678,7 +864,9 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
         }
     }
     // a DC-only block is exact in both float32 and float64 (no rounding happens at all)
-    const float band = (float)(HIC_INV_KAPPA * 4.0 / 16777216.0 / 256.0) * energy + 3.0517578125e-5f;
+    // energy = sum |coef| q w(u, v) margin: the rigorous per-input error weights of hic_dct_bound.h; 2^-15 covers the
+    // rounding of the final + 128 (half an ulp of a value below 512) and of this comparison
+    const float band = (float)(4.0 / 16777216.0 / 256.0) * energy + 3.0517578125e-5f;
     if (ac_bits != 0 && margin <= band) {
         const uint32_t slot = atomicAdd(&stats[0], 1u);
         if (slot < tie_capacity) {
@@ -989,8 +1177,10 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
     int dev = 0;
     HIC_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
         if (dev < 64) attr_set[dev] = true;
     }
     // TMA path: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
@@ -1019,10 +1209,19 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         if (r != CUDA_SUCCESS) use_tma = false;       // fall back to the generic loader
         if (getenv("HIC_DEBUG")) fprintf(stderr, "[hic] tensor map encode -> %d (use_tma=%d)\n", (int)r, (int)use_tma);
     }
-    if (use_tma)
-        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
-    else
-        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    // HIC_K1_BPT (environment, 1 | 2): blocks per thread in the transform stage (A/B timing; same results)
+    static const int bpt = getenv("HIC_K1_BPT") ? atoi(getenv("HIC_K1_BPT")) : 1;
+    if (bpt == 2) {
+        if (use_tma)
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+        else
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    } else {
+        if (use_tma)
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+        else
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    }
     HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     return HIC_OK;
 }

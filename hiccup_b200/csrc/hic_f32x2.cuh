@@ -44,4 +44,7 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     return r;
 }
 
+// the generic name the transform templates of hic_core.cuh use
+__device__ __forceinline__ f2 eo_fma(f2 a, f2 b, f2 c) { return fma2(a, b, c); }
+
 }  // namespace hic

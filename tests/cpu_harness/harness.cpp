@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include "../../hiccup_b200/csrc/hic_core.cuh"
 #include "../../hiccup_b200/csrc/hic_replay.cuh"
+#include "../../hiccup_b200/csrc/hic_dct_bound.h"
 
 using namespace hic;
 
@@ -20,17 +21,32 @@ void hx_ducc_dct3(double* x, int n) { for (int i = 0; i < n; ++i) ducc_dct3_8(x 
 int hx_exact_coef(const int16_t* px, int u, int v, int q) { return exact_quantised_coef(px, u, v, q); }
 double hx_exact_sample(const int32_t* cq, int y, int x) { return exact_decoded_sample(cq, y, x); }
 
-// float32 forward path of K1's transform_block, restated on the host with the same primitives.
+// The rigorous error-bound tables the library builds at initialisation (csrc/hic_dct_bound.h): natural order.
+void hx_dct_bounds(double* kappa_fwd, double* w_inv, double* fwd_scale, double* inv_prescale) {
+    const DctBounds b = dct_bounds();
+    for (int i = 0; i < 64; ++i) {
+        kappa_fwd[i] = b.kappa_fwd[i];
+        w_inv[i] = b.w_inv[i];
+    }
+    for (int k = 0; k < 8; ++k) {
+        fwd_scale[k] = eo_forward_scale(k);
+        inv_prescale[k] = eo_inverse_prescale(k);
+    }
+}
+
+// float32 forward path of K1's transform_pair, restated on the host with the same primitives.
 // px: [nb][64] int16 (x-128, row major); out: [nb][64] int16 in scan order (float32 result, before
 // fix-up); mask: [nb] near-tie masks; ratio: [nb] max over AC coefficients of
-// |v32 - v64| * q / (4 * 2^-24 * E)  (the quantity HIC_TIE_KAPPA must bound).
+// |v32 - v64| * q / (kappa(u, v) * 4 * 2^-24 * E): the observed float32 error as a fraction of the rigorous
+// bound of that coefficient (must stay below 1; the kernel's band is the bound times HIC_BAND_MARGIN).
 void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64_t* mask, double* ratio) {
     const int* q = kind == 0 ? LUM : CHROMA;
-    float rq[64], qf[64];
+    const DctBounds bounds = dct_bounds();
+    float rq[64], kq[64];
     for (int u = 0; u < 8; ++u)
         for (int v = 0; v < 8; ++v) {
-            rq[8 * u + v] = (float)(4.0 * aan_g(u) * aan_g(v) / q[8 * u + v]);
-            qf[8 * u + v] = (float)q[8 * u + v];
+            rq[8 * u + v] = (float)(4.0 / (eo_forward_scale(u) * eo_forward_scale(v) * q[8 * u + v]));
+            kq[8 * u + v] = (float)(bounds.kappa_fwd[8 * u + v] * HIC_BAND_MARGIN * 4.0 / 16777216.0 / q[8 * u + v]);
         }
     const float MAGIC = 12582912.0f;
     for (int b = 0; b < nb; ++b) {
@@ -38,10 +54,9 @@ void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64
         float abs_sum = 0.f;
         for (int i = 0; i < 64; ++i) { v[i] = (float)px[64 * b + i]; abs_sum += fabsf(v[i]); }
         for (int r = 0; r < 8; ++r)
-            aan_forward8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
+            eo_forward8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
         for (int c = 0; c < 8; ++c)
-            aan_forward8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
-        const float band = (float)(HIC_TIE_KAPPA * 4.0 / 16777216.0) * abs_sum;
+            eo_forward8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
         // float64 truth for the ratio
         double truth[64];
         {
@@ -69,11 +84,11 @@ void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64
             out[64 * b + k] = (int16_t)(bits & 0xFFFF);
             if (k != 0) {
                 const float d = fmaf(v[nat], rq[nat], MAGIC - t);
-                if ((0.5f - fabsf(d)) * qf[nat] <= band) m |= (1ull << k);
+                if (fmaf(abs_sum, kq[nat], fabsf(d)) >= 0.499999f) m |= (1ull << k);
                 if (abs_sum > 0.f) {
                     const double v32 = (double)v[nat] * (double)rq[nat];
                     const double v64 = truth[nat] / q[nat];
-                    const double r = fabs(v32 - v64) * q[nat] / (4.0 / 16777216.0 * abs_sum);
+                    const double r = fabs(v32 - v64) * q[nat] / (bounds.kappa_fwd[nat] * 4.0 / 16777216.0 * abs_sum);
                     if (r > worst) worst = r;
                 }
             }
@@ -85,30 +100,36 @@ void hx_forward_blocks(const int16_t* px, int nb, int kind, int16_t* out, uint64
 
 // float32 inverse path of K7's inverse_block.  coef: [nb][64] int16 scan order; out [nb][64] uint8
 // (float32 result before fix-up); mask: samples within the near-integer band; ratio: max over
-// samples of |p32 - p64| / (2^-24 * 4 * S / 256), S = sum |coef * q| (what HIC_INV_KAPPA must bound);
-// exact: [nb][64] uint8 from the float64 emulation.
+// samples of |p32 - p64| / (2^-24 * 4 / 256 * sum_k w_k |coef_k q_k|): the observed error as a fraction of the
+// rigorous bound (must stay below 1); exact: [nb][64] uint8 from the float64 emulation.
 void hx_inverse_blocks(const int16_t* coef, int nb, int kind, uint8_t* out, uint64_t* mask, double* ratio, uint8_t* exact) {
     const int* q = kind == 0 ? LUM : CHROMA;
-    float dq[64];
+    const DctBounds bounds = dct_bounds();
+    float dq[64], qw[64];
     for (int u = 0; u < 8; ++u)
-        for (int v = 0; v < 8; ++v) dq[8 * u + v] = (float)(q[8 * u + v] * aan_h(u) * aan_h(v) / 256.0);
+        for (int v = 0; v < 8; ++v) {
+            dq[8 * u + v] = (float)(q[8 * u + v] * eo_inverse_prescale(u) * eo_inverse_prescale(v) / 256.0);
+            qw[8 * u + v] = (float)(q[8 * u + v] * bounds.w_inv[8 * u + v] * HIC_BAND_MARGIN);
+        }
     for (int b = 0; b < nb; ++b) {
         float v[64];
         int32_t cq[64];
         float S = 0.f;
+        double S_exact = 0.0;
         bool ac = false;
         for (int k = 0; k < 64; ++k) {
             const int c = coef[64 * b + k];
             v[ZZ[k]] = (float)c * dq[ZZ[k]];
             cq[ZZ[k]] = c * q[ZZ[k]];
-            S += fabsf((float)c) * (float)q[ZZ[k]];
+            S = fmaf(fabsf((float)c), qw[ZZ[k]], S);
+            S_exact += fabs((double)c) * q[ZZ[k]] * bounds.w_inv[ZZ[k]];
             if (k && c) ac = true;
         }
         for (int r = 0; r < 8; ++r)
-            aan_inverse8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
+            eo_inverse8(v[8*r], v[8*r+1], v[8*r+2], v[8*r+3], v[8*r+4], v[8*r+5], v[8*r+6], v[8*r+7]);
         for (int c = 0; c < 8; ++c)
-            aan_inverse8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
-        const float band = (float)(HIC_INV_KAPPA * 4.0 / 16777216.0 / 256.0) * S;
+            eo_inverse8(v[c], v[8+c], v[16+c], v[24+c], v[32+c], v[40+c], v[48+c], v[56+c]);
+        const float band = (float)(4.0 / 16777216.0 / 256.0) * S + 3.0517578125e-5f;
         uint64_t m = 0;
         double worst = 0.0;
         for (int i = 0; i < 64; ++i) {
@@ -117,8 +138,10 @@ void hx_inverse_blocks(const int16_t* coef, int nb, int kind, uint8_t* out, uint
             const double p64 = exact_decoded_sample(cq, i >> 3, i & 7);
             exact[64 * b + i] = wrap_u8(p64);
             if (ac && fabsf(p - rintf(p)) <= band) m |= (1ull << i);
-            if (S > 0.f) {
-                const double r = fabs((double)p - p64) / (4.0 / 16777216.0 / 256.0 * S);
+            if (S_exact > 0.0) {
+                // (the final + 128 rounds to 2^-15 at most: taken off before the comparison, as the band adds it back)
+                const double err = fabs((double)p - p64) - 1.52587890625e-5;
+                const double r = err / (4.0 / 16777216.0 / 256.0 * S_exact);
                 if (r > worst) worst = r;
             }
         }
