@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhiccup_b200.so")
+LIB_PATH = os.environ.get("HIC_LIB_PATH") or os.path.join(HERE, "libhiccup_b200.so")      # HIC_LIB_PATH: an experimental build (development aid)
 
 c_void_p, c_int, c_int32, c_uint32, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
                                                 ctypes.c_uint32, ctypes.c_size_t)

@@ -305,6 +305,44 @@ class PipelinedCodec:
         payload, _ = self._run(tickets, on_encoded, trace, resident, from_device, copy_only)
         return payload
 
+    def upload_resident(self, rgb):
+        """Park the batch in the slots' device buffers (chunk c in slot c; needs slots == chunks)."""
+        assert self.slots == self.n_chunks, "one slot per chunk"
+        for c, codec in enumerate(self.codecs):
+            codec.upload(rgb[c * self.chunk:(c + 1) * self.chunk])
+            _lib.sync(codec.stream)
+
+    def device_steps(self, repeat=1):
+        """`repeat` encode+decode passes over the batch parked by upload_resident(), everything in HBM: every
+        slot runs its chunk's kernels on its own CUDA stream from its own host thread, so one chunk's
+        latency-bound stretches (the serial heapq replays of the Huffman builder, the table builds, the
+        stream scans) run under another chunk's bandwidth-bound kernels.  No host<->device traffic besides
+        the few status words the C ABI reads back.  Results are what encode_device() / decode_device() of
+        each slot's codec leave on the device."""
+        import threading
+        assert self.slots == self.n_chunks, "one slot per chunk"
+        errors = []
+
+        def work(slot):
+            try:
+                if self.device is not None:
+                    _lib.check(_lib.load().hic_set_device(int(self.device)))
+                codec = self.codecs[slot]
+                for _ in range(repeat):
+                    codec.encode_device()
+                    codec.decode_device()
+                _lib.sync(codec.stream)
+            except Exception as e:
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(s,)) for s in range(self.slots)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
     def run_job(self, job, repeat=1, on_encoded=None, from_device=True, copy_only=False, trace=None):
         """This rank's share of a box-wide job (hiccup_b200/jobs.py): chunks of EVERY rank's batch are handed
         out from one shared ticket counter, so a GPU whose path to host memory is faster -- PCIe root ports

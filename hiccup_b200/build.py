@@ -28,14 +28,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: an experimental variant beside the product library (development aid; load it with
+    HIC_LIB_PATH=...)."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if out is not None:
+        return _build_to(nvcc, out, verbose, list(extra_flags))
     if not force and not _stale():
         return LIB_PATH
+    return _build_to(nvcc, LIB_PATH, verbose, [])
+
+
+def _build_to(nvcc, LIB_PATH, verbose, extra):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build %s" % LIB_PATH)
     cmd = [nvcc, *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
            "--expt-relaxed-constexpr"]
+    cmd += extra
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB_PATH + ".tmp", *sources()]
@@ -49,4 +58,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="--verbose" in sys.argv))
+    if "--out" in sys.argv:           # python -m hiccup_b200.build --out path.so -DHIC_K1_TH=32 ...
+        o = sys.argv[sys.argv.index("--out") + 1]
+        print(build(out=o, verbose="--verbose" in sys.argv, extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))
+    else:
+        print(build(force=True, verbose="--verbose" in sys.argv))

@@ -106,8 +106,12 @@ namespace k1 {
 // start offset of a box must be a multiple of 16 bytes (a 12-byte-aligned start faults with "illegal
 // instruction"; probed in tools/scratch/tma_test.cu), and 3 * (x0 - lead) is a multiple of 16 only for
 // lead = 0 mod 16.
+#ifndef HIC_K1_TH
+#define HIC_K1_TH 64
+#endif
 constexpr int TW = 128;
-constexpr int TH = 64;
+constexpr int TH = HIC_K1_TH;          // tile height: 64 (4 CTAs per SM) or 32 (7 lighter CTAs per SM)
+constexpr int CTAS_PER_SM = TH == 64 ? 4 : 7;
 constexpr int RH = TH + 3;            // staged rows
 constexpr int RWORDS = 112;           // staged row pitch in 32-bit words (448 bytes = 149 pixels)
 constexpr int RPIX = 136;             // pixels converted per staged row (34 groups of 4)
@@ -154,7 +158,7 @@ struct Smem {
     };
     alignas(8) unsigned long long bar;
 };
-static_assert(sizeof(Smem) <= 57344, "four CTAs per SM: (228 KB - 4 x 1 KB reserved) / 4");
+static_assert(sizeof(Smem) <= (TH == 64 ? 57344 : 32256), "CTAS_PER_SM CTAs per SM: (228 KB - 1 KB reserved each) / CTAS_PER_SM");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -354,10 +358,10 @@ __device__ __forceinline__ void push_ties(unsigned flagged, uint32_t block_index
 // BPT = blocks per thread in the transform stage: 2 -> 96 threads, everything packed, no re-pairing between the
 // passes, 168 registers (12 warps per SM); 1 -> 192 threads, 80-odd registers (24 warps per SM).
 template <bool USE_TMA, int BPT>
-__global__ void __launch_bounds__(threads_of(BPT), 4)
+__global__ void __launch_bounds__(threads_of(BPT), BPT == 2 ? 4 : CTAS_PER_SM)
 forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
                hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
-               uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+               uint32_t tie_capacity, uint32_t* __restrict__ stats, int debug_skip) {
     constexpr int THREADS = threads_of(BPT);
     constexpr int WARPS = THREADS / 32;
     constexpr int R16 = THREADS / 16;          // rows per step of the 16-lanes-per-row stages
@@ -382,7 +386,7 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
             // pull the tile of a CTA two waves ahead (4 CTAs on each of 148 SMs per wave) into L2, so that
             // its own load finds the data there
             const unsigned per_img = gridDim.x * gridDim.y;
-            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 2u * 4u * 148u;
+            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 2u * (unsigned)CTAS_PER_SM * 148u;
             if (ahead < per_img * gridDim.z) {
                 const unsigned pz = ahead / per_img, rem = ahead - pz * per_img;
                 const unsigned py = rem / gridDim.x, pxb = rem - py * gridDim.x;
@@ -451,6 +455,32 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
 
+    // (measurement aid, HIC_K1_DEBUG: 1 = stop after the load and store the tile's blocks as they are --
+    // the memory-side floor of this tiling; 2 = the same after the colour / pyramid stages)
+    auto debug_store = [&]() {
+        const int nby = TH / 8, nbx = TW / 8;
+        for (int b = tid; b < NY_BLOCKS + 2 * NC_BLOCKS; b += THREADS) {
+            int64_t idx;
+            if (b < NY_BLOCKS) {
+                const int BY = blockIdx.y * nby + b / nbx, BX = blockIdx.x * nbx + b % nbx;
+                if (BY >= g.nby_l || BX >= g.nbx_l) continue;
+                idx = (int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX;
+            } else {
+                const int c = b - NY_BLOCKS, plane = c / NC_BLOCKS, l = c % NC_BLOCKS;
+                const int BY = blockIdx.y * (CH / 8) + l / (CW / 8), BX = blockIdx.x * (CW / 8) + l % (CW / 8);
+                if (BY >= g.nby_c || BX >= g.nbx_c) continue;
+                idx = (int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c + (int64_t)BY * g.nbx_c + BX;
+            }
+            int4* out = reinterpret_cast<int4*>(coef + idx * 64);
+            const int4 v = *reinterpret_cast<const int4*>(&s.rgb[(b * 4) % (RH * RWORDS - 4) & ~3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j] = v;
+        }
+    };
+    if (debug_skip == 1) {
+        debug_store();
+        return;
+    }
     // ---- stage 1: colour conversion, four pixels (three words) at a time ----
     // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes.  Groups 1..32
     // of a row (the 128 tile columns) go one per lane, rows warp + WARPS k; the two halo groups per row
@@ -500,8 +530,11 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         for (int k = 0; k < (RH + R16 - 1) / R16; ++k) {
             const int ry = (tid >> 4) + R16 * k, j = tid & 15;
             if (ry < RH) {
-                const uint32_t* row = reinterpret_cast<const uint32_t*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + 2 * j;
-                const uint32_t wa = row[0], wb = row[1], wc = row[2], wd = row[3];
+                // (two 8-byte loads: a half-warp's 16 lanes cover one row's 128 bytes without a bank conflict; four
+                // 4-byte loads of the two rows a warp works on collide pairwise)
+                const uint2* row = reinterpret_cast<const uint2*>(ch == 0 ? s.cr[ry] : s.cb[ry]) + j;
+                const uint2 lo = row[0], hi = row[1];
+                const uint32_t wa = lo.x, wb = lo.y, wc = hi.x, wd = hi.y;
                 const uint32_t o0 = __dp4a(wb, 0x00010406u, __dp4a(wa, 0x04010000u, 0u));
                 const uint32_t o1 = __dp4a(wc, 0x00000001u, __dp4a(wb, 0x04060401u, 0u));
                 const uint32_t o2 = __dp4a(wc, 0x00010406u, __dp4a(wb, 0x04010000u, 0u));
@@ -512,23 +545,25 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
     __syncthreads();
-    // ---- stage 2b: vertical on two 16-bit lanes per word (sums stay below 2^16), (sum + 128) >> 8 ----
+    // ---- stage 2b: vertical on two 16-bit lanes per word (sums stay below 2^16), (sum + 128) >> 8.  A thread
+    // makes two consecutive output rows from seven loads (the rows they share are loaded once) ----
+    static_assert(CH % 2 == 0 && 2 * CH + 2 < RH + 1, "row pairs of stage 2b");
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
-        for (int k = 0; k < (CH + R16 - 1) / R16; ++k) {
-            const int cy = (tid >> 4) + R16 * k, j = tid & 15;
-            if (cy < CH) {
-                uint32_t v0 = 0x00800080u, v1 = 0x00800080u;
+        for (int k = 0; k < (CH / 2 + R16 - 1) / R16; ++k) {
+            const int cp = (tid >> 4) + R16 * k, j = tid & 15;
+            if (cp < CH / 2) {
+                uint2 t[7];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const uint2 t = *reinterpret_cast<const uint2*>(&s.hpass[ch][2 * cy + q][4 * j]);
-                    const uint32_t wt = q == 2 ? 6u : ((q == 1 || q == 3) ? 4u : 1u);
-                    v0 += wt * t.x;
-                    v1 += wt * t.y;
-                }
-                const uint32_t packed = __byte_perm(v0, v1, 0x7531);       // the high byte of each 16-bit lane
-                *reinterpret_cast<uint32_t*>(ch == 0 ? &s.crd[cy][4 * j] : &s.cbd[cy][4 * j]) = packed;
+                for (int q = 0; q < 7; ++q) t[q] = *reinterpret_cast<const uint2*>(&s.hpass[ch][4 * cp + q][4 * j]);
+                const uint32_t a0 = 0x00800080u + t[0].x + 4u * t[1].x + 6u * t[2].x + 4u * t[3].x + t[4].x;
+                const uint32_t a1 = 0x00800080u + t[0].y + 4u * t[1].y + 6u * t[2].y + 4u * t[3].y + t[4].y;
+                const uint32_t b0 = 0x00800080u + t[2].x + 4u * t[3].x + 6u * t[4].x + 4u * t[5].x + t[6].x;
+                const uint32_t b1 = 0x00800080u + t[2].y + 4u * t[3].y + 6u * t[4].y + 4u * t[5].y + t[6].y;
+                uint8_t (*dstp)[CD_PITCH] = ch == 0 ? s.crd : s.cbd;
+                *reinterpret_cast<uint32_t*>(&dstp[2 * cp][4 * j]) = __byte_perm(a0, a1, 0x7531);       // the high byte of each 16-bit lane
+                *reinterpret_cast<uint32_t*>(&dstp[2 * cp + 1][4 * j]) = __byte_perm(b0, b1, 0x7531);
             }
         }
     }
@@ -562,6 +597,10 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
 
+    if (debug_skip == 2) {
+        debug_store();
+        return;
+    }
     // ---- stage 3: the 8x8 blocks ----
     unsigned fl = 0;
     uint32_t ia = 0, ib = 0;
@@ -572,14 +611,14 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         bool have_a = false, have_b = false;
         if (tid < NY_PAIRS) {
             const int by = tid / (TW / 8), bx = tid % (TW / 8);          // blocks (by, bx) and (by + 4, bx)
-            const int BYa = blockIdx.y * (TH / 8) + by, BYb = BYa + 4, BX = blockIdx.x * (TW / 8) + bx;
+            const int BYa = blockIdx.y * (TH / 8) + by, BYb = BYa + TH / 16, BX = blockIdx.x * (TW / 8) + bx;
             have_a = BYa < g.nby_l && BX < g.nbx_l;
             have_b = BYb < g.nby_l && BX < g.nbx_l;
             pa = &s.y[8 * by][8 * bx];
-            pb = &s.y[8 * by + 32][8 * bx];
+            pb = &s.y[8 * by + TH / 2][8 * bx];
             pitch = TW;
             ia = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BYa * g.nbx_l + BX);
-            ib = ia + 4u * (uint32_t)g.nbx_l;
+            ib = ia + (uint32_t)(TH / 16) * (uint32_t)g.nbx_l;
             rows_a = h - 8 * BYa;
             rows_b = h - 8 * BYb;
             cols = w - 8 * BX;
@@ -1211,16 +1250,17 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
     }
     // HIC_K1_BPT (environment, 1 | 2): blocks per thread in the transform stage (A/B timing; same results)
     static const int bpt = getenv("HIC_K1_BPT") ? atoi(getenv("HIC_K1_BPT")) : 1;
+    static const int dbg = getenv("HIC_K1_DEBUG") ? atoi(getenv("HIC_K1_DEBUG")) : 0;       // measurement aid: WRONG results when set
     if (bpt == 2) {
         if (use_tma)
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
         else
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
     } else {
         if (use_tma)
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
         else
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
     }
     HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
     return HIC_OK;
