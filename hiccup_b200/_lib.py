@@ -68,6 +68,7 @@ SIGNATURES = {
     "hic_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_profile_timeline": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_dct_geometry_of": (c_int, [c_int32, c_int32, ctypes.POINTER(Geometry)]),
+    "hic_dct_tie_capacity": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(c_uint32)]),
     "hic_dct_forward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
     "hic_blocks_to_planes": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_planes_to_blocks": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -157,6 +158,13 @@ def geometry(h, w):
     g = Geometry()
     check(load().hic_dct_geometry_of(int(h), int(w), ctypes.byref(g)))
     return g
+
+
+def tie_capacity(n, h, w):
+    """Records the tie buffer of hic_dct_forward must hold (one per block + K1's flag words)."""
+    cap = c_uint32()
+    check(load().hic_dct_tie_capacity(int(n), int(h), int(w), ctypes.byref(cap)))
+    return int(cap.value)
 
 
 class DeviceBuffer:

@@ -336,7 +336,8 @@ class BandWorker:
         self.layout, self.nb, self.block_off = lay, nb, off
         self.d_rgb = _lib.DeviceBuffer(hs * w * 3)
         self.d_coef = _lib.DeviceBuffer(g.blocks_per_image * 128)
-        self.d_ties = _lib.DeviceBuffer(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
+        self.tie_capacity = _lib.tie_capacity(1, hs, w)
+        self.d_ties = _lib.DeviceBuffer(self.tie_capacity * _lib.TIE_RECORD_BYTES)
         self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
         self.encoder = entropy.EntropyEncoder(lay, value_bins)
         self.rgb, self._pinned, self._h_bytes = None, None, None
@@ -359,7 +360,7 @@ class BandWorker:
         self._use_device()
         self.d_rgb.upload(self.rgb, st)
         _lib.check(lib.hic_dct_forward(self.d_rgb.ptr, 1, self.s1 - self.s0, self.w, self.d_coef.ptr, self.d_ties.ptr,
-                                       g.blocks_per_image, self.d_stats.ptr, st))
+                                       self.tie_capacity, self.d_stats.ptr, st))
         first_nz, last_nz = enc.scan(self.d_coef.ptr, st)
         last_dc = [int(self.d_coef.download(np.int16, 1, st, offset=128 * (self.block_off[c] + self.nb[c] - 1))[0])
                    for c in range(3)]

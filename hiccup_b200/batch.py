@@ -169,7 +169,8 @@ class DctBatchCodec(_BatchCodec):
         self.blocks = int(n) * g.blocks_per_image
         super().__init__(n, h, w, _lib.layout_dct(int(n), h, w), self.blocks * 128, (g.out_h, g.out_w), value_bins,
                          device, stream, device_codes)
-        self.d_ties = _lib.DeviceBuffer(self.blocks * _lib.TIE_RECORD_BYTES)
+        self.tie_capacity = _lib.tie_capacity(n, h, w)
+        self.d_ties = _lib.DeviceBuffer(self.tie_capacity * _lib.TIE_RECORD_BYTES)
         self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
         self.d_y = _lib.DeviceBuffer(self.n * h * w)
         self.d_cr = _lib.DeviceBuffer(self.n * g.hc * g.wc)
@@ -180,7 +181,7 @@ class DctBatchCodec(_BatchCodec):
 
     def _forward(self):
         _lib.check(self.lib.hic_dct_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.d_ties.ptr,
-                                            self.blocks, self.d_stats.ptr, self.stream))
+                                            self.tie_capacity, self.d_stats.ptr, self.stream))
 
     def _inverse(self):
         _lib.check(self.lib.hic_dct_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_y.ptr, self.d_cr.ptr,

@@ -31,9 +31,10 @@ def dct_forward_device(d_rgb, n, h, w, stream=None):
     g = _lib.geometry(h, w)
     blocks = n * g.blocks_per_image
     coef = _lib.DeviceBuffer(blocks * 128)
-    ties = _lib.DeviceBuffer(blocks * _lib.TIE_RECORD_BYTES)
+    capacity = _lib.tie_capacity(n, h, w)
+    ties = _lib.DeviceBuffer(capacity * _lib.TIE_RECORD_BYTES)
     stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
-    _lib.check(lib.hic_dct_forward(d_rgb, n, h, w, coef.ptr, ties.ptr, blocks, stats.ptr, stream))
+    _lib.check(lib.hic_dct_forward(d_rgb, n, h, w, coef.ptr, ties.ptr, capacity, stats.ptr, stream))
     st = stats.download(np.uint32, _lib.TIE_STATS, stream)
     if st[3]:
         raise _lib.HicError("tie list overflow (%d records dropped)" % st[3])

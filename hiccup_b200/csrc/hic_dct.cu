@@ -97,10 +97,11 @@ static int geometry_of(int h, int w, hic_dct_geometry* g) {
 // ------------------------------------------------------------------------------------------------
 namespace k1 {
 // Tile: 128 x 64 luminance pixels = 16 x 8 Y blocks + 8 x 4 Cr blocks + 8 x 4 Cb blocks = 192 blocks.
-// In the transform stage a thread carries TWO blocks, one in each lane of the packed f32x2 registers
-// (two luminance blocks four block rows apart, or the Cr and the Cb block of one position): every
-// butterfly, FMA and quantiser step is one instruction for both, nothing is ever transposed between the
-// row and the column pass, and the constants are loaded once per pair -- 96 threads per tile.
+// In the transform stage a thread carries one block, two rows (then two columns) in each packed f32x2
+// register pair -- 192 threads per tile.  The quantised blocks are staged in shared memory (the RGB region
+// is dead by then) in the 128-byte-swizzle pattern and leave through two TMA tensor stores: a thread's
+// eight 16-byte pieces of its 128-byte block would otherwise be a global store of 32 different lines per
+// warp instruction, and those stores alone were half of the kernel's LSU wavefronts.
 // The staged RGB region covers image columns x0-16 .. x0+132 and rows y0-2 .. y0+64 (pyrDown needs
 // columns x0-2 .. x0+128 and rows y0-2 .. y0+64).  The 16-pixel lead is what TMA demands: the innermost
 // start offset of a box must be a multiple of 16 bytes (a 12-byte-aligned start faults with "illegal
@@ -125,8 +126,8 @@ constexpr int CH = TH / 2;
 constexpr int CD_PITCH = CW + 8;      // pitch of the downsampled chroma tiles: block rows land in different banks
 constexpr int NY_BLOCKS = (TW / 8) * (TH / 8);       // 128
 constexpr int NC_BLOCKS = (CW / 8) * (CH / 8);       // 32 per chroma plane
-constexpr int NY_PAIRS = NY_BLOCKS / 2;              // two blocks per thread: 64 threads carry blocks (by, bx) and (by + 4, bx)
-constexpr int threads_of(int bpt) { return bpt == 2 ? NY_PAIRS + NC_BLOCKS : NY_BLOCKS + 2 * NC_BLOCKS; }      // 96 | 192
+constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // one block per thread: 192
+constexpr int WARPS = THREADS / 32;
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
 constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
 
@@ -143,9 +144,10 @@ constexpr uint32_t W_B = 4u * 1868u;                             // dp2a.hi: B (
 constexpr uint32_t K_CR = 4u * 11682u, K_CB = 4u * 9241u;
 constexpr uint32_t C4 = 4u * ((128u << 14) + 8192u);
 struct Smem {
-    union alignas(128) {
+    union alignas(1024) {
         uint32_t rgb[RH * RWORDS];                   // stage 0/1 (TMA destination)
         uint16_t hpass[2][RH][CW];                   // stage 2 (rgb is dead by then)
+        int4 stage[THREADS * 8];                     // stage 3 -> TMA stores (hpass is dead by then): block t = row t, 128-byte swizzle
     };
     alignas(16) uint8_t y[TH][TW];
     union alignas(16) {
@@ -159,97 +161,19 @@ struct Smem {
     alignas(8) unsigned long long bar;
 };
 static_assert(sizeof(Smem) <= (TH == 64 ? 57344 : 32256), "CTAS_PER_SM CTAs per SM: (228 KB - 1 KB reserved each) / CTAS_PER_SM");
+static_assert(sizeof(int4) * THREADS * 8 <= sizeof(uint32_t) * RH * RWORDS, "the staged blocks fit in the RGB region");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Two 8x8 blocks (each as 16 words of bytes, rows of 8; block A rides in the low lane, B in the high lane)
-// -> quantised zigzag int16 of both + their near-tie flags (bit 0: A, bit 1: B).  `kind` (0 = luminance,
-// 1 = chroma tables) is a run-time value so that there is ONE instance of this long straight-line code for
-// all warps of the CTA: the kernel's top stall is instruction fetch.
-__device__ __forceinline__ unsigned transform_pair(int kind, const uint32_t (&wa)[16], const uint32_t (&wb)[16],
-                                                   int16_t* __restrict__ dst_a, int16_t* __restrict__ dst_b) {
-    // E = sum |x - 128| over each block (exact, integer) for the error band
-    uint32_t ea = 0, eb = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        ea = __vsadu4(wa[i], 0x80808080u) + ea;
-        eb = __vsadu4(wb[i], 0x80808080u) + eb;
-    }
-    const float fea = (float)ea, feb = (float)eb;
-
-    // row pass.  Bytes become floats by splicing them into 2^23 (value 2^23 + byte); the level shift
-    // folds into the first butterflies: d_i = x_i - x_{7-i} is exact as it stands, and with
-    // y_i = x_{7-i} - (2^23 + 128),  s_i = (x_i - 128) + (x_{7-i} - 128) = 2 y_i + d_i, exact as well.
-    const f2 shift(-(8388608.0f + 128.0f)), two(2.0f);
-    f2 a[64];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        f2 x[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float fa = __uint_as_float(__byte_perm(wa[2 * r + (c >> 2)], 0x4B000000u, 0x7540 + (c & 3)));
-            const float fb = __uint_as_float(__byte_perm(wb[2 * r + (c >> 2)], 0x4B000000u, 0x7540 + (c & 3)));
-            x[c] = f2(fa, fb);
-        }
-        f2 s[4], d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            d[i] = x[i] - x[7 - i];
-            s[i] = fma2(two, x[7 - i] + shift, d[i]);
-        }
-        eo_forward8_tail(s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3], a[8 * r + 0], a[8 * r + 1], a[8 * r + 2],
-                         a[8 * r + 3], a[8 * r + 4], a[8 * r + 5], a[8 * r + 6], a[8 * r + 7]);
-    }
-    // column pass, in place: a[8 u + v] = coefficient (u, v) of both blocks
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        eo_forward8(a[c], a[8 + c], a[16 + c], a[24 + c], a[32 + c], a[40 + c], a[48 + c], a[56 + c]);
-    // quantise: t = RN(v * rq + MAGIC) holds round-half-even(v * rq) in its low mantissa bits;
-    // d = v * rq - round(v * rq); near a tie when |d| + E * kq >= 1/2 (kq = the rigorous error bound of this
-    // coefficient per unit E, hic_dct_bound.h; 0 for DC, which is an exact integer)
-    float worst_a = 0.f, worst_b = 0.f;
-    const f2 magic2(MAGIC);
-    const float2* __restrict__ rq2 = c_tab.rq2[kind];
-    const float* __restrict__ kqt = c_tab.kq[kind];
-#pragma unroll
-    for (int nat = 0; nat < 64; ++nat) {
-        f2 rq;
-        rq.v = *reinterpret_cast<const unsigned long long*>(&rq2[nat]);
-        const f2 t = fma2(a[nat], rq, magic2);
-        const f2 d = fma2(a[nat], rq, magic2 - t);
-        a[nat] = t;
-        if (nat != 0) {
-            const float kq = kqt[nat];
-            worst_a = fmaxf(worst_a, fmaf(fea, kq, fabsf(d.lo())));
-            worst_b = fmaxf(worst_b, fmaf(feb, kq, fabsf(d.hi())));
-        }
-    }
-    constexpr uint8_t zz[64] = HIC_ZIGZAG8;
-    int4* out_a = reinterpret_cast<int4*>(dst_a);
-    int4* out_b = reinterpret_cast<int4*>(dst_b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        int4 wa4, wb4;
-        int* pa = reinterpret_cast<int*>(&wa4);
-        int* pb = reinterpret_cast<int*>(&wb4);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const f2 t0 = a[zz[8 * j + 2 * e]], t1 = a[zz[8 * j + 2 * e + 1]];
-            pa[e] = __byte_perm(__float_as_int(t0.lo()), __float_as_int(t1.lo()), 0x5410);
-            pb[e] = __byte_perm(__float_as_int(t0.hi()), __float_as_int(t1.hi()), 0x5410);
-        }
-        out_a[j] = wa4;
-        if (dst_b) out_b[j] = wb4;
-    }
-    // some coefficient is within the float32 error band of a rounding tie: the fix-up kernel redoes the
-    // block in float64 (the slack covers the roundings of this very comparison)
-    return (worst_a >= 0.499999f ? 1u : 0u) | (worst_b >= 0.499999f ? 2u : 0u);
-}
-
-// One 8x8 block per thread: two rows (then two columns) ride in each f32x2 register pair.  Half the
-// registers of transform_pair (twice the warps per SM) at the price of re-pairing the 64 values between the
-// passes.
-__device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&wv)[16], int16_t* __restrict__ dst) {
+// One 8x8 block per thread: two rows (then two columns) ride in each f32x2 register pair; the 64 values are
+// re-paired between the passes.  The quantised zigzag int16 of the block go to its 128-byte row of the
+// staging area, 16-byte piece j at position j ^ sw (the TMA 128-byte swizzle; sw = row & 7), so that the
+// eight threads of a quarter warp hit all 32 banks.  rows / cols < 8: the block hangs over the bottom /
+// right edge of its plane -- the reference crops the coefficient plane back to the channel shape
+// (transform.py:63) and re-pads it with zeros (codec.py:288,294), so coefficients at vertical frequency
+// >= rows or horizontal frequency >= cols are zero.
+__device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&wv)[16], int4* __restrict__ out, int sw,
+                                                     int rows, int cols) {
     uint32_t abs_sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) abs_sum = __vsadu4(wv[i], 0x80808080u) + abs_sum;
@@ -302,8 +226,16 @@ __device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&
         if (p != 0) worst = fmaxf(worst, fmaf(fe, kqt[n0], fabsf(d.lo())));      // DC is exact
         worst = fmaxf(worst, fmaf(fe, kqt[n0 + 1], fabsf(d.hi())));
     }
+    if (rows < 8 || cols < 8) {          // (edge blocks of shapes that are not multiples of 8: MAGIC carries a zero)
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const int u = p >> 2, v0 = 2 * (p & 3);
+            const float lo = (u >= rows || v0 >= cols) ? MAGIC : b[p].lo();
+            const float hi = (u >= rows || v0 + 1 >= cols) ? MAGIC : b[p].hi();
+            b[p] = f2(lo, hi);
+        }
+    }
     constexpr uint8_t zz[64] = HIC_ZIGZAG8;
-    int4* out = reinterpret_cast<int4*>(dst);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int4 w4;
@@ -315,36 +247,75 @@ __device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&
             const int v0 = __float_as_int((n_lo & 1) ? t0.hi() : t0.lo()), v1 = __float_as_int((n_hi & 1) ? t1.hi() : t1.lo());
             pw[e] = __byte_perm(v0, v1, 0x5410);
         }
-        out[j] = w4;
+        out[j ^ sw] = w4;
     }
     return worst >= 0.499999f ? 1u : 0u;
 }
 
-// Blocks that hang over the bottom / right edge of their plane: the reference crops the coefficient plane
-// back to the channel shape (transform.py:63) and re-pads it with zeros (codec.py:288,294), so
-// coefficients at rows >= rows or columns >= cols of such a block are zero.  Rare (edge blocks of shapes
-// that are not multiples of 8): a separate pass over the 128 bytes the thread has just stored.
-__device__ __noinline__ void crop_block(int16_t* __restrict__ blk, int rows, int cols) {
-    for (int k = 0; k < 64; ++k) {
-        const int nat = c_zigzag[k];
-        if ((nat >> 3) >= rows || (nat & 7) >= cols) blk[k] = 0;
+// Which block thread `tid` of tile (tbx, tby) of image `img` carries: threads 0..NY_BLOCKS-1 the luminance
+// blocks of the tile row by row, then the Cr and the Cb blocks.  false: the block lies outside its plane.
+struct TileBlock {
+    uint32_t index;        // block index in the coefficient buffer
+    int kind;              // 0 = luminance, 1 = chroma
+    int by, bx;            // block position inside the tile
+    int plane;             // 0 = Cr, 1 = Cb (chroma)
+    int rows, cols;        // samples of the block inside its plane (>= 8: all)
+};
+__device__ __forceinline__ bool tile_block(int tid, int tbx, int tby, int img, const hic_dct_geometry& g, int h, int w,
+                                           TileBlock& t) {
+    if (tid < NY_BLOCKS) {
+        t.kind = 0;
+        t.plane = 0;
+        t.by = tid / (TW / 8);
+        t.bx = tid % (TW / 8);
+        const int BY = tby * (TH / 8) + t.by, BX = tbx * (TW / 8) + t.bx;
+        t.index = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
+        t.rows = h - 8 * BY;
+        t.cols = w - 8 * BX;
+        return BY < g.nby_l && BX < g.nbx_l;
     }
+    t.kind = 1;
+    t.plane = (tid - NY_BLOCKS) / NC_BLOCKS;
+    const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
+    t.by = local / (CW / 8);
+    t.bx = local % (CW / 8);
+    const int BY = tby * (CH / 8) + t.by, BX = tbx * (CW / 8) + t.bx;
+    t.index = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)t.plane * g.nb_c + (int64_t)BY * g.nbx_c + BX);
+    t.rows = g.hc - 8 * BY;
+    t.cols = g.wc - 8 * BX;
+    return BY < g.nby_c && BX < g.nbx_c;
 }
 
-__device__ __forceinline__ void push_ties(unsigned flagged, uint32_t block_index, hic_tie_record* __restrict__ ties,
-                                          uint32_t tie_capacity, uint32_t* __restrict__ stats) {
-    // one slot request per warp
-    const unsigned m = __ballot_sync(0xffffffffu, flagged != 0);
-    if (m) {
-        const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&stats[0], (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (flagged) {
-            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+// K1 leaves one word per warp: the ballot of its threads' near-tie flags (a plain store -- a slot request
+// through an atomic made every warp wait for the round trip at the end of its tile).  This kernel turns the
+// words into the list of flagged blocks the fix-up kernel works through.
+__global__ void __launch_bounds__(256)
+tie_list_kernel(const uint32_t* __restrict__ flagmap, uint32_t n_words, int tiles_x, int tiles_y, hic_dct_geometry g, int h,
+                int w, hic_tie_record* __restrict__ ties, uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_words; base += gridDim.x * blockDim.x) {
+        const uint32_t wi = base + lane;
+        const uint32_t m = wi < n_words ? flagmap[wi] : 0u;
+        const uint32_t cnt = __popc(m);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (unsigned)off) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(&stats[0], total);
+        slot = __shfl_sync(0xffffffffu, slot, 0) + incl - cnt;
+        const uint32_t tile = wi / WARPS, warp = wi - tile * WARPS;
+        const int tbx = (int)(tile % tiles_x), tby = (int)((tile / tiles_x) % tiles_y), img = (int)(tile / ((uint32_t)tiles_x * tiles_y));
+        for (uint32_t rest = m; rest; rest &= rest - 1, ++slot) {
+            TileBlock t;
+            tile_block((int)(warp * 32 + __ffs(rest) - 1), tbx, tby, img, g, h, w, t);
             if (slot < tie_capacity) {
                 hic_tie_record rec;
-                rec.block = block_index;
+                rec.block = t.index;
                 rec.reserved = 0;
                 rec.mask = ~0ull;
                 ties[slot] = rec;
@@ -355,17 +326,14 @@ __device__ __forceinline__ void push_ties(unsigned flagged, uint32_t block_index
     }
 }
 
-// BPT = blocks per thread in the transform stage: 2 -> 96 threads, everything packed, no re-pairing between the
-// passes, 168 registers (12 warps per SM); 1 -> 192 threads, 80-odd registers (24 warps per SM).
-template <bool USE_TMA, int BPT>
-__global__ void __launch_bounds__(threads_of(BPT), BPT == 2 ? 4 : CTAS_PER_SM)
-forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ rgb, int h, int w,
-               hic_dct_geometry g, int16_t* __restrict__ coef, hic_tie_record* __restrict__ ties,
-               uint32_t tie_capacity, uint32_t* __restrict__ stats, int debug_skip) {
-    constexpr int THREADS = threads_of(BPT);
-    constexpr int WARPS = THREADS / 32;
+// tmap: the RGB batch (load); tmap_l / tmap_c: the luminance / chroma blocks of the coefficient buffer (stores).
+template <bool USE_TMA>
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
+forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_l,
+               const __grid_constant__ CUtensorMap tmap_c, const uint8_t* __restrict__ rgb, int h, int w,
+               hic_dct_geometry g, uint32_t* __restrict__ flagmap) {
     constexpr int R16 = THREADS / 16;          // rows per step of the 16-lanes-per-row stages
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
@@ -455,32 +423,6 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
 
-    // (measurement aid, HIC_K1_DEBUG: 1 = stop after the load and store the tile's blocks as they are --
-    // the memory-side floor of this tiling; 2 = the same after the colour / pyramid stages)
-    auto debug_store = [&]() {
-        const int nby = TH / 8, nbx = TW / 8;
-        for (int b = tid; b < NY_BLOCKS + 2 * NC_BLOCKS; b += THREADS) {
-            int64_t idx;
-            if (b < NY_BLOCKS) {
-                const int BY = blockIdx.y * nby + b / nbx, BX = blockIdx.x * nbx + b % nbx;
-                if (BY >= g.nby_l || BX >= g.nbx_l) continue;
-                idx = (int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX;
-            } else {
-                const int c = b - NY_BLOCKS, plane = c / NC_BLOCKS, l = c % NC_BLOCKS;
-                const int BY = blockIdx.y * (CH / 8) + l / (CW / 8), BX = blockIdx.x * (CW / 8) + l % (CW / 8);
-                if (BY >= g.nby_c || BX >= g.nbx_c) continue;
-                idx = (int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c + (int64_t)BY * g.nbx_c + BX;
-            }
-            int4* out = reinterpret_cast<int4*>(coef + idx * 64);
-            const int4 v = *reinterpret_cast<const int4*>(&s.rgb[(b * 4) % (RH * RWORDS - 4) & ~3]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) out[j] = v;
-        }
-    };
-    if (debug_skip == 1) {
-        debug_store();
-        return;
-    }
     // ---- stage 1: colour conversion, four pixels (three words) at a time ----
     // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two dot products on the weight bytes.  Groups 1..32
     // of a row (the 128 tile columns) go one per lane, rows warp + WARPS k; the two halo groups per row
@@ -597,101 +539,46 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         }
     }
 
-    if (debug_skip == 2) {
-        debug_store();
-        return;
-    }
     // ---- stage 3: the 8x8 blocks ----
     unsigned fl = 0;
-    uint32_t ia = 0, ib = 0;
-    if (BPT == 2) {
-        uint32_t wa[16], wb[16];
-        const uint8_t *pa = nullptr, *pb = nullptr;
-        int pitch = 0, kind = 0, rows_a = 8, rows_b = 8, cols = 8;
-        bool have_a = false, have_b = false;
-        if (tid < NY_PAIRS) {
-            const int by = tid / (TW / 8), bx = tid % (TW / 8);          // blocks (by, bx) and (by + 4, bx)
-            const int BYa = blockIdx.y * (TH / 8) + by, BYb = BYa + TH / 16, BX = blockIdx.x * (TW / 8) + bx;
-            have_a = BYa < g.nby_l && BX < g.nbx_l;
-            have_b = BYb < g.nby_l && BX < g.nbx_l;
-            pa = &s.y[8 * by][8 * bx];
-            pb = &s.y[8 * by + TH / 2][8 * bx];
-            pitch = TW;
-            ia = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BYa * g.nbx_l + BX);
-            ib = ia + (uint32_t)(TH / 16) * (uint32_t)g.nbx_l;
-            rows_a = h - 8 * BYa;
-            rows_b = h - 8 * BYb;
-            cols = w - 8 * BX;
-        } else {
-            const int local = tid - NY_PAIRS;                               // Cr block in the low lane, Cb in the high lane
-            const int by = local / (CW / 8), bx = local % (CW / 8);
-            const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
-            have_a = have_b = BY < g.nby_c && BX < g.nbx_c;
-            pa = &s.crd[8 * by][8 * bx];
-            pb = &s.cbd[8 * by][8 * bx];
-            pitch = CD_PITCH;
-            kind = 1;
-            ia = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)BY * g.nbx_c + BX);
-            ib = ia + (uint32_t)g.nb_c;
-            rows_a = rows_b = g.hc - 8 * BY;
-            cols = g.wc - 8 * BX;
-        }
-        if (have_a) {            // (false only for block rows / columns past the plane, at the bottom / right edge)
+    {
+        TileBlock t;
+        if (tile_block(tid, blockIdx.x, blockIdx.y, img, g, h, w, t)) {   // (false only for blocks past the plane, at the bottom / right edge)
+            const uint8_t* pa = t.kind == 0 ? &s.y[8 * t.by][8 * t.bx] : (t.plane == 0 ? &s.crd[8 * t.by][8 * t.bx] : &s.cbd[8 * t.by][8 * t.bx]);
+            const int pitch = t.kind == 0 ? TW : CD_PITCH;
+            uint32_t wv[16];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const uint2 ta = *reinterpret_cast<const uint2*>(pa + r * pitch);
-                const uint2 tb = *reinterpret_cast<const uint2*>(pb + r * pitch);
-                wa[2 * r] = ta.x;
-                wa[2 * r + 1] = ta.y;
-                wb[2 * r] = tb.x;
-                wb[2 * r + 1] = tb.y;
+                const uint2 v = *reinterpret_cast<const uint2*>(pa + r * pitch);
+                wv[2 * r] = v.x;
+                wv[2 * r + 1] = v.y;
             }
-            fl = transform_pair(kind, wa, wb, coef + (size_t)ia * 64, have_b ? coef + (size_t)ib * 64 : nullptr);
-            if (!have_b) fl &= 1u;
-            if (cols < 8 || rows_a < 8) crop_block(coef + (size_t)ia * 64, min(8, rows_a), min(8, cols));
-            if (have_b && (cols < 8 || rows_b < 8)) crop_block(coef + (size_t)ib * 64, min(8, rows_b), min(8, cols));
-        }
-    } else {
-        uint32_t wv[16];
-        const uint8_t* pa = nullptr;
-        int pitch = 0, kind = 0, rows = 8, cols = 8;
-        bool have = false;
-        if (tid < NY_BLOCKS) {
-            const int by = tid / (TW / 8), bx = tid % (TW / 8);
-            const int BY = blockIdx.y * (TH / 8) + by, BX = blockIdx.x * (TW / 8) + bx;
-            have = BY < g.nby_l && BX < g.nbx_l;
-            pa = &s.y[8 * by][8 * bx];
-            pitch = TW;
-            ia = (uint32_t)((int64_t)img * g.blocks_per_image + (int64_t)BY * g.nbx_l + BX);
-            rows = h - 8 * BY;
-            cols = w - 8 * BX;
-        } else {
-            const int plane = (tid - NY_BLOCKS) / NC_BLOCKS;          // 0 = Cr, 1 = Cb
-            const int local = (tid - NY_BLOCKS) % NC_BLOCKS;
-            const int by = local / (CW / 8), bx = local % (CW / 8);
-            const int BY = blockIdx.y * (CH / 8) + by, BX = blockIdx.x * (CW / 8) + bx;
-            have = BY < g.nby_c && BX < g.nbx_c;
-            pa = plane == 0 ? &s.crd[8 * by][8 * bx] : &s.cbd[8 * by][8 * bx];
-            pitch = CD_PITCH;
-            kind = 1;
-            ia = (uint32_t)((int64_t)img * g.blocks_per_image + g.nb_l + (int64_t)plane * g.nb_c + (int64_t)BY * g.nbx_c + BX);
-            rows = g.hc - 8 * BY;
-            cols = g.wc - 8 * BX;
-        }
-        if (have) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const uint2 t = *reinterpret_cast<const uint2*>(pa + r * pitch);
-                wv[2 * r] = t.x;
-                wv[2 * r + 1] = t.y;
-            }
-            fl = transform_single(kind, wv, coef + (size_t)ia * 64);
-            if (cols < 8 || rows < 8) crop_block(coef + (size_t)ia * 64, min(8, rows), min(8, cols));
+            fl = transform_single(t.kind, wv, &s.stage[tid * 8], tid & 7, t.rows, t.cols);
         }
     }
     // the warps are whole (luminance and chroma threads never share one) and converged again here
-    push_ties(fl & 1u, ia, ties, tie_capacity, stats);
-    if (BPT == 2) push_ties(fl & 2u, ib, ties, tie_capacity, stats);
+    const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+    if ((tid & 31) == 0)
+        flagmap[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WARPS + (tid >> 5)] = m;
+    // ---- stage 4: the staged blocks leave through TMA: the tile's luminance blocks as one box, its Cr and
+    // Cb blocks as another; blocks past the planes are clipped by the tensor bounds ----
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const int lx = blockIdx.x * (TW / 8), ly = blockIdx.y * (TH / 8);
+        const int cx = blockIdx.x * (CW / 8), cy = blockIdx.y * (CH / 8);
+        if (lx < g.nbx_l && ly < g.nby_l)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_l)), "r"(0), "r"(lx), "r"(ly), "r"(img), "r"(smem_u32(s.stage))
+                         : "memory");
+        if (cx < g.nbx_c && cy < g.nby_c)
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_c)), "r"(0), "r"(cx), "r"(cy), "r"(0), "r"(img),
+                         "r"(smem_u32(&s.stage[NY_BLOCKS * 8]))
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the staging area must outlive the reads
+    }
 }
 
 // Float64 re-evaluation of every flagged block with scipy's exact operation order.  A warp takes FOUR
@@ -1197,6 +1084,21 @@ extern "C" {
 
 int hic_dct_geometry_of(int32_t h, int32_t w, hic_dct_geometry* out) { return hic::geometry_of(h, w, out); }
 
+int hic_dct_tie_capacity(int32_t n, int32_t h, int32_t w, uint32_t* out) {
+    using namespace hic;
+    HIC_REQUIRE(out != nullptr, "capacity output is NULL");
+    HIC_REQUIRE(n >= 1 && n <= 65535, "batch size must be in 1..65535 (got %d)", n);
+    hic_dct_geometry g;
+    const int rc = geometry_of(h, w, &g);
+    if (rc) return rc;
+    const int ext_x = max(8 * g.nbx_l, 16 * g.nbx_c), ext_y = max(8 * g.nby_l, 16 * g.nby_c);
+    const uint64_t words = (uint64_t)ceil_div(ext_x, k1::TW) * ceil_div(ext_y, k1::TH) * n * k1::WARPS;
+    const uint64_t cap = (uint64_t)n * g.blocks_per_image + (words * 4 + sizeof(hic_tie_record) - 1) / sizeof(hic_tie_record) + 1;
+    HIC_REQUIRE(cap < (1ull << 32), "batch too large: %llu tie records", (unsigned long long)cap);
+    *out = (uint32_t)cap;
+    return HIC_OK;
+}
+
 int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16_t* d_coef, hic_tie_record* d_ties,
                     uint32_t tie_capacity, uint32_t* d_stats, void* stream) {
     using namespace hic;
@@ -1212,57 +1114,75 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
     HIC_CUDA(cudaMemsetAsync(d_stats, 0, HIC_TIE_STATS * sizeof(uint32_t), st));
     const int ext_x = max(8 * g.nbx_l, 16 * g.nbx_c), ext_y = max(8 * g.nby_l, 16 * g.nby_c);
     dim3 grid(ceil_div(ext_x, k1::TW), ceil_div(ext_y, k1::TH), n);
+    // the flag words of K1 (one per warp) live at the tail of the tie buffer, the list of flagged blocks at its head
+    const uint64_t flag_words64 = (uint64_t)grid.x * grid.y * grid.z * k1::WARPS;
+    HIC_REQUIRE(flag_words64 < (1ull << 32), "batch too large: %llu tiles", (unsigned long long)(flag_words64 / k1::WARPS));
+    const uint32_t flag_words = (uint32_t)flag_words64, flag_slots = (flag_words * 4u + (uint32_t)sizeof(hic_tie_record) - 1u) / (uint32_t)sizeof(hic_tie_record);
+    if (tie_capacity <= flag_slots)
+        return hic::fail(HIC_ERR_CAPACITY, "tie_capacity %u is too small: the flag words alone take %u records (hic_dct_tie_capacity)", tie_capacity, flag_slots);
+    const uint32_t list_capacity = tie_capacity - flag_slots;
+    uint32_t* flagmap = reinterpret_cast<uint32_t*>(d_ties + list_capacity);
+    HIC_REQUIRE((reinterpret_cast<uintptr_t>(d_coef) & 127) == 0, "d_coef must be 128-byte aligned");
     static bool attr_set[64] = {false};
     int dev = 0;
     HIC_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
-        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
+        HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
         if (dev < 64) attr_set[dev] = true;
     }
-    // TMA path: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    // TMA load: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     bool use_tma = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0) && getenv("HIC_NO_TMA") == nullptr;
     if (use_tma) {
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            HIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (qres != cudaDriverEntryPointSuccess || !fn) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-            encode = reinterpret_cast<EncodeFn>(fn);
-        }
         const cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)n};
         const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
         const cuuint32_t box[3] = {(cuuint32_t)k1::RWORDS, (cuuint32_t)k1::RH, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(d_rgb), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) use_tma = false;       // fall back to the generic loader
         if (getenv("HIC_DEBUG")) fprintf(stderr, "[hic] tensor map encode -> %d (use_tma=%d)\n", (int)r, (int)use_tma);
     }
-    // HIC_K1_BPT (environment, 1 | 2): blocks per thread in the transform stage (A/B timing; same results)
-    static const int bpt = getenv("HIC_K1_BPT") ? atoi(getenv("HIC_K1_BPT")) : 1;
-    static const int dbg = getenv("HIC_K1_DEBUG") ? atoi(getenv("HIC_K1_DEBUG")) : 0;       // measurement aid: WRONG results when set
-    if (bpt == 2) {
-        if (use_tma)
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
-        else
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 2><<<grid, k1::threads_of(2), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
-    } else {
-        if (use_tma)
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
-        else
-            HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false, 1><<<grid, k1::threads_of(1), sizeof(k1::Smem), st>>>(tmap, d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats, dbg));
+    // TMA stores: the coefficient buffer as [image][block row][block column][64 int16] (luminance) and
+    // [image][plane][block row][block column][64 int16] (Cr, Cb), one 128-byte block = one swizzle row
+    CUtensorMap tmap_l, tmap_c;
+    {
+        const cuuint64_t blk = 128, img_stride = blk * (cuuint64_t)g.blocks_per_image;
+        const cuuint64_t dims_l[4] = {64, (cuuint64_t)g.nbx_l, (cuuint64_t)g.nby_l, (cuuint64_t)n};
+        const cuuint64_t str_l[3] = {blk, blk * (cuuint64_t)g.nbx_l, img_stride};
+        const cuuint32_t box_l[4] = {64, k1::TW / 8, k1::TH / 8, 1};
+        CUresult r = encode(&tmap_l, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, d_coef, dims_l, str_l, box_l, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled (luminance blocks) failed: %d", (int)r);
+        const cuuint64_t dims_c[5] = {64, (cuuint64_t)g.nbx_c, (cuuint64_t)g.nby_c, 2, (cuuint64_t)n};
+        const cuuint64_t str_c[4] = {blk, blk * (cuuint64_t)g.nbx_c, blk * (cuuint64_t)g.nb_c, img_stride};
+        const cuuint32_t box_c[5] = {64, k1::CW / 8, k1::CH / 8, 2, 1};
+        r = encode(&tmap_c, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, d_coef + (size_t)g.nb_l * 64, dims_c, str_c, box_c, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled (chroma blocks) failed: %d", (int)r);
     }
-    HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, tie_capacity, d_stats));
+    if (use_tma)
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
+    else
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
+    HIC_LAUNCH("tie_list_kernel", st, k1::tie_list_kernel<<<min(148u * 8u, (flag_words + 255u) / 256u), 256, 0, st>>>(flagmap, flag_words, (int)grid.x, (int)grid.y, g, h, w, d_ties, list_capacity, d_stats));
+    HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, list_capacity, d_stats));
     return HIC_OK;
 }
 

@@ -111,8 +111,11 @@ typedef struct hic_tie_record {
  * zigzag of transform.ac_components (transform.py:260-266).  float32 butterflies; every value
  * within the float32 error band of a rounding tie is then re-evaluated by a second kernel in
  * float64 with scipy's exact operation order, so the output equals the reference's bit for bit.
- * d_ties needs room for tie_capacity records (blocks_per_image * n is always enough);
+ * d_ties needs room for tie_capacity records -- hic_dct_tie_capacity() gives the count that is
+ * always enough: one record per block plus the per-warp flag words K1 leaves at the buffer's tail;
+ * d_coef must be 128-byte aligned (its blocks leave through TMA tensor stores);
  * d_stats is HIC_TIE_STATS uint32, zeroed by this call. */
+int hic_dct_tie_capacity(int32_t n, int32_t h, int32_t w, uint32_t* out);
 int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16_t* d_coef,
                     hic_tie_record* d_ties, uint32_t tie_capacity, uint32_t* d_stats, void* stream);
 

@@ -26,5 +26,5 @@ for r in rows:
         a = lines.setdefault(key, [0, 0]); a[0] += n; a[1] += smp
 tot = sum(v[0] for v in lines.values()); tots = sum(v[1] for v in lines.values())
 print("total warp instructions %.0f, samples %.0f" % (tot, tots))
-for (f, ln, src), (n, smp) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln, src), (n, smp) in sorted(lines.items(), key=lambda kv: -kv[1][1 if "--by-samples" in sys.argv else 0])[:top]:
     print("%5.2f%% inst %5.2f%% smp  %s:%d  %s" % (100 * n / tot, 100 * smp / max(tots, 1), f, ln, src[:110]))

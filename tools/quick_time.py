@@ -16,7 +16,8 @@ def main():
     rgb = torch.from_numpy(np.concatenate([base] * reps)[:n].copy()).to(dev).contiguous()
     blocks = n * g.blocks_per_image
     coef = torch.empty(blocks * 64, dtype=torch.int16, device=dev)
-    ties = torch.empty(blocks * 16, dtype=torch.uint8, device=dev)
+    cap = _lib.tie_capacity(n, h, w)
+    ties = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
     stats = torch.zeros(4, dtype=torch.int32, device=dev)
     yp = torch.empty(n * h * w, dtype=torch.uint8, device=dev)
     crp = torch.empty(n * g.hc * g.wc, dtype=torch.uint8, device=dev)
@@ -24,7 +25,7 @@ def main():
     out = torch.empty(n * g.out_h * g.out_w * 3, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     def fwd():
-        _lib.check(lib.hic_dct_forward(rgb.data_ptr(), n, h, w, coef.data_ptr(), ties.data_ptr(), blocks, stats.data_ptr(), st))
+        _lib.check(lib.hic_dct_forward(rgb.data_ptr(), n, h, w, coef.data_ptr(), ties.data_ptr(), cap, stats.data_ptr(), st))
     def inv():
         _lib.check(lib.hic_dct_inverse(coef.data_ptr(), n, h, w, yp.data_ptr(), crp.data_ptr(), cbp.data_ptr(), out.data_ptr(), ties.data_ptr(), blocks, stats.data_ptr(), st))
     for name, fn, bpp in (("forward", fwd, 6.0), ("inverse", inv, 6.0)):
