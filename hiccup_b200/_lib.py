@@ -43,6 +43,16 @@ class WaveletGeometry(ctypes.Structure):
                 ("band_off", ctypes.c_int64 * 10), ("len", ctypes.c_int64)]
 
 
+class WaveletPyramid(ctypes.Structure):
+    _fields_ = [("h", c_int32), ("w", c_int32), ("levels", c_int32), ("n_bands", c_int32), ("lh", c_int32 * 6),
+                ("lw", c_int32 * 6), ("band_off", ctypes.c_int64 * 16), ("len", ctypes.c_int64)]
+
+
+class WaveletParams(ctypes.Structure):
+    _fields_ = [("levels", c_int32), ("reserved", c_int32), ("multiplier", ctypes.c_double),
+                ("threshold", ctypes.c_double), ("threshold_index", ctypes.c_int64)]
+
+
 #: every symbol include/hiccup_b200.h declares -> (restype, argtypes)
 SIGNATURES = {
     "hic_version": (c_int, []),
@@ -79,6 +89,12 @@ SIGNATURES = {
     "hic_wavelet_inverse": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hic_wavelet_flat_to_bands": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hic_wavelet_bands_to_flat": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_wavelet_pyramid_of": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(WaveletPyramid)]),
+    "hic_wavelet_general_work_bytes": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(c_size_t)]),
+    "hic_wavelet_forward_general": (c_int, [c_void_p, c_int32, c_int32, c_int32, ctypes.POINTER(WaveletParams), c_void_p, c_void_p, c_void_p]),
+    "hic_wavelet_inverse_general": (c_int, [c_void_p, c_int32, c_int32, c_int32, ctypes.POINTER(WaveletParams), c_void_p, c_void_p, c_void_p]),
+    "hic_wavelet_flat_to_bands_general": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hic_wavelet_bands_to_flat_general": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hic_layout_dct": (c_int, [c_int32, c_int32, c_int32, ctypes.POINTER(StreamLayout)]),
     "hic_layout_flat": (c_int, [c_int32, ctypes.c_int64, ctypes.POINTER(StreamLayout)]),
     "hic_entropy_plan_create": (c_int, [ctypes.POINTER(StreamLayout), c_int32, ctypes.POINTER(c_void_p)]),
@@ -241,6 +257,18 @@ def wavelet_geometry(h, w):
     g = WaveletGeometry()
     check(load().hic_wavelet_geometry_of(int(h), int(w), ctypes.byref(g)))
     return g
+
+
+def wavelet_pyramid(h, w, levels):
+    g = WaveletPyramid()
+    check(load().hic_wavelet_pyramid_of(int(h), int(w), int(levels), ctypes.byref(g)))
+    return g
+
+
+def wavelet_work_bytes(n, h, w):
+    out = c_size_t()
+    check(load().hic_wavelet_general_work_bytes(int(n), int(h), int(w), ctypes.byref(out)))
+    return int(out.value)
 
 
 def layout_dct(n, h, w):

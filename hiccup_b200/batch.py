@@ -216,23 +216,45 @@ class DctBatchCodec(_BatchCodec):
 
 
 class WaveletBatchCodec(_BatchCodec):
-    """Wavelet ("HIC") mode: K9 -> flat-mode entropy stage -> K10.  h and w must be multiples of 8
-    to decode (the reference's decoder needs exact halvings, codec.py:182-189)."""
+    """Wavelet ("HIC") mode: K9 -> flat-mode entropy stage -> K10 at the default settings, the general
+    level-by-level kernels (csrc/hic_wavelet_general.cu) at any other settings.py values, read when the codec
+    is made.  To decode, h and w must be multiples of 2^levels (the reference's decoder needs exact halvings,
+    codec.py:182-189)."""
 
     def __init__(self, n, h, w, value_bins=entropy.DEFAULT_VALUE_BINS, device=None, stream=None, device_codes=True):
+        import ctypes
+        from hiccup_b200 import settings, wavelet
         _lib.require_device()
+        settings.check_wavelet_supported()
         if device is not None:
             _lib.check(_lib.load().hic_set_device(int(device)))
-        g = self.g = _lib.wavelet_geometry(h, w)
+        self.general = not settings.wavelet_defaults()
+        if self.general:
+            g = self.g = _lib.wavelet_pyramid(h, w, settings.WAVELET_NUM_LEVELS)
+            self.params = wavelet._params(g)
+            self._params_ref = ctypes.byref(self.params)
+        else:
+            g = self.g = _lib.wavelet_geometry(h, w)
         self.chan_elems = 64 * ((int(g.len) + 63) // 64)
         super().__init__(n, h, w, _lib.layout_flat(int(n), int(g.len)), 2 * self.chan_elems * 3 * int(n), (h, w),
                          value_bins, device, stream, device_codes)
+        if self.general:
+            self.d_work = _lib.DeviceBuffer(_lib.wavelet_work_bytes(n, h, w))
+            self._buffers.append(self.d_work)
 
     def _forward(self):
-        _lib.check(self.lib.hic_wavelet_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.stream))
+        if self.general:
+            _lib.check(self.lib.hic_wavelet_forward_general(self.d_rgb.ptr, self.n, self.h, self.w, self._params_ref,
+                                                            self.d_work.ptr, self.d_coef.ptr, self.stream))
+        else:
+            _lib.check(self.lib.hic_wavelet_forward(self.d_rgb.ptr, self.n, self.h, self.w, self.d_coef.ptr, self.stream))
 
     def _inverse(self):
-        _lib.check(self.lib.hic_wavelet_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_out.ptr, self.stream))
+        if self.general:
+            _lib.check(self.lib.hic_wavelet_inverse_general(self.d_coef_dec.ptr, self.n, self.h, self.w, self._params_ref,
+                                                            self.d_work.ptr, self.d_out.ptr, self.stream))
+        else:
+            _lib.check(self.lib.hic_wavelet_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_out.ptr, self.stream))
 
     def hic_images(self, enc):
         from hiccup_b200 import wavelet

@@ -20,6 +20,7 @@
 // sub-band region, which are contiguous runs of the zigzag order.
 #include "hic_core.cuh"
 #include "hic_runtime.cuh"
+#include "hic_wavelet_common.cuh"
 
 namespace hic {
 namespace wv {
@@ -41,21 +42,6 @@ __host__ __device__ constexpr int stage_off(int band) {
     return band >= 7 ? (band - 7) * 4096 : (band >= 4 ? 12288 + (band - 4) * 1024 : 15360 + band * 256);
 }
 __host__ __device__ constexpr int band_level(int band) { return band >= 7 ? 1 : (band >= 4 ? 2 : 3); }
-
-// number of zigzag positions before anti-diagonal d of an h x w matrix (transform._zigzag_indices)
-__device__ __forceinline__ int64_t diag_start(int d, int h, int w) {
-    const int m = min(h, w), M = max(h, w);
-    if (d <= m) return (int64_t)d * (d + 1) / 2;
-    if (d <= M - 1) return (int64_t)m * (m + 1) / 2 + (int64_t)(d - m) * m;
-    const int64_t r = (int64_t)h + w - 1 - d;
-    return (int64_t)h * w - r * (r + 1) / 2;
-}
-// zigzag position of (y, x): even diagonals run with y ascending, odd ones with y descending
-__device__ __forceinline__ int64_t zigzag_pos(int y, int x, int h, int w) {
-    const int d = x + y;
-    const int y_lo = max(0, d - (w - 1)), y_hi = min(d, h - 1);
-    return diag_start(d, h, w) + ((d & 1) ? (y_hi - y) : (y - y_lo));
-}
 
 __device__ __forceinline__ void haar_pair(double even, double odd, double& a, double& d) {
     const double ce = dmul(C, even), co = dmul(C, odd);

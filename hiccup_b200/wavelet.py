@@ -3,11 +3,15 @@
     wavelet_compression(rgb)      compression.py:59-85      wavelet_encode(c)    codec.py:116-163
     wavelet_decompression(c)      compression.py:88-100     wavelet_decode(hic)  codec.py:199-239
 
-The numeric work runs in csrc/hic_wavelet.cu (K9 / K10) and the shared entropy kernels in flat mode
-(include/hiccup_b200.h).  The transform restates PyWavelets' db1 wavedec2 / waverec2 in float64;
-PyWavelets itself could not be installed, so coefficient values are parity-checked against the
-reference run on oracle/pywt_standin.py only.
+The numeric work runs in csrc/hic_wavelet.cu (K9 / K10, the fused kernels for the default settings),
+csrc/hic_wavelet_general.cu (any WAVELET_NUM_LEVELS in 1..5, multiplier, threshold and quality factor:
+settings.py:12-16) and the shared entropy kernels in flat mode (include/hiccup_b200.h).  The transform
+restates PyWavelets' db1 wavedec2 / waverec2 in float64; PyWavelets itself could not be installed, so
+coefficient values are parity-checked against the reference run on oracle/pywt_standin.py only
+(DESIGN.md section 8).
 """
+import ctypes
+
 import numpy as np
 
 from hiccup_b200 import _lib, entropy, hicimage, iohelper, model, settings
@@ -16,9 +20,26 @@ CHANNELS = ("lum", "cr", "cb")
 
 
 def band_shapes(g):
-    """Shapes of the ten sub-bands [cA3, cH3, cV3, cD3, cH2, ..., cD1] of one channel."""
-    lvl = [3, 3, 3, 3, 2, 2, 2, 1, 1, 1]
+    """Shapes of the 3 L + 1 sub-bands [cA_L, cH_L, cV_L, cD_L, cH_(L-1), ..., cD_1] of one channel."""
+    levels = int(getattr(g, "levels", 3))
+    lvl = [levels] + [l for l in range(levels, 0, -1) for _ in range(3)]
     return [(int(g.lh[l]), int(g.lw[l])) for l in lvl]
+
+
+def _params(g):
+    """settings -> hic_wavelet_params for a channel of g.len coefficients (quantization.py:84-94 for the index)."""
+    p = _lib.WaveletParams()
+    p.levels = int(settings.WAVELET_NUM_LEVELS)
+    p.multiplier = float(settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER)
+    p.threshold = float(settings.WAVELET_THRESHOLD)
+    p.threshold_index = -1
+    if settings.WAVELET_QUALITY_FACTOR != 1:
+        n = int(g.len)
+        keep = int(np.ceil(n * settings.WAVELET_QUALITY_FACTOR))
+        if keep < 1:
+            raise IndexError("list index out of range")          # what the reference's s[len(vals)] raises
+        p.threshold_index = n - keep
+    return p
 
 
 def _as_rgb(rgb):
@@ -35,11 +56,22 @@ def _flat_elems(g):
 
 
 def forward_device(d_rgb, n, h, w, stream=None):
-    """K9 on a device-resident batch -> (flat stream buffer, geometry)."""
+    """K9 (default settings) or the general path on a device-resident batch -> (flat stream buffer, geometry)."""
     lib = _lib.load()
-    g = _lib.wavelet_geometry(h, w)
+    if settings.wavelet_defaults():
+        g = _lib.wavelet_geometry(h, w)
+        flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3 * n)
+        _lib.check(lib.hic_wavelet_forward(d_rgb, n, h, w, flat.ptr, stream))
+        return flat, g
+    g = _lib.wavelet_pyramid(h, w, settings.WAVELET_NUM_LEVELS)
     flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3 * n)
-    _lib.check(lib.hic_wavelet_forward(d_rgb, n, h, w, flat.ptr, stream))
+    work = _lib.DeviceBuffer(_lib.wavelet_work_bytes(n, h, w))
+    try:
+        params = _params(g)
+        _lib.check(lib.hic_wavelet_forward_general(d_rgb, n, h, w, ctypes.byref(params), work.ptr, flat.ptr, stream))
+        _lib.sync(stream)
+    finally:
+        work.free()
     return flat, g
 
 
@@ -57,7 +89,7 @@ def _split_bands(arr, g, dtype):
 
 
 def wavelet_compression(rgb_image: np.ndarray) -> model.CompressedImage:
-    """RGB -> YCrCb, x - 256, 3-level db1, sub-band quantisation, threshold; ten int32 sub-bands per channel."""
+    """RGB -> YCrCb, x - 256, L-level db1, sub-band quantisation, thresholds; 3 L + 1 int32 sub-bands per channel."""
     settings.check_wavelet_supported()
     _lib.require_device()
     lib = _lib.load()
@@ -67,41 +99,45 @@ def wavelet_compression(rgb_image: np.ndarray) -> model.CompressedImage:
     d_rgb.upload(img)
     flat, g = forward_device(d_rgb.ptr, 1, h, w)
     d_bands = _lib.DeviceBuffer(4 * int(g.len) * 3)
-    _lib.check(lib.hic_wavelet_flat_to_bands(flat.ptr, 1, h, w, d_bands.ptr, None))
+    _lib.check(lib.hic_wavelet_flat_to_bands_general(flat.ptr, 1, h, w, _levels_of(g), d_bands.ptr, None))
     arr = d_bands.download(np.int32, int(g.len) * 3).reshape(3, int(g.len))
     for b in (d_rgb, flat, d_bands):
         b.free()
     return model.CompressedImage.from_dict(_split_bands(arr, g, np.int32))
 
 
+def _levels_of(g):
+    return int(getattr(g, "levels", 3))
+
+
 def _image_shape_of(bands):
-    """(h, w) of the image a channel's sub-band list belongs to: the level-1 bands are ceil(n / 2)."""
-    if len(bands) != 10:
-        raise ValueError("expected ten sub-bands per channel (3 levels), got %d" % len(bands))
-    return tuple(int(v) for v in np.asarray(bands[-1]).shape)
+    """(h1, w1, levels) of a channel's sub-band list: the level-1 bands are ceil(n / 2) on a side."""
+    if len(bands) < 4 or (len(bands) - 1) % 3 or (len(bands) - 1) // 3 > 5:
+        raise ValueError("expected 3 L + 1 sub-bands per channel (L in 1..5), got %d" % len(bands))
+    h1, w1 = (int(v) for v in np.asarray(bands[-1]).shape)
+    return h1, w1, (len(bands) - 1) // 3
 
 
 def _bands_to_device_flat(compressed, stream=None):
     """Upload a wavelet CompressedImage and build the flat zigzag stream on the device."""
     lib = _lib.load()
     d = compressed.as_dict
-    h1, w1 = _image_shape_of(d["lum"])
+    h1, w1, levels = _image_shape_of(d["lum"])
     # the image shape is not stored: any (h, w) with ceil(h/2) = h1 gives the same sub-band shapes
     h, w = 2 * h1, 2 * w1
-    g = _lib.wavelet_geometry(h, w)
+    g = _lib.wavelet_pyramid(h, w, levels)
     shapes = band_shapes(g)
     cat = np.empty((3, int(g.len)), np.int32)
     max_abs = 0
     for ci, ch in enumerate(CHANNELS):
         bands = d[ch]
-        if len(bands) != 10:
-            raise ValueError("expected ten sub-bands in channel %s" % ch)
+        if len(bands) != len(shapes):
+            raise ValueError("expected %d sub-bands in channel %s" % (len(shapes), ch))
         off = 0
         for b, shp in zip(bands, shapes):
             a = np.asarray(b)
             if a.shape != shp:
-                raise ValueError("sub-band shape %r does not fit a 3-level db1 pyramid (expected %r); only shapes the "
-                                 "reference's own decoder handles are supported" % (a.shape, shp))
+                raise ValueError("sub-band shape %r does not fit a %d-level db1 pyramid (expected %r)" % (a.shape, levels, shp))
             if a.dtype.kind == "f":
                 r = np.rint(a)
                 if not np.array_equal(r, a):
@@ -117,7 +153,7 @@ def _bands_to_device_flat(compressed, stream=None):
     d_bands = _lib.DeviceBuffer(cat.nbytes)
     d_bands.upload(cat, stream)
     flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3)
-    _lib.check(lib.hic_wavelet_bands_to_flat(d_bands.ptr, 1, h, w, flat.ptr, stream))
+    _lib.check(lib.hic_wavelet_bands_to_flat_general(d_bands.ptr, 1, h, w, levels, flat.ptr, stream))
     _lib.sync(stream)
     d_bands.free()
     return flat, g, max_abs
@@ -185,12 +221,19 @@ def decode_to_device_flat(hic, stream=None):
     p = hic.payloads
     small, big = tuple(int(v) for v in p[12].numbers), tuple(int(v) for v in p[13].numbers)
     h, w = 2 * big[0], 2 * big[1]
-    g = _lib.wavelet_geometry(h, w)
+    # codec.wavelet_decoded_subbands_shapes (codec.py:182-189): the level count is int(sqrt(big // small)) + 1 and
+    # every level doubles exactly.  That formula is right for 2, 3 and 5 levels only; a 1- or 4-level file (or one
+    # of inexact halvings) is mis-read by the reference itself, so it is refused here rather than mis-read too.
+    if small[0] < 1 or small[1] < 1:
+        raise ValueError("empty sub-band shape %r" % (small,))
+    levels = int(np.sqrt(big[0] // small[0])) + 1
+    if not 1 <= levels <= 5:
+        raise ValueError("sub-band shapes %r .. %r imply %d levels" % (small, big, levels))
+    g = _lib.wavelet_pyramid(h, w, levels)
     shapes = band_shapes(g)
-    # codec.wavelet_decoded_subbands_shapes (codec.py:182-189) assumes every level doubles exactly
-    if shapes[0] != small or h % 8 or w % 8:
-        raise ValueError("sub-band shapes %r .. %r are not a 3-level pyramid of exact halvings; the reference's "
-                         "decoder cannot read such a file either (codec.py:182-189)" % (small, big))
+    if shapes[0] != small or h % (1 << levels) or w % (1 << levels):
+        raise ValueError("sub-band shapes %r .. %r are not a pyramid of exact halvings the reference's decoder reads "
+                         "as it was written (codec.py:182-189)" % (small, big))
     # stream order s = channel * 3 + kind; kind 0 (DC) is absent in flat mode
     empty = hicimage.PayloadStringP.from_rows([])
     tabs, bit_payloads = [], []
@@ -227,7 +270,7 @@ def wavelet_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     lib = _lib.load()
     flat, g = decode_to_device_flat(hic)
     d_bands = _lib.DeviceBuffer(4 * int(g.len) * 3)
-    _lib.check(lib.hic_wavelet_flat_to_bands(flat.ptr, 1, int(g.h), int(g.w), d_bands.ptr, None))
+    _lib.check(lib.hic_wavelet_flat_to_bands_general(flat.ptr, 1, int(g.h), int(g.w), _levels_of(g), d_bands.ptr, None))
     arr = d_bands.download(np.int32, int(g.len) * 3).reshape(3, int(g.len))
     flat.free()
     d_bands.free()
@@ -236,18 +279,29 @@ def wavelet_decode(hic: hicimage.HicImage) -> model.CompressedImage:
 
 
 def wavelet_decompression(channels: model.CompressedImage) -> np.ndarray:
-    """Dequantise, inverse 3-level db1, + 256, uint8 cast, YCrCb -> RGB."""
+    """Dequantise, inverse L-level db1, + 256, uint8 cast, YCrCb -> RGB.  The image is 2 ceil(h/2) x 2 ceil(w/2)
+    as pywt.waverec2 returns it (compression.py:88-100); L comes from the number of sub-bands."""
     settings.check_wavelet_supported()
     _lib.require_device()
     lib = _lib.load()
     flat, g, _ = _bands_to_device_flat(channels)
-    h, w = int(g.h), int(g.w)
-    if h % 8 or w % 8:
-        flat.free()
-        raise ValueError("wavelet decode needs image sides that are multiples of 8 (sub-bands imply %dx%d)" % (h, w))
+    h, w, levels = int(g.h), int(g.w), _levels_of(g)
     rgb = _lib.DeviceBuffer(h * w * 3)
-    _lib.check(lib.hic_wavelet_inverse(flat.ptr, 1, h, w, rgb.ptr, None))
-    out = rgb.download(np.uint8, h * w * 3).reshape(h, w, 3)
-    flat.free()
-    rgb.free()
+    try:
+        if levels == 3 and settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER == 1 and h % 8 == 0 and w % 8 == 0:
+            _lib.check(lib.hic_wavelet_inverse(flat.ptr, 1, h, w, rgb.ptr, None))
+        else:
+            params = _lib.WaveletParams()
+            params.levels, params.multiplier = levels, float(settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER)
+            params.threshold, params.threshold_index = 0.0, -1
+            work = _lib.DeviceBuffer(_lib.wavelet_work_bytes(1, h, w))
+            try:
+                _lib.check(lib.hic_wavelet_inverse_general(flat.ptr, 1, h, w, ctypes.byref(params), work.ptr, rgb.ptr, None))
+                _lib.sync()
+            finally:
+                work.free()
+        out = rgb.download(np.uint8, h * w * 3).reshape(h, w, 3)
+    finally:
+        flat.free()
+        rgb.free()
     return out

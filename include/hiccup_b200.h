@@ -167,6 +167,41 @@ int hic_wavelet_inverse(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, 
 int hic_wavelet_flat_to_bands(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, int32_t* d_bands, void* stream);
 int hic_wavelet_bands_to_flat(const int32_t* d_bands, int32_t n, int32_t h, int32_t w, int16_t* d_flat, void* stream);
 
+/* Wavelet mode at settings other than the defaults (reference settings.py:12-16): WAVELET_NUM_LEVELS in
+ * 1..HIC_WAVELET_MAX_LEVELS, any non-zero WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER, any WAVELET_THRESHOLD,
+ * and WAVELET_QUALITY_FACTOR < 1 -- the order statistic of quantization.quality_threshold_value
+ * (quantization.py:84-94) over all coefficients of a channel, taken on the device from a 65536-bin
+ * histogram.  db1 / haar only (model.py:31-35).  Same arithmetic as K9 / K10, level by level. */
+#define HIC_WAVELET_MAX_LEVELS 5
+typedef struct hic_wavelet_params {
+    int32_t levels;            /* settings.WAVELET_NUM_LEVELS */
+    int32_t reserved;
+    double multiplier;         /* settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER (!= 0) */
+    double threshold;          /* settings.WAVELET_THRESHOLD (0: none) */
+    int64_t threshold_index;   /* len - ceil(len * WAVELET_QUALITY_FACTOR), or -1 for a quality factor of 1 */
+} hic_wavelet_params;
+typedef struct hic_wavelet_pyramid {
+    int32_t h, w, levels, n_bands;     /* n_bands = 3 levels + 1: [cA_L, (cH, cV, cD)_L, ..., (cH, cV, cD)_1] */
+    int32_t lh[6], lw[6];              /* [0] = image, [l] = sub-band shape at level l */
+    int64_t band_off[16];
+    int64_t len;                       /* coefficients per channel */
+} hic_wavelet_pyramid;
+int hic_wavelet_pyramid_of(int32_t h, int32_t w, int32_t levels, hic_wavelet_pyramid* out);
+/* bytes of device scratch the two transforms below need (float64 planes of the running approximation) */
+int hic_wavelet_general_work_bytes(int32_t n, int32_t h, int32_t w, size_t* out);
+/* compression.wavelet_compression (compression.py:59-85) + the sub-band zigzag of codec.wavelet_encode
+ * (codec.py:123-126); d_flat as for hic_wavelet_forward with len = pyramid.len */
+int hic_wavelet_forward_general(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, const hic_wavelet_params* params,
+                                void* d_work, int16_t* d_flat, void* stream);
+/* compression.wavelet_decompression (compression.py:88-100).  h and w: the even sides 2 lh[1], 2 lw[1] of the
+ * image pywt.waverec2 returns (it trims the extra row / column between levels of odd size) */
+int hic_wavelet_inverse_general(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, const hic_wavelet_params* params,
+                                void* d_work, uint8_t* d_rgb_out, void* stream);
+int hic_wavelet_flat_to_bands_general(const int16_t* d_flat, int32_t n, int32_t h, int32_t w, int32_t levels, int32_t* d_bands,
+                                      void* stream);
+int hic_wavelet_bands_to_flat_general(const int32_t* d_bands, int32_t n, int32_t h, int32_t w, int32_t levels, int16_t* d_flat,
+                                      void* stream);
+
 /* ---- entropy stage ---------------------------------------------------------------------------- */
 /* A batch is 3 n "channel streams" (image i, channel c in lum, cr, cb).  Each channel stream is a
  * run of 64-element int16 blocks.  DCT mode (skip_first = 1): element 0 of every block is its DC

@@ -26,7 +26,7 @@ def _golden_comp(g):
 
 
 def _same_bands(a, b):
-    return all(len(a[ch]) == len(b[ch]) == 10 and
+    return all(len(a[ch]) == len(b[ch]) and
                all(np.asarray(x).shape == np.asarray(y).shape and np.array_equal(x, y) for x, y in zip(a[ch], b[ch]))
                for ch in CH)
 

@@ -101,3 +101,43 @@ def test_oracle_against_live_reference(shape, seed):
         with contextlib.redirect_stdout(io.StringIO()):
             dec = rcodec.jpeg_decode(hi)
         assert np.array_equal(rcomp.jpeg_decompression(dec), orc.jpeg_decompression(planes))
+
+
+WAVELET_SETTINGS = [
+    dict(levels=1, multiplier=1, threshold=5, quality_factor=1),
+    dict(levels=2, multiplier=2, threshold=3, quality_factor=1),
+    dict(levels=4, multiplier=1, threshold=0, quality_factor=0.5),
+    dict(levels=5, multiplier=0.5, threshold=5, quality_factor=0.9),
+    dict(levels=3, multiplier=1.5, threshold=2.5, quality_factor=0.25),
+]
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("cfg", WAVELET_SETTINGS)
+@pytest.mark.parametrize("shape", [(64, 96), (50, 38)])
+def test_oracle_wavelet_settings_against_live_reference(cfg, shape):
+    """The oracle at non-default wavelet settings (reference settings.py:12-16) against the unmodified
+    reference's wavelet_compression / wavelet_decompression (both on the pywt stand-in)."""
+    from oracle import refshim
+    rsettings = refshim.install()
+    import hiccup.compression as rcomp
+    import hiccup.model as rmodel
+    saved = (rsettings.WAVELET, rsettings.WAVELET_NUM_LEVELS, rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER,
+             rsettings.WAVELET_THRESHOLD, rsettings.WAVELET_QUALITY_FACTOR)
+    try:
+        rsettings.WAVELET = rmodel.Wavelet.HAAR if cfg["levels"] % 2 else rmodel.Wavelet.DAUBECHIE
+        rsettings.WAVELET_NUM_LEVELS = cfg["levels"]
+        rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER = cfg["multiplier"]
+        rsettings.WAVELET_THRESHOLD = cfg["threshold"]
+        rsettings.WAVELET_QUALITY_FACTOR = cfg["quality_factor"]
+        rgb = orc.synthetic_image(shape[0], shape[1], 300 + cfg["levels"])
+        want = rcomp.wavelet_compression(rgb)
+        got = orc.wavelet_compression(rgb, **cfg)
+        for ch in orc.CHANNELS:
+            assert len(got[ch]) == len(want.as_dict[ch]) == 3 * cfg["levels"] + 1
+            for a, b in zip(got[ch], want.as_dict[ch]):
+                assert a.shape == b.shape and np.array_equal(a, b)
+        assert np.array_equal(orc.wavelet_decompression(got, cfg["multiplier"]), rcomp.wavelet_decompression(want))
+    finally:
+        (rsettings.WAVELET, rsettings.WAVELET_NUM_LEVELS, rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER,
+         rsettings.WAVELET_THRESHOLD, rsettings.WAVELET_QUALITY_FACTOR) = saved
