@@ -49,7 +49,14 @@ def _symbol_types(dtype):
     return dc_type, ac_type
 
 
-def jpeg_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
+def jpeg_encode(compressed: model.CompressedImage, restarts: bool = False) -> hicimage.HicImage:
+    """restarts=True appends the restart records of the nine bit strings as an extension entry (hicimage.RestartP):
+    the reference's reader ignores it, this package's decoder then skips the synchronisation passes."""
+    hic = _jpeg_encode(compressed)
+    return add_restart_records(hic) if restarts else hic
+
+
+def _jpeg_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
     settings.check_supported()
     _lib.require_device()
     d = compressed.as_dict if hasattr(compressed, "as_dict") else model.CompressedImage.as_dict.fget(compressed)
@@ -106,6 +113,100 @@ def _gather_payload_bytes(bit_payloads):
     return data, offs, nbits
 
 
+def _stream_order(hic):
+    """File payload index of the table / bit string of every stream s of the entropy stage, (tables, bits);
+    None where the stream does not exist (the DC streams of a wavelet file)."""
+    kind_is_jpeg = hic.hic_type == model.Compression.JPEG or getattr(hic.hic_type, "value", None) == "JPEG"
+    if kind_is_jpeg:       # reference order is (kind, channel); stream order is s = channel * 3 + kind
+        order = [kind * 3 + c for c in range(3) for kind in range(3)]
+        return order, [9 + i for i in order], 9
+    tabs, bits = [], []
+    for c in range(3):     # kind 0 (DC) is absent in flat mode
+        tabs += [None, c, 3 + c]
+        bits += [None, 6 + c, 9 + c]
+    return tabs, bits, 6
+
+
+def _records_in_stream_order(hic, nbits):
+    """The file's restart records re-ordered to stream order and concatenated, or None when the file has none
+    (or they do not fit its bit strings: the extension is advisory, the decoder then synchronises by itself)."""
+    ext = getattr(hic, "restarts", None)
+    if ext is None:
+        return None
+    _, bits, first = _stream_order(hic)
+    n_bits = len(bits) - bits.count(None)
+    if len(ext.records) != n_bits:
+        return None
+    want = entropy.EntropyDecoder.subsequences(nbits)
+    offs, cnts = [], []
+    for s, i in enumerate(bits):
+        if i is None:
+            continue
+        off, cnt = ext.records[i - first]
+        if off.size != want[s] or cnt.size != want[s]:
+            return None
+        offs.append(off)
+        cnts.append(cnt)
+    return np.concatenate(offs) if offs else np.zeros(0, np.uint8), np.concatenate(cnts) if cnts else np.zeros(0, np.uint8)
+
+
+def _entropy_decode(dec, hic, rows, syms, lens, codes, data, offs, nbits, d_coef, stream=None):
+    records = _records_in_stream_order(hic, nbits)
+    if records is not None:
+        try:
+            dec.decode(rows, syms, lens, codes, data, offs, nbits, d_coef, stream, restarts=records)
+            return True
+        except _lib.HicError:
+            pass           # records that do not belong to the streams: decode the long way (and fail there if the streams are bad)
+    dec.decode(rows, syms, lens, codes, data, offs, nbits, d_coef, stream)
+    return False
+
+
+def add_restart_records(hic: hicimage.HicImage) -> hicimage.HicImage:
+    """A copy of `hic` carrying the restart records of its bit strings (an extension entry the reference's reader
+    never reads): D1's synchronisation passes run once, here, instead of at every decode."""
+    _lib.require_device()
+    p = hic.payloads
+    tabs, bits, first = _stream_order(hic)
+    empty = hicimage.PayloadStringP.from_rows([])
+    rows, syms, lens, codes = _tables_to_arrays([empty if i is None else p[i] for i in tabs])
+    jpeg = first == 9
+    offs, nbits, chunks, pos = [], [], [], 0
+    for i in bits:
+        if i is None:
+            offs.append(0)
+            nbits.append(0)
+            continue
+        framed = bytes(p[i].byte_stream)
+        offs.append(pos)
+        nbits.append(iohelper.payload_bit_count(framed))
+        pad = (-len(framed)) % 4
+        chunks.append(framed + b"\0" * pad)
+        pos += len(framed) + pad
+    data = np.frombuffer(b"".join(chunks) + b"\0" * 16, dtype=np.uint8)
+    if jpeg:
+        h, w = (int(v) for v in p[18].numbers)
+        layout = _lib.layout_dct(1, h, w)
+    else:
+        from hiccup_b200 import wavelet
+        layout = _lib.layout_flat(1, int(wavelet.pyramid_of_file(hic).len))
+    dec = entropy.EntropyDecoder(layout)
+    try:
+        off, cnt = dec.decode(rows, syms, lens, codes, data, offs, nbits, None, sync_only=True)
+    finally:
+        dec.close()
+    n_sub = entropy.EntropyDecoder.subsequences(nbits)
+    records, at = {}, 0
+    for s, i in enumerate(bits):
+        if i is None:
+            continue
+        records[i - first] = (off[at:at + n_sub[s]], cnt[at:at + n_sub[s]])
+        at += n_sub[s]
+    ext = hicimage.RestartP([records[k] for k in sorted(records)])
+    others = [e for e in hic.extensions if not isinstance(e, hicimage.RestartP)]
+    return hicimage.HicImage(hic.hic_type, hic.settings, list(p), others + [ext])
+
+
 def jpeg_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     settings.check_supported()
     _lib.require_device()
@@ -125,7 +226,7 @@ def jpeg_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     dec = entropy.EntropyDecoder(layout)
     lib = _lib.load()
     try:
-        dec.decode(rows, syms, lens, codes, data, offs, nbits, coef.ptr)
+        _entropy_decode(dec, hic, rows, syms, lens, codes, data, offs, nbits, coef.ptr)
         lum = _lib.DeviceBuffer(4 * h * w)
         cr = _lib.DeviceBuffer(4 * g.hc * g.wc)
         cb = _lib.DeviceBuffer(4 * g.hc * g.wc)
@@ -142,9 +243,10 @@ def jpeg_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     return out
 
 
-def wavelet_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
+def wavelet_encode(compressed: model.CompressedImage, restarts: bool = False) -> hicimage.HicImage:
     from hiccup_b200 import wavelet
-    return wavelet.wavelet_encode(compressed)
+    hic = wavelet.wavelet_encode(compressed)
+    return add_restart_records(hic) if restarts else hic
 
 
 def wavelet_decode(hic: hicimage.HicImage) -> model.CompressedImage:

@@ -701,6 +701,53 @@ __global__ void sync_tile_scan_kernel(int n_ss, const uint32_t* __restrict__ ss_
     nsym_out[s] = run;
 }
 
+// Restart records (the `.hic` extension of hiccup_b200/hicimage.py; the reference's format has none,
+// codec.py:319-334): for every SUB_BITS-bit subsequence of a stream, one byte `off` = how many bits past the
+// subsequence's upper boundary the first codeword that starts at or after it begins (< 58), and one byte
+// `cnt` = how many codewords start inside the span that ends there (<= SUB_BITS).  They are exactly what the
+// sync passes converge to; a decoder that has them skips those passes.  The write kernel still checks every
+// span against them, so a wrong record is reported as corruption, never decoded silently.
+__global__ void __launch_bounds__(SUB_PER_CTA)
+restart_export_kernel(const SyncTile* __restrict__ tiles, const uint64_t* __restrict__ nbits, const uint32_t* __restrict__ sub_end,
+                      const uint16_t* __restrict__ sub_cnt, uint8_t* __restrict__ off, uint8_t* __restrict__ cnt) {
+    const SyncTile t = tiles[blockIdx.x];
+    const uint32_t end = (uint32_t)(8 + nbits[t.ss]);
+    const uint32_t n_sub = (end + SUB_BITS - 1) / SUB_BITS;
+    const uint32_t sub = t.sub0 + threadIdx.x;
+    if (sub >= n_sub) return;
+    const uint64_t g = t.sub_base + threadIdx.x;
+    off[g] = sub == n_sub - 1 ? (uint8_t)0 : (uint8_t)(sub_end[g] - (sub + 1) * SUB_BITS);
+    cnt[g] = (uint8_t)sub_cnt[g];
+}
+
+__global__ void __launch_bounds__(SUB_PER_CTA)
+restart_load_kernel(const SyncTile* __restrict__ tiles, const uint64_t* __restrict__ nbits, const uint8_t* __restrict__ off,
+                    const uint8_t* __restrict__ cnt, uint32_t* __restrict__ sub_end, uint16_t* __restrict__ sub_cnt,
+                    uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_red[SUB_PER_CTA / 32];
+    const SyncTile t = tiles[blockIdx.x];
+    const uint32_t end = (uint32_t)(8 + nbits[t.ss]);
+    const uint32_t n_sub = (end + SUB_BITS - 1) / SUB_BITS;
+    const uint32_t sub = t.sub0 + threadIdx.x;
+    const bool active = sub < n_sub;
+    const uint64_t g = t.sub_base + threadIdx.x;
+    uint32_t v = 0;
+    if (active) {
+        v = cnt[g];
+        sub_end[g] = sub == n_sub - 1 ? end : min(end, (sub + 1) * SUB_BITS + off[g]);
+        sub_cnt[g] = (uint16_t)v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < SUB_PER_CTA / 32; ++w) tot += s_red[w];
+        tile_cnt[blockIdx.x] = tot;
+    }
+}
+
 // The CTA's symbols are one contiguous run of the output, so they are staged in shared memory and
 // written out coalesced (a thread's own run is only a few symbols long: writing it straight to global
 // memory costs a 32-byte sector per 1- or 2-byte store).
@@ -1088,6 +1135,8 @@ struct hic_decode_plan {
     uint32_t* d_sub_end = nullptr;
     uint16_t* d_sub_cnt = nullptr;
     uint64_t sub_capacity = 0;
+    uint8_t* d_restart = nullptr;               // 2 x sub_capacity: `off` bytes then `cnt` bytes of the restart records
+    uint64_t last_n_sub = 0, last_n_tiles = 0;  // of the most recent run (what hic_decode_export_restarts exports)
     uint32_t* d_tile_start = nullptr;
     uint32_t* d_tile_cnt = nullptr;
     uint32_t* d_tile_symoff = nullptr;
@@ -1119,7 +1168,7 @@ extern "C" {
 int hic_decode_plan_destroy(hic_decode_plan* p) {
     if (!p) return HIC_OK;
     p->xfer.destroy();
-    void* ptrs[] = {p->d_pklut, p->d_mlut, p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
+    void* ptrs[] = {p->d_restart, p->d_pklut, p->d_mlut, p->d_dc, p->d_values, p->d_lengths, p->d_lut1, p->d_lut2, p->d_sorted_left, p->d_sorted_row, p->d_tiles, p->d_ss_tile0, p->d_sub_end,
                     p->d_sub_cnt, p->d_tile_start, p->d_tile_cnt, p->d_tile_symoff, p->d_index_own, p->d_row_sym_own,
                     p->d_row_packed_own, p->d_byte_off, p->d_nbits, p->d_nsym, p->d_err, p->d_tile_sum,
                     p->d_tile_off, p->d_stream_total};
@@ -1272,9 +1321,14 @@ int hic_decode_set_tables(hic_decode_plan* p, const uint32_t* h_rows, const int3
     return HIC_OK;
 }
 
-int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
-                   int16_t* d_coef, void* stream) {
-    HIC_REQUIRE(p && d_bytes && h_byte_off && h_nbits && d_coef, "NULL argument");
+}  // extern "C"
+
+// mode 0: the whole decode; mode 1: D1's synchronisation only (what the restart records are exported from);
+// h_roff / h_rcnt: restart records of every subsequence in stream order, or NULL
+static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
+                           int16_t* d_coef, void* stream, int mode, const uint8_t* h_roff, const uint8_t* h_rcnt,
+                           uint64_t n_restart) {
+    HIC_REQUIRE(p && d_bytes && h_byte_off && h_nbits && (d_coef || mode == 1), "NULL argument");
     HIC_REQUIRE(p->tables_ready, "hic_decode_set_tables has not run");
     HIC_REQUIRE((reinterpret_cast<uintptr_t>(d_bytes) & 3) == 0, "d_bytes must be 4-byte aligned");
     const dec::Geom& g = p->g;
@@ -1318,10 +1372,19 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     if (n_sub_total > p->sub_capacity) {
         if (p->d_sub_end) cudaFree(p->d_sub_end);
         if (p->d_sub_cnt) cudaFree(p->d_sub_cnt);
-        p->d_sub_end = nullptr; p->d_sub_cnt = nullptr;
+        if (p->d_restart) cudaFree(p->d_restart);
+        p->d_sub_end = nullptr; p->d_sub_cnt = nullptr; p->d_restart = nullptr;
         p->sub_capacity = n_sub_total + n_sub_total / 4 + 1024;
         HIC_CUDA(dalloc2(&p->d_sub_end, p->sub_capacity));
         HIC_CUDA(dalloc2(&p->d_sub_cnt, p->sub_capacity));
+        HIC_CUDA(dalloc2(&p->d_restart, 2 * p->sub_capacity));
+    }
+    p->last_n_sub = n_sub_total;
+    p->last_n_tiles = n_tiles;
+    const bool restarts = h_roff != nullptr;
+    if (restarts) {
+        HIC_REQUIRE(h_rcnt != nullptr && n_restart == n_sub_total, "restart records for %llu subsequences, the streams have %llu",
+                    (unsigned long long)n_restart, (unsigned long long)n_sub_total);
     }
     {
         int rc = hic::small_h2d(p->xfer, p->d_ss_tile0, ss_tile0.data(), sizeof(uint32_t) * (nss + 1), st);
@@ -1337,8 +1400,15 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
         a.bytes = d_bytes; a.byte_off = p->d_byte_off; a.nbits = p->d_nbits; a.lut1 = p->d_lut1; a.lut2 = p->d_lut2; a.mlut = p->d_mlut; a.pklut = p->d_pklut; a.l2_cap = p->l2_cap; a.sorted_left = p->d_sorted_left; a.sorted_row = p->d_sorted_row;
         a.index = p->d_index; a.row_sym = p->d_row_sym; a.row_packed = p->d_row_packed; a.tiles = p->d_tiles; a.sub_end = p->d_sub_end;
         a.sub_cnt = p->d_sub_cnt; a.tile_start = p->d_tile_start; a.tile_cnt = p->d_tile_cnt; a.changed = p->d_err + 1;
-        HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
-        for (int round = 0; round < 1024; ++round) {
+        if (restarts) {
+            HIC_CUDA(cudaMemcpyAsync(p->d_restart, h_roff, n_sub_total, cudaMemcpyHostToDevice, st));
+            HIC_CUDA(cudaMemcpyAsync(p->d_restart + p->sub_capacity, h_rcnt, n_sub_total, cudaMemcpyHostToDevice, st));
+            HIC_LAUNCH("restart_load_kernel", st, restart_load_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(p->d_tiles, p->d_nbits, p->d_restart,
+                                                                  p->d_restart + p->sub_capacity, p->d_sub_end, p->d_sub_cnt, p->d_tile_cnt));
+        } else {
+            HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
+        }
+        for (int round = 0; round < 1024 && !restarts; ++round) {
             HIC_CUDA(cudaMemsetAsync(p->d_err + 1, 0, sizeof(uint32_t), st));
             HIC_LAUNCH("huffman_resync_kernel", st, huffman_sync_kernel<true><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
             const void* h_changed = nullptr;
@@ -1350,6 +1420,11 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
             if (!*static_cast<const volatile uint32_t*>(h_changed)) break;
         }
         HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
+        if (mode == 1) {
+            HIC_CUDA(cudaStreamSynchronize(st));
+            p->xfer.reset();
+            return HIC_OK;
+        }
         {
             constexpr int WRITE_SMEM = 4 * (CHUNK_WORDS + CHUNK_SLACK) + 4 * L1_SIZE + 4 * PK_SIZE + 2 * WRITE_STAGE;
             static bool attr_set[64] = {false};
@@ -1361,6 +1436,11 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
             }
             HIC_LAUNCH("huffman_write_kernel", st, huffman_write_kernel<<<(unsigned)n_tiles, SUB_PER_CTA, WRITE_SMEM, st>>>(a, g, p->d_tile_symoff, p->d_dc, p->d_values, p->d_lengths, p->d_err));
         }
+    }
+    if (mode == 1) {
+        HIC_CUDA(cudaStreamSynchronize(st));
+        p->xfer.reset();
+        return HIC_OK;
     }
     HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)((p->total_xtiles + XTHREADS / 32 - 1) / (XTHREADS / 32)), XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum, p->total_xtiles));
     HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
@@ -1384,7 +1464,44 @@ int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h
     HIC_CUDA(cudaStreamSynchronize(st));
     const uint32_t flags0 = static_cast<const volatile uint32_t*>(h_flags)[0];
     p->xfer.reset();                 // everything staged has been consumed
-    if (flags0) return hic::fail(HIC_ERR_CORRUPT, "bit streams did not decode cleanly (flags 0x%x)", flags0);
+    if (flags0) return hic::fail(HIC_ERR_CORRUPT, "bit streams did not decode cleanly (flags 0x%x)%s", flags0,
+                                 restarts ? " -- or the restart records do not belong to them" : "");
+    return HIC_OK;
+}
+
+extern "C" {
+
+int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
+                   int16_t* d_coef, void* stream) {
+    return decode_run_impl(p, d_bytes, h_byte_off, h_nbits, d_coef, stream, 0, nullptr, nullptr, 0);
+}
+
+int hic_decode_run_restarts(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
+                            const uint8_t* h_off, const uint8_t* h_cnt, uint64_t n_sub, int16_t* d_coef, void* stream) {
+    HIC_REQUIRE(h_off && h_cnt, "NULL restart records");
+    return decode_run_impl(p, d_bytes, h_byte_off, h_nbits, d_coef, stream, 0, h_off, h_cnt, n_sub);
+}
+
+int hic_decode_sync(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
+                    uint64_t* n_sub_out, void* stream) {
+    const int rc = decode_run_impl(p, d_bytes, h_byte_off, h_nbits, nullptr, stream, 1, nullptr, nullptr, 0);
+    if (rc) return rc;
+    if (n_sub_out) *n_sub_out = p->last_n_sub;
+    return HIC_OK;
+}
+
+int hic_decode_export_restarts(hic_decode_plan* p, uint8_t* h_off, uint8_t* h_cnt, uint64_t capacity, void* stream) {
+    HIC_REQUIRE(p && h_off && h_cnt, "NULL argument");
+    if (capacity < p->last_n_sub)
+        return hic::fail(HIC_ERR_CAPACITY, "room for %llu restart records, the last run has %llu", (unsigned long long)capacity,
+                         (unsigned long long)p->last_n_sub);
+    if (p->last_n_sub == 0) return HIC_OK;
+    cudaStream_t st = as_stream(stream);
+    HIC_LAUNCH("restart_export_kernel", st, restart_export_kernel<<<(unsigned)p->last_n_tiles, SUB_PER_CTA, 0, st>>>(p->d_tiles, p->d_nbits, p->d_sub_end, p->d_sub_cnt,
+                                                                  p->d_restart, p->d_restart + p->sub_capacity));
+    HIC_CUDA(cudaMemcpyAsync(h_off, p->d_restart, p->last_n_sub, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaMemcpyAsync(h_cnt, p->d_restart + p->sub_capacity, p->last_n_sub, cudaMemcpyDeviceToHost, st));
+    HIC_CUDA(cudaStreamSynchronize(st));
     return HIC_OK;
 }
 

@@ -279,9 +279,17 @@ class EntropyDecoder:
         self._in.upload(data, stream)
         self.run(self._in.ptr, enc.byte_off, enc.nbits, d_coef, stream)      # synchronises: host arrays may go
 
-    def decode(self, rows, symbols, lens, codes, data, byte_off, nbits, d_coef, stream=None, d_data=None):
+    @staticmethod
+    def subsequences(nbits):
+        """128-bit subsequences of each stream (one restart record each): the 8 framing bits count."""
+        return [(8 + int(b) + 127) // 128 if int(b) else 0 for b in nbits]
+
+    def decode(self, rows, symbols, lens, codes, data, byte_off, nbits, d_coef, stream=None, d_data=None, restarts=None,
+               sync_only=False):
         """rows/symbols/lens/codes: concatenated code tables; data: uint8 host array holding every
-        framed payload at byte_off[s] (4-byte aligned); nbits[s]: payload bits.  Fills d_coef."""
+        framed payload at byte_off[s] (4-byte aligned); nbits[s]: payload bits.  Fills d_coef.
+        restarts = (off, cnt): the restart records of every subsequence in stream order (the `.hic` extension):
+        the synchronisation passes are skipped.  sync_only: run only those passes and return the records."""
         rows = np.ascontiguousarray(rows, np.uint32)
         symbols = np.ascontiguousarray(symbols, np.int32)
         lens = np.ascontiguousarray(lens, np.uint8)
@@ -299,4 +307,18 @@ class EntropyDecoder:
                 self._in = _lib.DeviceBuffer(need + need // 4)
             self._in.upload(data, stream)
             d_data = self._in.ptr
+        if sync_only:
+            n_sub = ctypes.c_uint64()
+            _lib.check(self.lib.hic_decode_sync(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, ctypes.byref(n_sub), stream))
+            off, cnt = np.empty(n_sub.value, np.uint8), np.empty(n_sub.value, np.uint8)
+            _lib.check(self.lib.hic_decode_export_restarts(self.plan, off.ctypes.data, cnt.ctypes.data, n_sub.value, stream))
+            return off, cnt
+        if restarts is not None:
+            off = np.ascontiguousarray(restarts[0], np.uint8)
+            cnt = np.ascontiguousarray(restarts[1], np.uint8)
+            assert off.size == cnt.size
+            _lib.check(self.lib.hic_decode_run_restarts(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data,
+                                                        off.ctypes.data, cnt.ctypes.data, int(off.size), d_coef, stream))
+            return None
         _lib.check(self.lib.hic_decode_run(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, d_coef, stream))
+        return None

@@ -12,10 +12,62 @@ DCT mode: 9 tables, 9 bit strings, 2 shapes (21 entries); wavelet mode: 6, 6, 2 
 Unlike the reference, a bit payload may be held as its framed bytes (what the GPU bit-packer
 produces and what `from_bytes` receives) and is only expanded to a '0'/'1' string when `.payload`
 is read, so a multi-megabit stream never passes through Python string code on the fast path.
+
+Two things the reference's reader does not have:
+
+  * A tolerant, closed reader (`loads`).  The pickles inside a `.hic` file name a class
+    (`hiccup.hicimage.TupP`, hicimage.py:117-121) and -- for DC symbols -- numpy's scalar
+    reconstructor, whose module path differs between numpy 1 (`numpy.core.multiarray`) and numpy 2
+    (`numpy._core.multiarray`), so a file written in one environment does not load in another with
+    plain `pickle.loads`.  `loads` resolves exactly the handful of globals a `.hic` file can contain,
+    whatever environment wrote it (any pickle protocol, either numpy spelling, with or without the
+    reference package importable), and refuses every other global -- a `.hic` file from an untrusted
+    source cannot run code here.  `HicImage.write_file(path, portable=True)` writes symbols as plain
+    Python ints so that ANY environment's reference reader loads the file (not byte-identical to the
+    reference's own output, hence opt-in).
+  * Extension entries.  The reference's reader takes list entries 0..20 (DCT) or 0..14 (wavelet) and
+    never looks further (hicimage.py:124-142), so entries appended after them travel with the file and
+    the reference still decodes it.  `RestartP` (restart records for the parallel Huffman decode,
+    include/hiccup_b200.h) is such an entry.
 """
+import io
 import pickle
+import struct
+
+import numpy as np
 
 from hiccup_b200 import _compat, iohelper, model
+
+
+def _np_scalar(dtype, raw):
+    """numpy's scalar reconstructor, for either spelling of its module path."""
+    return np.frombuffer(raw, dtype=dtype, count=1)[0]
+
+
+class _HicUnpickler(pickle.Unpickler):
+    """Resolves the globals a `.hic` pickle may name and nothing else."""
+
+    def find_class(self, module, name):
+        if name == "TupP" and module.endswith("hicimage"):
+            return _compat.wire_tuple_class()
+        if module in ("numpy.core.multiarray", "numpy._core.multiarray") and name == "scalar":
+            return _np_scalar
+        if module == "numpy" and name == "dtype":
+            return np.dtype
+        if module == "_codecs" and name == "encode":           # how protocols < 3 spell a bytes object
+            import codecs
+            return codecs.encode
+        raise pickle.UnpicklingError("a .hic file may not reference %s.%s" % (module, name))
+
+
+def loads(b):
+    """pickle.loads for the pickles inside a `.hic` file: tolerant of the writer's environment, closed to
+    everything a `.hic` file has no business containing."""
+    return _HicUnpickler(io.BytesIO(bytes(b))).load()
+
+
+def load(f):
+    return _HicUnpickler(f).load()
 
 
 class Payload:
@@ -36,7 +88,7 @@ class TupP(Payload):
 
     @classmethod
     def from_bytes(cls, b):
-        a, c = pickle.loads(b)
+        a, c = loads(b)
         return cls(a, c)
 
     @property
@@ -119,7 +171,7 @@ class PayloadStringP(Payload):
 
     @classmethod
     def from_bytes(cls, b):
-        d = pickle.loads(b)
+        d = loads(b)
         # rows are plain pickled pairs; parse them directly rather than through d["type"] so that
         # files written by the reference and by this package read the same way
         return cls(d["type"], [TupP.from_bytes(x) for x in d["data"]])
@@ -138,8 +190,57 @@ class PayloadStringP(Payload):
         return pickle.dumps({"type": _compat.wire_tuple_class(),
                              "data": [p.byte_stream for p in self.payloads]})
 
+    def portable(self):
+        """The same table with every symbol as a plain Python number (no numpy scalar pickles)."""
+        plain = lambda v: v if type(v) in (int, float) else (float(v) if isinstance(v, (float, np.floating)) else int(v))
+        return PayloadStringP(self.t, [TupP(plain(p.n1), p.n2) for p in self.payloads])
+
     def __eq__(self, other):
         return hasattr(other, "payloads") and list(other.payloads) == list(self.payloads)
+
+    __hash__ = None
+
+
+class RestartP(Payload):
+    """Extension entry: restart records of the file's bit payloads, in the file's payload order.
+    records[i] = (off, cnt), two uint8 arrays with one element per 128-bit subsequence of the framed
+    payload i (include/hiccup_b200.h: hic_decode_run_restarts).  12.5 % of the coded size."""
+    MAGIC = b"hiccup_b200.restart.v1\0"
+
+    def __init__(self, records):
+        self.records = [(np.ascontiguousarray(o, np.uint8), np.ascontiguousarray(c, np.uint8)) for o, c in records]
+
+    @classmethod
+    def matches(cls, b):
+        return bytes(b[:len(cls.MAGIC)]) == cls.MAGIC
+
+    @classmethod
+    def from_bytes(cls, b):
+        b = bytes(b)
+        if not cls.matches(b):
+            raise ValueError("not a restart entry")
+        pos = len(cls.MAGIC)
+        (n,) = struct.unpack_from("<I", b, pos)
+        pos += 4
+        records = []
+        for _ in range(n):
+            (k,) = struct.unpack_from("<I", b, pos)
+            pos += 4
+            if pos + 2 * k > len(b):
+                raise ValueError("truncated restart entry")
+            records.append((np.frombuffer(b, np.uint8, k, pos), np.frombuffer(b, np.uint8, k, pos + k)))
+            pos += 2 * k
+        return cls(records)
+
+    @property
+    def byte_stream(self):
+        parts = [self.MAGIC, struct.pack("<I", len(self.records))]
+        for off, cnt in self.records:
+            parts += [struct.pack("<I", off.size), off.tobytes(), cnt.tobytes()]
+        return b"".join(parts)
+
+    def __eq__(self, other):
+        return isinstance(other, RestartP) and self.byte_stream == other.byte_stream
 
     __hash__ = None
 
@@ -147,8 +248,9 @@ class PayloadStringP(Payload):
 class HicImage:
     LAYOUT = {model.Compression.JPEG: (9, 9, 2), model.Compression.HIC: (6, 6, 2)}
 
-    def __init__(self, hic_type, settings, payloads):
+    def __init__(self, hic_type, settings, payloads, extensions=None):
         self.hic_type, self.settings, self._payloads = hic_type, settings, payloads
+        self.extensions = list(extensions or [])       # entries after the reference's own (it never reads them)
 
     @classmethod
     def jpeg_image(cls, payloads):
@@ -166,12 +268,15 @@ class HicImage:
         payloads = ([PayloadStringP.from_bytes(x) for x in raw_data[a:b]]
                     + [BitStringP.from_bytes(x) for x in raw_data[b:c]]
                     + [TupP.from_bytes(x) for x in raw_data[c:c + n_shape]])
-        return cls.jpeg_image(payloads) if kind == model.Compression.JPEG else cls.wavelet_image(payloads)
+        out = cls.jpeg_image(payloads) if kind == model.Compression.JPEG else cls.wavelet_image(payloads)
+        for x in raw_data[c + n_shape:]:
+            out.extensions.append(RestartP.from_bytes(x) if RestartP.matches(x) else bytes(x))
+        return out
 
     @classmethod
     def from_file(cls, path):
         with open(path, "rb") as f:
-            raw = pickle.load(f)
+            raw = load(f)
         assert raw is not None
         return cls.from_bytes(raw)
 
@@ -179,9 +284,24 @@ class HicImage:
     def payloads(self):
         return self._payloads
 
-    def byte_stream(self):
-        return [p.byte_stream for p in self.settings + self._payloads]
+    @property
+    def restarts(self):
+        """The file's restart records (a RestartP), or None."""
+        for e in self.extensions:
+            if isinstance(e, RestartP):
+                return e
+        return None
 
-    def write_file(self, path):
+    def portable(self):
+        """A copy whose tables hold plain Python numbers: loads in any environment's reference reader."""
+        n_tab = self.LAYOUT[self.hic_type if isinstance(self.hic_type, model.Compression) else model.Compression(self.hic_type.value)][0]
+        payloads = [p.portable() if i < n_tab else p for i, p in enumerate(self._payloads)]
+        return HicImage(self.hic_type, self.settings, payloads, self.extensions)
+
+    def byte_stream(self):
+        return ([p.byte_stream for p in self.settings + self._payloads]
+                + [e if isinstance(e, (bytes, bytearray)) else e.byte_stream for e in self.extensions])
+
+    def write_file(self, path, portable=False):
         with open(path, "wb") as f:
-            pickle.dump(self.byte_stream(), f)
+            pickle.dump((self.portable() if portable else self).byte_stream(), f)

@@ -215,9 +215,8 @@ def _tables_to_arrays(table_payloads):
     return rows, syms, lens, codes
 
 
-def decode_to_device_flat(hic, stream=None):
-    """Entropy-decode a wavelet HicImage into the flat zigzag stream on the device."""
-    assert hic.hic_type == model.Compression.HIC or getattr(hic.hic_type, "value", None) == "HIC"
+def pyramid_of_file(hic):
+    """The sub-band pyramid a wavelet HicImage's two shape payloads describe, read the way the reference reads them."""
     p = hic.payloads
     small, big = tuple(int(v) for v in p[12].numbers), tuple(int(v) for v in p[13].numbers)
     h, w = 2 * big[0], 2 * big[1]
@@ -234,6 +233,14 @@ def decode_to_device_flat(hic, stream=None):
     if shapes[0] != small or h % (1 << levels) or w % (1 << levels):
         raise ValueError("sub-band shapes %r .. %r are not a pyramid of exact halvings the reference's decoder reads "
                          "as it was written (codec.py:182-189)" % (small, big))
+    return g
+
+
+def decode_to_device_flat(hic, stream=None):
+    """Entropy-decode a wavelet HicImage into the flat zigzag stream on the device."""
+    assert hic.hic_type == model.Compression.HIC or getattr(hic.hic_type, "value", None) == "HIC"
+    p = hic.payloads
+    g = pyramid_of_file(hic)
     # stream order s = channel * 3 + kind; kind 0 (DC) is absent in flat mode
     empty = hicimage.PayloadStringP.from_rows([])
     tabs, bit_payloads = [], []
@@ -258,7 +265,8 @@ def decode_to_device_flat(hic, stream=None):
     flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3)
     dec = entropy.EntropyDecoder(layout)
     try:
-        dec.decode(rows, syms, lens, codes, data, offs, nbits, flat.ptr, stream)
+        from hiccup_b200 import codec
+        codec._entropy_decode(dec, hic, rows, syms, lens, codes, data, offs, nbits, flat.ptr, stream)
     finally:
         dec.close()
     return flat, g

@@ -353,6 +353,23 @@ int hic_decode_set_tables_device(hic_decode_plan* plan, const void* d_index, con
 int hic_decode_run(hic_decode_plan* plan, const uint8_t* d_bytes, const uint64_t* h_byte_off,
                    const uint64_t* h_nbits, int16_t* d_coef, void* stream);
 
+/* Restart records -- an EXTENSION beside the reference's format, which carries none (codec.py:319-334;
+ * hiccup_b200/hicimage.py appends them to a `.hic` file as one extra list entry the reference's reader never
+ * looks at).  For every 128-bit subsequence of every bit stream, in stream order: `off` = how many bits past the
+ * subsequence's upper boundary the next codeword starts, `cnt` = how many codewords start inside its span.
+ *   hic_decode_sync             runs only the synchronisation passes of D1 over the streams (n_sub_out =
+ *                               subsequences in all streams: 128-bit pieces of 8 + nbits bits each);
+ *   hic_decode_export_restarts  the records the most recent run or sync converged to, into host arrays;
+ *   hic_decode_run_restarts     hic_decode_run without the synchronisation passes.  Every span is still
+ *                               checked against its record: records that do not fit the streams give
+ *                               HIC_ERR_CORRUPT, never a silent mis-decode. */
+int hic_decode_sync(hic_decode_plan* plan, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
+                    uint64_t* n_sub_out, void* stream);
+int hic_decode_export_restarts(hic_decode_plan* plan, uint8_t* h_off, uint8_t* h_cnt, uint64_t capacity, void* stream);
+int hic_decode_run_restarts(hic_decode_plan* plan, const uint8_t* d_bytes, const uint64_t* h_byte_off,
+                            const uint64_t* h_nbits, const uint8_t* h_off, const uint8_t* h_cnt, uint64_t n_sub,
+                            int16_t* d_coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

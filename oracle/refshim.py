@@ -116,7 +116,8 @@ def install():
     # a hiccup alias installed by hiccup_b200._compat must not shadow the real package
     for name in [k for k in sys.modules if k == "hiccup" or k.startswith("hiccup.")]:
         mod = sys.modules[name]
-        if getattr(mod, "__hiccup_b200_alias__", False):
+        # (the alias package itself carries the flag; its sub-modules are hiccup_b200's own modules under a second name)
+        if getattr(mod, "__hiccup_b200_alias__", False) or getattr(mod, "__name__", "").startswith("hiccup_b200"):
             del sys.modules[name]
     import hiccup.settings as settings
     settings.DEBUG = False

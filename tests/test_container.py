@@ -62,3 +62,111 @@ def test_payload_equality_semantics():
     assert hicimage.TupP(1, "1") == hicimage.TupP(1, "1")
     assert hicimage.BitStringP("101") == hicimage.BitStringP.from_bytes(b"\x05\xa0")
     assert hicimage.BitStringP("101").bit_count == 3 == hicimage.BitStringP.from_bytes(b"\x05\xa0").bit_count
+
+
+# ---- the tolerant, closed reader and the extension entries (rank 4) ----
+def _foreign_numpy_spelling(b):
+    """Re-spell numpy 2's scalar reconstructor the way numpy 1 pickles it (textual GLOBAL opcode: protocols 0-2)."""
+    assert b"numpy._core.multiarray" in b
+    return b.replace(b"cnumpy._core.multiarray\nscalar", b"cnumpy.core.multiarray\nscalar")
+
+
+@pytest.mark.parametrize("protocol", [0, 1, 2, 3, 4, 5])
+def test_tables_load_from_any_pickle_protocol(protocol):
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import _compat, hicimage
+    rows = [(np.int32(-7), "101"), (np.int32(3), "0"), (0, "11"), (12.0, "100")]
+    tup = _compat.wire_tuple_class()
+    b = pickle.dumps({"type": tup, "data": [pickle.dumps(r, protocol=protocol) for r in rows]}, protocol=protocol)
+    got = hicimage.PayloadStringP.from_bytes(b).rows
+    assert [(type(a), a, c) for a, c in got] == [(type(a), a, c) for a, c in rows]
+    if protocol <= 2 and np.lib.NumpyVersion(np.__version__) >= "2.0.0":
+        # the same table as an environment with numpy 1 writes it
+        b1 = pickle.dumps({"type": tup, "data": [_foreign_numpy_spelling(pickle.dumps(r, protocol=protocol)) if isinstance(r[0], np.generic)
+                                                  else pickle.dumps(r, protocol=protocol) for r in rows]}, protocol=protocol)
+        got1 = hicimage.PayloadStringP.from_bytes(b1).rows
+        assert [(int(a), c) for a, c in got1] == [(int(a), c) for a, c in rows] and isinstance(got1[0][0], np.int32)
+
+
+def test_reader_resolves_the_table_class_without_the_reference_package():
+    """The class a table names (hiccup.hicimage.TupP, hicimage.py:117-121) resolves under any package spelling."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    row = pickle.dumps((5, "10"))
+    for module in (b"hiccup.hicimage", b"hiccup_b200.hicimage", b"vendored.hiccup.hicimage"):
+        b = (b"\x80\x02}q\x00(X\x04\x00\x00\x00typeq\x01c" + module + b"\nTupP\nq\x02X\x04\x00\x00\x00dataq\x03]q\x04"
+             + b"C" + bytes([len(row)]) + row + b"q\x05au.")
+        assert hicimage.PayloadStringP.from_bytes(b).rows == [(5, "10")]
+
+
+def test_reader_is_closed_to_other_globals():
+    from hiccup_b200 import hicimage
+    evil = b"cos\nsystem\n(S'echo pwned'\ntR."
+    with pytest.raises(pickle.UnpicklingError):
+        hicimage.loads(evil)
+    with pytest.raises(pickle.UnpicklingError):
+        hicimage.TupP.from_bytes(evil)
+    with pytest.raises(pickle.UnpicklingError):
+        hicimage.PayloadStringP.from_bytes(pickle.dumps({"type": pickle.Pickler, "data": []}))
+
+
+def test_portable_files_hold_plain_numbers(tmp_path):
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    g = load_golden("syn64")
+    hi = hicimage.HicImage.from_bytes(pickle.loads(g["hic"].tobytes()))
+    path = os.path.join(tmp_path, "p.hic")
+    hi.write_file(path, portable=True)
+    with open(path, "rb") as f:
+        raw = pickle.load(f)
+    assert not any(b"numpy" in x for x in raw)                       # nothing numpy-version-specific on the wire
+    back = hicimage.HicImage.from_file(path)
+    for a, b in zip(back.payloads[:9], hi.payloads[:9]):
+        assert [(int(s), c) for s, c in a.rows] == [(int(s), c) for s, c in b.rows]
+        assert all(type(s) in (int, float) for s, _ in a.rows)
+    assert [p.byte_stream for p in back.payloads[9:]] == [p.byte_stream for p in hi.payloads[9:]]
+
+
+def test_extension_entries_travel_with_the_file(tmp_path):
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    g = load_golden("syn64")
+    stream = pickle.loads(g["hic"].tobytes())
+    hi = hicimage.HicImage.from_bytes(stream)
+    rng = np.random.default_rng(3)
+    recs = [(rng.integers(0, 58, n, dtype=np.uint8), rng.integers(0, 129, n, dtype=np.uint8)) for n in (5, 0, 17, 1, 2, 3, 4, 5, 6)]
+    ext = hicimage.RestartP(recs)
+    assert hicimage.RestartP.from_bytes(ext.byte_stream) == ext
+    hx = hicimage.HicImage(hi.hic_type, hi.settings, hi.payloads, [ext, b"some other vendor's entry"])
+    out = hx.byte_stream()
+    assert out[:21] == stream and len(out) == 23                  # the reference's 21 entries are untouched
+    path = os.path.join(tmp_path, "x.hic")
+    hx.write_file(path)
+    back = hicimage.HicImage.from_file(path)
+    assert back.restarts == ext and back.extensions[1] == b"some other vendor's entry"
+    assert back.byte_stream() == out
+    assert hicimage.HicImage.from_bytes(stream).restarts is None
+    with pytest.raises(ValueError):
+        hicimage.RestartP.from_bytes(ext.byte_stream[:-3])
+
+
+@pytest.mark.reference
+def test_reference_reader_ignores_extension_entries_and_reads_portable_files():
+    """The unmodified reference loads a file that carries extension entries (it reads list entries 0..20 only,
+    hicimage.py:124-142) and one written with portable=True, to the same payloads."""
+    from oracle import refshim
+    refshim.install()
+    import hiccup.hicimage as rhic
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    g = load_golden("syn64")
+    stream = pickle.loads(g["hic"].tobytes())
+    hi = hicimage.HicImage.from_bytes(stream)
+    ext = hicimage.RestartP([(np.zeros(3, np.uint8), np.ones(3, np.uint8))] * 9)
+    want = rhic.HicImage.from_bytes(stream)
+    got = rhic.HicImage.from_bytes(hicimage.HicImage(hi.hic_type, hi.settings, hi.payloads, [ext]).byte_stream())
+    assert got.byte_stream() == want.byte_stream() == stream
+    port = rhic.HicImage.from_bytes(hi.portable().byte_stream())
+    for a, b in zip(port.payloads[:9], want.payloads[:9]):
+        assert [(int(p.numbers[0]), p.numbers[1]) for p in a.payloads] == [(int(p.numbers[0]), p.numbers[1]) for p in b.payloads]
+    assert [p.byte_stream for p in port.payloads[9:]] == [p.byte_stream for p in want.payloads[9:]]
