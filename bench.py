@@ -158,7 +158,9 @@ def kernel_bytes(name, P, B, s_ac, bits_bytes, rows, n_ss, bins, mode):
 
 
 CONFIGS = {
-    # BASELINE.json configs[1..3]; c5 (16384^2 band-sharded over 8 GPUs) is bench_bands.py
+    # BASELINE.json configs[0..3]; c5 (16384^2 band-sharded over 8 GPUs) is bench_bands.py.
+    # c1 is the reference's own CPU-runnable case: ONE 512x512 image through the eight drop-in functions (run_c1).
+    "c1": dict(mode="dct", images=1, height=512, width=512, label="resources/Lenna.png 512x512 RGB, DCT mode encode->decode round trip through the drop-in functions (%d image per call)"),
     "c2": dict(mode="dct", images=1024, height=426, width=640, label="batch of %d synthetic 640x426 RGB images per GPU, DCT mode encode+decode"),
     "c3": dict(mode="dct", images=256, height=2160, width=3840, label="batch of %d synthetic 4K (3840x2160) RGB images per GPU, DCT + Huffman encode+decode"),
     "c4": dict(mode="wavelet", images=1, height=4320, width=7680, label="%d synthetic 8K (7680x4320) RGB image per GPU, wavelet mode encode+decode"),
@@ -255,6 +257,143 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(line)
+    return 0
+
+
+def run_c1(args):
+    """BASELINE.json configs[0]: Lenna 512x512 through the reference's own call sequence (run.py:18-43):
+    jpeg_compression -> jpeg_encode -> .hic bytes -> HicImage.from_bytes -> jpeg_decode -> jpeg_decompression,
+    one image per call, host arrays in and out.  A latency workload: the line reports ms per call and per function.
+    The image and the unmodified reference's outputs for it come from tests/golden/lenna512.npz (written by
+    tests/golden/gen_golden.py from /root/reference/resources/Lenna.png; the reference needs 274 s for this)."""
+    import pickle
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hiccup_b200 import _lib, codec, compression, hicimage
+    from hiccup_b200.batch import DctBatchCodec
+    _lib.check(_lib.load().hic_set_device(local_rank))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lenna512.npz"))
+    rgb, want_hic, want_out = np.ascontiguousarray(g["rgb"]), pickle.loads(g["hic"].tobytes()), g["rgb_out"]
+    h, w = rgb.shape[:2]
+    names = ("jpeg_compression", "jpeg_encode", "to_bytes", "from_bytes", "jpeg_decode", "jpeg_decompression")
+    per_fn = {k: 0.0 for k in names}
+
+    def call(timed):
+        t = [time.perf_counter()]
+        comp = compression.jpeg_compression(rgb); t.append(time.perf_counter())
+        hic = codec.jpeg_encode(comp); t.append(time.perf_counter())
+        stream = hic.byte_stream(); t.append(time.perf_counter())
+        back = hicimage.HicImage.from_bytes(stream); t.append(time.perf_counter())
+        planes = codec.jpeg_decode(back); t.append(time.perf_counter())
+        out = compression.jpeg_decompression(planes); t.append(time.perf_counter())
+        if timed:
+            for k, a, b in zip(names, t, t[1:]):
+                per_fn[k] += (b - a) * 1e3
+        return stream, out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        stream, out = call(False)
+    same_bytes = stream == want_hic
+    same_pixels = bool(np.array_equal(out, want_out))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    t_start = time.time()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call(True)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    barrier()
+    # device-resident arm: the same image as a batch of one on the batched codec (K1 .. K8 + entropy, no copies)
+    bc = DctBatchCodec(1, h, w)
+    bc.upload(rgb[None])
+    for _ in range(args.warmup):
+        bc.encode_device(); bc.decode_device()
+    _lib.sync()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pairs = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        bc.encode_device(); bc.decode_device()
+        eb.record()
+        pairs.append((ea, eb))
+    torch.cuda.synchronize()
+    ms_dev = sum(a.elapsed_time(b) for a, b in pairs) / args.steps
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    for _ in range(args.steps):
+        bc.encode_device(); bc.decode_device()
+    _lib.sync()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end)
+    if dist is not None:
+        t = torch.tensor([ms_e2e, ms_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e, ms_dev = float(t[0].item()), float(t[1].item())
+    peak, peak_src = measured_peak()
+    k1 = prof.get("forward_kernel", (0.0, 1))
+    k1_ms = k1[0] / max(k1[1], 1)
+    dominant = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        _oracle_round_trip(rgb, "dct")
+        dt = time.perf_counter() - t0
+        cpu = {"value": h * w / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "this one image, full encode+decode through the oracle port (%.2f s); the unmodified reference needs 274 s for it (BASELINE.md)" % dt}
+    if rank == 0:
+        mp = h * w / 1e6
+        line = {
+            "metric": METRIC, "value": world * mp / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "Lenna (tests/golden/lenna512.npz)",
+            "config": {"workload": CONFIGS["c1"]["label"] % 1, "mode": "dct", "images_per_gpu": 1, "height": h, "width": w,
+                       "parallelism": "one image per call per GPU, %d GPU(s), no collective" % world,
+                       "l2": "L2 flushed (256 MB device fill) before every timed device-resident step",
+                       "note": "a latency workload: 0.26 MP per call cannot fill a B200; the per-call floor is launch latency and host work"},
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "peak_source": peak_src, "note": "launch-latency-bound at this size; see north_star_kernel",
+                         "north_star_kernel": {"kernel": "forward_kernel", "ms_per_launch": round(k1_ms, 4), "algorithmic_bytes": 6.0 * h * w,
+                                               "achieved": round(6.0 * h * w / k1_ms / 1e6, 1) if k1_ms else None, "peak": peak, "unit": "GB/s",
+                                               "frac": round(6.0 * h * w / k1_ms / 1e6 / peak, 4) if k1_ms else None}},
+            "kernels": {k: {"ms_per_launch": round(v[0] / max(v[1], 1), 4), "launches_per_step": v[1] / args.steps} for k, v in prof.items()},
+            "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": world * mp / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(rgb.nbytes + 4 * 1.5 * h * w * 2),
+                    "d2h_bytes_per_step": int(4 * 1.5 * h * w * 2 + sum(len(b) for b in stream) + out.nbytes),
+                    "api": "compression.jpeg_compression -> codec.jpeg_encode -> HicImage.byte_stream -> HicImage.from_bytes -> codec.jpeg_decode -> "
+                           "compression.jpeg_decompression, numpy arrays in and out, one call after another",
+                    "ms_per_function": {k: round(v / args.steps, 3) for k, v in per_fn.items()}},
+            "gpu_launches": int(sum(v[1] for v in prof.values())),
+            "parity": {"checked_images": 1, "mismatches": int(not (same_bytes and same_pixels)),
+                       "against": "the UNMODIFIED reference's .hic payloads and decoded pixels for this image (tests/golden/lenna512.npz)",
+                       "hic_bytes_equal": bool(same_bytes), "pixels_equal": same_pixels},
+        }
+        emit(line)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not (same_bytes and same_pixels):
+        sys.stderr.write("bench.py: PARITY FAILURE on Lenna\n")
+        return 3
     return 0
 
 
@@ -474,6 +613,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "c1" and not any(getattr(args, k) is not None for k in ("images", "height", "width", "mode")):
+        return run_c1(args)
     cfg = resolve_config(args)
     mode = cfg["mode"]
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "hic_last_error": (ctypes.c_char_p, []),
     "hic_device_count": (c_int, [ctypes.POINTER(c_int)]),
     "hic_set_device": (c_int, [c_int]),
+    "hic_get_device": (c_int, [ctypes.POINTER(c_int)]),
     "hic_device_name": (c_int, [ctypes.c_char_p, c_size_t]),
     "hic_malloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
     "hic_free": (c_int, [c_void_p]),
@@ -186,15 +187,79 @@ def tie_capacity(n, h, w):
     return int(cap.value)
 
 
-class DeviceBuffer:
-    """A device allocation owned through the C ABI (no torch involved)."""
+def current_device():
+    d = c_int()
+    check(load().hic_get_device(ctypes.byref(d)))
+    return int(d.value)
 
-    def __init__(self, nbytes):
+
+class _BufferPool:
+    """Freed device buffers of the single-image entry points, kept for the next call: compression.* and codec.*
+    allocate some twenty scratch buffers per image, and cudaMalloc / cudaFree serialise on a driver lock (tens of
+    milliseconds per call when anything else -- an nvidia-smi poll, another thread -- holds it).  Exact-size
+    reuse, per device, bounded; buffers above MAX_ONE bytes are never kept."""
+    MAX_ONE = 64 << 20
+    MAX_TOTAL = 512 << 20
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.free = {}            # (device, nbytes) -> [ptr, ...]
+        self.total = 0
+        self.enabled = os.environ.get("HIC_NO_POOL") is None
+
+    def take(self, nbytes):
+        if not self.enabled or nbytes > self.MAX_ONE:
+            return None
+        key = (current_device(), nbytes)
+        with self.lock:
+            ptrs = self.free.get(key)
+            if ptrs:
+                self.total -= nbytes
+                return ptrs.pop()
+        return None
+
+    def give(self, ptr, nbytes):
+        if not self.enabled or nbytes > self.MAX_ONE:
+            return False
+        key = (current_device(), nbytes)
+        with self.lock:
+            if self.total + nbytes > self.MAX_TOTAL:
+                return False
+            self.free.setdefault(key, []).append(ptr)
+            self.total += nbytes
+        return True
+
+    def clear(self):
+        """Return everything to the driver (buffers of other devices are freed on their own device)."""
+        with self.lock:
+            items, self.free, self.total = list(self.free.items()), {}, 0
+        lib = load()
+        here = current_device() if items else 0
+        for (dev, _), ptrs in items:
+            lib.hic_set_device(dev)
+            for p in ptrs:
+                lib.hic_free(p)
+        if items:
+            lib.hic_set_device(here)
+
+
+POOL = _BufferPool()
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (no torch involved).  pooled=True: taken from / returned to
+    POOL (the single-image entry points); the batch codecs own their buffers for their whole life."""
+
+    def __init__(self, nbytes, pooled=False):
         require_device()
         self.nbytes = int(nbytes)
-        p = c_void_p()
-        check(load().hic_malloc(ctypes.byref(p), self.nbytes))
-        self.ptr = p.value
+        self.pooled = pooled
+        ptr = POOL.take(self.nbytes) if pooled else None
+        if ptr is None:
+            p = c_void_p()
+            check(load().hic_malloc(ctypes.byref(p), self.nbytes))
+            ptr = p.value
+        self.ptr = ptr
 
     def upload(self, array, stream=None):
         a = np.ascontiguousarray(array)
@@ -216,7 +281,8 @@ class DeviceBuffer:
 
     def free(self):
         if self.ptr:
-            load().hic_free(self.ptr)
+            if not (self.pooled and POOL.give(self.ptr, self.nbytes)):
+                load().hic_free(self.ptr)
             self.ptr = None
 
     def __del__(self):
@@ -224,6 +290,11 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def scratch(nbytes):
+    """A pooled device buffer for the single-image entry points (see _BufferPool)."""
+    return DeviceBuffer(nbytes, pooled=True)
 
 
 class PinnedBuffer:

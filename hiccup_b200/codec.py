@@ -67,11 +67,10 @@ def _jpeg_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
     comp = model.CompressedImage(*planes)
     coef, g = compression.planes_to_device_blocks(comp)
     layout = _lib.layout_dct(1, g.h, g.w)
-    enc = entropy.EntropyEncoder(layout, bins)
+    enc = entropy.cached_encoder(layout, bins)
     try:
         res = enc.encode(coef.ptr)
     finally:
-        enc.close()
         coef.free()
     dc_type, ac_type = _symbol_types(src_dtype)
     tables, bits = [], []
@@ -190,11 +189,8 @@ def add_restart_records(hic: hicimage.HicImage) -> hicimage.HicImage:
     else:
         from hiccup_b200 import wavelet
         layout = _lib.layout_flat(1, int(wavelet.pyramid_of_file(hic).len))
-    dec = entropy.EntropyDecoder(layout)
-    try:
-        off, cnt = dec.decode(rows, syms, lens, codes, data, offs, nbits, None, sync_only=True)
-    finally:
-        dec.close()
+    dec = entropy.cached_decoder(layout)
+    off, cnt = dec.decode(rows, syms, lens, codes, data, offs, nbits, None, sync_only=True)
     n_sub = entropy.EntropyDecoder.subsequences(nbits)
     records, at = {}, 0
     for s, i in enumerate(bits):
@@ -222,14 +218,14 @@ def jpeg_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     rows, syms, lens, codes = _tables_to_arrays([p[i] for i in order])
     data, offs, nbits = _gather_payload_bytes([p[9 + i] for i in order])
     layout = _lib.layout_dct(1, h, w)
-    coef = _lib.DeviceBuffer(g.blocks_per_image * 128)
-    dec = entropy.EntropyDecoder(layout)
+    coef = _lib.scratch(g.blocks_per_image * 128)
+    dec = entropy.cached_decoder(layout)
     lib = _lib.load()
     try:
         _entropy_decode(dec, hic, rows, syms, lens, codes, data, offs, nbits, coef.ptr)
-        lum = _lib.DeviceBuffer(4 * h * w)
-        cr = _lib.DeviceBuffer(4 * g.hc * g.wc)
-        cb = _lib.DeviceBuffer(4 * g.hc * g.wc)
+        lum = _lib.scratch(4 * h * w)
+        cr = _lib.scratch(4 * g.hc * g.wc)
+        cb = _lib.scratch(4 * g.hc * g.wc)
         _lib.check(lib.hic_blocks_to_planes(coef.ptr, 1, h, w, lum.ptr, cr.ptr, cb.ptr, None))
         # the reference's decoded planes are float64 (transform.izigzag builds them with np.zeros)
         out = model.CompressedImage(lum.download(np.int32, h * w).reshape(h, w).astype(np.float64),
@@ -238,7 +234,6 @@ def jpeg_decode(hic: hicimage.HicImage) -> model.CompressedImage:
         for b in (lum, cr, cb):
             b.free()
     finally:
-        dec.close()
         coef.free()
     return out
 

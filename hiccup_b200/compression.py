@@ -30,10 +30,10 @@ def dct_forward_device(d_rgb, n, h, w, stream=None):
     lib = _lib.load()
     g = _lib.geometry(h, w)
     blocks = n * g.blocks_per_image
-    coef = _lib.DeviceBuffer(blocks * 128)
+    coef = _lib.scratch(blocks * 128)
     capacity = _lib.tie_capacity(n, h, w)
-    ties = _lib.DeviceBuffer(capacity * _lib.TIE_RECORD_BYTES)
-    stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+    ties = _lib.scratch(capacity * _lib.TIE_RECORD_BYTES)
+    stats = _lib.scratch(4 * _lib.TIE_STATS)
     _lib.check(lib.hic_dct_forward(d_rgb, n, h, w, coef.ptr, ties.ptr, capacity, stats.ptr, stream))
     st = stats.download(np.uint32, _lib.TIE_STATS, stream)
     if st[3]:
@@ -50,13 +50,13 @@ def jpeg_compression(rgb_image: np.ndarray) -> model.CompressedImage:
     img = _as_rgb(rgb_image)
     h, w = img.shape[:2]
     g = _lib.geometry(h, w)
-    d_rgb = _lib.DeviceBuffer(img.nbytes)
+    d_rgb = _lib.scratch(img.nbytes)
     d_rgb.upload(img)
     coef, st = dct_forward_device(d_rgb.ptr, 1, h, w)
     LAST_STATS.update(flagged_blocks=int(st[0]), reevaluated=int(st[1]), changed=int(st[2]))
-    lum = _lib.DeviceBuffer(4 * h * w)
-    cr = _lib.DeviceBuffer(4 * g.hc * g.wc)
-    cb = _lib.DeviceBuffer(4 * g.hc * g.wc)
+    lum = _lib.scratch(4 * h * w)
+    cr = _lib.scratch(4 * g.hc * g.wc)
+    cb = _lib.scratch(4 * g.hc * g.wc)
     _lib.check(lib.hic_blocks_to_planes(coef.ptr, 1, h, w, lum.ptr, cr.ptr, cb.ptr, None))
     out = model.CompressedImage(lum.download(np.int32, h * w).reshape(h, w),
                                 cr.download(np.int32, g.hc * g.wc).reshape(g.hc, g.wc),
@@ -85,10 +85,10 @@ def planes_to_device_blocks(compressed, stream=None):
                          % (cr.shape, cb.shape, lum.shape, (g.hc, g.wc)))
     bufs = []
     for a in (lum, cr, cb):
-        b = _lib.DeviceBuffer(a.nbytes)
+        b = _lib.scratch(a.nbytes)
         b.upload(a, stream)
         bufs.append(b)
-    coef = _lib.DeviceBuffer(g.blocks_per_image * 128)
+    coef = _lib.scratch(g.blocks_per_image * 128)
     _lib.check(lib.hic_planes_to_blocks(bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, 1, h, w, coef.ptr, stream))
     _lib.sync(stream)
     for b in bufs:
@@ -102,12 +102,12 @@ def jpeg_decompression(d: model.CompressedImage) -> np.ndarray:
     _lib.require_device()
     lib = _lib.load()
     coef, g = planes_to_device_blocks(d)
-    y = _lib.DeviceBuffer(g.h * g.w)
-    cr = _lib.DeviceBuffer(g.hc * g.wc)
-    cb = _lib.DeviceBuffer(g.hc * g.wc)
-    rgb = _lib.DeviceBuffer(g.out_h * g.out_w * 3)
-    ties = _lib.DeviceBuffer(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
-    stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+    y = _lib.scratch(g.h * g.w)
+    cr = _lib.scratch(g.hc * g.wc)
+    cb = _lib.scratch(g.hc * g.wc)
+    rgb = _lib.scratch(g.out_h * g.out_w * 3)
+    ties = _lib.scratch(g.blocks_per_image * _lib.TIE_RECORD_BYTES)
+    stats = _lib.scratch(4 * _lib.TIE_STATS)
     _lib.check(lib.hic_dct_inverse(coef.ptr, 1, g.h, g.w, y.ptr, cr.ptr, cb.ptr, rgb.ptr, ties.ptr,
                                    g.blocks_per_image, stats.ptr, None))
     out = rgb.download(np.uint8, g.out_h * g.out_w * 3).reshape(g.out_h, g.out_w, 3)

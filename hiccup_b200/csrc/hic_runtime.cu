@@ -240,6 +240,12 @@ int hic_set_device(int device) {
     return HIC_OK;
 }
 
+int hic_get_device(int* device) {
+    HIC_REQUIRE(device != nullptr, "device is NULL");
+    HIC_CUDA(cudaGetDevice(device));
+    return HIC_OK;
+}
+
 int hic_set_blocking_sync(int on) {
     // how host threads wait for the device: yielding the core (blocking) instead of spinning (opt-in: the
     // pipelined batch path keeps one host thread per slot waiting most of the time)

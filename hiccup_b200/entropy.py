@@ -322,3 +322,52 @@ class EntropyDecoder:
             return None
         _lib.check(self.lib.hic_decode_run(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, d_coef, stream))
         return None
+
+
+# ------------------------------------------------------------------------------------------------
+# plan cache of the single-image entry points (codec.jpeg_encode / jpeg_decode / wavelet_*): an entropy plan
+# is some forty device allocations, and an image-at-a-time caller (run.compress over a directory, the
+# reference's own usage) keeps asking for the same shape.  A few plans per thread, least recently used out.
+# ------------------------------------------------------------------------------------------------
+import threading
+
+_PLAN_CACHE = threading.local()
+PLAN_CACHE_SIZE = 4
+
+
+def _layout_key(layout):
+    return (int(layout.n_images), int(layout.skip_first), int(layout.blocks_per_image), tuple(int(v) for v in layout.nb),
+            tuple(int(v) for v in layout.block_off), tuple(int(v) for v in layout.len))
+
+
+def _cached(kind, key, make):
+    cache = getattr(_PLAN_CACHE, "plans", None)
+    if cache is None:
+        cache = _PLAN_CACHE.plans = []            # [(kind, key, object)], most recent last
+    for i, (k, q, obj) in enumerate(cache):
+        if k == kind and q == key:
+            cache.append(cache.pop(i))
+            return obj
+    obj = make()
+    cache.append((kind, key, obj))
+    while len(cache) > PLAN_CACHE_SIZE:
+        cache.pop(0)[2].close()
+    return obj
+
+
+def cached_encoder(layout, value_bins=DEFAULT_VALUE_BINS):
+    """An EntropyEncoder for this layout that outlives the call (do not close it)."""
+    key = (_lib.current_device(), _layout_key(layout), int(value_bins))
+    return _cached("enc", key, lambda: EntropyEncoder(layout, value_bins))
+
+
+def cached_decoder(layout):
+    """An EntropyDecoder for this layout that outlives the call (do not close it)."""
+    key = (_lib.current_device(), _layout_key(layout))
+    return _cached("dec", key, lambda: EntropyDecoder(layout))
+
+
+def drop_cached_plans():
+    cache = getattr(_PLAN_CACHE, "plans", None) or []
+    while cache:
+        cache.pop()[2].close()

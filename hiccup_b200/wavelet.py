@@ -60,12 +60,12 @@ def forward_device(d_rgb, n, h, w, stream=None):
     lib = _lib.load()
     if settings.wavelet_defaults():
         g = _lib.wavelet_geometry(h, w)
-        flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3 * n)
+        flat = _lib.scratch(2 * _flat_elems(g) * 3 * n)
         _lib.check(lib.hic_wavelet_forward(d_rgb, n, h, w, flat.ptr, stream))
         return flat, g
     g = _lib.wavelet_pyramid(h, w, settings.WAVELET_NUM_LEVELS)
-    flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3 * n)
-    work = _lib.DeviceBuffer(_lib.wavelet_work_bytes(n, h, w))
+    flat = _lib.scratch(2 * _flat_elems(g) * 3 * n)
+    work = _lib.scratch(_lib.wavelet_work_bytes(n, h, w))
     try:
         params = _params(g)
         _lib.check(lib.hic_wavelet_forward_general(d_rgb, n, h, w, ctypes.byref(params), work.ptr, flat.ptr, stream))
@@ -95,10 +95,10 @@ def wavelet_compression(rgb_image: np.ndarray) -> model.CompressedImage:
     lib = _lib.load()
     img = _as_rgb(rgb_image)
     h, w = img.shape[:2]
-    d_rgb = _lib.DeviceBuffer(img.nbytes)
+    d_rgb = _lib.scratch(img.nbytes)
     d_rgb.upload(img)
     flat, g = forward_device(d_rgb.ptr, 1, h, w)
-    d_bands = _lib.DeviceBuffer(4 * int(g.len) * 3)
+    d_bands = _lib.scratch(4 * int(g.len) * 3)
     _lib.check(lib.hic_wavelet_flat_to_bands_general(flat.ptr, 1, h, w, _levels_of(g), d_bands.ptr, None))
     arr = d_bands.download(np.int32, int(g.len) * 3).reshape(3, int(g.len))
     for b in (d_rgb, flat, d_bands):
@@ -150,9 +150,9 @@ def _bands_to_device_flat(compressed, stream=None):
             off += a.size
     if max_abs > 32767:
         raise ValueError("coefficients up to %d do not fit the int16 symbol path" % max_abs)
-    d_bands = _lib.DeviceBuffer(cat.nbytes)
+    d_bands = _lib.scratch(cat.nbytes)
     d_bands.upload(cat, stream)
-    flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3)
+    flat = _lib.scratch(2 * _flat_elems(g) * 3)
     _lib.check(lib.hic_wavelet_bands_to_flat_general(d_bands.ptr, 1, h, w, levels, flat.ptr, stream))
     _lib.sync(stream)
     d_bands.free()
@@ -194,11 +194,10 @@ def wavelet_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
     _lib.require_device()
     flat, g, max_abs = _bands_to_device_flat(compressed)
     layout = _lib.layout_flat(1, int(g.len))
-    enc = entropy.EntropyEncoder(layout, _value_bins(max_abs))
+    enc = entropy.cached_encoder(layout, _value_bins(max_abs))
     try:
         res = enc.encode(flat.ptr)
     finally:
-        enc.close()
         flat.free()
     return encode_streams_to_hic(res, g)
 
@@ -262,13 +261,14 @@ def decode_to_device_flat(hic, stream=None):
         pos += len(framed) + pad
     data = np.frombuffer(b"".join(chunks) + b"\0" * 16, dtype=np.uint8)
     layout = _lib.layout_flat(1, int(g.len))
-    flat = _lib.DeviceBuffer(2 * _flat_elems(g) * 3)
-    dec = entropy.EntropyDecoder(layout)
+    flat = _lib.scratch(2 * _flat_elems(g) * 3)
+    dec = entropy.cached_decoder(layout)
     try:
         from hiccup_b200 import codec
         codec._entropy_decode(dec, hic, rows, syms, lens, codes, data, offs, nbits, flat.ptr, stream)
-    finally:
-        dec.close()
+    except Exception:
+        flat.free()
+        raise
     return flat, g
 
 
@@ -277,7 +277,7 @@ def wavelet_decode(hic: hicimage.HicImage) -> model.CompressedImage:
     _lib.require_device()
     lib = _lib.load()
     flat, g = decode_to_device_flat(hic)
-    d_bands = _lib.DeviceBuffer(4 * int(g.len) * 3)
+    d_bands = _lib.scratch(4 * int(g.len) * 3)
     _lib.check(lib.hic_wavelet_flat_to_bands_general(flat.ptr, 1, int(g.h), int(g.w), _levels_of(g), d_bands.ptr, None))
     arr = d_bands.download(np.int32, int(g.len) * 3).reshape(3, int(g.len))
     flat.free()
@@ -294,7 +294,7 @@ def wavelet_decompression(channels: model.CompressedImage) -> np.ndarray:
     lib = _lib.load()
     flat, g, _ = _bands_to_device_flat(channels)
     h, w, levels = int(g.h), int(g.w), _levels_of(g)
-    rgb = _lib.DeviceBuffer(h * w * 3)
+    rgb = _lib.scratch(h * w * 3)
     try:
         if levels == 3 and settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER == 1 and h % 8 == 0 and w % 8 == 0:
             _lib.check(lib.hic_wavelet_inverse(flat.ptr, 1, h, w, rgb.ptr, None))
@@ -302,7 +302,7 @@ def wavelet_decompression(channels: model.CompressedImage) -> np.ndarray:
             params = _lib.WaveletParams()
             params.levels, params.multiplier = levels, float(settings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER)
             params.threshold, params.threshold_index = 0.0, -1
-            work = _lib.DeviceBuffer(_lib.wavelet_work_bytes(1, h, w))
+            work = _lib.scratch(_lib.wavelet_work_bytes(1, h, w))
             try:
                 _lib.check(lib.hic_wavelet_inverse_general(flat.ptr, 1, h, w, ctypes.byref(params), work.ptr, rgb.ptr, None))
                 _lib.sync()

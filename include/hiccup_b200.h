@@ -46,6 +46,7 @@ int hic_version(void);
 const char* hic_last_error(void);
 int hic_device_count(int* count);
 int hic_set_device(int device);
+int hic_get_device(int* device);          /* the calling thread's current CUDA device */
 /* How host threads wait for the current device from now on: 1 = block (yield the core), 0 = the driver's
  * default (spin when cores are plentiful).  Optional: PipelinedCodec(blocking_sync=True) uses it for its
  * per-slot host threads; on the boxes measured spinning was faster (batch.py). */

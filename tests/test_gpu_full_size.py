@@ -65,16 +65,16 @@ def test_c2_batch_of_1024_640x426():
 
 
 def test_c3_batch_of_4k_images():
-    """configs[2] at a quarter of the batch (64 x 3840x2160; the full 256 only repeats the same launches
-    four times over): repeats are identical, one whole 4K image equals the oracle (streams and pixels)."""
+    """configs[2] at its full size (256 x 3840x2160): repeats are identical wherever they sit in the batch, one
+    whole 4K image equals the oracle (streams and pixels)."""
     from hiccup_b200.batch import DctBatchCodec
-    n, h, w, distinct = 64, 2160, 3840, 2
+    n, h, w, distinct = 256, 2160, 3840, 2
     rgb = _batch(n, h, w, distinct, 4100)
     codec = DctBatchCodec(n, h, w)
     enc = codec.encode(rgb)
     out = codec.decode(enc).copy()
     _check_image_against_oracle(codec, enc, rgb[1], 1, out)
-    for i in (2, 17, 63):
+    for i in (2, 17, 63, 128, 255):
         j = i % distinct
         assert all(enc.framed(i * 9 + k) == enc.framed(j * 9 + k) for k in range(9))
         assert _digest(out[i]) == _digest(out[j])
@@ -127,4 +127,17 @@ def test_c5_16384_square_in_eight_bands():
     zc = orc.blocks_zigzag(want["cr"]).reshape(win // 16, win // 16, 64)
     cr = coef[g.nb_l:g.nb_l + g.nb_c].reshape(g.nby_c, g.nbx_c, 64)[y0 // 16:(y0 + win) // 16, x0 // 16:(x0 + win) // 16]
     assert np.array_equal(cr[1:-1, 1:-1], zc[1:-1, 1:-1])
+    # decode of the stitched stream: the same window of PIXELS against the oracle's decode of the window's own
+    # coefficients (equal to the image's there, as just checked), away from the window border where the chroma
+    # pyramid (pyrUp's 5-tap filter on top of the border blocks above) sees other neighbours
+    from hiccup_b200 import codec as codec_mod, compression
+    hic = bands.encode_banded(rgb, 8)
+    out = compression.jpeg_decompression(codec_mod.jpeg_decode(hic))
+    assert out.shape == rgb.shape
+    ref = orc.jpeg_decompression(want)
+    m = 32
+    assert np.array_equal(out[y0 + m:y0 + win - m, x0 + m:x0 + win - m], ref[m:-m, m:-m])
+    # and the whole image through a size-independent property: the input repeats with period 2048, so must the
+    # output away from the image border
+    assert _digest(out[2048:4096, 2048:4096]) == _digest(out[4096:6144, 6144:8192])
     codec.close()
