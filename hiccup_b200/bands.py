@@ -76,27 +76,33 @@ def seam_state(edges, b):
 def merge_histograms(band_hists, band_nsym):
     """band_hists[b][s]: (symbols, counts, first_local) arrays of band b's symbol stream s (s = channel*3+kind);
     band_nsym[b][s]: symbols of that stream in band b.  Returns per stream (symbols, counts) ordered by
-    first occurrence in the stitched stream (utils.group_by order, utils.py:83-96)."""
+    first occurrence in the stitched stream (utils.group_by order, utils.py:83-96).
+    Dense accumulators over the symbol range of the stream (symbols are int16): a handful of numpy calls per
+    stream whatever the number of bands."""
     n_streams = len(band_hists[0])
     merged = []
     for s in range(n_streams):
         syms, cnts, firsts, base = [], [], [], 0
         for b, hists in enumerate(band_hists):
             sym, cnt, first = hists[s]
-            syms.append(np.asarray(sym, np.int64))
-            cnts.append(np.asarray(cnt, np.int64))
-            firsts.append(np.asarray(first, np.int64) + base)
+            if len(sym):
+                syms.append(np.asarray(sym, np.int64))
+                cnts.append(np.asarray(cnt, np.int64))
+                firsts.append(np.asarray(first, np.int64) + base)
             base += int(band_nsym[b][s])
-        sym, cnt, first = np.concatenate(syms), np.concatenate(cnts), np.concatenate(firsts)
-        if not sym.size:
+        if not syms:
             merged.append((np.zeros(0, np.int32), np.zeros(0, np.uint32)))
             continue
-        uniq, inv = np.unique(sym, return_inverse=True)
-        total = np.bincount(inv, weights=cnt.astype(np.float64), minlength=uniq.size).astype(np.int64)
-        gfirst = np.full(uniq.size, np.iinfo(np.int64).max, np.int64)
-        np.minimum.at(gfirst, inv, first)
-        order = np.argsort(gfirst, kind="stable")
-        merged.append((uniq[order].astype(np.int32), total[order].astype(np.uint32)))
+        sym, cnt, first = np.concatenate(syms), np.concatenate(cnts), np.concatenate(firsts)
+        lo = int(sym.min())
+        idx = sym - lo
+        size = int(idx.max()) + 1
+        total = np.bincount(idx, weights=cnt.astype(np.float64), minlength=size).astype(np.int64)   # counts < 2^53: exact
+        gfirst = np.full(size, np.iinfo(np.int64).max, np.int64)
+        np.minimum.at(gfirst, idx, first)
+        present = np.flatnonzero(total)
+        order = present[np.argsort(gfirst[present])]          # (first occurrences are distinct positions: no ties)
+        merged.append(((order + lo).astype(np.int32), total[order].astype(np.uint32)))
     return merged
 
 
@@ -118,18 +124,29 @@ def build_tables(merged, huffman_build):
 
 def band_bits(tables, hists):
     """Coded bits of one band's streams under the shared tables: sum of count * code length."""
+    return all_band_bits(tables, [hists])[0]
+
+
+def all_band_bits(tables, band_hists):
+    """band_bits for every band at once: one dense symbol -> code length table per stream, shared by the bands."""
     index, syms, packed = tables
-    out = np.zeros(len(hists), np.uint64)
-    for s, (sym, cnt, _) in enumerate(hists):
-        if not len(sym):
-            continue
+    out = [np.zeros(len(h), np.uint64) for h in band_hists]
+    for s in range(len(band_hists[0])):
         a, n = int(index[s, 0]), int(index[s, 1])
+        if not n:
+            assert all(not len(h[s][0]) for h in band_hists), "band symbols but an empty merged table"
+            continue
         tab_sym = syms[a:a + n].astype(np.int64)
-        tab_len = (packed[a:a + n] >> np.uint64(58)).astype(np.int64)
-        order = np.argsort(tab_sym, kind="stable")
-        pos = np.searchsorted(tab_sym[order], np.asarray(sym, np.int64))
-        assert np.array_equal(tab_sym[order][pos], np.asarray(sym, np.int64)), "band symbol missing from the merged table"
-        out[s] = int((np.asarray(cnt, np.int64) * tab_len[order][pos]).sum())
+        lo = int(tab_sym.min())
+        lut = np.zeros(int(tab_sym.max()) - lo + 1, np.int64)
+        lut[tab_sym - lo] = (packed[a:a + n] >> np.uint64(58)).astype(np.int64)
+        for b, h in enumerate(band_hists):
+            sym, cnt, _ = h[s]
+            if not len(sym):
+                continue
+            i = np.asarray(sym, np.int64) - lo
+            assert i.min() >= 0 and i.max() < lut.size and lut[i].all(), "band symbol missing from the merged table"
+            out[b][s] = int((np.asarray(cnt, np.int64) * lut[i]).sum())
     return out
 
 
@@ -216,27 +233,71 @@ class DistComm:
         views the root received stay valid until the gather after the next one."""
         if isinstance(obj, dict) and isinstance(obj.get("bytes"), list):
             lens_mine = [int(len(b)) for b in obj["bytes"]]
-            self._turn = getattr(self, "_turn", 0) ^ 1
-            mm = self._shared_file(self.rank, self._turn, sum(lens_mine), create=True)
-            pos = 0
-            for b, n in zip(obj["bytes"], lens_mine):
-                mm[pos:pos + n] = np.frombuffer(b, np.uint8) if isinstance(b, (bytes, bytearray)) else b
-                pos += n
-            lens = self.all_gather(lens_mine)           # also orders every rank's copy before the root's reads
+            offs_mine = self._offsets_in_staging(obj["bytes"])
+            if offs_mine is None:                       # the strings live elsewhere: one copy into the shared file
+                self._turn = getattr(self, "_turn", 0) ^ 1
+                mm = self._shared_file(self.rank, self._turn, sum(lens_mine), create=True)
+                pos, offs_mine = 0, []
+                for b, n in zip(obj["bytes"], lens_mine):
+                    mm[pos:pos + n] = np.frombuffer(b, np.uint8) if isinstance(b, (bytes, bytearray)) else b
+                    offs_mine.append(pos)
+                    pos += n
+            self._staged = None
+            # (the all-gather also orders every rank's writes before the root's reads)
+            meta = self.all_gather((lens_mine, offs_mine))
             if self.rank != root:
                 return None
             out = []
-            for r, ls in enumerate(lens):
-                raw = self._shared_file(r, self._turn, sum(ls), create=False)
-                parts, pos = [], 0
-                for n in ls:
-                    parts.append(raw[pos:pos + n])
-                    pos += n
-                out.append(dict(bytes=parts))
+            for r, (ls, os_) in enumerate(meta):
+                need = max([o + n for o, n in zip(os_, ls)] + [1])
+                raw = self._shared_file(r, self._turn, need, create=False)
+                out.append(dict(bytes=[raw[o:o + n] for o, n in zip(os_, ls)]))
             return out
         out = [None] * self.size if self.rank == root else None
         self.dist.gather_object(obj, out, dst=root, group=self.group)
         return out
+
+    def staging(self, nbytes):
+        """`nbytes` of this rank's shared-memory file for the NEXT gather of band strings, page-locked where CUDA
+        is available: the device->host copy of the packed strings lands where the root will read them, and the
+        gather itself moves only offsets and lengths."""
+        self._turn = getattr(self, "_turn", 0) ^ 1
+        mm = self._shared_file(self.rank, self._turn, max(int(nbytes), 1), create=True)
+        self._staged = mm
+        return mm[:nbytes]
+
+    def _offsets_in_staging(self, parts):
+        """Offsets of the byte strings inside the staging view handed out by staging(), or None."""
+        mm = getattr(self, "_staged", None)
+        if mm is None:
+            return None
+        base, offs = mm.ctypes.data, []
+        for b in parts:
+            if not isinstance(b, np.ndarray):
+                return None
+            if b.size == 0:
+                offs.append(0)
+                continue
+            o = b.ctypes.data - base
+            if o < 0 or o + b.size > mm.size:
+                return None
+            offs.append(int(o))
+        return offs
+
+    def _register(self, arr):
+        """Page-lock a mapping for CUDA (best effort: without a device, or if the driver refuses, it stays pageable)."""
+        try:
+            from hiccup_b200 import _lib
+            if _lib.load().hic_host_register(arr.ctypes.data, arr.size) == 0:
+                self._pinned = getattr(self, "_pinned", {})
+                self._pinned[arr.ctypes.data] = True
+        except Exception:
+            pass
+
+    def _unregister(self, arr):
+        if getattr(self, "_pinned", {}).pop(arr.ctypes.data, None):
+            from hiccup_b200 import _lib
+            _lib.load().hic_host_unregister(arr.ctypes.data)
 
     def _shared_file(self, rank, turn, nbytes, create):
         """uint8 view of rank `rank`'s shared-memory file number `turn`, at least `nbytes` long.  The owner
@@ -253,17 +314,25 @@ class DistComm:
                 size = 1 << max(20, int(nbytes - 1).bit_length())
                 with open(path, "ab") as f:
                     f.truncate(size)
+                if cur is not None:
+                    self._unregister(cur)
                 cur = np.memmap(path, dtype=np.uint8, mode="r+", shape=(size,))
                 self._maps[(rank, turn)] = cur
+                self._register(cur)
         elif cur is None or cur.size < nbytes:
-            cur = np.memmap(path, dtype=np.uint8, mode="r", shape=(os.path.getsize(path),))
+            if cur is not None:
+                self._unregister(cur)
+            # (mapped writable although only read: CUDA page-locks writable mappings without a special flag)
+            cur = np.memmap(path, dtype=np.uint8, mode="r+", shape=(os.path.getsize(path),))
             self._maps[(rank, turn)] = cur
+            self._register(cur)
         return cur
 
     def close(self):
         """Unmap and remove this rank's shared-memory files."""
         import os
         for (rank, turn), mm in list(getattr(self, "_maps", {}).items()):
+            self._unregister(mm)
             del mm
             if rank == self.rank:
                 try:
@@ -341,6 +410,7 @@ class BandWorker:
         self.d_stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
         self.encoder = entropy.EntropyEncoder(lay, value_bins)
         self.rgb, self._pinned, self._h_bytes = None, None, None
+        self.staging = None          # optional callable(nbytes) -> uint8 array for the packed strings (DistComm.staging)
 
     def load(self, image):
         """image: the whole H x W x 3 host array (only this band's slice is uploaded)."""
@@ -356,7 +426,10 @@ class BandWorker:
             self._lib.check(self._lib.load().hic_set_device(int(self.device)))
 
     def steps(self):
+        import time
         _lib, lib, st, enc, g = self._lib, self._lib.load(), self.stream, self.encoder, self.g
+        self.trace = trace = [("start", time.perf_counter())]       # (phase that just ended, host clock): where a step's time goes
+        mark = lambda name: trace.append((name, time.perf_counter()))
         self._use_device()
         self.d_rgb.upload(self.rgb, st)
         _lib.check(lib.hic_dct_forward(self.d_rgb.ptr, 1, self.s1 - self.s0, self.w, self.d_coef.ptr, self.d_ties.ptr,
@@ -364,8 +437,10 @@ class BandWorker:
         first_nz, last_nz = enc.scan(self.d_coef.ptr, st)
         last_dc = [int(self.d_coef.download(np.int16, 1, st, offset=128 * (self.block_off[c] + self.nb[c] - 1))[0])
                    for c in range(3)]
+        mark("upload + K1 + scan")
         edges = yield ("all_gather", dict(first_nz=first_nz.tolist(), last_nz=last_nz.tolist(),
                                           length=[63 * n for n in self.nb], last_dc=last_dc))
+        mark("exchange: edges")
         self._use_device()
         enc.emit(self.d_coef.ptr, seam_state(edges, self.band), st)
         index, entries, nsym_rl = enc.histograms(st)
@@ -375,23 +450,32 @@ class BandWorker:
             e = entries[a:a + n]
             hists.append((e[:, 0].copy(), e[:, 1].astype(np.uint32), e[:, 2].astype(np.uint32)))
             nsym.append(self.nb[s // 3] if s % 3 == KIND_DC else int(nsym_rl[s // 3]))
+        mark("emit + histograms")
         gathered = yield ("all_gather", dict(hists=hists, nsym=nsym))
+        mark("exchange: histograms")
         self._use_device()
         tables = build_tables(merge_histograms([m["hists"] for m in gathered], [m["nsym"] for m in gathered]), _host_huffman)
-        all_bits = [band_bits(tables, m["hists"]) for m in gathered]
+        all_bits = all_band_bits(tables, [m["hists"] for m in gathered])
         start_bit, _ = bit_layout(all_bits, self.band)
+        mark("merge + Huffman tables (host)")
         enc.set_codes(tables[0], tables[1], tables[2], np.array(nsym, np.uint32), all_bits[self.band], start_bit, st)
         out = enc.pack(st)
         nbytes = int(enc.total_bytes)
-        if self._h_bytes is None or self._h_bytes.nbytes < nbytes:
-            if self._h_bytes is not None:
-                self._h_bytes.free()
-            self._h_bytes = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
-        data = out.download(np.uint8, nbytes, st, out=self._h_bytes.array(np.uint8, nbytes)) if nbytes else np.zeros(0, np.uint8)
+        if self.staging is not None:                 # (a communicator's shared, page-locked memory: no copy at the gather)
+            host = self.staging(nbytes)
+        else:
+            if self._h_bytes is None or self._h_bytes.nbytes < nbytes:
+                if self._h_bytes is not None:
+                    self._h_bytes.free()
+                self._h_bytes = _lib.PinnedBuffer(nbytes + nbytes // 4 + 4096)
+            host = self._h_bytes.array(np.uint8, nbytes)
+        data = out.download(np.uint8, nbytes, st, out=host) if nbytes else np.zeros(0, np.uint8)
         # views of the pinned staging (valid until this worker's next pack)
         mine = [data[int(enc.byte_off[s]):int(enc.byte_off[s]) + int(enc.byte_len[s])] for s in range(9)]
         self.stats = self.d_stats.download(np.uint32, _lib.TIE_STATS, st)
+        mark("pack + download")
         final = yield ("gather", dict(bytes=mine))               # the strings go to the root only
+        mark("exchange: band strings")
         if final is None:
             return None
         return dict(tables=tables, all_bits=all_bits, band_bytes=[m["bytes"] for m in final])
@@ -432,6 +516,40 @@ def to_encoded_streams(result, h, w, out=None):
     off, length, nbits = stitch_into(buf, result["band_bytes"], result["all_bits"], 9)
     return entropy.EncodedStreams(_lib.layout_dct(1, h, w), index, np.zeros(9, np.uint32), np.array(nbits, np.uint64),
                                   np.array(off, np.uint64), np.array(length, np.uint64), syms, packed, buf[:size - 16])
+
+
+def upload_stitched(result, d_data, stream=None):
+    """The stitched framed payloads (stitch_into's layout) assembled in the DEVICE buffer `d_data` straight from the
+    band strings: every band's interior bytes are one host->device copy to their place, and only the bytes two
+    neighbours share (and the pad-count byte of each stream) are combined on the host.  Saves the host pass over
+    the whole coded image that stitch_into() makes before an upload.  Returns (byte offsets, payload bits)."""
+    from hiccup_b200 import _lib
+    lib = _lib.load()
+    all_bits, band_bytes = result["all_bits"], result["band_bytes"]
+    off, length, nbits, size = stitch_layout(all_bits, 9)
+    assert d_data.nbytes >= size
+    _lib.check(lib.hic_memset(d_data.ptr, 0, size, stream))
+    firsts = [bit_layout(all_bits, b)[1] for b in range(len(band_bytes))]
+    shared = {}
+    for s in range(9):
+        shared[off[s]] = 8 - (nbits[s] % 8)
+        for b, per_band in enumerate(band_bytes):
+            chunk = per_band[s] if isinstance(per_band[s], np.ndarray) else np.frombuffer(per_band[s], np.uint8)
+            n = chunk.size
+            if not n:
+                continue
+            a = off[s] + int(firsts[b][s])
+            if n > 2:
+                _lib.check(lib.hic_memcpy_h2d(d_data.ptr + a + 1, chunk.ctypes.data + 1, n - 2, stream))
+            shared[a] = shared.get(a, 0) | int(chunk[0])
+            if n > 1:
+                shared[a + n - 1] = shared.get(a + n - 1, 0) | int(chunk[n - 1])
+    keys = sorted(shared)
+    vals = np.array([shared[k] for k in keys], np.uint8)
+    for i, k in enumerate(keys):
+        _lib.check(lib.hic_memcpy_h2d(d_data.ptr + k, vals.ctypes.data + i, 1, stream))
+    _lib.sync(stream)                  # `vals` and the band strings may go
+    return np.array(off, np.uint64), np.array(nbits, np.uint64)
 
 
 def encode_banded(image, n_bands, devices=None, value_bins=8192):

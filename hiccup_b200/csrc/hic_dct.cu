@@ -129,7 +129,14 @@ constexpr int NC_BLOCKS = (CW / 8) * (CH / 8);       // 32 per chroma plane
 constexpr int THREADS = NY_BLOCKS + 2 * NC_BLOCKS;   // one block per thread: 192
 constexpr int WARPS = THREADS / 32;
 constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: float add rounds to integer, RN-even
-constexpr uint32_t TILE_BYTES = RH * RWORDS * 4;
+// The staged region can arrive as LOAD_CHUNKS TMA boxes of CHUNK_ROWS rows, each with its own barrier, so that stage 1
+// starts on the first rows while the rest is in flight.  Measured on C2: two boxes 0.566 ms against 0.543 ms for one
+// (the second wait and the second descriptor cost more than the earlier start gains; four boxes of 18 rows do not fit
+// the shared-memory budget of four CTAs per SM) -- so one box it is.
+constexpr int LOAD_CHUNKS = 1;
+constexpr int CHUNK_ROWS = 2 * ((RH + 2 * LOAD_CHUNKS - 1) / (2 * LOAD_CHUNKS));
+constexpr uint32_t CHUNK_BYTES = CHUNK_ROWS * RWORDS * 4;
+static_assert(CHUNK_BYTES % 128 == 0, "a TMA box lands on a 128-byte boundary of shared memory (an even number of 448-byte rows)");
 
 // Colour conversion constants (cv2's 14-bit fixed point, compression.py:21), scaled by 4 so that every
 // result lands in byte 2 of its accumulator and the packing PRMTs pick it up without a shift:
@@ -145,7 +152,7 @@ constexpr uint32_t K_CR = 4u * 11682u, K_CB = 4u * 9241u;
 constexpr uint32_t C4 = 4u * ((128u << 14) + 8192u);
 struct Smem {
     union alignas(1024) {
-        uint32_t rgb[RH * RWORDS];                   // stage 0/1 (TMA destination)
+        uint32_t rgb[LOAD_CHUNKS * CHUNK_ROWS * RWORDS];      // stage 0/1 (TMA destination)
         uint16_t hpass[2][RH][CW];                   // stage 2 (rgb is dead by then)
         int4 stage[THREADS * 8];                     // stage 3 -> TMA stores (hpass is dead by then): block t = row t, 128-byte swizzle
     };
@@ -158,7 +165,7 @@ struct Smem {
         uint8_t cb[RH][C_PITCH];
         uint8_t cbd[CH][CD_PITCH];
     };
-    alignas(8) unsigned long long bar;
+    alignas(8) unsigned long long bar[LOAD_CHUNKS];
 };
 static_assert(sizeof(Smem) <= (TH == 64 ? 57344 : 32256), "CTAS_PER_SM CTAs per SM: (228 KB - 1 KB reserved each) / CTAS_PER_SM");
 static_assert(sizeof(int4) * THREADS * 8 <= sizeof(uint32_t) * RH * RWORDS, "the staged blocks fit in the RGB region");
@@ -326,10 +333,10 @@ tie_list_kernel(const uint32_t* __restrict__ flagmap, uint32_t n_words, int tile
     }
 }
 
-// tmap: the RGB batch (load); tmap_l / tmap_c: the luminance / chroma blocks of the coefficient buffer (stores).
+// tmap: the RGB batch with a whole tile as its box (L2 prefetch), tmap_rows: with a CHUNK_ROWS-row box (loads); tmap_l / tmap_c: the luminance / chroma blocks of the coefficient buffer (stores).
 template <bool USE_TMA>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
-forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_l,
+forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_l,
                const __grid_constant__ CUtensorMap tmap_c, const uint8_t* __restrict__ rgb, int h, int w,
                hic_dct_geometry g, uint32_t* __restrict__ flagmap) {
     constexpr int R16 = THREADS / 16;          // rows per step of the 16-lanes-per-row stages
@@ -342,15 +349,20 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // ---- stage 0: RGB region -> shared memory ----
     if (USE_TMA) {
         if (tid == 0) {
-            const uint32_t bar = smem_u32(&s.bar);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+#pragma unroll
+            for (int c = 0; c < LOAD_CHUNKS; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s.bar[c])));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TILE_BYTES) : "memory");
-            const int c0 = (3 * x0 - 3 * LEAD) / 4, c1 = y0 - 2, c2 = img;
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(smem_u32(s.rgb)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-                : "memory");
+            const int c0 = (3 * x0 - 3 * LEAD) / 4, c2 = img;
+#pragma unroll
+            for (int c = 0; c < LOAD_CHUNKS; ++c) {
+                const uint32_t bar = smem_u32(&s.bar[c]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CHUNK_BYTES) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(smem_u32(s.rgb + c * CHUNK_ROWS * RWORDS)), "l"(reinterpret_cast<uint64_t>(&tmap_rows)), "r"(c0),
+                    "r"(y0 - 2 + c * CHUNK_ROWS), "r"(c2), "r"(bar)
+                    : "memory");
+            }
             // pull the tile of a CTA two waves ahead (4 CTAs on each of 148 SMs per wave) into L2, so that
             // its own load finds the data there
             const unsigned per_img = gridDim.x * gridDim.y;
@@ -378,23 +390,33 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             o[2] = q[2];
         }
     }
-    __syncthreads();           // barrier initialised / generic load visible
+    __syncthreads();           // barriers initialised / generic load visible
+    unsigned arrived = USE_TMA ? 0u : ~0u;             // chunks this thread has already seen complete
+    auto wait_chunk = [&](int c) {
+        if (!((arrived >> c) & 1u)) {
+            asm volatile(
+                "{\n"
+                ".reg .pred P1;\n"
+                "LAB_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+                "@P1 bra DONE;\n"
+                "bra LAB_WAIT;\n"
+                "DONE:\n"
+                "}\n" ::"r"(smem_u32(&s.bar[c]))
+                : "memory");
+            arrived |= 1u << c;
+        }
+    };
     if (USE_TMA) {
-        const uint32_t bar = smem_u32(&s.bar);
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "LAB_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
-            "@P1 bra DONE;\n"
-            "bra LAB_WAIT;\n"
-            "DONE:\n"
-            "}\n" ::"r"(bar)
-            : "memory");
         // TMA zero-fills outside the image; cv2.pyrDown wants BORDER_REFLECT_101 there.  Only the
-        // two pixels next to each edge are ever read by a valid output: patch them in place.
+        // two pixels next to each edge are ever read by a valid output: patch them in place (edge tiles
+        // wait for their whole region first).
         uint8_t* r8 = reinterpret_cast<uint8_t*>(s.rgb);
         const bool left = x0 == 0, right = x0 - LEAD + SPIX > w, top = y0 == 0, bottom = y0 - 2 + RH > h;
+        if (left | right | top | bottom) {
+#pragma unroll
+            for (int c = 0; c < LOAD_CHUNKS; ++c) wait_chunk(c);
+        }
         if (left | right) {
             for (int i = tid; i < RH * 4; i += THREADS) {
                 const int ry = i >> 2, k = i & 3;
@@ -454,8 +476,13 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < (RH + WARPS - 1) / WARPS; ++k) {
             const int ry = warp + WARPS * k;
-            if (ry < RH) convert_group(ry, lane + 1, ry >= 2 && ry < 2 + TH);
+            if (ry < RH) {
+                wait_chunk(ry / CHUNK_ROWS);
+                convert_group(ry, lane + 1, ry >= 2 && ry < 2 + TH);
+            }
         }
+#pragma unroll
+        for (int c = 0; c < LOAD_CHUNKS; ++c) wait_chunk(c);
 #pragma unroll
         for (int k = 0; k < (2 * RH + THREADS - 1) / THREADS; ++k) {
             const int i = tid + THREADS * k;
@@ -1144,8 +1171,9 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
     }
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     // TMA load: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_rows;
     memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap_rows, 0, sizeof(tmap_rows));
     bool use_tma = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0) && getenv("HIC_NO_TMA") == nullptr;
     if (use_tma) {
         const cuuint64_t dims[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)n};
@@ -1154,7 +1182,11 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(d_rgb), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) use_tma = false;       // fall back to the generic loader
+        const cuuint32_t box_rows[3] = {(cuuint32_t)k1::RWORDS, (cuuint32_t)k1::CHUNK_ROWS, 1};
+        const CUresult r2 = encode(&tmap_rows, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(d_rgb), dims, strides, box_rows, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) use_tma = false;       // fall back to the generic loader
         if (getenv("HIC_DEBUG")) fprintf(stderr, "[hic] tensor map encode -> %d (use_tma=%d)\n", (int)r, (int)use_tma);
     }
     // TMA stores: the coefficient buffer as [image][block row][block column][64 int16] (luminance) and
@@ -1178,9 +1210,9 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         if (r != CUDA_SUCCESS) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled (chroma blocks) failed: %d", (int)r);
     }
     if (use_tma)
-        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<true><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_rows, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
     else
-        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
+        HIC_LAUNCH("forward_kernel", st, k1::forward_kernel<false><<<grid, k1::THREADS, sizeof(k1::Smem), st>>>(tmap, tmap_rows, tmap_l, tmap_c, d_rgb, h, w, g, flagmap));
     HIC_LAUNCH("tie_list_kernel", st, k1::tie_list_kernel<<<min(148u * 8u, (flag_words + 255u) / 256u), 256, 0, st>>>(flagmap, flag_words, (int)grid.x, (int)grid.y, g, h, w, d_ties, list_capacity, d_stats));
     HIC_LAUNCH("fixup_kernel", st, k1::fixup_kernel<<<148 * 8, 32 * k1::FIX_WARPS, 0, st>>>(d_rgb, h, w, g, d_coef, d_ties, list_capacity, d_stats));
     return HIC_OK;

@@ -262,6 +262,15 @@ class EntropyDecoder:
         nbits = np.ascontiguousarray(nbits, np.uint64)
         _lib.check(self.lib.hic_decode_run(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, d_coef, stream))
 
+    def decode_device_data(self, index, symbols, packed, d_data, byte_off, nbits, d_coef, stream=None):
+        """Packed host tables + framed payloads already on the device (d_data: pointer; byte_off 4-byte aligned)."""
+        index = np.ascontiguousarray(index, np.uint32)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        packed = np.ascontiguousarray(packed, np.uint64)
+        _lib.check(self.lib.hic_decode_set_tables_packed(self.plan, index.ctypes.data, symbols.ctypes.data,
+                                                         packed.ctypes.data, int(symbols.size), stream))
+        self.run(d_data, byte_off, nbits, d_coef, stream)                     # synchronises: host arrays may go
+
     def decode_streams(self, enc, d_coef, stream=None):
         """Decode an EncodedStreams (packed tables; no per-row host work)."""
         index = np.ascontiguousarray(enc.index, np.uint32)

@@ -132,3 +132,36 @@ def test_shared_memory_band_files_grow_and_remap(monkeypatch):
         owner.close()
         reader.close()
     assert not [f for f in os.listdir("/dev/shm") if ("test%d" % os.getpid()) in f]
+
+
+def test_staged_strings_are_gathered_without_a_copy(monkeypatch):
+    """DistComm.staging(): strings written into the rank's shared file are announced by offset and length only;
+    the root's views alias the owner's memory.  (One process plays both ranks; the all-gather is stubbed.)"""
+    monkeypatch.setenv("MASTER_PORT", "stg%d" % os.getpid())
+    owner, root = object.__new__(bands.DistComm), object.__new__(bands.DistComm)
+    owner.rank, owner.size, root.rank, root.size = 1, 2, 0, 2
+    try:
+        box = {}
+        owner.all_gather = lambda meta: box.setdefault("owner", meta) and None
+        st = owner.staging(300)
+        st[:300] = np.arange(300, dtype=np.uint8)
+        parts = [st[0:100], st[100:100], st[104:300]]
+        assert owner.gather(dict(bytes=parts), root=0) is None
+        lens, offs = box["owner"]
+        assert lens == [100, 0, 196] and offs == [0, 0, 104]
+        # the root's side of the same exchange: its own strings (copied: they are plain bytes) + the owner's views
+        root.all_gather = lambda meta: [meta, box["owner"]]
+        got = root.gather(dict(bytes=[b"abc", b"", b"xy"]), root=0)
+        assert [bytes(b) for b in got[0]["bytes"]] == [b"abc", b"", b"xy"]
+        assert [bytes(b) for b in got[1]["bytes"]] == [bytes(p) for p in parts]
+        st[5] = 200                                              # a view, not a copy
+        assert got[1]["bytes"][0][5] == 200
+        # strings that are not in the staging area still travel (by one copy)
+        box.clear()
+        owner.all_gather = lambda meta: box.setdefault("owner", meta) and None
+        owner.gather(dict(bytes=[np.arange(10, dtype=np.uint8)]), root=0)
+        assert box["owner"][0] == [10]
+    finally:
+        owner.close()
+        root.close()
+    assert not [f for f in os.listdir("/dev/shm") if ("stg%d" % os.getpid()) in f]

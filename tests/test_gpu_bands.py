@@ -48,3 +48,39 @@ def test_banded_encode_equals_oracle_and_decodes():
         assert stream[10 + i] == orc.padded_bits_to_bytes(enc["bits"][i])
     out = compression.jpeg_decompression(codec.jpeg_decode(hicimage.HicImage.from_bytes(stream)))
     assert np.array_equal(out, orc.jpeg_decompression(planes))
+
+
+@pytest.mark.parametrize("shape,k", [((426, 640), 4), ((1080, 1920), 8), ((96, 80), 2)])
+def test_device_side_stitching_equals_host_stitching(shape, k):
+    """bands.upload_stitched (band strings copied to their places on the device) against bands.stitch_into, and the
+    decode of what it built against the decode of the host-stitched file."""
+    from hiccup_b200 import _lib, bands
+    from hiccup_b200.batch import DctBatchCodec
+    rgb = orc.synthetic_image(shape[0], shape[1], 31)
+    cuts = bands.plan_bands(shape[0], k)
+    workers = []
+    for b in range(len(cuts) - 1):
+        wk = bands.BandWorker(b, len(cuts) - 1, shape[0], shape[1], cuts[b], cuts[b + 1])
+        wk.load(rgb)
+        workers.append(wk)
+    try:
+        res = bands.run_local(workers)[0]
+        size = bands.stitch_layout(res["all_bits"], 9)[3]
+        host = np.zeros(size, np.uint8)
+        off, length, nbits = bands.stitch_into(host, res["band_bytes"], res["all_bits"], 9)
+        d = _lib.DeviceBuffer(size)
+        off_d, nbits_d = bands.upload_stitched(res, d)
+        assert off_d.tolist() == list(off) and nbits_d.tolist() == list(nbits)
+        assert np.array_equal(d.download(np.uint8, size), host)
+        codec = DctBatchCodec(1, shape[0], shape[1])
+        want = codec.decode(bands.to_encoded_streams(res, shape[0], shape[1])).copy()
+        index, syms, packed = res["tables"]
+        codec.decoder.decode_device_data(index, syms, packed, d.ptr, off_d, nbits_d, codec.d_coef_dec.ptr)
+        codec._inverse()
+        assert np.array_equal(codec.fetch(), want)
+        assert np.array_equal(want[0], orc.jpeg_decompression(orc.jpeg_compression(rgb)))
+        codec.close()
+        d.free()
+    finally:
+        for wk in workers:
+            wk.close()
