@@ -111,15 +111,28 @@ def build_tables(merged, huffman_build):
     codes uint64[n]) must replay the reference's heapq construction (hic_huffman_build_host).
     Returns the packed table layout: index (n_streams, 2), symbols int32, packed uint64."""
     index, syms, packed, pos = [], [], [], 0
-    for sym, cnt in merged:
+    # the nine constructions are independent C calls (ctypes drops the GIL): a few threads take them side by side
+    built = list(_pool().map(lambda sc: huffman_build(sc[1]) if sc[0].size else None, merged))
+    for (sym, cnt), lc in zip(merged, built):
         if sym.size:
-            lens, codes = huffman_build(cnt)
+            lens, codes = lc
             syms.append(sym)
             packed.append((lens.astype(np.uint64) << np.uint64(58)) | (codes & CODE_MASK))
         index.append((pos, sym.size))
         pos += sym.size
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
     return np.array(index, np.uint32).reshape(-1, 2), cat(syms, np.int32), cat(packed, np.uint64)
+
+
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=3)
+    return _POOL
 
 
 def band_bits(tables, hists):
@@ -213,14 +226,62 @@ def stitch(band_bytes, all_bits, n_streams):
 # communicators
 # ------------------------------------------------------------------------------------------------
 class DistComm:
-    """One process per band under torch.distributed (object collectives: metadata only)."""
+    """One process per band under torch.distributed.  The ranks of one box exchange their metadata through a
+    mailbox in shared memory (a slot per rank and turn, a sequence word per rank: an all-gather is one pickle, one
+    write and a short spin -- ~0.1 ms where a gloo object collective over eight ranks takes 2 ms, three times per
+    encode); anything that does not fit a slot, and every exchange when `mailbox=False`, goes through the
+    group's object collectives."""
+    MAIL_SLOT = 4 << 20
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, mailbox=True):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        self._mail, self._seq = None, 0
+        if mailbox:
+            self._open_mailbox()
+
+    def _open_mailbox(self):
+        import os
+        token = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "0"))
+        self._mail_path = "/dev/shm/hic_band_%s_mail.bin" % token
+        size = 4096 + 2 * self.size * self.MAIL_SLOT
+        try:
+            if self.rank == 0:
+                with open(self._mail_path, "wb") as f:
+                    f.truncate(size)
+            self.dist.barrier(group=self.group)
+            self._mail = np.memmap(self._mail_path, dtype=np.uint8, mode="r+", shape=(size,))
+            self._mail_seq = self._mail[:8 * self.size].view(np.int64)
+            self.dist.barrier(group=self.group)
+        except OSError:
+            self._mail = None
+
+    def _mail_slot(self, turn, rank):
+        a = 4096 + (turn * self.size + rank) * self.MAIL_SLOT
+        return self._mail[a:a + self.MAIL_SLOT]
 
     def all_gather(self, obj):
+        import pickle
+        import time
+        if self._mail is not None:
+            raw = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+            fits = len(raw) + 8 <= self.MAIL_SLOT
+            k, turn = self._seq, self._seq & 1
+            slot = self._mail_slot(turn, self.rank)
+            if fits:
+                slot[8:8 + len(raw)] = np.frombuffer(raw, np.uint8)
+            slot[:8].view(np.int64)[0] = len(raw) if fits else -1
+            self._mail_seq[self.rank] = k + 1                    # published: the payload was written before (x86 store order)
+            self._seq += 1
+            deadline = time.perf_counter() + 120.0
+            while int(self._mail_seq.min()) < k + 1:
+                if time.perf_counter() > deadline:
+                    raise RuntimeError("band mailbox: a rank did not arrive within 120 s")
+            sizes = [int(self._mail_slot(turn, r)[:8].view(np.int64)[0]) for r in range(self.size)]
+            if all(n >= 0 for n in sizes):
+                return [pickle.loads(self._mail_slot(turn, r)[8:8 + n].tobytes()) for r, n in enumerate(sizes)]
+            # somebody's contribution did not fit: everybody saw that, everybody takes the collective
         out = [None] * self.size
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
@@ -340,6 +401,14 @@ class DistComm:
                 except OSError:
                     pass
         self._maps = {}
+        if getattr(self, "_mail", None) is not None:
+            self._mail_seq = None
+            self._mail = None
+            if self.rank == 0:
+                try:
+                    os.remove(self._mail_path)
+                except OSError:
+                    pass
 
 
 def run_local(workers):

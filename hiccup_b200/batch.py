@@ -335,30 +335,35 @@ class PipelinedCodec:
             codec.upload(rgb[c * self.chunk:(c + 1) * self.chunk])
             _lib.sync(codec.stream)
 
-    def device_steps(self, repeat=1):
+    def device_steps(self, repeat=1, threads=None):
         """`repeat` encode+decode passes over the batch parked by upload_resident(), everything in HBM: every
         slot runs its chunk's kernels on its own CUDA stream from its own host thread, so one chunk's
         latency-bound stretches (the serial heapq replays of the Huffman builder, the table builds, the
         stream scans) run under another chunk's bandwidth-bound kernels.  No host<->device traffic besides
         the few status words the C ABI reads back.  Results are what encode_device() / decode_device() of
-        each slot's codec leave on the device."""
+        each slot's codec leave on the device.  threads: host threads to drive the slots with (default one per
+        slot; fewer when several ranks share the box's cores -- a thread then takes its slots in turn)."""
         import threading
         assert self.slots == self.n_chunks, "one slot per chunk"
         errors = []
+        n_threads = self.slots if not threads else max(1, min(int(threads), self.slots))
 
-        def work(slot):
+        def work(first):
             try:
                 if self.device is not None:
                     _lib.check(_lib.load().hic_set_device(int(self.device)))
-                codec = self.codecs[slot]
+                mine = [self.codecs[s] for s in range(first, self.slots, n_threads)]
                 for _ in range(repeat):
-                    codec.encode_device()
-                    codec.decode_device()
-                _lib.sync(codec.stream)
+                    for codec in mine:
+                        codec.encode_device()
+                    for codec in mine:
+                        codec.decode_device()
+                for codec in mine:
+                    _lib.sync(codec.stream)
             except Exception as e:
                 errors.append(e)
 
-        threads = [threading.Thread(target=work, args=(s,)) for s in range(self.slots)]
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
         for t in threads:
             t.start()
         for t in threads:
