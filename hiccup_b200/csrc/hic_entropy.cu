@@ -597,10 +597,11 @@ __global__ void lut_scatter_kernel(Geom g, const int32_t* __restrict__ row_sym, 
 
 // ------------------------------------------------------------------------------------------------
 // E2 on the device: the same heapq replay as csrc/hic_huffman.cuh, in three kernels.
-//   huffman_sort_kernel    one CTA per symbol stream: bitonic sort of the stream's compacted histogram
-//                          entries by first-occurrence index (= the reference's leaf order); writes the
-//                          leaf frequencies and the table's symbol column, and files the stream in a
-//                          size tier.
+//   huffman_sort_kernel    one CTA per symbol stream: the stream's compacted histogram entries in order of
+//                          first occurrence (= the reference's leaf order) -- ranked through a bitmap of the
+//                          first-occurrence positions, or sorted by a bitonic network when the stream is too
+//                          long for the bitmap; writes the leaf frequencies and the table's symbol column,
+//                          and files the stream in a size tier.
 //   huffman_replay_kernel  the serial part.  heapify / heappop / heappush with frequency-only
 //                          comparisons is one dependent chain per stream, so its throughput is set by
 //                          (streams resident per SM) / (latency of one heap level).  One LANE per
@@ -623,59 +624,119 @@ constexpr int SORT_THREADS = 256;
 constexpr int REPLAY_SMEM_BUDGET = 48 * 1024;
 constexpr int REPLAY_NARROW_BUDGET = 44 * 1024;
 
+constexpr int SORT_MAP_WORDS = 8192;          // first-occurrence bitmap of the ranking path: 262 144 symbol positions
+constexpr int SORT_SMEM = 8 * SORT_MAP_WORDS; // bitmap + word prefixes (the bitonic fallback needs 6 * 8192 of it)
+
+// Leaf order = order of first occurrence.  First occurrences are distinct symbol positions, so when the stream's
+// positions fit a bitmap in shared memory the rank of an entry is a population count: set the bit of every entry's
+// first occurrence, prefix-sum the words' counts, and entry i goes to slot prefix[word] + popc(bits below) -- O(n +
+// positions / 32) with three barriers, where the bitonic network needs log^2 n of them (66 for a 1700-leaf DC
+// alphabet: it was 1.5 ms of a C2 step).  Streams with more than 262 144 symbols (single huge images) still sort.
 __global__ void __launch_bounds__(SORT_THREADS)
-huffman_sort_kernel(Geom g, int sel, int n_lo, int n_hi, int allow_narrow, const CompactEntry* __restrict__ entries,
+huffman_sort_kernel(Geom g, int sel, int allow_narrow, const CompactEntry* __restrict__ entries,
                     const CompactIndex* __restrict__ index,
                     uint32_t* __restrict__ leaf_freq, int32_t* __restrict__ row_sym, uint32_t* __restrict__ tier_count,
                     uint32_t* __restrict__ tier_list, int n_ss, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t sort_raw[];
     __shared__ unsigned long long s_total;
+    __shared__ uint32_t s_kmax, s_scan[SORT_THREADS / 32];
     const int ss = selected_stream(sel, blockIdx.x);
     const CompactIndex ix = index[ss];
     const int n = (int)ix.count;
     if (n == 0) return;
     if (n > 8192) {
-        if (threadIdx.x == 0 && n_hi == 8192) atomicOr(err, 2u);
+        if (threadIdx.x == 0) atomicOr(err, 2u);
         return;
     }
-    if (n <= n_lo || n > n_hi) return;            // another launch (with a fitting shared-memory size) takes it
-    int P = 1;
-    while (P < n) P <<= 1;
-    uint32_t* key = reinterpret_cast<uint32_t*>(sort_raw);
-    uint16_t* order = reinterpret_cast<uint16_t*>(sort_raw + 4 * P);
     const CompactEntry* my = entries + ix.offset;
-    if (threadIdx.x == 0) s_total = 0;
-    __syncthreads();
-    unsigned long long my_total = 0;
-    for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
-        key[i] = i < n ? my[i].first : 0xFFFFFFFFu;
-        order[i] = (uint16_t)(i < n ? i : 0);
-        if (i < n) my_total += my[i].count;
+    if (threadIdx.x == 0) {
+        s_total = 0;
+        s_kmax = 0;
     }
-    if (my_total) atomicAdd(&s_total, my_total);
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const uint32_t a = key[i], b = key[l];
-                    if ((a > b) == up) {
-                        key[i] = b;
-                        key[l] = a;
-                        const uint16_t t = order[i];
-                        order[i] = order[l];
-                        order[l] = t;
-                    }
-                }
+    {
+        unsigned long long my_total = 0;
+        uint32_t kmax = 0;
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            my_total += my[i].count;
+            kmax = max(kmax, my[i].first);
+        }
+        if (my_total) atomicAdd(&s_total, my_total);
+        atomicMax(&s_kmax, kmax);
+    }
+    __syncthreads();
+    const uint32_t words = (s_kmax >> 5) + 1u;
+    if (words <= (uint32_t)SORT_MAP_WORDS) {
+        uint32_t* map = reinterpret_cast<uint32_t*>(sort_raw);
+        uint32_t* pre = map + SORT_MAP_WORDS;
+        for (uint32_t w = threadIdx.x; w < words; w += SORT_THREADS) map[w] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            const uint32_t f = my[i].first;
+            atomicOr(&map[f >> 5], 1u << (f & 31));
+        }
+        __syncthreads();
+        // exclusive prefix of the words' population counts, SORT_THREADS words at a time
+        uint32_t running = 0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint32_t w0 = 0; w0 < words; w0 += SORT_THREADS) {
+            const uint32_t w = w0 + threadIdx.x;
+            const uint32_t c = w < words ? (uint32_t)__popc(map[w]) : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += o;
             }
+            if (lane == 31) s_scan[warp] = inc;
+            __syncthreads();
+            uint32_t base = running;
+            for (int k = 0; k < SORT_THREADS / 32; ++k) {
+                if (k < warp) base += s_scan[k];
+                running += s_scan[k];
+            }
+            if (w < words) pre[w] = base + inc - c;
             __syncthreads();
         }
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
-        const CompactEntry e = my[order[i]];
-        leaf_freq[ix.offset + i] = e.count;
-        row_sym[ix.offset + i] = e.sym;
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            const CompactEntry e = my[i];
+            const uint32_t r = pre[e.first >> 5] + (uint32_t)__popc(map[e.first >> 5] & ((1u << (e.first & 31)) - 1u));
+            leaf_freq[ix.offset + r] = e.count;
+            row_sym[ix.offset + r] = e.sym;
+        }
+    } else {
+        int P = 1;
+        while (P < n) P <<= 1;
+        uint32_t* key = reinterpret_cast<uint32_t*>(sort_raw);
+        uint16_t* order = reinterpret_cast<uint16_t*>(sort_raw + 4 * P);
+        for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
+            key[i] = i < n ? my[i].first : 0xFFFFFFFFu;
+            order[i] = (uint16_t)(i < n ? i : 0);
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P; i += SORT_THREADS) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & k) == 0;
+                        const uint32_t a = key[i], b = key[l];
+                        if ((a > b) == up) {
+                            key[i] = b;
+                            key[l] = a;
+                            const uint16_t t = order[i];
+                            order[i] = order[l];
+                            order[l] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            const CompactEntry e = my[order[i]];
+            leaf_freq[ix.offset + i] = e.count;
+            row_sym[ix.offset + i] = e.sym;
+        }
     }
     if (threadIdx.x == 0 && n >= 2) {
         int t = 0;
@@ -1382,8 +1443,7 @@ static int builder_prepare(hic_entropy_plan* p) {
     const int max_stride = 8 * (h_tier_bound[N_TIERS - 1] + 2);
     if (dev >= 64 || !attr_set[dev]) {
         HIC_CUDA(cudaFuncSetAttribute(huffman_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_stride));
-        // (the sort kernel's 48 KB of dynamic shared memory plus its static word need the opt-in too)
-        HIC_CUDA(cudaFuncSetAttribute(huffman_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192));
+        HIC_CUDA(cudaFuncSetAttribute(huffman_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM));
         HIC_CUDA(cudaFuncSetAttribute(huffman_replay_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, REPLAY_SMEM_BUDGET));
         HIC_CUDA(cudaFuncSetAttribute(huffman_replay_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, REPLAY_SMEM_BUDGET));
         if (dev < 64) attr_set[dev] = true;
@@ -1408,11 +1468,8 @@ static int builder_sort_pass(hic_entropy_plan* p, int sel, uint32_t* tier_count,
     const unsigned grid = (unsigned)selected_count(sel, p->n_cs);
     HIC_CUDA(cudaMemsetAsync(tier_count, 0, 2 * N_TIERS * sizeof(uint32_t), s0));
     const int narrow = replay_allow_narrow() ? 1 : 0;
-    // two launches by alphabet size: the small one keeps many CTAs resident (6 bytes of shared memory per padded leaf)
-    HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 1024, s0>>>(
-        g, sel, 0, 1024, narrow, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
-    HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, 6 * 8192, s0>>>(
-        g, sel, 1024, 8192, narrow, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
+    HIC_LAUNCH("huffman_sort_kernel", s0, huffman_sort_kernel<<<grid, SORT_THREADS, SORT_SMEM, s0>>>(
+        g, sel, narrow, p->d_entries, p->d_index, p->d_leaf_freq, p->d_row_sym, tier_count, tier_list, p->n_ss, p->d_err));
     return HIC_OK;
 }
 
