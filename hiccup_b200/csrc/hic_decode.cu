@@ -1329,6 +1329,16 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
                            int16_t* d_coef, void* stream, int mode, const uint8_t* h_roff, const uint8_t* h_rcnt,
                            uint64_t n_restart) {
     HIC_REQUIRE(p && d_bytes && h_byte_off && h_nbits && (d_coef || mode == 1), "NULL argument");
+    // whatever way this call ends, the staging area of the small transfers is free again for the next one (an
+    // early return used to leave it filled: after a few failed calls every small_d2h returned HIC_ERR_CAPACITY)
+    struct XferGuard {
+        hic::SmallXfer& x;
+        cudaStream_t st;
+        ~XferGuard() {
+            cudaStreamSynchronize(st);          // nothing in flight reads or writes the staging any more
+            x.reset();
+        }
+    } xfer_guard{p->xfer, as_stream(stream)};
     HIC_REQUIRE(p->tables_ready, "hic_decode_set_tables has not run");
     HIC_REQUIRE((reinterpret_cast<uintptr_t>(d_bytes) & 3) == 0, "d_bytes must be 4-byte aligned");
     const dec::Geom& g = p->g;
@@ -1408,7 +1418,15 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
         } else {
             HIC_LAUNCH("huffman_sync_kernel", st, huffman_sync_kernel<false><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
         }
-        for (int round = 0; round < 1024 && !restarts; ++round) {
+        // A resynchronisation round carries a correction across at least one tile boundary, so a stream of T tiles
+        // is settled after at most T rounds (codes that never self-synchronise -- complete trees of equal code
+        // length 3, 5, 6 or 7, whose codewords straddle the 128-bit subsequences -- need them all).  More rounds
+        // than the longest stream has tiles means the passes are not converging: that is reported as such, not as
+        // a corrupt stream.
+        uint64_t max_tiles_per_stream = 1;
+        for (int s = 0; s < nss; ++s) max_tiles_per_stream = std::max<uint64_t>(max_tiles_per_stream, ss_tile0[s + 1] - ss_tile0[s]);
+        bool settled = restarts;
+        for (uint64_t round = 0; round <= max_tiles_per_stream && !settled; ++round) {
             HIC_CUDA(cudaMemsetAsync(p->d_err + 1, 0, sizeof(uint32_t), st));
             HIC_LAUNCH("huffman_resync_kernel", st, huffman_sync_kernel<true><<<(unsigned)n_tiles, SUB_PER_CTA, 0, st>>>(a));
             const void* h_changed = nullptr;
@@ -1417,8 +1435,13 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
                 if (rc) return rc;
             }
             HIC_CUDA(cudaStreamSynchronize(st));
-            if (!*static_cast<const volatile uint32_t*>(h_changed)) break;
+            p->xfer.reset();
+            if (!*static_cast<const volatile uint32_t*>(h_changed)) settled = true;
         }
+        if (!settled)
+            return hic::fail(HIC_ERR_INVALID, "the Huffman synchronisation passes did not settle within %llu rounds (the longest stream has "
+                                              "that many tiles): not a corrupt stream, a decoder fault",
+                             (unsigned long long)max_tiles_per_stream + 1);
         HIC_LAUNCH("sync_tile_scan_kernel", st, sync_tile_scan_kernel<<<(nss + 127) / 128, 128, 0, st>>>(nss, p->d_ss_tile0, p->d_tile_cnt, p->d_tile_symoff, p->d_nsym));
         if (mode == 1) {
             HIC_CUDA(cudaStreamSynchronize(st));

@@ -153,3 +153,33 @@ def test_long_huffman_codes_round_trip():
         assert stream_bytes[7 + i] == orc.padded_bits_to_bytes(enc["bits"][i]), "bit string %d" % i
     back = codec.wavelet_decode(hicimage.HicImage.from_bytes(stream_bytes))
     assert _same_bands(back.as_dict, planes)
+
+
+def test_codes_that_never_self_synchronise_round_trip():
+    """Eight equally frequent values give a complete tree of 3-bit codes: codewords straddle the decoder's
+    128-bit subsequences in a fixed phase, so a wrong start never finds the true boundaries by itself and the
+    resynchronisation needs one round per 4 KB tile (24 here).  The decode must still be exact."""
+    from hiccup_b200 import codec, hicimage, model
+    shapes = [(64, 64)] * 4 + [(128, 128)] * 3 + [(256, 256)] * 3
+    total = sum(a * b for a, b in shapes)
+    rng = np.random.default_rng(12)
+    planes = {}
+    for ci, ch in enumerate(CH):
+        vals = np.repeat(np.arange(1, 9, dtype=np.int32) * (ci + 1), total // 8)
+        stream = rng.permutation(vals)
+        bands, off = [], 0
+        for (bh, bw) in shapes:
+            bands.append(stream[off:off + bh * bw].reshape(bh, bw).copy())
+            off += bh * bw
+        planes[ch] = bands
+    enc = orc.wavelet_encode(planes)
+    assert set(len(c) for _, c in enc["tables"][0]) == {3}
+    hi = codec.wavelet_encode(model.CompressedImage.from_dict(planes))
+    stream_bytes = hi.byte_stream()
+    for i in range(6):
+        assert stream_bytes[7 + i] == orc.padded_bits_to_bytes(enc["bits"][i]), "bit string %d" % i
+    back = codec.wavelet_decode(hicimage.HicImage.from_bytes(stream_bytes))
+    assert _same_bands(back.as_dict, planes)
+    # and with restart records there is nothing to synchronise
+    back2 = codec.wavelet_decode(codec.add_restart_records(hi))
+    assert _same_bands(back2.as_dict, planes)
