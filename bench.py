@@ -515,11 +515,20 @@ def run_e2e(args, cfg, codec, pipe, host_rgb, rank, local_rank, world, dist, bar
                                         "changed": int(codec.forward_stats[2])},
                        "inverse_ties": {"flagged_blocks": int(codec.inverse_stats[0]), "reevaluated": int(codec.inverse_stats[1]),
                                         "changed": int(codec.inverse_stats[2])}})
+    # (3) what `e2e` stops short of: the `.hic` container objects and their byte strings (one pickle per table row,
+    # as the format demands -- host Python, one core, a sample of this batch's images; not in the timed region)
+    sample = list(range(0, n, max(1, n // 32)))[:32]
+    t0 = time.perf_counter()
+    hic_bytes = sum(sum(len(b) for b in hi.byte_stream()) for hi in codec.hic_images(enc_res, images=sample))
+    hic_ms = (time.perf_counter() - t0) * 1e3 / len(sample)
+    hic_level = {"ms_per_image": round(hic_ms, 3), "images": len(sample), "cores": 1, "bytes_per_image": hic_bytes // len(sample),
+                 "what": "batch codec hic_images() + HicImage.byte_stream() on the host: the step from the packed tables and framed "
+                         "bit strings `e2e` delivers to the reference's list of pickled payloads (what write_file() dumps)"}
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms / steps, "api": api,
            "copy_floor_ms": ms_floor / steps, "frac_of_copy_floor": (ms_floor / ms) if ms else None,
            "copy_floor_how": "the same call with copy_only=True: identical bulk copies, slot threads and gates, no kernels, all ranks at once",
-           "matches_unchunked": e2e_same}
+           "matches_unchunked": e2e_same, "hic_container": hic_level}
     if ms_drained is not None:
         e2e["drained_value"] = world * pixels / 1e6 / (ms_drained / steps / 1e3)
         e2e["drained_ms_per_step"] = ms_drained / steps

@@ -199,11 +199,12 @@ class DctBatchCodec(_BatchCodec):
         c = self.d_coef.download(np.int16, self.blocks * 64, self.stream)
         return c.reshape(self.n, self.g.blocks_per_image, 64)
 
-    def hic_images(self, enc):
-        """Materialise the reference's container objects (codec.jpeg_encode's return value) per image."""
+    def hic_images(self, enc, images=None):
+        """Materialise the reference's container objects (codec.jpeg_encode's return value) per image
+        (images: the indices wanted; default all)."""
         g = self.g
         out = []
-        for i in range(self.n):
+        for i in (range(self.n) if images is None else images):
             tables, bits = [], []
             for kind in range(3):
                 for c in range(3):
@@ -256,9 +257,9 @@ class WaveletBatchCodec(_BatchCodec):
         else:
             _lib.check(self.lib.hic_wavelet_inverse(self.d_coef_dec.ptr, self.n, self.h, self.w, self.d_out.ptr, self.stream))
 
-    def hic_images(self, enc):
+    def hic_images(self, enc, images=None):
         from hiccup_b200 import wavelet
-        return [wavelet.encode_streams_to_hic(enc, self.g, image=i) for i in range(self.n)]
+        return [wavelet.encode_streams_to_hic(enc, self.g, image=i) for i in (range(self.n) if images is None else images)]
 
 
 class PipelinedCodec:

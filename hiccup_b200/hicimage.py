@@ -70,6 +70,111 @@ def load(f):
     return _HicUnpickler(f).load()
 
 
+class _RowCodec:
+    """The pickle of one Huffman table row, `pickle.dumps((symbol, code))` (hicimage.py:57-60 through TupP), written
+    and parsed directly.  A table has hundreds to thousands of rows and the format pickles each one on its own: for
+    one 512x512 image that is 3 600 `pickle.dumps` + 3 600 unpicklings, three quarters of the time of a whole
+    encode + decode call on the GPU.  A row is (int | np.int32, str of '0'/'1'), whose protocol-4 pickle has a fixed
+    shape; the byte strings built here are calibrated against `pickle.dumps` when the module loads (prefix and
+    infix of the numpy scalar form are READ from a sample, not assumed) and verified on a set of samples -- if
+    anything differs (another default protocol, another numpy), `ok` stays False and every row goes through
+    `pickle` as before.  The parser accepts exactly the canonical forms and hands anything else to the closed
+    unpickler above."""
+    HEAD = b"\x80\x04\x95"
+    TAIL = b"\x94\x86\x94."
+
+    def __init__(self):
+        self.ok = False
+        self.np_pre = self.np_mid = None
+        try:
+            self._calibrate()
+        except Exception:
+            self.ok = False
+
+    def _calibrate(self):
+        if pickle.DEFAULT_PROTOCOL != 4:
+            return
+        sample = pickle.dumps((np.int32(0x01020304), "01"))
+        marker = b"C\x04" + (0x01020304).to_bytes(4, "little")
+        pos = sample.index(marker)
+        self.np_pre = sample[11:pos + 2]
+        rest = sample[pos + 6:]
+        cut = rest.index(b"\x8c\x0201")
+        self.np_mid = rest[:cut]
+        if rest[cut + 4:] != self.TAIL:
+            return
+        self.ok = True
+        codes = ["0", "1", "101", "0" * 58, "1100110011"]
+        syms = [0, 1, 5, 255, 256, 300, 65535, 65536, 70000, -1, -7, -300, -70000, 2 ** 31 - 1, -2 ** 31]
+        for code in codes:
+            for v in syms:
+                for sym in ((v, np.int32(v))):
+                    want = pickle.dumps((sym, code))
+                    got = self.dumps(sym, code)
+                    back = self.loads(want)
+                    if got != want or back is None or type(back[0]) is not type(sym) or back[0] != sym or back[1] != code:
+                        self.ok = False
+                        return
+
+    def dumps(self, sym, code):
+        """The bytes `pickle.dumps((sym, code))` would give, or None when the row is not of the fast shape."""
+        if not self.ok or type(code) is not str or len(code) > 255:
+            return None
+        t = type(sym)
+        if t is int:
+            if 0 <= sym < 256:
+                e = b"K" + bytes((sym,))
+            elif 256 <= sym < 65536:
+                e = b"M" + sym.to_bytes(2, "little")
+            elif -2147483648 <= sym < 2147483648:
+                e = b"J" + sym.to_bytes(4, "little", signed=True)
+            else:
+                return None
+        elif t is np.int32:
+            e = self.np_pre + int(sym).to_bytes(4, "little", signed=True) + self.np_mid
+        else:
+            return None
+        try:
+            c = code.encode("ascii")
+        except UnicodeEncodeError:
+            return None
+        body = e + b"\x8c" + bytes((len(c),)) + c + self.TAIL
+        return self.HEAD + len(body).to_bytes(8, "little") + body
+
+    def loads(self, row):
+        """(sym, code) of a canonical row pickle, or None (the caller then uses the closed unpickler)."""
+        if not self.ok:
+            return None
+        row = bytes(row)
+        n = len(row)
+        if n < 20 or row[:3] != self.HEAD or int.from_bytes(row[3:11], "little") != n - 11 or row[-4:] != self.TAIL:
+            return None
+        op = row[11]
+        if op == 0x4B:                                   # BININT1
+            sym, p = row[12], 13
+        elif op == 0x4D:                                 # BININT2
+            sym, p = int.from_bytes(row[12:14], "little"), 14
+        elif op == 0x4A:                                 # BININT
+            sym, p = int.from_bytes(row[12:16], "little", signed=True), 16
+        elif row.startswith(self.np_pre, 11):
+            a = 11 + len(self.np_pre)
+            p = a + 4 + len(self.np_mid)
+            if row[a + 4:p] != self.np_mid:
+                return None
+            sym = np.int32(int.from_bytes(row[a:a + 4], "little", signed=True))
+        else:
+            return None
+        if p + 2 > n - 4 or row[p] != 0x8C or p + 2 + row[p + 1] != n - 4:
+            return None
+        try:
+            return sym, row[p + 2:n - 4].decode("ascii")
+        except UnicodeDecodeError:
+            return None
+
+
+ROWS = _RowCodec()
+
+
 class Payload:
     @classmethod
     def from_bytes(cls, b):
@@ -88,7 +193,8 @@ class TupP(Payload):
 
     @classmethod
     def from_bytes(cls, b):
-        a, c = loads(b)
+        fast = ROWS.loads(b)
+        a, c = fast if fast is not None else loads(b)
         return cls(a, c)
 
     @property
@@ -97,7 +203,8 @@ class TupP(Payload):
 
     @property
     def byte_stream(self):
-        return pickle.dumps((self.n1, self.n2))
+        fast = ROWS.dumps(self.n1, self.n2)
+        return fast if fast is not None else pickle.dumps((self.n1, self.n2))
 
     def __eq__(self, other):
         return hasattr(other, "numbers") and tuple(other.numbers) == self.numbers

@@ -170,3 +170,28 @@ def test_reference_reader_ignores_extension_entries_and_reads_portable_files():
     for a, b in zip(port.payloads[:9], want.payloads[:9]):
         assert [(int(p.numbers[0]), p.numbers[1]) for p in a.payloads] == [(int(p.numbers[0]), p.numbers[1]) for p in b.payloads]
     assert [p.byte_stream for p in port.payloads[9:]] == [p.byte_stream for p in want.payloads[9:]]
+
+
+def test_fast_row_pickles_equal_pickle():
+    """The directly written / parsed table rows (hicimage._RowCodec) against pickle itself, on every symbol type and
+    size class a table can hold; and rows of any other shape still go through pickle."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    assert hicimage.ROWS.ok, "the fast row path did not calibrate in this environment (it must fall back, not fail)"
+    rng = np.random.default_rng(4)
+    syms = [0, 1, 255, 256, 65535, 65536, -1, -129, 2 ** 31 - 1, -2 ** 31] + [int(v) for v in rng.integers(-40000, 40000, 200)]
+    for v in syms:
+        code = "".join(rng.choice(["0", "1"], size=int(rng.integers(1, 59))))
+        for sym in (v, np.int32(v)):
+            want = pickle.dumps((sym, code))
+            t = hicimage.TupP(sym, code)
+            assert t.byte_stream == want
+            back = hicimage.TupP.from_bytes(want)
+            assert type(back.n1) is type(sym) and back.numbers == (sym, code)
+    for odd in ((2 ** 40, "1"), (3.5, "10"), (np.int64(7), "1"), (True, "0"), (5, 7), (512, 384)):
+        want = pickle.dumps(odd)
+        assert hicimage.TupP(*odd).byte_stream == want
+        assert hicimage.TupP.from_bytes(want).numbers == odd
+    # a row that merely LOOKS canonical at its ends is not fast-parsed wrongly
+    assert hicimage.ROWS.loads(pickle.dumps(((1, 2), "101"))) is None
+    assert hicimage.ROWS.loads(pickle.dumps((5, "101"), protocol=2)) is None
