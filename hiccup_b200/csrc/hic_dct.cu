@@ -110,6 +110,9 @@ namespace k1 {
 #ifndef HIC_K1_TH
 #define HIC_K1_TH 64
 #endif
+#ifndef HIC_K1_PF_WAVES
+#define HIC_K1_PF_WAVES 2          // L2 prefetch distance in waves of resident CTAs (0: none)
+#endif
 constexpr int TW = 128;
 constexpr int TH = HIC_K1_TH;          // tile height: 64 (4 CTAs per SM) or 32 (7 lighter CTAs per SM)
 constexpr int CTAS_PER_SM = TH == 64 ? 4 : 7;
@@ -366,8 +369,8 @@ forward_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             // pull the tile of a CTA two waves ahead (4 CTAs on each of 148 SMs per wave) into L2, so that
             // its own load finds the data there
             const unsigned per_img = gridDim.x * gridDim.y;
-            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 2u * (unsigned)CTAS_PER_SM * 148u;
-            if (ahead < per_img * gridDim.z) {
+            const unsigned ahead = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + (unsigned)HIC_K1_PF_WAVES * (unsigned)CTAS_PER_SM * 148u;
+            if (HIC_K1_PF_WAVES > 0 && ahead < per_img * gridDim.z) {
                 const unsigned pz = ahead / per_img, rem = ahead - pz * per_img;
                 const unsigned py = rem / gridDim.x, pxb = rem - py * gridDim.x;
                 const int p0 = (3 * (int)(pxb * TW) - 3 * LEAD) / 4, p1 = (int)(py * TH) - 2, p2 = (int)pz;
