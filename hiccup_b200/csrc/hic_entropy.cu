@@ -217,13 +217,24 @@ rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __res
     }
 }
 
-// pass B: one thread per channel stream walks its tiles, producing the carries and stream totals,
-// and writes the trailing (0, 0) symbol (with its histogram contribution).
-__global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_seg, const BandCarry* __restrict__ band,
-                                       TileCarry* __restrict__ carry, StreamTotals* __restrict__ totals,
-                                       int16_t* __restrict__ values, uint8_t* __restrict__ lengths,
-                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ first) {
-    const int cs = blockIdx.x * blockDim.x + threadIdx.x;
+// pass B: one CTA per channel stream scans its tile summaries (the segment monoid), producing the carries and
+// stream totals, and writes the trailing (0, 0) symbol (with its histogram contribution).  The virtual non-zero
+// a row band inherits from the bands above (`prev0`) is applied to the scanned prefix, not scanned itself.
+constexpr int SCAN_TB = 256;
+__device__ __forceinline__ Segment seg_shfl_up(const Segment& s, int off) {
+    Segment o;
+    o.first = __shfl_up_sync(0xffffffffu, s.first, off);
+    o.last = __shfl_up_sync(0xffffffffu, s.last, off);
+    o.count = __shfl_up_sync(0xffffffffu, s.count, off);
+    return o;
+}
+__global__ void __launch_bounds__(SCAN_TB)
+rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_seg, const BandCarry* __restrict__ band,
+                       TileCarry* __restrict__ carry, StreamTotals* __restrict__ totals,
+                       int16_t* __restrict__ values, uint8_t* __restrict__ lengths,
+                       uint32_t* __restrict__ hist, uint32_t* __restrict__ first) {
+    __shared__ Segment s_warp[SCAN_TB / 32];
+    const int cs = blockIdx.x;
     if (cs >= g.L.n_images * 3) return;
     const int img = cs / 3, c = cs % 3;
     int64_t t0 = (int64_t)img * g.tiles_per_image;
@@ -232,23 +243,47 @@ __global__ void rle_stream_scan_kernel(Geom g, const Segment* __restrict__ tile_
     const BandCarry bc = band ? band[cs] : BandCarry{0, 0, 0, 1};
     const int prev0 = -1 - bc.carry_zeros;       // a virtual non-zero that far back, carrying no symbol
     const int base = bc.carry_zeros / 15;        // fillers inside the carried run were emitted by earlier bands
-    Segment run{prev0, prev0, 0};
-    bool any = false;
-    int first_nz = -1;
-    for (int t = 0; t < g.tiles[c]; ++t) {
-        const int start = t * per_tile;
-        TileCarry tc;
-        tc.prev_last = run.last;
-        tc.sym_off = (uint32_t)(run.count + (start - 1 - run.last) / 15 - base);
-        carry[t0 + t] = tc;
-        const Segment s = tile_seg[t0 + t];
-        if (s.first >= 0) {
-            if (!any) first_nz = s.first;
-            run.count += s.count + (s.first - run.last - 1) / 15;
-            run.last = s.last;
-            any = true;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Segment none{-1, -1, 0};
+    Segment acc = none;                          // every real segment of the tiles before this chunk
+    const int n_tiles = g.tiles[c];
+    for (int tb = 0; tb < n_tiles; tb += SCAN_TB) {
+        const int t = tb + threadIdx.x;
+        const Segment mine = t < n_tiles ? tile_seg[t0 + t] : none;
+        Segment inc = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const Segment o = seg_shfl_up(inc, off);
+            if (lane >= off) inc = seg_combine(o, inc);
         }
+        if (lane == 31) s_warp[warp] = inc;
+        Segment ex = seg_shfl_up(inc, 1);
+        if (lane == 0) ex = none;
+        __syncthreads();
+        Segment before = acc, chunk = none;
+        for (int k = 0; k < SCAN_TB / 32; ++k) {
+            if (k < warp) before = seg_combine(before, s_warp[k]);
+            chunk = seg_combine(chunk, s_warp[k]);
+        }
+        const Segment x = seg_combine(before, ex);          // the real segments of all tiles before tile t
+        if (t < n_tiles) {
+            const int last = x.first >= 0 ? x.last : prev0;
+            const int count = x.first >= 0 ? x.count + (x.first - prev0 - 1) / 15 : 0;
+            TileCarry tc;
+            tc.prev_last = last;
+            tc.sym_off = (uint32_t)(count + (t * per_tile - 1 - last) / 15 - base);
+            carry[t0 + t] = tc;
+        }
+        acc = seg_combine(acc, chunk);
+        __syncthreads();
     }
+    if (threadIdx.x != 0) return;
+    const bool any = acc.first >= 0;
+    const int first_nz = any ? acc.first : -1;
+    Segment run;
+    run.first = prev0;
+    run.last = any ? acc.last : prev0;
+    run.count = any ? acc.count + (acc.first - prev0 - 1) / 15 : 0;
     const int len = (int)g.L.len[c];
     StreamTotals st;
     st.first_nz = first_nz;
@@ -1572,7 +1607,7 @@ static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry
             if (rc) return rc;
         }
     }
-    HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_tile_seg, d_band, p->d_carry, p->d_totals,
+    HIC_LAUNCH("rle_stream_scan_kernel", st, rle_stream_scan_kernel<<<p->n_cs, SCAN_TB, 0, st>>>(g, p->d_tile_seg, d_band, p->d_carry, p->d_totals,
                                                                  p->d_values, p->d_lengths, p->d_hist, p->d_first));
     {
         static bool emit_attr[64] = {false};
