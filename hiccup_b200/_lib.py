@@ -125,6 +125,7 @@ SIGNATURES = {
     "hic_decode_set_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_decode_set_tables_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_decode_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_decode_set_data_bytes": (c_int, [c_void_p, ctypes.c_uint64]),
     "hic_decode_sync": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint64), c_void_p]),
     "hic_decode_export_restarts": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_decode_run_restarts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p]),

@@ -1159,6 +1159,7 @@ struct hic_decode_plan {
     uint16_t* d_sub_cnt = nullptr;
     uint64_t sub_capacity = 0;
     uint8_t* d_restart = nullptr;               // 2 x sub_capacity: `off` bytes then `cnt` bytes of the restart records
+    uint64_t data_bytes = 0;                    // size of the caller's d_bytes buffer when it said so (0: unknown, not checked)
     uint64_t last_n_sub = 0, last_n_tiles = 0;  // of the most recent run (what hic_decode_export_restarts exports)
     uint32_t* d_tile_start = nullptr;
     uint32_t* d_tile_cnt = nullptr;
@@ -1368,8 +1369,14 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
     cudaStream_t st = as_stream(stream);
     const int nss = p->n_ss;
     std::vector<uint64_t> nbits(h_nbits, h_nbits + nss), off(h_byte_off, h_byte_off + nss);
-    for (int s = 0; s < nss; ++s)
+    for (int s = 0; s < nss; ++s) {
         HIC_REQUIRE((off[s] & 3) == 0, "stream %d is not 4-byte aligned", s);
+        // a framed payload is its pad-count byte + ceil(nbits / 8) bytes; the decoders read whole 32-bit words of it
+        if (p->data_bytes && nbits[s])
+            HIC_REQUIRE(off[s] + 4 * ((8 + nbits[s] + 31) / 32) <= p->data_bytes,
+                        "stream %d (%llu bits at byte %llu) runs past the %llu bytes of d_bytes", s, (unsigned long long)nbits[s],
+                        (unsigned long long)off[s], (unsigned long long)p->data_bytes);
+    }
     {
         int rc = hic::small_h2d(p->xfer, p->d_byte_off, off.data(), sizeof(uint64_t) * nss, st);
         if (rc) return rc;
@@ -1516,6 +1523,12 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
 }
 
 extern "C" {
+
+int hic_decode_set_data_bytes(hic_decode_plan* p, uint64_t nbytes) {
+    HIC_REQUIRE(p != nullptr, "plan is NULL");
+    p->data_bytes = nbytes;
+    return HIC_OK;
+}
 
 int hic_decode_run(hic_decode_plan* p, const uint8_t* d_bytes, const uint64_t* h_byte_off, const uint64_t* h_nbits,
                    int16_t* d_coef, void* stream) {

@@ -316,6 +316,9 @@ class EntropyDecoder:
                 self._in = _lib.DeviceBuffer(need + need // 4)
             self._in.upload(data, stream)
             d_data = self._in.ptr
+            _lib.check(self.lib.hic_decode_set_data_bytes(self.plan, int(data.nbytes)))
+        else:
+            _lib.check(self.lib.hic_decode_set_data_bytes(self.plan, 0))
         if sync_only:
             n_sub = ctypes.c_uint64()
             _lib.check(self.lib.hic_decode_sync(self.plan, d_data, byte_off.ctypes.data, nbits.ctypes.data, ctypes.byref(n_sub), stream))

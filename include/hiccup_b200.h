@@ -351,6 +351,9 @@ int hic_decode_set_tables_device(hic_decode_plan* plan, const void* d_index, con
  * h_nbits[s] is the payload bit count of stream s (8 * (framed length - 1) - pad count, 0 for an
  * absent stream).  d_coef receives zigzag blocks.  Synchronises `stream` and returns
  * HIC_ERR_CORRUPT if a stream decodes to the wrong length. */
+/* The C ABI takes d_bytes without a length; a caller that knows it says so here and every later run checks that
+ * each stream's words lie inside the buffer (0 = unknown again).  Returns HIC_ERR_INVALID from the run otherwise. */
+int hic_decode_set_data_bytes(hic_decode_plan* plan, uint64_t nbytes);
 int hic_decode_run(hic_decode_plan* plan, const uint8_t* d_bytes, const uint64_t* h_byte_off,
                    const uint64_t* h_nbits, int16_t* d_coef, void* stream);
 

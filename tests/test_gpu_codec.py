@@ -266,3 +266,38 @@ def test_file_driver_writes_reference_files(tmp_path):
     out = run.compress(pw, str(tmp_path), model.Compression.HIC)
     assert open(out, "rb").read() == pickle.dumps(pickle.loads(w["hic"].tobytes()))
     assert np.array_equal(run.decompress(out), w["rgb_out"])
+
+
+def test_argument_checks_of_the_new_entry_points():
+    """hic_dct_tie_capacity sizes the tie buffer; a smaller one is refused (HIC_ERR_CAPACITY), and a bit stream that
+    would run past the bytes the caller declared is refused before any kernel reads it."""
+    import ctypes
+    from hiccup_b200 import _lib, codec, compression, entropy
+    lib = _lib.load()
+    h, w = 64, 96
+    g = _lib.geometry(h, w)
+    cap = _lib.tie_capacity(1, h, w)
+    assert cap > g.blocks_per_image
+    rgb = orc.synthetic_image(h, w, 77)
+    d_rgb = _lib.DeviceBuffer(rgb.nbytes)
+    d_rgb.upload(rgb)
+    coef = _lib.DeviceBuffer(g.blocks_per_image * 128)
+    ties = _lib.DeviceBuffer(cap * _lib.TIE_RECORD_BYTES)
+    stats = _lib.DeviceBuffer(4 * _lib.TIE_STATS)
+    assert lib.hic_dct_forward(d_rgb.ptr, 1, h, w, coef.ptr, ties.ptr, 1, stats.ptr, None) == -3          # HIC_ERR_CAPACITY
+    assert lib.hic_dct_forward(d_rgb.ptr, 1, h, w, coef.ptr, ties.ptr, cap, stats.ptr, None) == 0
+    _lib.sync()
+    hi = codec.jpeg_encode(compression.jpeg_compression(rgb))
+    p = hi.payloads
+    order = [kind * 3 + c for c in range(3) for kind in range(3)]
+    rows, syms, lens, codes = codec._tables_to_arrays([p[i] for i in order])
+    data, offs, nbits = codec._gather_payload_bytes([p[9 + i] for i in order])
+    dec = entropy.EntropyDecoder(_lib.layout_dct(1, h, w))
+    try:
+        dec.decode(rows, syms, lens, codes, data, offs, nbits, coef.ptr)                                 # fits
+        with pytest.raises(_lib.HicError):
+            dec.decode(rows, syms, lens, codes, data[:len(data) // 2], offs, nbits, coef.ptr)           # declared too short
+    finally:
+        dec.close()
+        for b in (d_rgb, coef, ties, stats):
+            b.free()
