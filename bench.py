@@ -148,9 +148,9 @@ def kernel_bytes(name, P, B, s_ac, bits_bytes, rows, n_ss, bins, mode):
         "huffman_resync_kernel": bits_bytes,
         "huffman_write_kernel": bits_bytes + sym,
         "expand_tile_sum_kernel": 1.0 * s_ac,
-        "expand_scatter_kernel": 3.0 * s_ac + 2.0 * s_ac,
+        "expand_scatter_kernel": 3.0 * s_ac + 2.0 * s_ac + 2.0 * n_dc,
         "dc_tile_sum_kernel": 2.0 * n_dc,
-        "dc_write_kernel": 4.0 * n_dc,
+        "dc_prefix_kernel": 4.0 * n_dc,
         "inverse_kernel": coef + 1.5 * P,
         "upsample_colour_kernel": 4.5 * P,
     }

@@ -978,7 +978,7 @@ __device__ __forceinline__ uint32_t block_excl_sum32(uint32_t v, uint32_t* smem,
 
 // Every tile of 2048 symbols owns the run of positions its symbols cover (at most 15 each).  The run is
 // staged in shared memory in OUTPUT order -- zeros included, and in the block layout with the DC slot
-// of every block it crosses (written as zero here; dc_write_kernel fills the DC values afterwards) --
+// of every block it crosses (filled from the DC values dc_prefix_kernel has left, one int16 per block) --
 // and leaves as 16-byte vectors; only the partial vectors at the two ends of the run go out element by
 // element.  The tiles of a stream also share the zero tail behind the last symbol.  Every AC position
 // is therefore written exactly once and the coefficient buffer needs no memset.
@@ -986,7 +986,7 @@ constexpr int XSTAGE = 8192;                 // staged output elements per pass 
 
 __global__ void __launch_bounds__(XTHREADS)
 expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t* __restrict__ lengths,
-                      const uint32_t* __restrict__ nsym_arr, const int64_t* __restrict__ tile_off,
+                      const int16_t* __restrict__ dcval, const uint32_t* __restrict__ nsym_arr, const int64_t* __restrict__ tile_off,
                       const int64_t* __restrict__ stream_total, int16_t* __restrict__ coef, uint32_t* __restrict__ err) {
     __shared__ uint32_t s[XTHREADS / 32];
     __shared__ __align__(16) int16_t stage[XSTAGE];
@@ -997,6 +997,11 @@ expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t*
     const int64_t stream_len = g.L.len[r.c];
     int16_t* dst = coef + bb * 64;
     const bool skip = g.L.skip_first != 0;
+    // DCT mode: element 0 of every block is its DC value (dc_prefix_kernel has turned the decoded differences
+    // into values, one int16 per block).  A tile writes the DC slots inside its run of outputs, plus the one just
+    // before it when its run starts a block; the zero tail writes those of the blocks it covers -- every DC slot
+    // exactly once, and no separate pass of 2-byte stores into 128-byte lines (it moved 20x its bytes).
+    const int16_t* dcs = dcval + bb;
     // positions fit 31 bits (hic_decode_plan_create): 32-bit arithmetic, division by the constant 63
     auto out_index = [&](uint32_t q) { return skip ? q + q / 63u + 1u : q; };
     const uint32_t tile_first = (uint32_t)r.tile * XT;
@@ -1032,12 +1037,15 @@ expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t*
             if (threadIdx.x == 0) atomicOr(err, 2u);
         } else {
             const uint32_t p0 = (uint32_t)p0_64;
-            const uint32_t o_begin = out_index(p0), o_end = out_index(p0 + tile_total - 1u) + 1u;
+            const uint32_t o_begin = out_index(p0) - ((skip && p0 % 63u == 0u) ? 1u : 0u), o_end = out_index(p0 + tile_total - 1u) + 1u;
             for (uint32_t base = o_begin & ~7u; base < o_end; base += XSTAGE) {
                 const uint32_t span = min((uint32_t)XSTAGE, o_end - base);
                 const uint32_t nvec = (span + 7u) >> 3;
                 for (uint32_t i = threadIdx.x; i < nvec; i += XTHREADS) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
                 __syncthreads();
+                if (skip) {         // the DC slots of this pass (at most 128): one load per thread, all in flight together
+                    for (uint32_t d = ((base + 63u) >> 6) + threadIdx.x; 64u * d < base + span; d += XTHREADS) stage[64u * d - base] = dcs[d];
+                }
                 uint32_t pos = p0 + rank;
 #pragma unroll
                 for (int j = 0; j < XSPT; ++j) {
@@ -1064,7 +1072,15 @@ expand_scatter_kernel(Geom g, const int16_t* __restrict__ values, const uint8_t*
     const int64_t tail0 = min(stream_total[cs], stream_len);
     const int64_t share = (stream_len - tail0 + g.xtiles[r.c] - 1) / g.xtiles[r.c];
     const int64_t a = tail0 + share * r.tile, b = min(stream_len, a + share);
-    for (int64_t p = a + threadIdx.x; p < b; p += XTHREADS) dst[out_index((uint32_t)p)] = 0;
+    for (int64_t p = a + threadIdx.x; p < b; p += XTHREADS) {
+        if (skip) {
+            const uint32_t q = (uint32_t)p, blk = q / 63u;
+            dst[q + blk + 1u] = 0;
+            if (q == 63u * blk) dst[64u * blk] = dcs[blk];
+        } else {
+            dst[p] = 0;
+        }
+    }
 }
 
 // validates each channel stream's expanded length (codec.py:109-111: only a trailing (0,0) may
@@ -1106,14 +1122,13 @@ dc_tile_sum_kernel(Geom g, const int16_t* __restrict__ dc, int64_t* __restrict__
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
+// the decoded DC differences of every channel stream become DC values in place (one int16 per block)
 __global__ void __launch_bounds__(XTHREADS)
-dc_write_kernel(Geom g, const int16_t* __restrict__ dc, const int64_t* __restrict__ tile_off,
-                int16_t* __restrict__ coef) {
+dc_prefix_kernel(Geom g, int16_t* __restrict__ dc, const int64_t* __restrict__ tile_off) {
     __shared__ int64_t s[XTHREADS / 32];
     const XRef r = locate(g.dtiles, g.dtiles_per_image, blockIdx.x);
     const int64_t nb = g.L.nb[r.c];
-    const int64_t bb = cs_block_base(g, r.img, r.c);
-    const int16_t* src = dc + bb;
+    int16_t* src = dc + cs_block_base(g, r.img, r.c);
     const int64_t start = (int64_t)r.tile * XT + threadIdx.x * XSPT;
     int d[XSPT];
     int64_t sum = 0;
@@ -1127,7 +1142,7 @@ dc_write_kernel(Geom g, const int16_t* __restrict__ dc, const int64_t* __restric
     for (int j = 0; j < XSPT; ++j) {
         if (start + j >= nb) break;
         run += d[j];
-        coef[(bb + start + j) * 64] = (int16_t)run;
+        src[start + j] = (int16_t)run;
     }
 }
 
@@ -1495,20 +1510,20 @@ static int decode_run_impl(hic_decode_plan* p, const uint8_t* d_bytes, const uin
         p->xfer.reset();
         return HIC_OK;
     }
-    HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)((p->total_xtiles + XTHREADS / 32 - 1) / (XTHREADS / 32)), XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum, p->total_xtiles));
-    HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<p->n_cs, SCAN_THREADS, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
-                                                               g.xtiles_per_image, p->d_tile_sum, p->d_tile_off,
-                                                               p->d_stream_total));
-    HIC_LAUNCH("expand_scatter_kernel", st, expand_scatter_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym,
-                                                                         p->d_tile_off, p->d_stream_total, d_coef, p->d_err));
-    HIC_LAUNCH("validate_kernel", st, validate_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym, p->d_stream_total, p->d_err));
-    if (g.L.skip_first) {
+    if (g.L.skip_first) {           // D3 first: the expansion below writes the DC values with the blocks they belong to
         HIC_LAUNCH("dc_tile_sum_kernel", st, dc_tile_sum_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_sum));
         HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<p->n_cs, SCAN_THREADS, 0, st>>>(p->n_cs, g.dtiles[0], g.dtiles[1], g.dtiles[2],
                                                                    g.dtiles_per_image, p->d_tile_sum, p->d_tile_off,
                                                                    p->d_stream_total));
-        HIC_LAUNCH("dc_write_kernel", st, dc_write_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_off, d_coef));
+        HIC_LAUNCH("dc_prefix_kernel", st, dc_prefix_kernel<<<(unsigned)p->total_dtiles, XTHREADS, 0, st>>>(g, p->d_dc, p->d_tile_off));
     }
+    HIC_LAUNCH("expand_tile_sum_kernel", st, expand_tile_sum_kernel<<<(unsigned)((p->total_xtiles + XTHREADS / 32 - 1) / (XTHREADS / 32)), XTHREADS, 0, st>>>(g, p->d_lengths, p->d_nsym, p->d_tile_sum, p->total_xtiles));
+    HIC_LAUNCH("stream_scan64_kernel", st, stream_scan64_kernel<<<p->n_cs, SCAN_THREADS, 0, st>>>(p->n_cs, g.xtiles[0], g.xtiles[1], g.xtiles[2],
+                                                               g.xtiles_per_image, p->d_tile_sum, p->d_tile_off,
+                                                               p->d_stream_total));
+    HIC_LAUNCH("expand_scatter_kernel", st, expand_scatter_kernel<<<(unsigned)p->total_xtiles, XTHREADS, 0, st>>>(g, p->d_values, p->d_lengths, p->d_dc, p->d_nsym,
+                                                                         p->d_tile_off, p->d_stream_total, d_coef, p->d_err));
+    HIC_LAUNCH("validate_kernel", st, validate_kernel<<<(p->n_cs + 127) / 128, 128, 0, st>>>(g, p->d_values, p->d_lengths, p->d_nsym, p->d_stream_total, p->d_err));
     const void* h_flags = nullptr;
     {
         int rc = hic::small_d2h(p->xfer, p->d_err, 4 * sizeof(uint32_t), st, &h_flags);

@@ -15,6 +15,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1; echo "launch list rc=$?"
 HIC_ENTROPY_SERIAL=1 python tools/step_once.py 1024 426 640 2 > gpurun_out/step_once_${TAG}.log 2>&1 && \
 HIC_ENTROPY_SERIAL=1 ncu --set full --clock-control none --import-source on \
-    -k regex:"forward_kernel|tie_list|fixup_kernel|rle_tile_summary|rle_emit|dc_diff|pack_tile_bits|pack_emit|build_tables|huffman_sync|huffman_write|expand_tile_sum|expand_scatter|dc_write|inverse_kernel|upsample" \
+    -k regex:"forward_kernel|tie_list|fixup_kernel|rle_tile_summary|rle_emit|dc_diff|pack_tile_bits|pack_emit|build_tables|huffman_sync|huffman_write|expand_tile_sum|expand_scatter|dc_prefix|inverse_kernel|upsample" \
     --launch-skip 18 --launch-count 18 -o gpurun_out/prof_c2_kernels_${TAG} -f python tools/step_once.py 1024 426 640 2 > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full rc=$?"
 tail -3 gpurun_out/ncu_full_${TAG}.log
