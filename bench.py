@@ -135,7 +135,7 @@ def kernel_bytes(name, P, B, s_ac, bits_bytes, rows, n_ss, bins, mode):
         "forward_kernel": 6.0 * P,                      # 3 B/pixel RGB in, 1.5 samples x int16 out
         "wavelet_forward_kernel": 9.0 * P,              # 3 B/pixel in, 3 samples x int16 out
         "wavelet_inverse_kernel": 9.0 * P,
-        "rle_tile_summary_kernel": coef,
+        "rle_tile_summary_kernel": coef + 2.0 * n_dc,           # (whole images: the DC differences leave from here too)
         "rle_emit_kernel": coef + sym,
         "compact_kernel": 8.0 * n_ss * bins + 12.0 * rows,
         "huffman_sort_kernel": 20.0 * rows,

@@ -174,10 +174,17 @@ __device__ __forceinline__ void load_block(const int16_t* __restrict__ src, int 
 }
 #define HIC_ELEM(w, e) (((e) & 1) ? ((w)[(e) >> 1] >> 16) : (int)(short)((w)[(e) >> 1] & 0xFFFF))
 
-// pass A: per-tile segment summary
-template <bool SKIP>
+__device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t* __restrict__ first, size_t bin, uint32_t index);
+
+// pass A: per-tile segment summary.  FUSE_DC (whole images, DCT mode): the thread has its block in registers, so the
+// DC difference, its store and its histogram entry happen here too -- dc_diff_kernel read every 128-byte block
+// again for the one int16 at its head (928 MB of DRAM traffic for 13 MB of DC values on C2).  Row bands cannot
+// fuse: a band's first difference needs the DC of the band above, known only after the exchange between the
+// two passes.
+template <bool SKIP, bool FUSE_DC>
 __global__ void __launch_bounds__(RLE_TB)
-rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __restrict__ tile_seg) {
+rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __restrict__ tile_seg, int16_t* __restrict__ dc_out,
+                        uint32_t* __restrict__ hist, uint32_t* __restrict__ first, uint32_t* __restrict__ err) {
     __shared__ Segment warp_seg[RLE_TB / 32];
     const TileRef tr = locate_tile(g, blockIdx.x);
     const int64_t nb = g.L.nb[tr.c];
@@ -185,7 +192,17 @@ rle_tile_summary_kernel(const int16_t* __restrict__ coef, Geom g, Segment* __res
     Segment s{-1, -1, 0};
     if (b < nb) {
         int w[32];
-        load_block(coef + (cs_block_base(g, tr.img, tr.c) + b) * 64, w);
+        const int64_t block_base = cs_block_base(g, tr.img, tr.c);
+        load_block(coef + (block_base + b) * 64, w);
+        if (FUSE_DC) {
+            const int dc = (int)(short)(w[0] & 0xFFFF);
+            const int prev = b > 0 ? (int)__ldg(coef + (block_base + b - 1) * 64) : 0;      // (the neighbouring thread's line)
+            const int diff = dc - prev;
+            dc_out[block_base + b] = (int16_t)diff;
+            const int bin = diff + g.nb_bins / 2;
+            if (bin < 0 || bin >= g.nb_bins) atomicOr(err, 1u);
+            else hist_add(hist, first, ((size_t)(tr.img * 3 + tr.c) * 3 + HIC_KIND_DC) * g.nb_bins + bin, (uint32_t)b);
+        }
         const int len = (int)g.L.len[tr.c];
         const int base = SKIP ? (int)(63 * b) - 1 : (int)(64 * b);       // position of element e is base + e
         int zmod = 0, pend = 0;
@@ -1275,6 +1292,7 @@ struct hic_entropy_plan {
     uint32_t* d_leaf_freq = nullptr;            // builder scratch: leaf frequencies at the compaction offsets
     uint32_t* d_parent = nullptr;               // builder scratch: two uint16 parent links per entry
     bool hist_clean = false;                    // d_hist / d_first hold their reset values
+    bool dc_fused = false;                      // the scan pass of this batch has already produced the DC differences
     cudaEvent_t ev_dc = nullptr;                // DC histograms compacted (recorded by the emit pass)
     bool dc_early = false;                      // the last emit pass recorded ev_dc
     bool prefer_device = false;                 // the last code build ran on the device: start the next DC pass eagerly
@@ -1567,7 +1585,7 @@ static int join_dc_pass(hic_entropy_plan* p, cudaStream_t st) {
 
 static bool serial_build() { return getenv("HIC_ENTROPY_SERIAL") != nullptr; }
 
-static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st) {
+static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st, bool fuse_dc = false) {
     const Geom& g = p->g;
     p->codes_ready = false;
     {
@@ -1582,10 +1600,13 @@ static int scan_pass(hic_entropy_plan* p, const int16_t* d_coef, cudaStream_t st
     p->hist_clean = false;
     HIC_CUDA(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(uint32_t), st));
     const unsigned tiles = (unsigned)p->total_tiles;
-    if (g.L.skip_first)
-        HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
+    p->dc_fused = fuse_dc && g.L.skip_first;
+    if (p->dc_fused)
+        HIC_LAUNCH("rle_tile_summary_kernel", st, (rle_tile_summary_kernel<true, true><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg, p->d_dc, p->d_hist, p->d_first, p->d_err)));
+    else if (g.L.skip_first)
+        HIC_LAUNCH("rle_tile_summary_kernel", st, (rle_tile_summary_kernel<true, false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg, p->d_dc, p->d_hist, p->d_first, p->d_err)));
     else
-        HIC_LAUNCH("rle_tile_summary_kernel", st, rle_tile_summary_kernel<false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg));
+        HIC_LAUNCH("rle_tile_summary_kernel", st, (rle_tile_summary_kernel<false, false><<<tiles, RLE_TB, 0, st>>>(d_coef, g, p->d_tile_seg, p->d_dc, p->d_hist, p->d_first, p->d_err)));
     return HIC_OK;
 }
 
@@ -1594,7 +1615,8 @@ static int emit_pass(hic_entropy_plan* p, const int16_t* d_coef, const BandCarry
     const unsigned tiles = (unsigned)p->total_tiles;
     p->dc_early = false;
     if (g.L.skip_first) {
-        HIC_LAUNCH("dc_diff_kernel", st, dc_diff_kernel<<<tiles, RLE_TB, 0, st>>>(d_coef, g, d_band, p->d_dc, p->d_hist, p->d_first, p->d_err));
+        if (!p->dc_fused)
+            HIC_LAUNCH("dc_diff_kernel", st, dc_diff_kernel<<<tiles, RLE_TB, 0, st>>>(d_coef, g, d_band, p->d_dc, p->d_hist, p->d_first, p->d_err));
         HIC_LAUNCH("compact_kernel", st, compact_kernel<<<selected_count(SEL_DC, p->n_cs), 256, 0, st>>>(g, SEL_DC, p->d_hist, p->d_first, p->d_entries, p->d_index, p->d_err + 1));
         HIC_CUDA(cudaEventRecord(p->ev_dc, st));
         p->dc_early = true;
@@ -1643,7 +1665,7 @@ int hic_entropy_symbolize(hic_entropy_plan* p, const int16_t* d_coef, void* stre
     HIC_REQUIRE(p && d_coef, "NULL argument");
     cudaStream_t st = as_stream(stream);
     p->band_mode = false;
-    int rc = scan_pass(p, d_coef, st);
+    int rc = scan_pass(p, d_coef, st, true);
     if (rc) return rc;
     return emit_pass(p, d_coef, nullptr, st);
 }
