@@ -761,8 +761,9 @@ fixup_kernel(const uint8_t* __restrict__ rgb, int h, int w, hic_dct_geometry g, 
 namespace k7 {
 constexpr float MAGIC = 12582912.0f;
 
+// in: the block's 128-byte row of the staging area (TMA 128-byte swizzle: piece j sits at position j ^ sw)
 template <int KIND>
-__device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, uint8_t* __restrict__ plane, int ph,
+__device__ __forceinline__ void inverse_block(const int4* __restrict__ in, int sw, uint8_t* __restrict__ plane, int ph,
                                               int pw, int BY, int BX, uint32_t block_index,
                                               hic_tie_record* __restrict__ ties, uint32_t tie_capacity,
                                               uint32_t* __restrict__ stats) {
@@ -770,10 +771,9 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
     float v[64];
     float energy = 0.f;          // sum |coef * q| * w: the error band of the samples
     int ac_bits = 0;
-    const int4* in = reinterpret_cast<const int4*>(src);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int4 wv = __ldg(in + j);
+        const int4 wv = in[j ^ sw];
         const int words[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -837,25 +837,60 @@ __device__ __forceinline__ void inverse_block(const int16_t* __restrict__ src, u
     }
 }
 
-__global__ void __launch_bounds__(128)
-inverse_kernel(const int16_t* __restrict__ coef, hic_dct_geometry g, int n, uint8_t* __restrict__ yp,
+// A CTA takes K7_THREADS consecutive blocks of the coefficient buffer: ONE TMA tensor load (the buffer as
+// [block][64 int16], box {64, K7_THREADS}, 128-byte swizzle) brings their 16 KB into shared memory, and a
+// thread reads its own block from there with conflict-free 16-byte loads.  (A thread loading its 128-byte
+// line straight from global memory is a load of 32 different lines per warp instruction -- the same LSU
+// wavefront bill K1's stores used to pay.)
+constexpr int K7_THREADS = 128;
+struct K7Smem {
+    alignas(1024) int4 blk[K7_THREADS * 8];
+    alignas(8) unsigned long long bar;
+};
+
+__global__ void __launch_bounds__(K7_THREADS)
+inverse_kernel(const __grid_constant__ CUtensorMap tmap_blocks, hic_dct_geometry g, int n, uint8_t* __restrict__ yp,
                uint8_t* __restrict__ crp, uint8_t* __restrict__ cbp, hic_tie_record* __restrict__ ties,
                uint32_t tie_capacity, uint32_t* __restrict__ stats) {
+    __shared__ K7Smem s;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sizeof(s.blk)) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(s.blk)), "l"(reinterpret_cast<uint64_t>(&tmap_blocks)), "r"(0),
+            "r"((int)(blockIdx.x * K7_THREADS)), "r"(bar)
+            : "memory");
+    }
+    __syncthreads();
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
     const int64_t total = (int64_t)n * g.blocks_per_image;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     const int64_t img = gid / g.blocks_per_image;
     int64_t local = gid - img * g.blocks_per_image;
-    const int16_t* src = coef + (size_t)gid * 64;
+    const int4* src = &s.blk[threadIdx.x * 8];
+    const int sw = threadIdx.x & 7;
     if (local < g.nb_l) {
-        inverse_block<0>(src, yp + (size_t)img * g.h * g.w, g.h, g.w, (int)(local / g.nbx_l), (int)(local % g.nbx_l),
+        inverse_block<0>(src, sw, yp + (size_t)img * g.h * g.w, g.h, g.w, (int)(local / g.nbx_l), (int)(local % g.nbx_l),
                          (uint32_t)gid, ties, tie_capacity, stats);
     } else {
         local -= g.nb_l;
         const int plane = (int)(local / g.nb_c);
         local -= (int64_t)plane * g.nb_c;
         uint8_t* base = (plane == 0 ? crp : cbp) + (size_t)img * g.hc * g.wc;
-        inverse_block<1>(src, base, g.hc, g.wc, (int)(local / g.nbx_c), (int)(local % g.nbx_c), (uint32_t)gid, ties,
+        inverse_block<1>(src, sw, base, g.hc, g.wc, (int)(local / g.nbx_c), (int)(local % g.nbx_c), (uint32_t)gid, ties,
                          tie_capacity, stats);
     }
 }
@@ -1105,6 +1140,23 @@ planes_to_blocks_kernel(const int32_t* __restrict__ lum, const int32_t* __restri
 
 static inline unsigned grid_for(int64_t items, int threads) { return (unsigned)((items + threads - 1) / threads); }
 
+// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tensor_map_encoder(EncodeTiledFn* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = encode;
+    return HIC_OK;
+}
+
 }  // namespace hic
 
 // ------------------------------------------------------------------------------------------------
@@ -1161,17 +1213,9 @@ int hic_dct_forward(const uint8_t* d_rgb, int32_t n, int32_t h, int32_t w, int16
         HIC_CUDA(cudaFuncSetAttribute(k1::forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k1::Smem)));
         if (dev < 64) attr_set[dev] = true;
     }
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        HIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
+    EncodeTiledFn encode = nullptr;
+    rc = tensor_map_encoder(&encode);
+    if (rc) return rc;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     // TMA load: the image batch as a 3-D tensor of 32-bit words (3W/4 words, H rows, n images)
     CUtensorMap tmap, tmap_rows;
@@ -1264,7 +1308,22 @@ int hic_dct_inverse(const int16_t* d_coef, int32_t n, int32_t h, int32_t w, uint
     cudaStream_t st = as_stream(stream);
     HIC_CUDA(cudaMemsetAsync(d_stats, 0, HIC_TIE_STATS * sizeof(uint32_t), st));
     const int64_t blocks = (int64_t)n * g.blocks_per_image;
-    HIC_LAUNCH("inverse_kernel", st, k7::inverse_kernel<<<grid_for(blocks, 128), 128, 0, st>>>(d_coef, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
+    HIC_REQUIRE((reinterpret_cast<uintptr_t>(d_coef) & 127) == 0, "d_coef must be 128-byte aligned");
+    CUtensorMap tmap_blocks;
+    {
+        EncodeTiledFn encode = nullptr;
+        rc = tensor_map_encoder(&encode);
+        if (rc) return rc;
+        const cuuint64_t dims[2] = {64, (cuuint64_t)blocks};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {64, (cuuint32_t)k7::K7_THREADS};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&tmap_blocks, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t*>(d_coef), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return hic::fail(HIC_ERR_CUDA, "cuTensorMapEncodeTiled (coefficient blocks) failed: %d", (int)r);
+    }
+    HIC_LAUNCH("inverse_kernel", st, k7::inverse_kernel<<<grid_for(blocks, k7::K7_THREADS), k7::K7_THREADS, 0, st>>>(tmap_blocks, g, n, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
     HIC_LAUNCH("inverse_fixup_kernel", st, k7::inverse_fixup_kernel<<<148 * 4, 128, 0, st>>>(d_coef, g, d_y, d_cr, d_cb, d_ties, tie_capacity, d_stats));
     const int64_t quads = (int64_t)n * g.hc * g.wc;
     const bool word_rows = g.wc % 4 == 0 && g.w % 8 == 0 && ((g.h * (int64_t)g.w) % 8 == 0) && ((g.hc * (int64_t)g.wc) % 4 == 0) &&
