@@ -493,6 +493,13 @@ def run_e2e(args, cfg, codec, pipe, host_rgb, rank, local_rank, world, dist, bar
         # still copies its whole batch in and its streams, tables and pixels out
         ms, payload = timed(lambda: pipe.round_trip(host_in, host_out, on_encoded=on_encoded, repeat=steps))
         ms_floor, _ = timed(lambda: pipe.round_trip(host_in, host_out, repeat=steps, copy_only=True))
+        # (c) the same stream of batches with every chunk decoded from the HOST copy of its payload and tables (uploaded
+        # again, as decoding a file would): what the device-resident hand-over of (b) saves
+        pipe.round_trip(host_in, host_out, from_device=False)
+        ms_reupload, _ = timed(lambda: pipe.round_trip(host_in, host_out, repeat=steps, from_device=False))
+        extra = {"decode_from_host_copy": {"ms_per_step": ms_reupload / steps, "value": pixels / 1e6 / (ms_reupload / steps / 1e3),
+                                           "what": "round_trip(from_device=False): each chunk's compressed payload and code tables go "
+                                                   "back up over PCIe before its decode"}}
         h2d = int(host_rgb.nbytes)
         d2h = int(payload + table_bytes[0] // max(steps, 1) + host_out.nbytes)
         api = ("PipelinedCodec.round_trip(repeat=steps): chunks of %d images over 8 slots, steps streamed back to back; each "
