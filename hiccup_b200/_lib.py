@@ -125,6 +125,10 @@ SIGNATURES = {
     "hic_decode_set_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_decode_set_tables_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_decode_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hic_hicfile_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32,
+                                      c_void_p, ctypes.c_uint64, c_void_p]),
+    "hic_hicfile_parse_rows": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "hic_decode_set_data_bytes": (c_int, [c_void_p, ctypes.c_uint64]),
     "hic_decode_sync": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint64), c_void_p]),
     "hic_decode_export_restarts": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),

@@ -567,10 +567,9 @@ def assemble(result, h, w):
         for c in range(3):
             s = c * 3 + kind
             a, n = int(index[s, 0]), int(index[s, 1])
-            conv = np.int32 if kind == KIND_DC else int
-            rows = [(conv(v), format(int(pk & CODE_MASK), "0%db" % int(pk >> np.uint64(58))))
-                    for v, pk in zip(syms[a:a + n].tolist(), packed[a:a + n])]
-            tables.append(hicimage.PayloadStringP.from_rows(rows))
+            pk = packed[a:a + n]
+            tables.append(hicimage.PayloadStringP.from_arrays(syms[a:a + n], (pk >> np.uint64(58)).astype(np.uint8), pk & CODE_MASK,
+                                                              kind == KIND_DC))
             bits.append(hicimage.BitStringP.from_framed(payloads[s]))
     return hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(h, w), hicimage.TupP(h // 2, w // 2)])
 

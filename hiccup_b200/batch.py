@@ -209,8 +209,8 @@ class DctBatchCodec(_BatchCodec):
             for kind in range(3):
                 for c in range(3):
                     s = (i * 3 + c) * 3 + kind
-                    conv = np.int32 if kind == entropy.KIND_DC else int
-                    tables.append(hicimage.PayloadStringP.from_rows([(conv(a), b) for a, b in enc.table(s)]))
+                    sym, lens, codes = enc.stream_rows(s)
+                    tables.append(hicimage.PayloadStringP.from_arrays(sym, lens, codes, kind == entropy.KIND_DC))
                     bits.append(hicimage.BitStringP.from_framed(enc.framed(s)))
             out.append(hicimage.HicImage.jpeg_image(tables + bits + [hicimage.TupP(g.h, g.w), hicimage.TupP(g.hc, g.wc)]))
         return out

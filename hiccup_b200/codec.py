@@ -78,7 +78,11 @@ def _jpeg_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
         for c in range(3):
             s = c * 3 + kind
             conv = dc_type if kind == entropy.KIND_DC else (ac_type if kind == entropy.KIND_VALUE else int)
-            tables.append(hicimage.PayloadStringP.from_rows([(conv(sym), code) for sym, code in res.table(s)]))
+            if conv is int or conv is np.int32:       # the usual case: the table stays three arrays (hicimage.from_arrays)
+                sym, lens, codes = res.stream_rows(s)
+                tables.append(hicimage.PayloadStringP.from_arrays(sym, lens, codes, conv is np.int32))
+            else:
+                tables.append(hicimage.PayloadStringP.from_rows([(conv(sym), code) for sym, code in res.table(s)]))
             bits.append(hicimage.BitStringP.from_framed(res.framed(s)))
     lum_shape = tuple(int(v) for v in planes[0].shape)
     cr_shape = tuple(int(v) for v in planes[1].shape)
@@ -89,13 +93,20 @@ def _jpeg_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
 def _tables_to_arrays(table_payloads):
     rows, syms, lens, codes = [], [], [], []
     for t in table_payloads:
+        arrays = t.arrays() if hasattr(t, "arrays") else None
+        if arrays is not None:
+            rows.append(int(arrays[0].size))
+            syms.append(arrays[0])
+            lens.append(arrays[1])
+            codes.append(arrays[2])
+            continue
         r = t.rows if hasattr(t, "rows") else [p.numbers for p in t.payloads]
         rows.append(len(r))
-        for sym, code in r:
-            syms.append(int(sym))
-            lens.append(len(code))
-            codes.append(int(code, 2))
-    return rows, syms, lens, codes
+        syms.append(np.array([int(sym) for sym, _ in r], np.int32))
+        lens.append(np.array([len(code) for _, code in r], np.uint8))
+        codes.append(np.array([int(code, 2) for _, code in r], np.uint64))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt, copy=False) if xs else np.zeros(0, dt)
+    return rows, cat(syms, np.int32), cat(lens, np.uint8), cat(codes, np.uint64)
 
 
 def _gather_payload_bytes(bit_payloads):

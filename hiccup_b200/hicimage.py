@@ -175,6 +175,87 @@ class _RowCodec:
 ROWS = _RowCodec()
 
 
+class _NativeRows:
+    """The same row pickles written and parsed for a whole table at once by the C library (csrc/hic_hicfile.cu; host
+    code, no device): a table is then three arrays (symbols, code lengths, codes) + a per-row flag "the symbol is a
+    numpy.int32 scalar", and the thousands of Python objects per image never exist unless somebody asks for `.rows`.
+    Calibrated like _RowCodec: `ok` only if the library's bytes equal pickle.dumps on the sample set."""
+
+    def __init__(self):
+        self.ok = False
+        try:
+            self._calibrate()
+        except Exception:
+            self.ok = False
+
+    def _calibrate(self):
+        if not ROWS.ok:
+            return
+        from hiccup_b200 import _lib
+        self._lib = _lib
+        self._fn = _lib.load()
+        self._pre = np.frombuffer(ROWS.np_pre, np.uint8).copy()
+        self._mid = np.frombuffer(ROWS.np_mid, np.uint8).copy()
+        self.ok = True
+        syms = np.array([0, 1, 255, 256, 65535, 65536, -1, -300, 2 ** 31 - 1, -2 ** 31, 7, 7], np.int32)
+        lens = np.array([1, 3, 58, 10, 2, 5, 7, 1, 20, 33, 4, 4], np.uint8)
+        codes = np.array([1, 5, (1 << 57) | 1, 0x2AA, 2, 17, 100, 0, 12345, 1 << 32, 9, 9], np.uint64)
+        flags = np.array([0, 1] * 6, np.uint8)
+        want = [pickle.dumps(((np.int32(v) if f else int(v)), format(int(c), "0%db" % int(n))))
+                for v, n, c, f in zip(syms, lens, codes, flags)]
+        got = self.pack(syms, lens, codes, flags)
+        back = self.parse(want)
+        if got != want or back is None or not all(np.array_equal(a, b) for a, b in zip(back, (syms, lens, codes, flags))):
+            self.ok = False
+
+    def pack(self, symbols, lens, codes, flags):
+        """[bytes] of the rows, byte-identical to pickle.dumps((symbol, code)) of each."""
+        n = int(symbols.size)
+        if n == 0:
+            return []
+        cap = n * (11 + len(self._pre) + 4 + len(self._mid) + 2 + 58 + 4)
+        out = np.empty(cap, np.uint8)
+        off = np.empty(n + 1, np.uint64)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        codes = np.ascontiguousarray(codes, np.uint64)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        self._lib.check(self._fn.hic_hicfile_pack_rows(symbols.ctypes.data, lens.ctypes.data, codes.ctypes.data, n, flags.ctypes.data,
+                                                       self._pre.ctypes.data, self._pre.size, self._mid.ctypes.data, self._mid.size,
+                                                       out.ctypes.data, cap, off.ctypes.data))
+        raw = out[:int(off[n])].tobytes()
+        o = off.tolist()
+        return [raw[a:b] for a, b in zip(o, o[1:])]
+
+    def parse(self, rows):
+        """(symbols, lens, codes, flags) of a list of row pickles, or None if any row is not canonical."""
+        import ctypes
+        n = len(rows)
+        sizes = np.fromiter((len(r) for r in rows), np.uint64, n)
+        off = np.zeros(n + 1, np.uint64)
+        np.cumsum(sizes, out=off[1:])
+        data = np.frombuffer(b"".join(rows), np.uint8) if n else np.zeros(1, np.uint8)
+        symbols, lens = np.empty(n, np.int32), np.empty(n, np.uint8)
+        codes, flags = np.empty(n, np.uint64), np.empty(n, np.uint8)
+        bad = ctypes.c_int64(-1)
+        self._lib.check(self._fn.hic_hicfile_parse_rows(data.ctypes.data, off.ctypes.data, n, self._pre.ctypes.data, self._pre.size,
+                                                        self._mid.ctypes.data, self._mid.size, symbols.ctypes.data, lens.ctypes.data,
+                                                        codes.ctypes.data, flags.ctypes.data, ctypes.byref(bad)))
+        if bad.value >= 0:
+            return None
+        return symbols, lens, codes, flags
+
+
+NATIVE = None
+
+
+def _native():
+    global NATIVE
+    if NATIVE is None:
+        NATIVE = _NativeRows()
+    return NATIVE
+
+
 class Payload:
     @classmethod
     def from_bytes(cls, b):
@@ -271,17 +352,38 @@ class PlainStringP(Payload):
 
 
 class PayloadStringP(Payload):
-    """A run of payloads of one type -- in practice the rows of one Huffman table."""
+    """A run of payloads of one type -- in practice the rows of one Huffman table.  Held either as the reference
+    holds it (a list of TupP) or as arrays (`from_arrays`, and `from_bytes` when every row is canonical); the other
+    form is made when somebody asks for it."""
 
     def __init__(self, t, payloads):
-        self.t, self.payloads = t, payloads
+        self.t, self._payloads, self._arrays = t, payloads, None
+
+    @classmethod
+    def from_arrays(cls, symbols, lens, codes, numpy_scalar):
+        """symbols int32, lens uint8 (1..58), codes uint64; numpy_scalar: bool or per-row uint8 -- the symbols are
+        numpy.int32 scalars in the pickles (DC tables, non-zero wavelet values) rather than Python ints."""
+        obj = cls(_compat.wire_tuple_class(), None)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        flags = (np.full(symbols.size, 1 if numpy_scalar else 0, np.uint8) if np.isscalar(numpy_scalar) or isinstance(numpy_scalar, bool)
+                 else np.ascontiguousarray(numpy_scalar, np.uint8))
+        obj._arrays = (symbols, np.ascontiguousarray(lens, np.uint8), np.ascontiguousarray(codes, np.uint64), flags)
+        return obj
 
     @classmethod
     def from_bytes(cls, b):
         d = loads(b)
         # rows are plain pickled pairs; parse them directly rather than through d["type"] so that
         # files written by the reference and by this package read the same way
-        return cls(d["type"], [TupP.from_bytes(x) for x in d["data"]])
+        data = d["data"]
+        nat = _native()
+        if nat.ok and data:
+            arrays = nat.parse([bytes(x) for x in data])
+            if arrays is not None:
+                obj = cls(d["type"], None)
+                obj._arrays = arrays
+                return obj
+        return cls(d["type"], [TupP.from_bytes(x) for x in data])
 
     @classmethod
     def from_rows(cls, rows):
@@ -289,16 +391,57 @@ class PayloadStringP(Payload):
         return cls(_compat.wire_tuple_class(), [TupP(s, c) for s, c in rows])
 
     @property
+    def payloads(self):
+        if self._payloads is None:
+            sym, lens, codes, flags = self._arrays
+            self._payloads = [TupP(np.int32(v) if f else v, format(c, "0%db" % n))
+                              for v, n, c, f in zip(sym.tolist(), lens.tolist(), codes.tolist(), flags.tolist())]
+        return self._payloads
+
+    def arrays(self):
+        """(symbols int32, lens uint8, codes uint64, numpy-scalar flags uint8), or None when a row does not fit them
+        (a float symbol, a code of other characters, ...)."""
+        if self._arrays is None and self._payloads is not None:
+            try:
+                sym, lens, codes, flags = [], [], [], []
+                for p in self._payloads:
+                    a, c = p.n1, p.n2
+                    t = type(a)
+                    if t is int:
+                        flags.append(0)
+                    elif t is np.int32:
+                        flags.append(1)
+                    else:
+                        return None
+                    if type(c) is not str or not 1 <= len(c) <= 58 or not -2147483648 <= int(a) < 2147483648:
+                        return None
+                    sym.append(int(a))
+                    lens.append(len(c))
+                    codes.append(int(c, 2))
+                self._arrays = (np.array(sym, np.int32), np.array(lens, np.uint8), np.array(codes, np.uint64), np.array(flags, np.uint8))
+            except ValueError:
+                return None
+        return self._arrays
+
+    @property
     def rows(self):
         return [p.numbers for p in self.payloads]
 
     @property
     def byte_stream(self):
-        return pickle.dumps({"type": _compat.wire_tuple_class(),
-                             "data": [p.byte_stream for p in self.payloads]})
+        nat = _native()
+        arrays = self._arrays if self._arrays is not None else (self.arrays() if nat.ok else None)
+        if nat.ok and arrays is not None:
+            rows = nat.pack(*arrays)
+        else:
+            rows = [p.byte_stream for p in self.payloads]
+        return pickle.dumps({"type": _compat.wire_tuple_class(), "data": rows})
 
     def portable(self):
         """The same table with every symbol as a plain Python number (no numpy scalar pickles)."""
+        if self._arrays is not None:
+            sym, lens, codes, _ = self._arrays
+            return PayloadStringP.from_arrays(sym, lens, codes, False)
         plain = lambda v: v if type(v) in (int, float) else (float(v) if isinstance(v, (float, np.floating)) else int(v))
         return PayloadStringP(self.t, [TupP(plain(p.n1), p.n2) for p in self.payloads])
 

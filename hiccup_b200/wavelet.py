@@ -181,8 +181,10 @@ def encode_streams_to_hic(res, g, image=0):
     for kind in (entropy.KIND_VALUE, entropy.KIND_LENGTH):
         for c in range(3):
             s = (image * 3 + c) * 3 + kind
-            conv = _wavelet_symbol if kind == entropy.KIND_VALUE else int
-            tables.append(hicimage.PayloadStringP.from_rows([(conv(sym), code) for sym, code in res.table(s)]))
+            sym, lens, codes = res.stream_rows(s)
+            # (_wavelet_symbol: non-zero values are np.int32 scalars in the pickles, zero and the zero counts Python ints)
+            flags = (np.asarray(sym) != 0).astype(np.uint8) if kind == entropy.KIND_VALUE else False
+            tables.append(hicimage.PayloadStringP.from_arrays(sym, lens, codes, flags))
             bits.append(hicimage.BitStringP.from_framed(res.framed(s)))
     shapes = band_shapes(g)
     payloads = tables + bits + [hicimage.TupP(*shapes[0]), hicimage.TupP(*shapes[-1])]
@@ -203,15 +205,8 @@ def wavelet_encode(compressed: model.CompressedImage) -> hicimage.HicImage:
 
 
 def _tables_to_arrays(table_payloads):
-    rows, syms, lens, codes = [], [], [], []
-    for t in table_payloads:
-        r = t.rows if hasattr(t, "rows") else [p.numbers for p in t.payloads]
-        rows.append(len(r))
-        for sym, code in r:
-            syms.append(int(sym))
-            lens.append(len(code))
-            codes.append(int(code, 2))
-    return rows, syms, lens, codes
+    from hiccup_b200 import codec
+    return codec._tables_to_arrays(table_payloads)
 
 
 def pyramid_of_file(hic):

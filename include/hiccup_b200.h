@@ -374,6 +374,20 @@ int hic_decode_run_restarts(hic_decode_plan* plan, const uint8_t* d_bytes, const
                             const uint64_t* h_nbits, const uint8_t* h_off, const uint8_t* h_cnt, uint64_t n_sub,
                             int16_t* d_coef, void* stream);
 
+/* ---- host-side helpers of the `.hic` container (no device involved) -------------------------------------
+ * The rows of one Huffman table to / from the byte strings the reference pickles them as, one pickle per row
+ * (hicimage.py:57-60, 103-121: TupP.byte_stream inside PayloadStringP).  numpy_scalar[i] != 0 (NULL: none): row i's symbol
+ * is a numpy.int32 scalar (DC tables, non-zero wavelet values), written as <np_pre> <4 value bytes> <np_mid> -- the bytes this environment's numpy puts
+ * around them, which hiccup_b200/hicimage.py reads off a sample pickle.  pack: row i is out[out_off[i] ..
+ * out_off[i + 1]) (out_off has n + 1 entries).  parse: accepts exactly the canonical forms; *bad_row = the first
+ * row that is anything else (the caller then unpickles the table the slow way), -1 if none. */
+int hic_hicfile_pack_rows(const int32_t* symbols, const uint8_t* lens, const uint64_t* codes, uint64_t n, const uint8_t* numpy_scalar,
+                          const uint8_t* np_pre, uint32_t np_pre_len, const uint8_t* np_mid, uint32_t np_mid_len,
+                          uint8_t* out, uint64_t out_capacity, uint64_t* out_off);
+int hic_hicfile_parse_rows(const uint8_t* data, const uint64_t* off, uint64_t n, const uint8_t* np_pre, uint32_t np_pre_len,
+                           const uint8_t* np_mid, uint32_t np_mid_len, int32_t* symbols, uint8_t* lens, uint64_t* codes,
+                           uint8_t* numpy_scalar, int64_t* bad_row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,3 +195,36 @@ def test_fast_row_pickles_equal_pickle():
     # a row that merely LOOKS canonical at its ends is not fast-parsed wrongly
     assert hicimage.ROWS.loads(pickle.dumps(((1, 2), "101"))) is None
     assert hicimage.ROWS.loads(pickle.dumps((5, "101"), protocol=2)) is None
+
+
+def test_native_table_rows_equal_pickle_and_fall_back():
+    """The library's whole-table row writer / parser (csrc/hic_hicfile.cu, host code) against pickle: tables of ints,
+    of numpy.int32 scalars and mixed ones (wavelet values: zero is a Python int) give the bytes the per-row pickles
+    give; a table holding anything else is still read and written the slow way."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import hicimage
+    nat = hicimage._native()
+    assert nat.ok, "the native row path did not calibrate in this environment (it must fall back, not fail)"
+    rng = np.random.default_rng(9)
+    n = 500
+    syms = rng.integers(-40000, 40000, n).astype(np.int32)
+    syms[:6] = [0, 255, 256, 65535, 65536, -1]
+    lens = rng.integers(1, 59, n).astype(np.uint8)
+    codes = np.array([int(rng.integers(0, 1 << 62)) & ((1 << int(k)) - 1) for k in lens], np.uint64)
+    for flags in (np.zeros(n, np.uint8), np.ones(n, np.uint8), (syms != 0).astype(np.uint8)):
+        rows = [((np.int32(v) if f else int(v)), format(int(c), "0%db" % int(k))) for v, k, c, f in zip(syms, lens, codes, flags)]
+        slow = hicimage.PayloadStringP.from_rows(rows)
+        want = pickle.dumps({"type": slow.t, "data": [pickle.dumps(r) for r in rows]})
+        fast = hicimage.PayloadStringP.from_arrays(syms, lens, codes, flags)
+        assert fast.byte_stream == want == slow.byte_stream
+        back = hicimage.PayloadStringP.from_bytes(want)
+        assert back._arrays is not None and all(np.array_equal(a, b) for a, b in zip(back.arrays(), (syms, lens, codes, flags)))
+        assert [(type(a), a, c) for a, c in back.rows] == [(type(a), a, c) for a, c in rows]
+        assert back == slow and back.byte_stream == want
+    odd = [(3.5, "10"), (7, "0"), (np.int64(2), "11")]
+    t = hicimage.PayloadStringP.from_rows(odd)
+    assert t.arrays() is None
+    b = t.byte_stream
+    assert b == pickle.dumps({"type": t.t, "data": [pickle.dumps(r) for r in odd]})
+    again = hicimage.PayloadStringP.from_bytes(b)
+    assert again._arrays is None and again.rows == odd
