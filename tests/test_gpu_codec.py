@@ -233,6 +233,29 @@ def test_pipelined_codec_equals_unchunked(mode, shape):
     whole.close()
 
 
+@pytest.mark.parametrize("threads", [None, 2, 1])
+def test_resident_multi_stream_steps_equal_the_single_codec(threads):
+    """PipelinedCodec.device_steps (the batch parked on the device as one chunk per slot, every slot on its own CUDA
+    stream, driven by `threads` host threads) leaves in every slot what the single codec leaves for those images."""
+    from hiccup_b200.batch import DctBatchCodec, PipelinedCodec
+    n, h, w, slots = 12, 72, 104, 4
+    rgb = np.stack([orc.synthetic_image(h, w, 500 + i) for i in range(n)])
+    whole = DctBatchCodec(n, h, w)
+    enc = whole.encode(rgb)
+    want = whole.decode(enc).copy()
+    pipe = PipelinedCodec(n, h, w, chunk=n // slots, slots=slots)
+    pipe.upload_resident(rgb)
+    pipe.device_steps(2, threads=threads)
+    per = n // slots
+    for s_, codec in enumerate(pipe.codecs):
+        got = codec.d_out.download(np.uint8, per * want[0].size).reshape((per,) + want.shape[1:])
+        assert np.array_equal(got, want[s_ * per:(s_ + 1) * per]), "slot %d" % s_
+        coef = codec.coefficients()
+        assert np.array_equal(coef, whole.coefficients()[s_ * per:(s_ + 1) * per])
+    pipe.close()
+    whole.close()
+
+
 def test_file_driver_writes_reference_files(tmp_path):
     """run.compress / run.decompress (reference run.py:18-43): the .hic file is byte-identical to the one
     the reference pickles, single file and directory (batched) mode alike."""
