@@ -28,12 +28,14 @@ def _read(path):
     return rgb
 
 
-def compress(path, output, c=model.Compression.JPEG):
+def compress(path, output, c=model.Compression.JPEG, restarts=False):
+    """restarts=True appends restart records to the file (an extension entry the reference's reader ignores;
+    this package's decoder then skips the synchronisation passes of the Huffman decode)."""
     rgb = _read(path)
     if c == model.Compression.JPEG:
-        hi = codec.jpeg_encode(compression.jpeg_compression(rgb))
+        hi = codec.jpeg_encode(compression.jpeg_compression(rgb), restarts=restarts)
     elif c == model.Compression.HIC:
-        hi = codec.wavelet_encode(compression.wavelet_compression(rgb))
+        hi = codec.wavelet_encode(compression.wavelet_compression(rgb), restarts=restarts)
     else:
         raise RuntimeError("Unknown compression type")
     out = os.path.join(output, img_name(path, c))
@@ -55,7 +57,7 @@ def decompress(path, save=None):
     return rgb
 
 
-def compress_many(paths, output, c=model.Compression.JPEG, max_batch=256):
+def compress_many(paths, output, c=model.Compression.JPEG, max_batch=256, restarts=False):
     """Encode many files; images of one shape go through the batched codec together (one launch of
     every kernel per group) and every `.hic` file equals what compress() writes for it."""
     import numpy as np
@@ -75,7 +77,7 @@ def compress_many(paths, output, c=model.Compression.JPEG, max_batch=256):
                 enc = bc.encode(np.stack([rgb for _, rgb in part]))
                 for (p, _), hi in zip(part, bc.hic_images(enc)):
                     out = os.path.join(output, img_name(p, c))
-                    hi.write_file(out)
+                    (codec.add_restart_records(hi) if restarts else hi).write_file(out)
                     written.append(out)
             finally:
                 bc.close()
@@ -89,11 +91,13 @@ def main(argv=None):
     ap.add_argument("--compression", "-s", metavar="STYLE", default=model.Compression.HIC.value,
                     choices=[model.Compression.HIC.value, model.Compression.JPEG.value])
     ap.add_argument("--output", "-o", metavar="OUT", default=".")
+    ap.add_argument("--restarts", "-r", action="store_true",
+                    help="append restart records to the .hic files (ignored by the reference's reader; faster decode here)")
     args = ap.parse_args(argv)
     style = model.Compression(args.compression)
     if args.compress:
-        for out in (compress_many(args.compress, args.output, style) if len(args.compress) > 1
-                    else [compress(args.compress[0], args.output, style)]):
+        for out in (compress_many(args.compress, args.output, style, restarts=args.restarts) if len(args.compress) > 1
+                    else [compress(args.compress[0], args.output, style, restarts=args.restarts)]):
             print(out)
     elif args.decompress:
         name = os.path.join(args.output, os.path.split(args.decompress)[-1] + ".png")

@@ -81,3 +81,29 @@ def test_wavelet_file_with_restart_records():
     assert "huffman_sync_kernel" not in kernels and "restart_load_kernel" in kernels
     assert all(np.array_equal(x, y) for ch in ("lum", "cr", "cb") for x, y in zip(got.as_dict[ch], want.as_dict[ch]))
     assert np.array_equal(compression.wavelet_decompression(got), orc.wavelet_decompression(orc.wavelet_compression(rgb)))
+
+
+def test_file_driver_writes_and_reads_restart_records(tmp_path):
+    """run.compress(restarts=True): the file's first 21 entries are what run.compress writes without them, and
+    run.decompress gives the same pixels from either file."""
+    import os
+    import pickle
+    import cv2
+    from hiccup_b200 import hicimage, model, run
+    rgb = orc.synthetic_image(96, 128, 61)
+    src = os.path.join(tmp_path, "img.png")
+    cv2.imwrite(src, rgb)
+    a_dir, b_dir = os.path.join(tmp_path, "a"), os.path.join(tmp_path, "b")
+    os.makedirs(a_dir)
+    os.makedirs(b_dir)
+    plain = run.compress(src, a_dir, model.Compression.JPEG)
+    ext = run.compress(src, b_dir, model.Compression.JPEG, restarts=True)
+    with open(plain, "rb") as f:
+        p = pickle.load(f)
+    with open(ext, "rb") as f:
+        e = pickle.load(f)
+    assert e[:21] == p and len(e) == 22 and hicimage.RestartP.matches(e[21])
+    assert np.array_equal(run.decompress(plain), run.decompress(ext))
+    many = run.compress_many([src, src], b_dir, model.Compression.JPEG, restarts=True)
+    with open(many[0], "rb") as f:
+        assert pickle.load(f) == e
