@@ -175,8 +175,8 @@ static_assert(sizeof(int4) * THREADS * 8 <= sizeof(uint32_t) * RH * RWORDS, "the
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// One 8x8 block per thread: two rows (then two columns) ride in each f32x2 register pair; the 64 values are
-// re-paired between the passes.  The quantised zigzag int16 of the block go to its 128-byte row of the
+// One 8x8 block per thread: the row pass in scalar float32, the column pass and the quantiser packed (two columns
+// per f32x2 register).  The quantised zigzag int16 of the block go to its 128-byte row of the
 // staging area, 16-byte piece j at position j ^ sw (the TMA 128-byte swizzle; sw = row & 7), so that the
 // eight threads of a quarter warp hit all 32 banks.  rows / cols < 8: the block hangs over the bottom /
 // right edge of its plane -- the reference crops the coefficient plane back to the channel shape
@@ -188,35 +188,32 @@ __device__ __forceinline__ unsigned transform_single(int kind, const uint32_t (&
 #pragma unroll
     for (int i = 0; i < 16; ++i) abs_sum = __vsadu4(wv[i], 0x80808080u) + abs_sum;
     const float fe = (float)abs_sum;
-    const f2 shift(-(8388608.0f + 128.0f)), two(2.0f);
-    f2 a[32];        // a[rp * 8 + v] = row-transformed (rows 2 rp, 2 rp + 1), horizontal frequency v
+    // Row pass in scalar float32, one row at a time; column pass packed, two columns per f32x2 register.  (Both
+    // passes packed -- two rows, then two columns per register -- needs the 64 values re-paired in between, and the
+    // register moves of that re-pairing were nearly as many as the packed operations they served: 0.557 ms against
+    // 0.549 ms on C2.  Same operations per value, same roundings: the results are bit-identical.)
+    const float shift = -(8388608.0f + 128.0f);
+    float T[64];     // T[r * 8 + v] = row-transformed row r, horizontal frequency v
 #pragma unroll
-    for (int rp = 0; rp < 4; ++rp) {
-        f2 x[8];
+    for (int r = 0; r < 8; ++r) {
+        float x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint32_t top = wv[4 * rp + (c >> 2)], bot = wv[4 * rp + 2 + (c >> 2)];
-            x[c] = f2(__uint_as_float(__byte_perm(top, 0x4B000000u, 0x7540 + (c & 3))),
-                      __uint_as_float(__byte_perm(bot, 0x4B000000u, 0x7540 + (c & 3))));
-        }
-        f2 s[4], d[4];
+        for (int c = 0; c < 8; ++c) x[c] = __uint_as_float(__byte_perm(wv[2 * r + (c >> 2)], 0x4B000000u, 0x7540 + (c & 3)));
+        float s[4], d[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             d[i] = x[i] - x[7 - i];
-            s[i] = fma2(two, x[7 - i] + shift, d[i]);
+            s[i] = fmaf(2.0f, x[7 - i] + shift, d[i]);
         }
-        eo_forward8_tail(s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3], a[8 * rp + 0], a[8 * rp + 1], a[8 * rp + 2],
-                         a[8 * rp + 3], a[8 * rp + 4], a[8 * rp + 5], a[8 * rp + 6], a[8 * rp + 7]);
+        eo_forward8_tail(s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3], T[8 * r + 0], T[8 * r + 1], T[8 * r + 2],
+                         T[8 * r + 3], T[8 * r + 4], T[8 * r + 5], T[8 * r + 6], T[8 * r + 7]);
     }
     f2 b[32];        // b[u * 4 + cp] = coefficients (u, 2 cp) and (u, 2 cp + 1)
 #pragma unroll
     for (int cp = 0; cp < 4; ++cp) {
         f2 d[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const f2 left = a[(r >> 1) * 8 + 2 * cp], right = a[(r >> 1) * 8 + 2 * cp + 1];
-            d[r] = (r & 1) ? f2(left.hi(), right.hi()) : f2(left.lo(), right.lo());
-        }
+        for (int r = 0; r < 8; ++r) d[r] = f2(T[8 * r + 2 * cp], T[8 * r + 2 * cp + 1]);
         eo_forward8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
 #pragma unroll
         for (int r = 0; r < 8; ++r) b[r * 4 + cp] = d[r];
