@@ -51,6 +51,10 @@ def _cases():
     cases["w_syn48x80"] = ("wavelet", orc.synthetic_image(48, 80, 22))
     cases["w_flat32"] = ("wavelet", np.full((32, 32, 3), 128, dtype=np.uint8))
     cases["w_gh256"] = ("wavelet", cv2.imread(os.path.join(ref, "hiccup/test/resources/gh.png")))
+    # wavelet mode at settings other than the defaults (settings.py:12-16): (mode, image, settings)
+    cases["ws_l2"] = ("wavelet", orc.synthetic_image(64, 96, 31), dict(levels=2, multiplier=2, threshold=3, quality_factor=0.6, haar=True))
+    cases["ws_l5"] = ("wavelet", orc.synthetic_image(64, 96, 32), dict(levels=5, multiplier=0.5, threshold=5, quality_factor=0.9, haar=False))
+    cases["ws_l4"] = ("wavelet", orc.synthetic_image(50, 38, 33), dict(levels=4, multiplier=1, threshold=0, quality_factor=0.5, haar=False))
     return cases
 
 
@@ -73,11 +77,31 @@ def _record(codec):
     return rec, (orig_dc, orig_rle)
 
 
-def run_case(name, mode, rgb):
+def run_case(name, mode, rgb, cfg=None):
+    import json
     import hiccup.compression as compression
     import hiccup.codec as codec
     import hiccup.hicimage as hicimage
+    import hiccup.model as model
+    import hiccup.settings as rsettings
     out = {"mode": np.array(mode), "rgb": rgb}
+    saved = (rsettings.WAVELET, rsettings.WAVELET_NUM_LEVELS, rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER,
+             rsettings.WAVELET_THRESHOLD, rsettings.WAVELET_QUALITY_FACTOR)
+    if cfg is not None:
+        out["settings"] = np.array(json.dumps(cfg))
+        rsettings.WAVELET = model.Wavelet.HAAR if cfg["haar"] else model.Wavelet.DAUBECHIE
+        rsettings.WAVELET_NUM_LEVELS = cfg["levels"]
+        rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER = cfg["multiplier"]
+        rsettings.WAVELET_THRESHOLD = cfg["threshold"]
+        rsettings.WAVELET_QUALITY_FACTOR = cfg["quality_factor"]
+    try:
+        _run_case(name, mode, rgb, out, compression, codec, hicimage)
+    finally:
+        (rsettings.WAVELET, rsettings.WAVELET_NUM_LEVELS, rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER,
+         rsettings.WAVELET_THRESHOLD, rsettings.WAVELET_QUALITY_FACTOR) = saved
+
+
+def _run_case(name, mode, rgb, out, compression, codec, hicimage):
     t0 = time.time()
     rec, orig = _record(codec)
     try:
@@ -120,8 +144,9 @@ def run_case(name, mode, rgb):
         rgb_out = compression.jpeg_decompression(dec) if mode == "jpeg" else compression.wavelet_decompression(dec)
         out["rgb_out"] = rgb_out
         out["decode_error"] = np.array("")
-    except AssertionError as e:
-        out["decode_error"] = np.array("AssertionError")
+    except (AssertionError, RuntimeError, ValueError, IndexError) as e:
+        # (level counts the reference's decoder mis-reads -- 1 and 4, codec.py:182-189 -- end here)
+        out["decode_error"] = np.array(type(e).__name__)
     print("  %s: decode %.1fs (%s)" % (name, time.time() - t0, str(out["decode_error"]) or "ok"), flush=True)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
@@ -133,11 +158,12 @@ def main():
     settings = refshim.install()
     settings.DEBUG = False
     cases = _cases()
-    for name, (mode, rgb) in cases.items():
+    for name, case in cases.items():
         if args.only and name not in args.only:
             continue
+        mode, rgb = case[0], case[1]
         print(name, mode, rgb.shape, flush=True)
-        run_case(name, mode, rgb)
+        run_case(name, mode, rgb, case[2] if len(case) > 2 else None)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ from tests.conftest import GOLDEN, load_golden
 pytestmark = pytest.mark.gpu
 
 JPEG_GOLDENS = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                      if not os.path.basename(f).startswith("w_"))
+                      if not os.path.basename(f).startswith(("w_", "ws_")))
 
 
 def _golden_comp(g):

@@ -14,7 +14,7 @@ from oracle import hiccup_oracle as orc
 from tests.conftest import GOLDEN, load_golden
 
 ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-JPEG = [n for n in ALL if not n.startswith("w_")]
+JPEG = [n for n in ALL if not n.startswith(("w_", "ws_"))]
 WAVELET = [n for n in ALL if n.startswith("w_")]
 
 
@@ -141,3 +141,38 @@ def test_oracle_wavelet_settings_against_live_reference(cfg, shape):
     finally:
         (rsettings.WAVELET, rsettings.WAVELET_NUM_LEVELS, rsettings.WAVELET_SUBBAND_QUANTIZATION_MULTIPLIER,
          rsettings.WAVELET_THRESHOLD, rsettings.WAVELET_QUALITY_FACTOR) = saved
+
+
+WS_GOLDENS = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "ws_*.npz")))
+
+
+@pytest.mark.parametrize("name", WS_GOLDENS)
+def test_oracle_equals_reference_wavelet_settings_goldens(name):
+    """Goldens the UNMODIFIED reference wrote at non-default wavelet settings (tests/golden/gen_golden.py, on the pywt
+    stand-in): sub-bands, run-length streams, tables, bit strings and -- where the reference's own decoder reads its
+    file back -- decoded pixels."""
+    import json
+    g = load_golden(name)
+    cfg = json.loads(str(g["settings"]))
+    kw = {k: cfg[k] for k in ("levels", "multiplier", "threshold", "quality_factor")}
+    planes = orc.wavelet_compression(g["rgb"], **kw)
+    n_bands = 3 * cfg["levels"] + 1
+    for ch in orc.CHANNELS:
+        assert len(planes[ch]) == n_bands
+        for i in range(n_bands):
+            assert np.array_equal(planes[ch][i], g["band_%s_%d" % (ch, i)])
+    st = orc.wavelet_streams(planes)
+    for ch in orc.CHANNELS:
+        assert np.array_equal(st["value"][ch], g["rle_val_" + ch])
+        assert np.array_equal(st["length"][ch], g["rle_len_" + ch])
+    enc = orc.wavelet_encode(planes)
+    tables, bits, shapes = _stream_content(pickle.loads(g["hic"].tobytes()), 6)
+    assert [[(int(a), b) for a, b in t] for t in enc["tables"]] == tables
+    assert [orc.padded_bits_to_bytes(b) for b in enc["bits"]] == bits
+    assert enc["shapes"] == shapes
+    if str(g["decode_error"]) == "":
+        dec = orc.wavelet_decode(enc)
+        for ch in orc.CHANNELS:
+            for i in range(n_bands):
+                assert np.array_equal(dec[ch][i], planes[ch][i])
+        assert np.array_equal(orc.wavelet_decompression(dec, cfg["multiplier"]), g["rgb_out"])
