@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--check", action="store_true", help="compare the stitched stream with a one-band encode on rank 0")
+    ap.add_argument("--shard-decode", action="store_true",
+                    help="inverse transform and pixel download of every band on its own GPU (coefficient bands over NCCL)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -99,6 +101,57 @@ def main():
         decoder._inverse()
         return decoder.fetch()
 
+    # ---- sharded decode: the root's entropy decode, then every band's K7 / K8 and download on its own GPU ----
+    class _Cai:          # a raw device pointer as a torch byte tensor (NCCL send / recv wants tensors, and has no int16)
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+    shard = bool(args.shard_decode and world > 1)
+    band_dec, image_coef, shared_out, shared_map = None, None, None, None
+    if shard:
+        band_dec = bands.BandDecoder(size, size, cuts[rank], cuts[rank + 1], device=local_rank)
+        path = "/dev/shm/hic_bands_out_%s.bin" % os.environ.get("MASTER_PORT", "0")
+        nbytes = size * size * 3
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        shared_map = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        _lib.load().hic_host_register(shared_map.ctypes.data, nbytes)
+        shared_out = shared_map.reshape(size, size, 3)
+        dist.barrier()
+
+    def decode_sharded(res):
+        nonlocal decoder, staging, image_coef
+        from hiccup_b200.batch import DctBatchCodec
+        g = band_dec.g_image
+        mine = torch.as_tensor(_Cai(band_dec.coef_ptr, band_dec.g.blocks_per_image * 128), device="cuda")     # 128 bytes per block
+        ops = []
+        if rank == 0:
+            if decoder is None:
+                decoder = DctBatchCodec(1, size, size)
+                staging = _lib.DeviceBuffer(bands.stitch_layout(res["all_bits"], 9)[3] + (1 << 20))
+            off, nbits = bands.upload_stitched(res, staging)
+            index, syms, packed = res["tables"]
+            decoder.decoder.decode_device_data(index, syms, packed, staging.ptr, off, nbits, decoder.d_coef_dec.ptr)
+            whole = torch.as_tensor(_Cai(decoder.d_coef_dec.ptr, g.blocks_per_image * 128), device="cuda")
+            for r in range(world):
+                s0, s1 = bands.band_slice(size, cuts[r], cuts[r + 1])
+                for (a, b), (c, d) in zip(bands.band_block_ranges(g, s0, s1), band_dec.dst if r == 0 else [(0, 0)] * 3):
+                    if r == 0:
+                        mine[128 * c:128 * d].copy_(whole[128 * a:128 * b])
+                    else:
+                        ops.append(dist.P2POp(dist.isend, whole[128 * a:128 * b], r))
+        else:
+            for c, d in band_dec.dst:
+                ops.append(dist.P2POp(dist.irecv, mine[128 * c:128 * d], 0))
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+        torch.cuda.synchronize()
+        band_dec.inverse()
+        band_dec.fetch_rows(shared_out[cuts[rank]:cuts[rank + 1]])
+
     res = None
     for _ in range(args.warmup):
         res = encode_step()
@@ -136,6 +189,21 @@ def main():
             ref = orc.jpeg_decompression(orc.jpeg_compression(image[y0:y0 + win, x0:x0 + win]))
             same = bool(same and np.array_equal(out[0][y0 + m:y0 + win - m, x0 + m:x0 + win - m], ref[m:-m, m:-m]))
     barrier()
+    t_dec_shard, shard_same = None, None
+    if shard:
+        decode_sharded(res)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            decode_sharded(res)
+            barrier()
+        t_dec_shard = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        t = torch.tensor([t_dec_shard], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dec_shard = float(t.item())
+        if rank == 0 and out is not None:
+            shard_same = bool(np.array_equal(shared_out, out[0]))
+    barrier()
     if rank == 0:
         mp = size * size / 1e6
         nbytes = sum(len(b) for b in hic.byte_stream())
@@ -151,9 +219,20 @@ def main():
             "encode": {"value": mp / t_enc, "unit": bench.UNIT, "ms": t_enc * 1e3,
                        "phases_ms_max_over_ranks": {k: round(v, 2) for k, v in phases}},
             "decode": {"value": mp / t_dec, "unit": bench.UNIT, "ms": t_dec * 1e3, "where": "rank 0 only"},
+            "decode_sharded": None if t_dec_shard is None else {
+                "value": mp / t_dec_shard, "unit": bench.UNIT, "ms": t_dec_shard * 1e3, "step_ms": (t_enc + t_dec_shard) * 1e3,
+                "equals_rank0_decode": shard_same,
+                "where": "entropy decode on rank 0, coefficient bands to their ranks over NCCL, K7 / K8 and the pixel download on every rank"},
             "matches_one_band_encode": same,
         }
         bench.emit(line)
+    if shard:
+        _lib.load().hic_host_unregister(shared_map.ctypes.data)
+        if rank == 0:
+            try:
+                os.remove("/dev/shm/hic_bands_out_%s.bin" % os.environ.get("MASTER_PORT", "0"))
+            except OSError:
+                pass
     if dist is not None:
         dist.barrier()
         comm.close()

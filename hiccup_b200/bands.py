@@ -620,6 +620,59 @@ def upload_stitched(result, d_data, stream=None):
     return np.array(off, np.uint64), np.array(nbits, np.uint64)
 
 
+# ------------------------------------------------------------------------------------------------
+# row-band sharded DECODE: the entropy decode of one image does not shard (the format has no restart points, so the
+# symbol streams are one chain per channel), but everything after it does.  The root decodes the stitched payloads
+# into the image's coefficient blocks, hands every band its block rows (plus one chroma block row of halo each side,
+# for the 5-tap pyrUp) GPU to GPU, and every rank runs K7 / K8 on its rows and downloads THEM -- the decoded pixels
+# (3 bytes per pixel, five times the coded image) leave through every GPU's PCIe link instead of the root's alone.
+# The exchange itself is the caller's (bench_bands.py uses NCCL send / recv over NVLink); this is the bookkeeping.
+# ------------------------------------------------------------------------------------------------
+def band_block_ranges(g, s0, s1):
+    """Block index ranges [first, last) of the rows [s0, s1) (multiples of 16) of an image with geometry g inside its
+    coefficient buffer: (luminance, Cr, Cb)."""
+    l0, l1 = (s0 // 8) * g.nbx_l, min(-(-s1 // 8), g.nby_l) * g.nbx_l
+    c0, c1 = (s0 // 16) * g.nbx_c, min(-(-(s1 // 2) // 8), g.nby_c) * g.nbx_c
+    return [(l0, l1), (g.nb_l + c0, g.nb_l + c1), (g.nb_l + g.nb_c + c0, g.nb_l + g.nb_c + c1)]
+
+
+class BandDecoder:
+    """One band's share of a sharded decode: a DctBatchCodec for the band's slice (its rows + halo) whose coefficient
+    buffer the caller fills with band_block_ranges() of the whole image's blocks; inverse() runs K7 / K8 on the
+    slice and fetch_rows() downloads the band's own rows."""
+
+    def __init__(self, h, w, r0, r1, device=None):
+        from hiccup_b200 import _lib
+        from hiccup_b200.batch import DctBatchCodec
+        self.h, self.w, self.r0, self.r1 = h, w, r0, r1
+        self.s0, self.s1 = band_slice(h, r0, r1)
+        self.g_image = _lib.geometry(h, w)
+        self.codec = DctBatchCodec(1, self.s1 - self.s0, w, device=device)
+        self.g = self.codec.g
+        self.src = band_block_ranges(self.g_image, self.s0, self.s1)          # in the image's buffer
+        self.dst = [(0, self.g.nb_l), (self.g.nb_l, self.g.nb_l + self.g.nb_c),
+                    (self.g.nb_l + self.g.nb_c, self.g.nb_l + 2 * self.g.nb_c)]                 # in the slice's buffer
+        for (a, b), (c, d) in zip(self.src, self.dst):
+            assert b - a == d - c, "band blocks %r do not fill the slice planes %r" % (self.src, self.dst)
+
+    @property
+    def coef_ptr(self):
+        return self.codec.d_coef_dec.ptr
+
+    def inverse(self):
+        self.codec._inverse()
+
+    def fetch_rows(self, out_rows):
+        """out_rows: uint8 array of the band's rows, (r1 - r0) x out_w x 3 (ideally page-locked)."""
+        ow = self.codec.out_w
+        n = (self.r1 - self.r0) * ow * 3
+        assert out_rows.size == n and out_rows.flags.c_contiguous
+        self.codec.d_out.download(np.uint8, n, self.codec.stream, offset=(self.r0 - self.s0) * ow * 3, out=out_rows.reshape(-1))
+
+    def close(self):
+        self.codec.close()
+
+
 def encode_banded(image, n_bands, devices=None, value_bins=8192):
     """Encode one image as `n_bands` row bands in this process (devices: optional list of CUDA device
     indices, one per band, cycled; default: the current device for all).  Returns the HicImage."""
