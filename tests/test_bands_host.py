@@ -165,3 +165,24 @@ def test_staged_strings_are_gathered_without_a_copy(monkeypatch):
         owner.close()
         root.close()
     assert not [f for f in os.listdir("/dev/shm") if ("stg%d" % os.getpid()) in f]
+
+
+@pytest.mark.parametrize("h,w,k", [(16384, 16384, 8), (2048, 512, 5), (426, 640, 4), (1080, 1920, 8), (96, 80, 2)])
+def test_band_block_ranges_fill_the_slice_geometry(h, w, k):
+    """The sharded decode hands band b the block rows of its slice (rows + halo): three contiguous ranges of the image's
+    coefficient buffer that must be exactly the three planes of the slice's own geometry, and the bands' own rows
+    (without halo) must tile the image."""
+    from hiccup_b200 import _lib
+    g = _lib.geometry(h, w)
+    cuts = bands.plan_bands(h, k)
+    covered = 0
+    for b in range(len(cuts) - 1):
+        s0, s1 = bands.band_slice(h, cuts[b], cuts[b + 1])
+        gs = _lib.geometry(s1 - s0, w)
+        (l0, l1), (r0, r1), (b0, b1) = bands.band_block_ranges(g, s0, s1)
+        assert (l1 - l0, r1 - r0, b1 - b0) == (gs.nb_l, gs.nb_c, gs.nb_c)
+        assert 0 <= l0 < l1 <= g.nb_l and g.nb_l <= r0 < r1 <= g.nb_l + g.nb_c and g.nb_l + g.nb_c <= b0 < b1 <= g.blocks_per_image
+        assert l0 == (s0 // 8) * g.nbx_l and r0 - g.nb_l == (s0 // 16) * g.nbx_c == b0 - g.nb_l - g.nb_c
+        assert s0 % 16 == 0 and (s1 % 16 == 0 or s1 == h) and s0 <= cuts[b] and cuts[b + 1] <= s1
+        covered += cuts[b + 1] - cuts[b]
+    assert covered == h
