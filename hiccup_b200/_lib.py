@@ -127,6 +127,10 @@ SIGNATURES = {
     "hic_decode_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hic_hicfile_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32,
                                       c_void_p, ctypes.c_uint64, c_void_p]),
+    "hic_hicfile_pack_table": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32,
+                                       c_void_p, c_uint32, c_void_p, ctypes.c_uint64, c_void_p]),
+    "hic_hicfile_parse_table": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32)]),
     "hic_hicfile_parse_rows": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "hic_decode_set_data_bytes": (c_int, [c_void_p, ctypes.c_uint64]),

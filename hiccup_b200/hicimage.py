@@ -30,9 +30,11 @@ Two things the reference's reader does not have:
     the reference still decodes it.  `RestartP` (restart records for the parallel Huffman decode,
     include/hiccup_b200.h) is such an entry.
 """
+import ctypes
 import io
 import pickle
 import struct
+import threading
 
 import numpy as np
 
@@ -183,10 +185,17 @@ class _NativeRows:
 
     def __init__(self):
         self.ok = False
+        self.table_ok = False
+        self._heads = {}
+        self._tls = threading.local()
         try:
             self._calibrate()
         except Exception:
             self.ok = False
+        try:
+            self._calibrate_tables()
+        except Exception:
+            self.table_ok = False
 
     def _calibrate(self):
         if not ROWS.ok:
@@ -226,6 +235,78 @@ class _NativeRows:
         raw = out[:int(off[n])].tobytes()
         o = off.tolist()
         return [raw[a:b] for a, b in zip(o, o[1:])]
+
+    # ---- whole table payloads --------------------------------------------------------------------
+    def _head(self, cls):
+        """The bytes pickle puts between PROTO/FRAME and the first row of {"type": cls, "data": [...]}, or None if this
+        pickle module does not lay the empty table out the way csrc/hic_hicfile.cu continues it."""
+        if cls not in self._heads:
+            raw = pickle.dumps({"type": cls, "data": []})
+            ok = (raw[:3] == b"\x80\x04\x95" and int.from_bytes(raw[3:11], "little") == len(raw) - 11 and raw[-4:] == b"]\x94u."
+                  and raw[11:13] == b"}\x94")
+            self._heads[cls] = np.frombuffer(raw[11:-2], np.uint8).copy() if ok else None
+        return self._heads[cls]
+
+    def _calibrate_tables(self):
+        """pack_table against pickle.dumps: no row, one row (APPEND, no MARK), a batch boundary (1000 rows), and tables
+        past one and two 64 KiB frames, with both kinds of symbol."""
+        if not self.ok or pickle.DEFAULT_PROTOCOL != 4:
+            return
+        cls = _compat.wire_tuple_class()
+        self.table_ok = True
+        rng = np.random.default_rng(7)
+        for n, flag in ((0, 0), (1, 0), (1, 1), (2, 1), (999, 0), (1000, 1), (1001, 0), (2300, 0), (2300, 1)):
+            lens = rng.integers(1, 59, n).astype(np.uint8)
+            codes = rng.integers(0, 1 << 62, n, dtype=np.uint64) & ((np.uint64(1) << lens.astype(np.uint64)) - np.uint64(1))
+            syms = rng.integers(-70000, 70000, n).astype(np.int32)
+            flags = np.full(n, flag, np.uint8)
+            want = pickle.dumps({"type": cls, "data": self.pack(syms, lens, codes, flags)})
+            back = self.parse_table(want)
+            if self.pack_table(cls, syms, lens, codes, flags) != want or back is None or \
+                    not all(np.array_equal(a, b) for a, b in zip(back, (syms, lens, codes, flags))):
+                self.table_ok = False
+                return
+
+    def pack_table(self, cls, symbols, lens, codes, flags):
+        """bytes of a whole table payload: pickle.dumps({"type": cls, "data": [row pickles]})."""
+        head = self._head(cls)
+        if head is None:
+            return None
+        n = int(symbols.size)
+        row_max = 11 + len(self._pre) + 4 + len(self._mid) + 2 + 58 + 4
+        cap = 64 + head.size + n * (row_max + 6) + 2 * (n // 1000 + 1)
+        cap += 9 * (cap // 65536 + 2)
+        tls = self._tls
+        out = getattr(tls, "out", None)                    # per-thread scratch, grown on demand
+        if out is None or out.size < cap:
+            out = tls.out = np.empty(max(cap, 1 << 20), np.uint8)
+            cap = out.size
+        size = ctypes.c_uint64(0)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        codes = np.ascontiguousarray(codes, np.uint64)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        self._lib.check(self._fn.hic_hicfile_pack_table(symbols.ctypes.data, lens.ctypes.data, codes.ctypes.data, n, flags.ctypes.data,
+                                                        self._pre.ctypes.data, self._pre.size, self._mid.ctypes.data, self._mid.size,
+                                                        head.ctypes.data, head.size, out.ctypes.data, cap, ctypes.byref(size)))
+        return out[:size.value].tobytes()
+
+    def parse_table(self, payload):
+        """(symbols, lens, codes, flags) of a whole table payload, or None if it is not in the canonical form (another
+        pickle protocol, a foreign class, a row of another shape, ...) -- the caller then takes the unpickler."""
+        size = len(payload)
+        cap = size // 23 + 1
+        symbols, lens = np.empty(cap, np.int32), np.empty(cap, np.uint8)
+        codes, flags = np.empty(cap, np.uint64), np.empty(cap, np.uint8)
+        n, canonical = ctypes.c_uint64(0), ctypes.c_int32(0)
+        data = np.frombuffer(payload, np.uint8) if size else np.zeros(1, np.uint8)
+        self._lib.check(self._fn.hic_hicfile_parse_table(data.ctypes.data, size, self._pre.ctypes.data, self._pre.size,
+                                                         self._mid.ctypes.data, self._mid.size, symbols.ctypes.data, lens.ctypes.data,
+                                                         codes.ctypes.data, flags.ctypes.data, cap, ctypes.byref(n), ctypes.byref(canonical)))
+        if not canonical.value:
+            return None
+        k = int(n.value)
+        return symbols[:k].copy(), lens[:k].copy(), codes[:k].copy(), flags[:k].copy()
 
     def parse(self, rows):
         """(symbols, lens, codes, flags) of a list of row pickles, or None if any row is not canonical."""
@@ -372,11 +453,17 @@ class PayloadStringP(Payload):
 
     @classmethod
     def from_bytes(cls, b):
+        nat = _native()
+        if nat.table_ok:
+            arrays = nat.parse_table(b)
+            if arrays is not None:
+                obj = cls(_compat.wire_tuple_class(), None)
+                obj._arrays = arrays
+                return obj
         d = loads(b)
         # rows are plain pickled pairs; parse them directly rather than through d["type"] so that
         # files written by the reference and by this package read the same way
         data = d["data"]
-        nat = _native()
         if nat.ok and data:
             arrays = nat.parse([bytes(x) for x in data])
             if arrays is not None:
@@ -431,6 +518,10 @@ class PayloadStringP(Payload):
     def byte_stream(self):
         nat = _native()
         arrays = self._arrays if self._arrays is not None else (self.arrays() if nat.ok else None)
+        if nat.table_ok and arrays is not None:
+            whole = nat.pack_table(_compat.wire_tuple_class(), *arrays)
+            if whole is not None:
+                return whole
         if nat.ok and arrays is not None:
             rows = nat.pack(*arrays)
         else:

@@ -387,6 +387,20 @@ int hic_hicfile_pack_rows(const int32_t* symbols, const uint8_t* lens, const uin
 int hic_hicfile_parse_rows(const uint8_t* data, const uint64_t* off, uint64_t n, const uint8_t* np_pre, uint32_t np_pre_len,
                            const uint8_t* np_mid, uint32_t np_mid_len, int32_t* symbols, uint8_t* lens, uint64_t* codes,
                            uint8_t* numpy_scalar, int64_t* bad_row);
+/* A whole table payload, byte-identical to pickle.dumps({"type": TupP, "data": [row pickles]}) (hicimage.py:103-121:
+ * PayloadStringP.byte_stream) under protocol 4: `head` = the pickle's bytes from the dict's opcode up to the list's MEMOIZE
+ * (they name the TupP class; read off a sample pickle by hiccup_b200/hicimage.py), then the rows as memoised bytes
+ * objects in batches of 1000, in 64 KiB frames as CPython's pickler cuts them.  *out_len = the payload's size. */
+int hic_hicfile_pack_table(const int32_t* symbols, const uint8_t* lens, const uint64_t* codes, uint64_t n, const uint8_t* numpy_scalar,
+                           const uint8_t* np_pre, uint32_t np_pre_len, const uint8_t* np_mid, uint32_t np_mid_len,
+                           const uint8_t* head, uint32_t head_len, uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
+/* The reverse (hicimage.py:97-101: PayloadStringP.from_bytes): walks a table payload written by pickle protocol 4 or 5 whose
+ * "type" is <any package>.hicimage.TupP and fills the row arrays (row_capacity entries each; size / 23 rows always
+ * suffice).  *canonical = 1 and *n_rows = the row count when every opcode and row is of the canonical form, else
+ * *canonical = 0 (the caller then unpickles the payload the slow way; nothing is trusted from the arrays). */
+int hic_hicfile_parse_table(const uint8_t* data, uint64_t size, const uint8_t* np_pre, uint32_t np_pre_len, const uint8_t* np_mid,
+                            uint32_t np_mid_len, int32_t* symbols, uint8_t* lens, uint64_t* codes, uint8_t* numpy_scalar,
+                            uint64_t row_capacity, uint64_t* n_rows, int32_t* canonical);
 
 #ifdef __cplusplus
 }

@@ -228,3 +228,114 @@ def test_native_table_rows_equal_pickle_and_fall_back():
     assert b == pickle.dumps({"type": t.t, "data": [pickle.dumps(r) for r in odd]})
     again = hicimage.PayloadStringP.from_bytes(b)
     assert again._arrays is None and again.rows == odd
+
+
+def _random_table(rng, n, flag_mode):
+    syms = rng.integers(-70000, 70000, n).astype(np.int32)
+    lens = rng.integers(1, 59, n).astype(np.uint8)
+    codes = rng.integers(0, 1 << 62, n, dtype=np.uint64) & ((np.uint64(1) << lens.astype(np.uint64)) - np.uint64(1))
+    flags = {0: np.zeros(n, np.uint8), 1: np.ones(n, np.uint8), 2: (syms % 3 != 0).astype(np.uint8)}[flag_mode]
+    return syms, lens, codes, flags
+
+
+def _pickled_table(cls, syms, lens, codes, flags):
+    rows = [((np.int32(v) if f else int(v)), format(int(c), "0%db" % int(k))) for v, k, c, f in zip(syms, lens, codes, flags)]
+    return pickle.dumps({"type": cls, "data": [pickle.dumps(r) for r in rows]})
+
+
+@pytest.mark.parametrize("flag_mode", [0, 1, 2])
+def test_native_whole_table_payloads_equal_pickle(flag_mode):
+    """hic_hicfile_pack_table / parse_table (csrc/hic_hicfile.cu, host code) write and read a table payload in one call;
+    the bytes must be pickle's own at every size class: no row, one row (APPEND without MARK), the 1000-row batches of
+    pickle's list writer, and tables past one, two and three of its 64 KiB frames."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import _compat, hicimage
+    nat = hicimage._native()
+    assert nat.table_ok, "the native table path did not calibrate in this environment (it must fall back, not fail)"
+    cls = _compat.wire_tuple_class()
+    rng = np.random.default_rng(100 + flag_mode)
+    sizes = [0, 1, 2, 3, 999, 1000, 1001, 1999, 2000, 2001, 3000, 5000] + [int(v) for v in rng.integers(4, 4000, 12)]
+    for n in sizes:
+        arrays = _random_table(rng, n, flag_mode)
+        want = _pickled_table(cls, *arrays)
+        assert nat.pack_table(cls, *arrays) == want, "table of %d rows" % n
+        t = hicimage.PayloadStringP.from_arrays(*arrays)
+        assert t.byte_stream == want
+        back = hicimage.PayloadStringP.from_bytes(want)
+        assert back._arrays is not None and all(np.array_equal(a, b) for a, b in zip(back.arrays(), arrays))
+        assert pickle.loads(want)["data"] == nat.pack(*arrays)       # and pickle reads it back to the same rows
+
+
+def test_native_table_frames_at_every_cut():
+    """The 64 KiB frame cut falls wherever the rows' sizes put it: tables whose byte count sweeps across the cut one
+    row and one code bit at a time."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import _compat, hicimage
+    nat = hicimage._native()
+    cls = _compat.wire_tuple_class()
+    rng = np.random.default_rng(5)
+    base = 65536 // 37                                     # rows of a 20-bit code and a one-byte symbol are ~37 bytes in the list
+    for n in range(base - 60, base + 60, 3):
+        syms = rng.integers(0, 256, n).astype(np.int32)
+        lens = np.full(n, 20, np.uint8)
+        lens[: n % 7] = 21 + (n % 5)
+        codes = rng.integers(0, 1 << 20, n, dtype=np.uint64)
+        flags = np.zeros(n, np.uint8)
+        want = _pickled_table(cls, syms, lens, codes, flags)
+        assert nat.pack_table(cls, syms, lens, codes, flags) == want, n
+        back = nat.parse_table(want)
+        assert back is not None and np.array_equal(back[0], syms) and np.array_equal(back[2], codes)
+
+
+def test_native_table_parser_never_misreads():
+    """Whatever the native parser accepts must be what the unpickler reads; anything else it must decline (the reader
+    then takes the unpickler): other protocols, foreign classes, truncations and random byte damage."""
+    import hiccup_b200  # noqa: F401
+    from hiccup_b200 import _compat, hicimage
+    nat = hicimage._native()
+    cls = _compat.wire_tuple_class()
+    rng = np.random.default_rng(11)
+    arrays = _random_table(rng, 1500, 2)
+    good = _pickled_table(cls, *arrays)
+    assert nat.parse_table(good) is not None
+    assert nat.parse_table(b"") is None and nat.parse_table(good[:-1]) is None and nat.parse_table(good + b".") is None
+    for cut in (1, 2, 11, 40, 100, len(good) // 2):
+        assert nat.parse_table(good[:cut]) is None
+    rows = nat.pack(*arrays)
+    for protocol in (0, 1, 2, 3):
+        assert nat.parse_table(pickle.dumps({"type": cls, "data": rows}, protocol=protocol)) is None
+    five = pickle.dumps({"type": cls, "data": rows}, protocol=5)
+    got = nat.parse_table(five)
+    assert got is not None and all(np.array_equal(a, b) for a, b in zip(got, arrays))
+    assert nat.parse_table(pickle.dumps({"type": pickle.Pickler, "data": rows})) is None
+    assert nat.parse_table(pickle.dumps({"data": rows, "type": cls})) is None
+    assert nat.parse_table(pickle.dumps({"type": cls, "data": rows, "more": 1})) is None
+    with pytest.raises(pickle.UnpicklingError):
+        hicimage.PayloadStringP.from_bytes(pickle.dumps({"type": pickle.Pickler, "data": rows}))
+
+    def slow(b):
+        d = hicimage.loads(b)
+        return [hicimage.TupP.from_bytes(bytes(x)).numbers for x in d["data"]]
+
+    declined = accepted = 0
+    small = _pickled_table(cls, *_random_table(rng, 40, 2))
+    for trial in range(3000):
+        b = bytearray(small)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        b = bytes(b)
+        got = nat.parse_table(b)
+        if got is None:
+            declined += 1
+            continue
+        accepted += 1
+        fast_rows = [((np.int32(v) if f else int(v)), format(int(c), "0%db" % int(k))) for v, k, c, f in zip(*[a.tolist() for a in got])]
+        try:
+            want_rows = slow(b)
+        except Exception:
+            # the unpickler is stricter in places that carry no table data (a frame length, a memo opcode's neighbour);
+            # what matters is that the rows the native parser returns are the rows written
+            want_rows = None
+        if want_rows is not None:
+            assert [(type(a), a, c) for a, c in fast_rows] == [(type(a), a, c) for a, c in want_rows], trial
+    assert declined > 0 and accepted > 0

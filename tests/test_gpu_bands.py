@@ -84,3 +84,38 @@ def test_device_side_stitching_equals_host_stitching(shape, k):
     finally:
         for wk in workers:
             wk.close()
+
+
+@pytest.mark.parametrize("shape,k", [((426, 640), 4), ((2048, 512), 5), ((96, 80), 2), ((1080, 1920), 8)])
+def test_sharded_decode_bands_equal_whole_image_decode(shape, k):
+    """bands.BandDecoder: every band runs K7 / K8 on its own block rows (+ halo) of the image's coefficients; its rows
+    must be the whole-image decode's rows (and the oracle's), seams included."""
+    from hiccup_b200 import bands
+    from hiccup_b200.batch import DctBatchCodec
+    h, w = shape
+    rgb = orc.synthetic_image(h, w, 41)
+    codec = DctBatchCodec(1, h, w)
+    codec.upload(rgb[None])
+    codec._forward()
+    coef = codec.coefficients()[0]
+    codec.d_coef_dec.upload(coef, codec.stream)
+    codec._inverse()
+    want = codec.fetch().reshape(codec.out_h, codec.out_w, 3).copy()
+    assert np.array_equal(want, orc.jpeg_decompression(orc.jpeg_compression(rgb)))
+    cuts = bands.plan_bands(h, k)
+    got = np.zeros_like(want)
+    for b in range(len(cuts) - 1):
+        dec = bands.BandDecoder(h, w, cuts[b], cuts[b + 1])
+        try:
+            mine = np.concatenate([coef[a:z] for a, z in dec.src])
+            assert mine.shape[0] == dec.g.blocks_per_image
+            dec.codec.d_coef_dec.upload(mine, dec.codec.stream)
+            dec.inverse()
+            rows = np.empty((cuts[b + 1] - cuts[b], codec.out_w, 3), np.uint8)
+            dec.fetch_rows(rows)
+            got[cuts[b]:cuts[b + 1]] = rows
+        finally:
+            dec.close()
+    assert np.array_equal(got, want)
+    codec.close()
+
