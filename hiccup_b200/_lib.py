@@ -34,6 +34,18 @@ class Geometry(ctypes.Structure):
                 ("out_h", c_int32), ("out_w", c_int32)]
 
 
+class HicfileEnv(ctypes.Structure):
+    _fields_ = [("np_pre", c_void_p), ("np_mid", c_void_p), ("head", c_void_p),
+                ("np_pre_len", c_uint32), ("np_mid_len", c_uint32), ("head_len", c_uint32), ("reserved", c_uint32)]
+
+
+class HicfileBatch(ctypes.Structure):
+    _fields_ = [("n_files", ctypes.c_uint64), ("tables_per_file", c_uint32), ("n_trail", c_uint32),
+                ("stream_of", c_void_p), ("flag_mode", c_void_p), ("index", c_void_p), ("symbols", c_void_p), ("packed", c_void_p),
+                ("data", c_void_p), ("byte_off", c_void_p), ("byte_len", c_void_p), ("lead", c_void_p), ("lead_len", ctypes.c_uint64),
+                ("trail", c_void_p), ("trail_len", c_void_p)]
+
+
 class BandCarry(ctypes.Structure):
     _fields_ = [("carry_zeros", c_int32), ("prev_dc", c_int32), ("more_after", c_int32), ("closes_stream", c_int32)]
 
@@ -131,6 +143,11 @@ SIGNATURES = {
                                        c_void_p, c_uint32, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_hicfile_parse_table": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32)]),
+    "hic_hicfile_files_bound": (c_int, [ctypes.POINTER(HicfileEnv), ctypes.POINTER(HicfileBatch), c_void_p]),
+    "hic_hicfile_pack_files": (c_int, [ctypes.POINTER(HicfileEnv), ctypes.POINTER(HicfileBatch), c_void_p, c_void_p, c_void_p, c_uint32]),
+    "hic_hicfile_scan_files": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32]),
+    "hic_hicfile_parse_files": (c_int, [ctypes.POINTER(HicfileEnv), c_void_p, ctypes.c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32]),
     "hic_hicfile_parse_rows": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "hic_decode_set_data_bytes": (c_int, [c_void_p, ctypes.c_uint64]),

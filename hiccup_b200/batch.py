@@ -15,7 +15,7 @@ import os
 
 import numpy as np
 
-from hiccup_b200 import _lib, entropy, hicimage
+from hiccup_b200 import _compat, _lib, entropy, hicimage, model
 
 
 class _BatchCodec:
@@ -49,6 +49,92 @@ class _BatchCodec:
     @property
     def out_shape(self):
         return (self.n, self.out_h, self.out_w, 3)
+
+    # ---- `.hic` files of a batch -----------------------------------------------------------------
+    def hic_files(self, enc, images=None, threads=None):
+        """The bytes of every image's `.hic` file (what HicImage.write_file dumps: pickle.dumps(hi.byte_stream()) for hi in
+        hic_images(enc)), written for the whole batch by host threads of the library (hic_hicfile_pack_files) instead of
+        one Python object per table row; files the library declines, or all of them where it did not calibrate against
+        this environment's pickle, come from hic_images().  Returns a list of bytes-like objects."""
+        import pickle
+        images = list(range(self.n) if images is None else images)
+        nat = hicimage._native()
+        res = None
+        if images and nat.files_ok:
+            stream_of, modes, lead, trail = self._file_plan(images)
+            res = nat.pack_files(_compat.wire_tuple_class(), enc.index, enc.symbols, enc.packed, enc.data, enc.byte_off, enc.byte_len,
+                                 stream_of, modes, lead, trail, threads)
+        out = []
+        for j, i in enumerate(images):
+            if res is not None and int(res[2][j]):
+                a = int(res[1][j])
+                out.append(memoryview(res[0])[a:a + int(res[2][j])])
+            else:
+                out.append(pickle.dumps(self.hic_images(enc, images=[i])[0].byte_stream()))
+        return out
+
+    def streams_from_files(self, files, threads=None):
+        """The reverse of hic_files(): n bytes-like `.hic` files of this codec's mode and image shape -> the EncodedStreams
+        decode() takes.  Canonical files (what pickle protocol 4 / 5 writes: the reference's and this package's) are walked
+        by host threads of the library (hic_hicfile_scan_files / _parse_files); anything else goes through HicImage.from_bytes.
+        Files of another mode or shape raise ValueError."""
+        files = list(files)
+        if len(files) != self.n:
+            raise ValueError("%d files for a codec of %d images" % (len(files), self.n))
+        stream_of, _, lead, trail = self._file_plan(list(range(self.n)))
+        n_streams = 9 * self.n
+        res = hicimage._native().parse_files(files, stream_of, n_streams, len(trail), threads) if self.n else None
+        if res is not None:
+            index, symbols, packed, data, byte_off, byte_len, nbits, leads, trails = res
+            if all(l == lead for l in leads) and all(t == trail for t in trails):
+                return entropy.EncodedStreams(self.layout, index, None, nbits, byte_off, byte_len, symbols, packed, data)
+        # the tolerant path: any pickle protocol, any spelling of the shapes
+        from hiccup_b200 import codec as codec_mod
+        rows = np.zeros(n_streams, np.uint32)
+        per_stream, framed = [None] * n_streams, [b""] * n_streams
+        tables = stream_of.shape[1]
+        for i, f in enumerate(files):
+            hi = hicimage.HicImage.from_bytes(hicimage.loads(bytes(f)))
+            if getattr(hi.hic_type, "value", hi.hic_type).encode() != lead or [tuple(int(v) for v in p.numbers) for p in hi.payloads[2 * tables:2 * tables + 2]] != \
+                    [tuple(int(v) for v in hicimage.TupP.from_bytes(t).numbers) for t in trail]:
+                raise ValueError("file %d is not a %s file of this codec's image shape" % (i, lead.decode()))
+            for k in range(tables):
+                s = int(stream_of[i, k])
+                r, sym, lens, codes = codec_mod._tables_to_arrays([hi.payloads[k]])
+                rows[s] = r[0]
+                per_stream[s] = (sym, (lens.astype(np.uint64) << np.uint64(58)) | (codes & entropy.CODE_MASK))
+                framed[s] = bytes(hi.payloads[tables + k].byte_stream)
+        index = np.zeros((n_streams, 2), np.uint32)
+        index[:, 1] = rows
+        index[1:, 0] = np.cumsum(rows[:-1], dtype=np.uint64).astype(np.uint32)
+        present = [p for p in per_stream if p is not None]
+        symbols = np.concatenate([p[0] for p in present]).astype(np.int32) if present else np.zeros(0, np.int32)
+        packed = np.concatenate([p[1] for p in present]).astype(np.uint64) if present else np.zeros(0, np.uint64)
+        byte_len = np.array([len(b) for b in framed], np.uint64)
+        padded = (byte_len + np.uint64(3)) & ~np.uint64(3)
+        byte_off = np.zeros(n_streams, np.uint64)
+        byte_off[1:] = np.cumsum(padded[:-1])
+        data = np.zeros(int(padded.sum()) + 16, np.uint8)
+        for b, a in zip(framed, byte_off.tolist()):
+            data[a:a + len(b)] = np.frombuffer(b, np.uint8)
+        nbits = np.array([hicimage.iohelper.payload_bit_count(b) if b else 0 for b in framed], np.uint64)
+        return entropy.EncodedStreams(self.layout, index, None, nbits, byte_off, byte_len, symbols, packed, data)
+
+    def read_files(self, paths, threads=None):
+        """streams_from_files() of files on disk."""
+        files = []
+        for path in paths:
+            with open(path, "rb") as f:
+                files.append(f.read())
+        return self.streams_from_files(files, threads)
+
+    def write_files(self, enc, paths, images=None, threads=None):
+        """hic_files() to disk: paths[j] receives the file of images[j]."""
+        files = self.hic_files(enc, images, threads)
+        assert len(files) == len(paths)
+        for path, b in zip(paths, files):
+            with open(path, "wb") as f:
+                f.write(b)
 
     # ---- transform hooks ---------------------------------------------------------------------
     def _forward(self):
@@ -216,6 +302,16 @@ class DctBatchCodec(_BatchCodec):
         return out
 
 
+    def _file_plan(self, images):
+        """(stream_of [files][9], flag modes, lead entry, trail entries) of hic_files(): the file order of
+        HicImage.jpeg_image -- tables then bit strings, each kind-major / channel-minor -- and the two shape payloads."""
+        g = self.g
+        stream_of = np.array([[(i * 3 + c) * 3 + kind for kind in range(3) for c in range(3)] for i in images], np.uint32).reshape(-1, 9)
+        modes = [1 if kind == entropy.KIND_DC else 0 for kind in range(3) for _ in range(3)]
+        return (stream_of, modes, hicimage.PlainStringP(model.Compression.JPEG.value).byte_stream,
+                [hicimage.TupP(g.h, g.w).byte_stream, hicimage.TupP(g.hc, g.wc).byte_stream])
+
+
 class WaveletBatchCodec(_BatchCodec):
     """Wavelet ("HIC") mode: K9 -> flat-mode entropy stage -> K10 at the default settings, the general
     level-by-level kernels (csrc/hic_wavelet_general.cu) at any other settings.py values, read when the codec
@@ -260,6 +356,16 @@ class WaveletBatchCodec(_BatchCodec):
     def hic_images(self, enc, images=None):
         from hiccup_b200 import wavelet
         return [wavelet.encode_streams_to_hic(enc, self.g, image=i) for i in (range(self.n) if images is None else images)]
+
+    def _file_plan(self, images):
+        """wavelet_image's order: 3 value tables, 3 length tables, their bit strings, cA_L's and cD_1's shapes (codec.py:147-163);
+        non-zero values are numpy scalars in the pickles, zero and the zero counts Python ints."""
+        from hiccup_b200 import wavelet
+        stream_of = np.array([[(i * 3 + c) * 3 + kind for kind in (entropy.KIND_VALUE, entropy.KIND_LENGTH) for c in range(3)]
+                              for i in images], np.uint32).reshape(-1, 6)
+        shapes = wavelet.band_shapes(self.g)
+        return (stream_of, [2, 2, 2, 0, 0, 0], hicimage.PlainStringP(model.Compression.HIC.value).byte_stream,
+                [hicimage.TupP(*shapes[0]).byte_stream, hicimage.TupP(*shapes[-1]).byte_stream])
 
 
 class PipelinedCodec:

@@ -32,6 +32,7 @@ Two things the reference's reader does not have:
 """
 import ctypes
 import io
+import os
 import pickle
 import struct
 import threading
@@ -186,6 +187,7 @@ class _NativeRows:
     def __init__(self):
         self.ok = False
         self.table_ok = False
+        self.files_ok = False
         self._heads = {}
         self._tls = threading.local()
         try:
@@ -196,6 +198,10 @@ class _NativeRows:
             self._calibrate_tables()
         except Exception:
             self.table_ok = False
+        try:
+            self._calibrate_files()
+        except Exception:
+            self.files_ok = False
 
     def _calibrate(self):
         if not ROWS.ok:
@@ -290,6 +296,143 @@ class _NativeRows:
                                                         self._pre.ctypes.data, self._pre.size, self._mid.ctypes.data, self._mid.size,
                                                         head.ctypes.data, head.size, out.ctypes.data, cap, ctypes.byref(size)))
         return out[:size.value].tobytes()
+
+    # ---- whole files of a batch ---------------------------------------------------------------------
+    def pack_files(self, cls, index, symbols, packed, data, byte_off, byte_len, stream_of, flag_mode, lead, trail, threads=None):
+        """The `.hic` files of a batch in one call, written by host threads of the library: file i is
+        pickle.dumps([lead, tables..., bit strings..., *trail]) with its k-th table and bit string taken from symbol stream
+        stream_of[i][k] of an encode result (index / symbols / packed: the packed table layout; data / byte_off / byte_len:
+        the framed payloads); flag_mode[k] as in include/hiccup_b200.h.  Returns (buffer, offsets, sizes): file i is
+        buffer[offsets[i]:offsets[i] + sizes[i]]; sizes[i] == 0 where the library left the file to the caller."""
+        head = self._head(cls)
+        if head is None or not self.files_ok:
+            return None
+        lib = self._lib
+        stream_of = np.ascontiguousarray(stream_of, np.uint32)
+        n, tables = stream_of.shape
+        flag_mode = np.ascontiguousarray(flag_mode, np.uint8)
+        assert flag_mode.size == tables
+        index = np.ascontiguousarray(index, np.uint32)
+        symbols = np.ascontiguousarray(symbols, np.int32)
+        packed = np.ascontiguousarray(packed, np.uint64)
+        data = np.ascontiguousarray(data, np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, np.uint64)
+        byte_len = np.ascontiguousarray(byte_len, np.uint64)
+        lead_a = np.frombuffer(bytes(lead), np.uint8)
+        trail_a = np.frombuffer(b"".join(trail) or b"\0", np.uint8)
+        trail_len = np.array([len(t) for t in trail] or [0], np.uint64)
+        env = lib.HicfileEnv(self._pre.ctypes.data, self._mid.ctypes.data, head.ctypes.data, self._pre.size, self._mid.size, head.size, 0)
+        batch = lib.HicfileBatch(n, tables, len(trail), stream_of.ctypes.data, flag_mode.ctypes.data, index.ctypes.data, symbols.ctypes.data,
+                                 packed.ctypes.data, data.ctypes.data, byte_off.ctypes.data, byte_len.ctypes.data, lead_a.ctypes.data,
+                                 lead_a.size, trail_a.ctypes.data, trail_len.ctypes.data)
+        bound = np.empty(n, np.uint64)
+        lib.check(self._fn.hic_hicfile_files_bound(ctypes.byref(env), ctypes.byref(batch), bound.ctypes.data))
+        off = np.zeros(n + 1, np.uint64)
+        np.cumsum((bound + np.uint64(63)) & ~np.uint64(63), out=off[1:])
+        out = np.empty(int(off[n]), np.uint8)
+        sizes = np.zeros(n, np.uint64)
+        if threads is None:
+            threads = min(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), 32)
+        lib.check(self._fn.hic_hicfile_pack_files(ctypes.byref(env), ctypes.byref(batch), out.ctypes.data, off.ctypes.data,
+                                                  sizes.ctypes.data, int(threads)))
+        return out, off[:-1], sizes
+
+    def parse_files(self, files, stream_of, n_streams, n_trail, threads=None):
+        """The reverse of pack_files for a list of bytes-like `.hic` files with stream_of.shape[1] tables each: returns
+        (index, symbols, packed, data, byte_off, byte_len, nbits, lead, trail) -- the encode-result layout over n_streams
+        symbol streams (streams no file names stay empty) plus the mode entry and the n_trail entries after the bit strings
+        of every file as lists of bytes -- or None if any file is not in the canonical form (the caller then reads the
+        batch with the unpickler)."""
+        if not self.files_ok:
+            return None
+        lib = self._lib
+        stream_of = np.ascontiguousarray(stream_of, np.uint32)
+        n, tables = stream_of.shape
+        assert n == len(files)
+        n_items = 1 + 2 * tables + n_trail
+        views = [np.frombuffer(f, np.uint8) for f in files]         # (kept: the pointers below are theirs)
+        sizes = np.fromiter((v.size for v in views), np.uint64, n)
+        ptrs = np.fromiter((v.ctypes.data if v.size else 0 for v in views), np.uint64, n)
+        if threads is None:
+            threads = min(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), 32)
+        item_off, item_len = np.zeros((n, n_items), np.uint64), np.zeros((n, n_items), np.uint64)
+        rows, canonical = np.zeros((n, tables), np.uint32), np.zeros(n, np.uint8)
+        lib.check(self._fn.hic_hicfile_scan_files(ptrs.ctypes.data, sizes.ctypes.data, n, tables, n_items, item_off.ctypes.data,
+                                                  item_len.ctypes.data, rows.ctypes.data, canonical.ctypes.data, int(threads)))
+        if not canonical.all():
+            return None
+        index = np.zeros((n_streams, 2), np.uint32)
+        index[stream_of.reshape(-1), 1] = rows.reshape(-1)
+        total = int(index[:, 1].sum(dtype=np.uint64))
+        if total >= 1 << 32:
+            return None
+        index[1:, 0] = np.cumsum(index[:-1, 1], dtype=np.uint64).astype(np.uint32)
+        byte_len = np.zeros(n_streams, np.uint64)
+        byte_len[stream_of.reshape(-1)] = item_len[:, 1 + tables:1 + 2 * tables].reshape(-1)
+        padded = (byte_len + np.uint64(3)) & ~np.uint64(3)
+        byte_off = np.zeros(n_streams, np.uint64)
+        byte_off[1:] = np.cumsum(padded[:-1])
+        data = np.zeros(int(padded.sum()) + 16, np.uint8)
+        symbols, packed = np.empty(max(1, total), np.int32), np.empty(max(1, total), np.uint64)
+        nbits, ok = np.zeros(n_streams, np.uint64), np.zeros(n, np.uint8)
+        head = self._head(_compat.wire_tuple_class())
+        env = lib.HicfileEnv(self._pre.ctypes.data, self._mid.ctypes.data, None if head is None else head.ctypes.data,
+                             self._pre.size, self._mid.size, 0 if head is None else head.size, 0)
+        lib.check(self._fn.hic_hicfile_parse_files(ctypes.byref(env), ptrs.ctypes.data, n, tables, n_items, item_off.ctypes.data,
+                                                   item_len.ctypes.data, stream_of.ctypes.data, index.ctypes.data, symbols.ctypes.data,
+                                                   packed.ctypes.data, data.ctypes.data, byte_off.ctypes.data, nbits.ctypes.data,
+                                                   ok.ctypes.data, int(threads)))
+        if not ok.all():
+            return None
+        entry = lambda i, e: views[i][int(item_off[i, e]):int(item_off[i, e] + item_len[i, e])].tobytes()
+        lead = [entry(i, 0) for i in range(n)]
+        trail = [[entry(i, 1 + 2 * tables + t) for t in range(n_trail)] for i in range(n)]
+        return index, symbols[:total], packed[:total], data, byte_off, byte_len, nbits, lead, trail
+
+    def _calibrate_files(self):
+        """pack_files against pickle.dumps of the list of entries: entries below 256 bytes, below and above the 64 KiB
+        frame size, in both flag modes."""
+        self.files_ok = False
+        if not self.table_ok:
+            return
+        self.files_ok = True
+        cls = _compat.wire_tuple_class()
+        rng = np.random.default_rng(3)
+        rows = np.array([3, 1200, 2, 2300, 40, 1], np.uint32)
+        first = np.concatenate(([0], np.cumsum(rows)[:-1])).astype(np.uint32)
+        total = int(rows.sum())
+        symbols = rng.integers(-300, 70000, total).astype(np.int32)
+        symbols[::7] = 0
+        lens = rng.integers(1, 59, total).astype(np.uint64)
+        packed = (lens << np.uint64(58)) | (rng.integers(0, 1 << 62, total, dtype=np.uint64) & ((np.uint64(1) << lens) - np.uint64(1)))
+        sizes = np.array([5, 300, 70000, 2, 65536, 65535], np.uint64)
+        byte_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.uint64)
+        data = rng.integers(0, 256, int(sizes.sum()), dtype=np.uint8)
+        stream_of = np.array([[0, 1, 2], [3, 4, 5], [5, 3, 1]], np.uint32)
+        modes = [1, 0, 2]
+        trail = [pickle.dumps((426, 640)), pickle.dumps((213, 320))]
+        res = self.pack_files(cls, np.stack([first, rows], 1), symbols, packed, data, byte_off, sizes, stream_of, modes, b"JPEG", trail, threads=2)
+        ok = res is not None
+        if ok:
+            out, off, got = res
+            for i in range(stream_of.shape[0]):
+                entries = [b"JPEG"]
+                for k, s_ in enumerate(stream_of[i]):
+                    a, b = int(first[s_]), int(first[s_] + rows[s_])
+                    sym = symbols[a:b]
+                    flags = {0: np.zeros(b - a, np.uint8), 1: np.ones(b - a, np.uint8), 2: (sym != 0).astype(np.uint8)}[modes[k]]
+                    entries.append(self.pack_table(cls, sym, (packed[a:b] >> np.uint64(58)).astype(np.uint8),
+                                                   packed[a:b] & np.uint64((1 << 58) - 1), flags))
+                entries += [data[int(byte_off[s_]):int(byte_off[s_] + sizes[s_])].tobytes() for s_ in stream_of[i]]
+                entries += trail
+                if out[int(off[i]):int(off[i] + got[i])].tobytes() != pickle.dumps(entries):
+                    ok = False
+        if ok:                                             # and back: files 0 and 1 name every stream once
+            back = self.parse_files([out[int(off[i]):int(off[i] + got[i])] for i in range(2)], stream_of[:2], 6, 2, threads=2)
+            ok = back is not None and np.array_equal(back[0][:, 1], rows) and np.array_equal(back[1], symbols) and \
+                np.array_equal(back[2], packed) and np.array_equal(back[5], sizes) and back[7] == [b"JPEG"] * 2 and back[8] == [trail] * 2 and \
+                all(np.array_equal(back[3][int(a):int(a + n_)], data[int(b):int(b + n_)]) for a, b, n_ in zip(back[4], byte_off, sizes))
+        self.files_ok = ok
 
     def parse_table(self, payload):
         """(symbols, lens, codes, flags) of a whole table payload, or None if it is not in the canonical form (another

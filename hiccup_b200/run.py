@@ -4,7 +4,9 @@ rank 1) plus a directory mode that feeds the batched GPU path.
     compress(path, output, style)      run.py:18-29   image file -> <output>/<name>.<STYLE>-hic
     decompress(path)                   run.py:32-43   .hic file -> pixels (the reference shows them in a window;
                                                        here they are returned, and written with `save=`)
-    compress_many(paths, output, ...)  additive: same-shaped images are encoded as one GPU batch
+    compress_many(paths, output, ...)  additive: same-shaped images are encoded as one GPU batch and their files
+                                       written by the library's host threads (batch.write_files)
+    decompress_many(paths, ...)        additive: same-shaped `.hic` files are read and decoded as one GPU batch
 
 Like the reference, `cv2.imread` delivers BGR and the codec treats channel 0 as R (run.py:19), so files
 are interchangeable with the reference's in both directions.  Command line: python -m hiccup_b200.run
@@ -75,13 +77,55 @@ def compress_many(paths, output, c=model.Compression.JPEG, max_batch=256, restar
             bc = cls(len(part), h, w)
             try:
                 enc = bc.encode(np.stack([rgb for _, rgb in part]))
-                for (p, _), hi in zip(part, bc.hic_images(enc)):
-                    out = os.path.join(output, img_name(p, c))
-                    (codec.add_restart_records(hi) if restarts else hi).write_file(out)
-                    written.append(out)
+                outs = [os.path.join(output, img_name(p, c)) for p, _ in part]
+                if restarts:
+                    for out, hi in zip(outs, bc.hic_images(enc)):
+                        codec.add_restart_records(hi).write_file(out)
+                else:
+                    bc.write_files(enc, outs)
+                written += outs
             finally:
                 bc.close()
     return written
+
+
+def _peek(raw):
+    """(mode, (h, w) of the image) of a `.hic` file's bytes, without touching its tables."""
+    entries = hicimage.loads(raw)
+    mode = model.Compression(hicimage.PlainStringP.from_bytes(entries[0]).payload)
+    if mode == model.Compression.JPEG:
+        shape = tuple(int(v) for v in hicimage.TupP.from_bytes(entries[19]).numbers)
+    else:
+        big = tuple(int(v) for v in hicimage.TupP.from_bytes(entries[14]).numbers)      # cD_1: half the image each way
+        shape = (2 * big[0], 2 * big[1])
+    return mode, shape
+
+
+def decompress_many(paths, save_dir=None, max_batch=256):
+    """Decode many `.hic` files; files of one mode and image shape go through the batched codec together.  Returns the
+    pixel arrays in the order of `paths` (equal to what decompress() returns for each); save_dir: also write them as PNG."""
+    from hiccup_b200.batch import DctBatchCodec, WaveletBatchCodec
+    groups, out = {}, [None] * len(paths)
+    for i, p in enumerate(paths):
+        with open(p, "rb") as f:
+            raw = f.read()
+        groups.setdefault(_peek(raw), []).append((i, raw))
+    for (mode, (h, w)), items in groups.items():
+        cls = DctBatchCodec if mode == model.Compression.JPEG else WaveletBatchCodec
+        for a in range(0, len(items), max_batch):
+            part = items[a:a + max_batch]
+            bc = cls(len(part), h, w)
+            try:
+                pixels = bc.decode(bc.streams_from_files([raw for _, raw in part]))
+                for (i, _), rgb in zip(part, pixels):
+                    out[i] = rgb.copy()
+            finally:
+                bc.close()
+    if save_dir is not None:
+        import cv2
+        for p, rgb in zip(paths, out):
+            cv2.imwrite(os.path.join(save_dir, os.path.split(p)[-1] + ".png"), rgb)
+    return out
 
 
 def main(argv=None):

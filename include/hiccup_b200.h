@@ -402,6 +402,57 @@ int hic_hicfile_parse_table(const uint8_t* data, uint64_t size, const uint8_t* n
                             uint32_t np_mid_len, int32_t* symbols, uint8_t* lens, uint64_t* codes, uint8_t* numpy_scalar,
                             uint64_t row_capacity, uint64_t* n_rows, int32_t* canonical);
 
+/* Whole `.hic` files of a batch, written by host threads (hicimage.py:165-183: pickle.dump(HicImage.byte_stream(), f), i.e.
+ * the pickled list [type string, table payloads, framed bit strings, shapes]).  env: what this environment's pickle and
+ * numpy write around the data (read off sample pickles by hiccup_b200/hicimage.py, which also checks these functions
+ * against pickle.dumps before using them).  batch: file i's k-th table and k-th bit string are symbol stream
+ * stream_of[i * tables_per_file + k] of an encode result in the layout of hic_entropy_tables_packed + the framed payloads
+ * of hic_entropy_pack; flag_mode[k]: 0 the table's symbols are Python ints, 1 numpy.int32 scalars (DC tables), 2
+ * numpy.int32 unless the symbol is 0 (wavelet value tables); lead: the first list entry (the mode string); trail: the
+ * n_trail entries after the bit strings (the two shape pickles), concatenated.
+ * files_bound: bound[i] = room that always suffices for file i.  pack_files: file i goes to out[out_off[i] ..) (room
+ * out_off[i + 1] - out_off[i]), its size to out_len[i]; out_len[i] = 0: left to the caller (an entry shorter than two
+ * bytes, which pickle may write as a memo reference).  threads: host threads to use (files are independent). */
+typedef struct hic_hicfile_env {
+    const uint8_t* np_pre;
+    const uint8_t* np_mid;
+    const uint8_t* head;
+    uint32_t np_pre_len, np_mid_len, head_len, reserved;
+} hic_hicfile_env;
+typedef struct hic_hicfile_batch {
+    uint64_t n_files;
+    uint32_t tables_per_file, n_trail;
+    const uint32_t* stream_of;
+    const uint8_t* flag_mode;
+    const uint32_t* index;
+    const int32_t* symbols;
+    const uint64_t* packed;
+    const uint8_t* data;
+    const uint64_t* byte_off;
+    const uint64_t* byte_len;
+    const uint8_t* lead;
+    uint64_t lead_len;
+    const uint8_t* trail;
+    const uint64_t* trail_len;
+} hic_hicfile_batch;
+int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch* batch, uint64_t* bound);
+int hic_hicfile_pack_files(const hic_hicfile_env* env, const hic_hicfile_batch* batch, uint8_t* out, const uint64_t* out_off,
+                           uint64_t* out_len, uint32_t threads);
+/* The reverse, for a batch of files in host memory (file i = file_len[i] bytes at files[i]), in two steps so that
+ * the caller can size the arrays exactly.  scan: positions (from the file's start) and sizes of each file's first n_items
+ * entries -- entry 0 the mode string, 1 .. T the tables, T + 1 .. 2T the bit strings, then the shapes -- and the row count
+ * of every table; canonical[i] = 0 where file i is not the plain list of byte strings pickle protocol 4 / 5 writes (the
+ * caller reads such files with the unpickler).  parse: table k of file i goes to rows index[2 s] .. + index[2 s + 1] of
+ * symbols / packed (the layout hic_decode_set_tables_packed takes; s = stream_of[i * T + k]; the counts must be scan's),
+ * its bit string to data + byte_off[s] and its payload bit count (iohelper.py: the signed pad byte) to nbits[s];
+ * ok[i] = 0 if a row of file i is not of the canonical form. */
+int hic_hicfile_scan_files(const uint8_t* const* files, const uint64_t* file_len, uint64_t n_files, uint32_t tables_per_file, uint32_t n_items,
+                           uint64_t* item_off, uint64_t* item_len, uint32_t* rows, uint8_t* canonical, uint32_t threads);
+int hic_hicfile_parse_files(const hic_hicfile_env* env, const uint8_t* const* files, uint64_t n_files, uint32_t tables_per_file, uint32_t n_items,
+                            const uint64_t* item_off, const uint64_t* item_len, const uint32_t* stream_of, const uint32_t* index,
+                            int32_t* symbols, uint64_t* packed, uint8_t* data, const uint64_t* byte_off, uint64_t* nbits,
+                            uint8_t* ok, uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

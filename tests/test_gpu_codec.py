@@ -291,6 +291,37 @@ def test_file_driver_writes_reference_files(tmp_path):
     assert np.array_equal(run.decompress(out), w["rgb_out"])
 
 
+@pytest.mark.parametrize("mode", ["dct", "wavelet"])
+def test_batch_files_round_trip(mode, tmp_path):
+    """batch.hic_files / streams_from_files (the library's host threads) on a real encode: the files are the ones the
+    per-image container path pickles, and reading them back decodes to the same pixels."""
+    from hiccup_b200 import hicimage, model, run
+    from hiccup_b200.batch import DctBatchCodec, WaveletBatchCodec
+    h, w, n = (136, 200, 6) if mode == "dct" else (64, 96, 4)
+    rgb = np.stack([orc.synthetic_image(h, w, 300 + i) for i in range(n)])
+    rgb[-1] = 77                                                    # a flat image: one-symbol tables, shortest bit strings
+    codec = (DctBatchCodec if mode == "dct" else WaveletBatchCodec)(n, h, w)
+    enc = codec.encode(rgb)
+    want_pixels = codec.decode(enc).copy()
+    want = [pickle.dumps(hi.byte_stream()) for hi in codec.hic_images(enc)]
+    assert hicimage._native().files_ok
+    files = codec.hic_files(enc)
+    assert [bytes(f) for f in files] == want
+    back = codec.streams_from_files(files)
+    assert np.array_equal(codec.decode(back), want_pixels)
+    paths = [str(tmp_path / ("%d.hic" % i)) for i in range(n)]
+    codec.write_files(enc, paths)
+    assert np.array_equal(codec.decode(codec.read_files(paths)), want_pixels)
+    codec.close()
+    # the file driver: same pixels as one file at a time, in the order asked for
+    order = [3, 0, 2]
+    many = run.decompress_many([paths[i] for i in order])
+    for i, got in zip(order, many):
+        assert np.array_equal(got, want_pixels[i]) and np.array_equal(got, run.decompress(paths[i]))
+    style = model.Compression.JPEG if mode == "dct" else model.Compression.HIC
+    assert run._peek(want[0]) == (style, (h, w))
+
+
 def test_argument_checks_of_the_new_entry_points():
     """hic_dct_tie_capacity sizes the tie buffer; a smaller one is refused (HIC_ERR_CAPACITY), and a bit stream that
     would run past the bytes the caller declared is refused before any kernel reads it."""
