@@ -20,6 +20,7 @@ import argparse
 import ctypes
 import json
 import os
+import pickle
 import statistics
 import subprocess
 import sys
@@ -531,6 +532,33 @@ def run_e2e(args, cfg, codec, pipe, host_rgb, rank, local_rank, world, dist, bar
     hic_level = {"ms_per_image": round(hic_ms, 3), "images": len(sample), "cores": 1, "bytes_per_image": hic_bytes // len(sample),
                  "what": "batch codec hic_images() + HicImage.byte_stream() on the host: the step from the packed tables and framed "
                          "bit strings `e2e` delivers to the reference's list of pickled payloads (what write_file() dumps)"}
+    # (4) the same step for the WHOLE batch through the library's host threads (batch.hic_files / streams_from_files:
+    # files byte-identical to (3)'s, checked on the sample), and the files -> pixels direction from those bytes
+    try:
+        threads = min(len(os.sched_getaffinity(0)), 32)
+        files = codec.hic_files(enc_res, threads=threads, reuse=True)
+        t0 = time.perf_counter()
+        files = codec.hic_files(enc_res, threads=threads, reuse=True)          # (into the codec's own buffer, like its other staging)
+        write_ms = (time.perf_counter() - t0) * 1e3
+        same_files = all(bytes(files[i]) == pickle.dumps(hi.byte_stream()) for i, hi in zip(sample[:4], codec.hic_images(enc_res, images=sample[:4])))
+        back = codec.streams_from_files(files, threads=threads)
+        t0 = time.perf_counter()
+        back = codec.streams_from_files(files, threads=threads)
+        read_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        codec.decode(back)
+        decode_ms = (time.perf_counter() - t0) * 1e3
+        same_pixels = bool(np.array_equal(codec._h_out.array(np.uint8)[:host_out.size], host_out.reshape(-1)))
+        hic_level["batch_files"] = {
+            "images": n, "host_threads": threads, "write_ms_per_batch": round(write_ms, 2), "read_ms_per_batch": round(read_ms, 2),
+            "write_ms_per_image": round(write_ms / n, 4), "read_ms_per_image": round(read_ms / n, 4),
+            "file_bytes_per_batch": int(sum(len(f) for f in files)), "files_equal_python_container": bool(same_files),
+            "decode_of_read_files_ms": round(decode_ms, 2), "decoded_pixels_equal": same_pixels,
+            "what": "hic_hicfile_pack_files / scan_files + parse_files: every image's whole `.hic` file written into / parsed from "
+                    "host memory by the library's threads, one call per batch (this rank's batch; not in the timed region)"}
+        del files, back
+    except Exception as exc:                                 # a reported figure, never a reason to lose the line
+        hic_level["batch_files"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": ms / steps, "api": api,
            "copy_floor_ms": ms_floor / steps, "frac_of_copy_floor": (ms_floor / ms) if ms else None,

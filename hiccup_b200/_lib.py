@@ -143,7 +143,7 @@ SIGNATURES = {
                                        c_void_p, c_uint32, c_void_p, ctypes.c_uint64, c_void_p]),
     "hic_hicfile_parse_table": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32)]),
-    "hic_hicfile_files_bound": (c_int, [ctypes.POINTER(HicfileEnv), ctypes.POINTER(HicfileBatch), c_void_p]),
+    "hic_hicfile_files_bound": (c_int, [ctypes.POINTER(HicfileEnv), ctypes.POINTER(HicfileBatch), c_void_p, c_uint32]),
     "hic_hicfile_pack_files": (c_int, [ctypes.POINTER(HicfileEnv), ctypes.POINTER(HicfileBatch), c_void_p, c_void_p, c_void_p, c_uint32]),
     "hic_hicfile_scan_files": (c_int, [c_void_p, c_void_p, ctypes.c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32]),
     "hic_hicfile_parse_files": (c_int, [ctypes.POINTER(HicfileEnv), c_void_p, ctypes.c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,

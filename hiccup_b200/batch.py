@@ -51,11 +51,12 @@ class _BatchCodec:
         return (self.n, self.out_h, self.out_w, 3)
 
     # ---- `.hic` files of a batch -----------------------------------------------------------------
-    def hic_files(self, enc, images=None, threads=None):
+    def hic_files(self, enc, images=None, threads=None, reuse=False):
         """The bytes of every image's `.hic` file (what HicImage.write_file dumps: pickle.dumps(hi.byte_stream()) for hi in
         hic_images(enc)), written for the whole batch by host threads of the library (hic_hicfile_pack_files) instead of
         one Python object per table row; files the library declines, or all of them where it did not calibrate against
-        this environment's pickle, come from hic_images().  Returns a list of bytes-like objects."""
+        this environment's pickle, come from hic_images().  Returns a list of bytes-like objects.  reuse=True writes into
+        a buffer the codec keeps (like its other staging: the result is valid until the next such call)."""
         import pickle
         images = list(range(self.n) if images is None else images)
         nat = hicimage._native()
@@ -63,7 +64,7 @@ class _BatchCodec:
         if images and nat.files_ok:
             stream_of, modes, lead, trail = self._file_plan(images)
             res = nat.pack_files(_compat.wire_tuple_class(), enc.index, enc.symbols, enc.packed, enc.data, enc.byte_off, enc.byte_len,
-                                 stream_of, modes, lead, trail, threads)
+                                 stream_of, modes, lead, trail, threads, reuse=self.__dict__.setdefault("_files_keep", {}) if reuse else None)
         out = []
         for j, i in enumerate(images):
             if res is not None and int(res[2][j]):
@@ -130,7 +131,7 @@ class _BatchCodec:
 
     def write_files(self, enc, paths, images=None, threads=None):
         """hic_files() to disk: paths[j] receives the file of images[j]."""
-        files = self.hic_files(enc, images, threads)
+        files = self.hic_files(enc, images, threads, reuse=True)
         assert len(files) == len(paths)
         for path, b in zip(paths, files):
             with open(path, "wb") as f:

@@ -491,21 +491,21 @@ int hic_hicfile_pack_table(const int32_t* symbols, const uint8_t* lens, const ui
     return HIC_OK;
 }
 
-int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch* b, uint64_t* bound) {
+int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch* b, uint64_t* bound, uint32_t threads) {
     HIC_REQUIRE(env && b && bound, "NULL argument");
     HIC_REQUIRE(check_batch(env, b), "incomplete batch description");
     const RowFormat fmt{env->np_pre, env->np_pre_len, env->np_mid, env->np_mid_len};
     uint64_t trail = 0;
     for (uint32_t t = 0; t < b->n_trail; ++t) trail += b->trail_len[t];
-    for (uint64_t i = 0; i < b->n_files; ++i) {
+    run_threads(b->n_files, threads, [&](uint64_t i) {
         uint64_t payload = b->lead_len + trail;
-        uint64_t items = 1 + 2ull * b->tables_per_file + b->n_trail;
+        const uint64_t items = 1 + 2ull * b->tables_per_file + b->n_trail;
         for (uint32_t k = 0; k < b->tables_per_file; ++k) {
             const uint32_t s = b->stream_of[i * b->tables_per_file + k];
             payload += table_bound(table_rows(b, s, k), fmt, env->head_len) + b->byte_len[s];
         }
         bound[i] = framed_bound(payload + 6 * items + 16, items);
-    }
+    });
     return HIC_OK;
 }
 
@@ -514,22 +514,22 @@ int hic_hicfile_pack_files(const hic_hicfile_env* env, const hic_hicfile_batch* 
     HIC_REQUIRE(env && b && out && out_off && out_len, "NULL argument");
     HIC_REQUIRE(check_batch(env, b), "incomplete batch description");
     const RowFormat fmt{env->np_pre, env->np_pre_len, env->np_mid, env->np_mid_len};
-    // rows first: a code length outside 1..58 is the caller's error, not something to find out on a worker thread
-    for (uint64_t i = 0; i < b->n_files; ++i)
-        for (uint32_t k = 0; k < b->tables_per_file; ++k) {
-            const TableRows r = table_rows(b, b->stream_of[i * b->tables_per_file + k], k);
-            for (uint64_t j = 0; j < r.n; ++j) {
-                const uint32_t len = (uint32_t)(r.packed[j] >> 58);
-                HIC_REQUIRE(len >= 1 && len <= 58, "code length %u out of range in a table of file %llu", len, (unsigned long long)i);
-            }
-        }
     std::atomic<int> failed{0};
     run_threads(b->n_files, threads, [&](uint64_t i) {
         thread_local std::vector<uint8_t> scratch;
+        out_len[i] = 0;
+        for (uint32_t k = 0; k < b->tables_per_file; ++k) {            // a code length outside 1..58 is the caller's error
+            const TableRows r = table_rows(b, b->stream_of[i * b->tables_per_file + k], k);
+            for (uint64_t j = 0; j < r.n; ++j) {
+                const uint32_t len = (uint32_t)(r.packed[j] >> 58);
+                if (len < 1 || len > 58) { failed.store(2); return; }
+            }
+        }
         const int64_t n = write_file(env, b, fmt, i, out + out_off[i], out_off[i + 1] - out_off[i], scratch);
-        if (n < 0) { failed.store(1); out_len[i] = 0; }
+        if (n < 0) failed.store(1);
         else out_len[i] = (uint64_t)n;
     });
+    if (failed.load() == 2) return hic::fail(HIC_ERR_INVALID, "a code length outside 1..58 in the batch's tables");
     if (failed.load()) return hic::fail(HIC_ERR_CAPACITY, "a file did not fit the room hic_hicfile_files_bound gives it");
     return HIC_OK;
 }

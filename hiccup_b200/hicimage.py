@@ -298,12 +298,14 @@ class _NativeRows:
         return out[:size.value].tobytes()
 
     # ---- whole files of a batch ---------------------------------------------------------------------
-    def pack_files(self, cls, index, symbols, packed, data, byte_off, byte_len, stream_of, flag_mode, lead, trail, threads=None):
+    def pack_files(self, cls, index, symbols, packed, data, byte_off, byte_len, stream_of, flag_mode, lead, trail, threads=None, reuse=None):
         """The `.hic` files of a batch in one call, written by host threads of the library: file i is
         pickle.dumps([lead, tables..., bit strings..., *trail]) with its k-th table and bit string taken from symbol stream
         stream_of[i][k] of an encode result (index / symbols / packed: the packed table layout; data / byte_off / byte_len:
         the framed payloads); flag_mode[k] as in include/hiccup_b200.h.  Returns (buffer, offsets, sizes): file i is
-        buffer[offsets[i]:offsets[i] + sizes[i]]; sizes[i] == 0 where the library left the file to the caller."""
+        buffer[offsets[i]:offsets[i] + sizes[i]]; sizes[i] == 0 where the library left the file to the caller.
+        reuse: a dict that keeps the output buffer between calls (the files of the previous call are then overwritten):
+        a fresh buffer of a batch's size costs as much in page faults as the writing itself."""
         head = self._head(cls)
         if head is None or not self.files_ok:
             return None
@@ -325,14 +327,18 @@ class _NativeRows:
         batch = lib.HicfileBatch(n, tables, len(trail), stream_of.ctypes.data, flag_mode.ctypes.data, index.ctypes.data, symbols.ctypes.data,
                                  packed.ctypes.data, data.ctypes.data, byte_off.ctypes.data, byte_len.ctypes.data, lead_a.ctypes.data,
                                  lead_a.size, trail_a.ctypes.data, trail_len.ctypes.data)
-        bound = np.empty(n, np.uint64)
-        lib.check(self._fn.hic_hicfile_files_bound(ctypes.byref(env), ctypes.byref(batch), bound.ctypes.data))
-        off = np.zeros(n + 1, np.uint64)
-        np.cumsum((bound + np.uint64(63)) & ~np.uint64(63), out=off[1:])
-        out = np.empty(int(off[n]), np.uint8)
-        sizes = np.zeros(n, np.uint64)
         if threads is None:
             threads = min(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), 32)
+        bound = np.empty(n, np.uint64)
+        lib.check(self._fn.hic_hicfile_files_bound(ctypes.byref(env), ctypes.byref(batch), bound.ctypes.data, int(threads)))
+        off = np.zeros(n + 1, np.uint64)
+        np.cumsum((bound + np.uint64(63)) & ~np.uint64(63), out=off[1:])
+        out = None if reuse is None else reuse.get("out")
+        if out is None or out.size < int(off[n]):
+            out = np.empty(int(off[n]) + (int(off[n]) // 8 if reuse is not None else 0), np.uint8)
+            if reuse is not None:
+                reuse["out"] = out
+        sizes = np.zeros(n, np.uint64)
         lib.check(self._fn.hic_hicfile_pack_files(ctypes.byref(env), ctypes.byref(batch), out.ctypes.data, off.ctypes.data,
                                                   sizes.ctypes.data, int(threads)))
         return out, off[:-1], sizes

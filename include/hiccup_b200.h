@@ -435,7 +435,7 @@ typedef struct hic_hicfile_batch {
     const uint8_t* trail;
     const uint64_t* trail_len;
 } hic_hicfile_batch;
-int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch* batch, uint64_t* bound);
+int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch* batch, uint64_t* bound, uint32_t threads);
 int hic_hicfile_pack_files(const hic_hicfile_env* env, const hic_hicfile_batch* batch, uint8_t* out, const uint64_t* out_off,
                            uint64_t* out_len, uint32_t threads);
 /* The reverse, for a batch of files in host memory (file i = file_len[i] bytes at files[i]), in two steps so that

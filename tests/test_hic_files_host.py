@@ -75,6 +75,12 @@ def test_dct_batch_files_equal_the_python_container(threads):
     sub = codec.hic_files(enc, images=[5, 0, 2], threads=threads)
     assert [bytes(b) for b in sub] == [want[5], want[0], want[2]]
     assert codec.hic_files(enc, images=[]) == []
+    # reuse=True: the same bytes, written into a buffer the codec keeps between calls
+    first = codec.hic_files(enc, threads=threads, reuse=True)
+    assert [bytes(b) for b in first] == want
+    keep = codec._files_keep["out"]
+    again = codec.hic_files(enc, images=[1, 4], threads=threads, reuse=True)
+    assert codec._files_keep["out"] is keep and [bytes(b) for b in again] == [want[1], want[4]]
 
 
 def test_dct_batch_files_big_image(tmp_path):
