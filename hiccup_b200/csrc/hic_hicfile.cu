@@ -1,5 +1,5 @@
-// hic_hicfile.cu -- host-side helpers for the `.hic` container (no device code): the rows of a Huffman table to and
-// from the byte strings the reference pickles them as.
+// hic_hicfile.cu -- host-side helpers for the `.hic` container (no device code): Huffman table rows, whole table
+// payloads and whole files to and from the byte strings the reference pickles them as.
 //
 // reference hiccup/hicimage.py:57-60, 103-121: a table payload is pickle.dumps({"type": TupP, "data": [pickle.dumps((symbol,
 // code)) for every row]}) -- one pickle PER ROW, thousands per image, which in Python costs more host time than the
@@ -14,6 +14,10 @@
 // The parser accepts exactly these canonical forms and reports the first row that is anything else.
 // hic_hicfile_pack_table writes the whole table payload -- the outer pickle with its frames, batches and memo opcodes
 // around the rows -- so that a table costs one call and one bytes object instead of one per row.
+// hic_hicfile_pack_files / scan_files / parse_files do the same for the whole file (hicimage.py:165-183:
+// pickle.dump of the list [mode string, table payloads, framed bit strings, shapes]) and for every image of a batch,
+// files shared out over host threads: from the encode result's packed tables and bit strings to file bytes and back,
+// with no Python object per row, table or file.
 #include <stdint.h>
 #include <string.h>
 #include <atomic>
