@@ -436,22 +436,33 @@ inline int64_t walk_file(const uint8_t* data, uint64_t size, uint64_t want, uint
     return r.pos == size ? items : -1;
 }
 
+// work(i) for i in [0, n) on up to `threads` host threads (the caller's included), items handed out one at a time.
+// Nothing may escape a C entry point: an exception in a worker (std::bad_alloc from a scratch buffer) stops the hand-out
+// and makes the call return false; a thread that cannot be started only means fewer workers.
 template <typename Work>
-inline void run_threads(uint64_t n, uint32_t threads, Work&& work) {
+inline bool run_threads(uint64_t n, uint32_t threads, Work&& work) {
     std::atomic<uint64_t> next{0};
+    std::atomic<bool> threw{false};
     auto loop = [&]() {
-        for (;;) {
-            const uint64_t i = next.fetch_add(1);
-            if (i >= n) break;
-            work(i);
+        try {
+            for (;;) {
+                const uint64_t i = next.fetch_add(1);
+                if (i >= n || threw.load()) break;
+                work(i);
+            }
+        } catch (...) {
+            threw.store(true);
         }
     };
     const uint64_t workers = threads < 1 ? 1 : (threads > n ? (n ? n : 1) : threads);
-    if (workers <= 1) { loop(); return; }
     std::vector<std::thread> pool;
-    for (uint64_t t = 0; t + 1 < workers; ++t) pool.emplace_back(loop);
+    try {
+        for (uint64_t t = 0; t + 1 < workers; ++t) pool.emplace_back(loop);
+    } catch (...) {
+    }
     loop();
     for (auto& t : pool) t.join();
+    return !threw.load();
 }
 
 }  // namespace
@@ -501,7 +512,7 @@ int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch*
     const RowFormat fmt{env->np_pre, env->np_pre_len, env->np_mid, env->np_mid_len};
     uint64_t trail = 0;
     for (uint32_t t = 0; t < b->n_trail; ++t) trail += b->trail_len[t];
-    run_threads(b->n_files, threads, [&](uint64_t i) {
+    const bool done = run_threads(b->n_files, threads, [&](uint64_t i) {
         uint64_t payload = b->lead_len + trail;
         const uint64_t items = 1 + 2ull * b->tables_per_file + b->n_trail;
         for (uint32_t k = 0; k < b->tables_per_file; ++k) {
@@ -510,6 +521,7 @@ int hic_hicfile_files_bound(const hic_hicfile_env* env, const hic_hicfile_batch*
         }
         bound[i] = framed_bound(payload + 6 * items + 16, items);
     });
+    HIC_REQUIRE(done, "a worker thread failed");
     return HIC_OK;
 }
 
@@ -519,7 +531,7 @@ int hic_hicfile_pack_files(const hic_hicfile_env* env, const hic_hicfile_batch* 
     HIC_REQUIRE(check_batch(env, b), "incomplete batch description");
     const RowFormat fmt{env->np_pre, env->np_pre_len, env->np_mid, env->np_mid_len};
     std::atomic<int> failed{0};
-    run_threads(b->n_files, threads, [&](uint64_t i) {
+    const bool done = run_threads(b->n_files, threads, [&](uint64_t i) {
         thread_local std::vector<uint8_t> scratch;
         out_len[i] = 0;
         for (uint32_t k = 0; k < b->tables_per_file; ++k) {            // a code length outside 1..58 is the caller's error
@@ -533,6 +545,7 @@ int hic_hicfile_pack_files(const hic_hicfile_env* env, const hic_hicfile_batch* 
         if (n < 0) failed.store(1);
         else out_len[i] = (uint64_t)n;
     });
+    if (!done) return hic::fail(HIC_ERR_CAPACITY, "out of host memory while writing the batch's files");
     if (failed.load() == 2) return hic::fail(HIC_ERR_INVALID, "a code length outside 1..58 in the batch's tables");
     if (failed.load()) return hic::fail(HIC_ERR_CAPACITY, "a file did not fit the room hic_hicfile_files_bound gives it");
     return HIC_OK;
@@ -573,7 +586,7 @@ int hic_hicfile_scan_files(const uint8_t* const* files, const uint64_t* file_len
                            uint64_t* item_off, uint64_t* item_len, uint32_t* rows, uint8_t* canonical, uint32_t threads) {
     HIC_REQUIRE(files && file_len && item_off && item_len && rows && canonical, "NULL argument");
     HIC_REQUIRE(n_items >= 1 + 2 * tables_per_file, "a file holds the mode entry, the tables and as many bit strings");
-    run_threads(n_files, threads, [&](uint64_t i) {
+    const bool done = run_threads(n_files, threads, [&](uint64_t i) {
         uint64_t* off = item_off + i * n_items;
         uint64_t* len = item_len + i * n_items;
         canonical[i] = 0;
@@ -587,6 +600,7 @@ int hic_hicfile_scan_files(const uint8_t* const* files, const uint64_t* file_len
         }
         canonical[i] = 1;
     });
+    HIC_REQUIRE(done, "a worker thread failed");
     return HIC_OK;
 }
 
@@ -597,7 +611,7 @@ int hic_hicfile_parse_files(const hic_hicfile_env* env, const uint8_t* const* fi
     HIC_REQUIRE(env && files && item_off && item_len && stream_of && index && symbols && packed && data && byte_off && nbits && ok,
                 "NULL argument");
     const RowFormat fmt{env->np_pre, env->np_pre_len, env->np_mid, env->np_mid_len};
-    run_threads(n_files, threads, [&](uint64_t i) {
+    const bool done = run_threads(n_files, threads, [&](uint64_t i) {
         const uint64_t* off = item_off + i * n_items;
         const uint64_t* len = item_len + i * n_items;
         ok[i] = 0;
@@ -625,6 +639,7 @@ int hic_hicfile_parse_files(const hic_hicfile_env* env, const uint8_t* const* fi
         }
         ok[i] = 1;
     });
+    HIC_REQUIRE(done, "a worker thread failed");
     return HIC_OK;
 }
 
