@@ -29,6 +29,10 @@ Two things the reference's reader does not have:
     never looks further (hicimage.py:124-142), so entries appended after them travel with the file and
     the reference still decodes it.  `RestartP` (restart records for the parallel Huffman decode,
     include/hiccup_b200.h) is such an entry.
+
+The format's one pickle per table row (thousands per image) is written and parsed by host code of the library
+(`_NativeRows` over csrc/hic_hicfile.cu: rows, whole table payloads, and whole files of a batch on host threads), each
+level calibrated against `pickle.dumps` in this environment before it is used and replaced by plain pickle otherwise.
 """
 import ctypes
 import io
