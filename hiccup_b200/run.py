@@ -10,7 +10,7 @@ rank 1) plus a directory mode that feeds the batched GPU path.
 
 Like the reference, `cv2.imread` delivers BGR and the codec treats channel 0 as R (run.py:19), so files
 are interchangeable with the reference's in both directions.  Command line: python -m hiccup_b200.run
--c IMG | -d HIC [-s JPEG|HIC] [-o OUT], the subset of bin/belch.py:26-49 that does not need a display.
+-c IMG... | -d HIC... [-s JPEG|HIC] [-o OUT] [-r], the subset of bin/belch.py:26-49 that does not need a display.
 """
 import argparse
 import os
@@ -131,7 +131,7 @@ def decompress_many(paths, save_dir=None, max_batch=256):
 def main(argv=None):
     ap = argparse.ArgumentParser(description="hiccup image compression on the GPU (no GUI)")
     ap.add_argument("--compress", "-c", metavar="IMG_PATH", nargs="+")
-    ap.add_argument("--decompress", "-d", metavar="HIC")
+    ap.add_argument("--decompress", "-d", metavar="HIC", nargs="+")
     ap.add_argument("--compression", "-s", metavar="STYLE", default=model.Compression.HIC.value,
                     choices=[model.Compression.HIC.value, model.Compression.JPEG.value])
     ap.add_argument("--output", "-o", metavar="OUT", default=".")
@@ -144,9 +144,12 @@ def main(argv=None):
                     else [compress(args.compress[0], args.output, style, restarts=args.restarts)]):
             print(out)
     elif args.decompress:
-        name = os.path.join(args.output, os.path.split(args.decompress)[-1] + ".png")
-        decompress(args.decompress, save=name)
-        print(name)
+        if len(args.decompress) > 1:
+            decompress_many(args.decompress, save_dir=args.output)
+        else:
+            decompress(args.decompress[0], save=os.path.join(args.output, os.path.split(args.decompress[0])[-1] + ".png"))
+        for p in args.decompress:
+            print(os.path.join(args.output, os.path.split(p)[-1] + ".png"))
     else:
         raise RuntimeError("Illegal state")
 
