@@ -1,5 +1,6 @@
-"""Host cost of the `.hic` container step for one 640x426 image, no GPU involved: the code tables and framed bit strings
-of the oracle's encode -> HicImage -> byte_stream() (what write_file dumps) and back through HicImage.from_bytes.
+"""Host cost of the `.hic` container step for one 640x426 image, no GPU involved: code tables and framed bit strings of
+the sizes a C2 image has (synthetic rows: 6 000 of them, codes of 2..24 bits, 150 KB of bits) -> HicImage ->
+byte_stream() (what write_file dumps) and back through HicImage.from_bytes.
 Prints one JSON line; `paths` says which of the native whole-table / native row / pure pickle paths calibrated here.
 
     python tools/hic_container_cpu.py [--reps 50]
@@ -13,7 +14,6 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import hiccup_oracle as orc      # noqa: E402  (input generator only)
 from hiccup_b200 import hicimage             # noqa: E402
 
 
@@ -24,12 +24,14 @@ def main():
                     help="which writer / reader to time: the whole-table native calls, the per-row native calls, or pickle alone")
     args = ap.parse_args()
     h, w = 426, 640
-    enc = orc.jpeg_encode(orc.jpeg_compression(orc.synthetic_image(h, w, 5)))
-    arrs = []
-    for rows in enc["tables"]:
-        arrs.append((np.array([int(a) for a, _ in rows], np.int32), np.array([len(b) for _, b in rows], np.uint8),
-                     np.array([int(b, 2) for _, b in rows], np.uint64)))
-    framed = [orc.padded_bits_to_bytes(b) for b in enc["bits"]]
+    rng = np.random.default_rng(1)
+    arrs, framed = [], []
+    for k, rows in enumerate([1717, 837, 851, 797, 596, 576, 15, 15, 15]):     # DC x3, run-length values x3, zero counts x3
+        sym = rng.permutation(np.arange(-(rows // 2), rows - rows // 2)).astype(np.int32)
+        lens = rng.integers(2, 25, rows).astype(np.uint8)
+        codes = rng.integers(0, 1 << 24, rows, dtype=np.uint64) & ((np.uint64(1) << lens.astype(np.uint64)) - np.uint64(1))
+        arrs.append((sym, lens, codes))
+        framed.append(bytes([3]) + rng.integers(0, 256, [9000, 4000, 4000, 45000, 20000, 20000, 25000, 12000, 12000][k], dtype=np.uint8).tobytes())
     nat = hicimage._native()
     paths = {"rows": bool(nat.ok), "table": bool(nat.table_ok)}
     if args.force != "table":
