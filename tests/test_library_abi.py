@@ -52,3 +52,14 @@ def test_no_cpu_fallback():
         pytest.skip("a CUDA device is present")
     with pytest.raises(_lib.HicError):
         compression.jpeg_compression(np.zeros((16, 16, 3), np.uint8))
+
+
+def test_product_and_tools_never_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under hiccup_b200/ (the product) or tools/ may import it."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for path in glob.glob(os.path.join(root, "hiccup_b200", "**", "*.py"), recursive=True) + glob.glob(os.path.join(root, "tools", "*.py")):
+        with open(path) as f:
+            assert not pat.search(f.read()), path
